@@ -1,0 +1,245 @@
+/*
+ * t2r_b200.h — C-ABI of libt2r_b200.so: the B200 (sm_100a) kernels underneath the
+ * Tensor2Robot per-replay-batch hot path.
+ *
+ * The reference (google-research/tensor2robot) has no FFI: every hot-path op is a
+ * TensorFlow library call made from Python.  Each entry point below therefore cites the
+ * reference *call site* (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain C types only.  Every function returns int32 status (0 = OK,
+ *     negative = T2R_ERR_*); t2r_last_error() returns a thread-local message.
+ *   - No hidden allocation: the caller (PyTorch caching allocator) owns every device and
+ *     pinned buffer.  Functions never synchronise; `stream` is a cudaStream_t passed as void*.
+ *   - Activations are NHWC ("channels last"), bf16 unless stated; parameters/optimizer
+ *     state are fp32; conv weights are OHWI ([Cout][KH][KW][Cin]).
+ *   - Descriptors are POD structs versioned by a leading uint32 struct_size.
+ */
+#ifndef T2R_B200_H_
+#define T2R_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2R_OK 0
+#define T2R_ERR_INVALID_ARG (-1)
+#define T2R_ERR_CUDA (-2)
+#define T2R_ERR_UNSUPPORTED (-3)
+#define T2R_ERR_PARSE (-4)
+#define T2R_ERR_IO (-5)
+
+/* ---- library ------------------------------------------------------------------------ */
+int32_t t2r_version(void);
+const char* t2r_last_error(void);
+/* Number of kernels launched by this library in this process (bench.py "gpu_launches"). */
+int64_t t2r_launch_count(void);
+void t2r_launch_count_reset(void);
+
+/* ---- convolution / GEMM on tcgen05 tensor cores -------------------------------------- */
+/* Replaces slim.conv2d / tf.layers.conv2d / slim.fully_connected call sites:
+ *   research/qtopt/networks.py:443-591 (Grasping44 convs, fc0/fc1),
+ *   layers/film_resnet_model.py:89-105 (conv2d_fixed_padding), :618 (final dense).
+ * Implicit GEMM: M = N*Ho*Wo output pixels, N = Cout, K = KH*KW*Cin; bf16 operands staged by
+ * TMA into 128B-swizzled shared memory, fp32 accumulation in TMEM. */
+#define T2R_EPI_BIAS 1      /* y += bias[c]                       */
+#define T2R_EPI_RESIDUAL 2  /* y += residual (same shape as y)     */
+#define T2R_EPI_RELU 4      /* y = max(y, 0)                       */
+#define T2R_EPI_OUT_F32 8   /* y written as fp32 instead of bf16   */
+
+typedef struct T2RConvDesc {
+  uint32_t struct_size;
+  int32_t N, H, W, Cin;   /* input  [N,H,W,Cin]                               */
+  int32_t Cout, KH, KW;   /* filter [Cout,KH,KW,Cin]                          */
+  int32_t stride;         /* 1 or 2, same in both dims                        */
+  int32_t pad_top, pad_left; /* zero padding before the first row / column    */
+  int32_t Ho, Wo;         /* output [N,Ho,Wo,Cout]; end padding is implied    */
+  int32_t flags;          /* T2R_EPI_* (fprop only)                           */
+} T2RConvDesc;
+
+/* TF padding arithmetic: SAME => out=ceil(in/s), pad_before=pad_total/2. */
+int32_t t2r_conv_same_padding(int32_t in, int32_t k, int32_t stride, int32_t* out,
+                              int32_t* pad_before);
+
+/* y = conv(x, w) (+bias)(+residual)(relu).  Requires Cin % 64 == 0, Cout % 64 == 0. */
+int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const void* w_ohwi,
+                         const float* bias, const void* residual, void* y, void* stream);
+/* dx = conv_transpose(dy, w).  w_dgrad is [Cin][KH*KW][Cout] bf16 (see t2r_pack_weights).
+ * accumulate != 0: dx += result.  Requires Cout % 64 == 0, Cin % 64 == 0. */
+int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const void* w_dgrad, void* dx,
+                         int32_t accumulate, void* stream);
+/* dw (fp32, OHWI) += dy^T * im2col(x): split-K over pixels with fp32 atomics; the caller
+ * zeroes dw once per step.  Requires Cin % 64 == 0, Cout % 64 == 0. */
+int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const void* dy, float* dw,
+                         void* stream);
+/* fp32 master OHWI -> bf16 OHWI (w_fprop) and bf16 [Cin][taps][Cout] (w_dgrad; may be NULL). */
+int32_t t2r_pack_weights(const float* w, void* w_fprop, void* w_dgrad, int32_t Cout,
+                         int32_t taps, int32_t Cin, void* stream);
+/* Small-Cin stem (Cin=3): explicit im2col into a K-padded bf16 matrix [N*Ho*Wo, Kpad]
+ * (column k = (kh*KW+kw)*Cin + c, zero for k >= KH*KW*Cin), consumed by the 1x1 path above.
+ * x is bf16 NHWC.  Replaces conv1_1 6x6/2 (networks.py:443-450) and the 7x7/2 ResNet stem
+ * (film_resnet_model.py:561-565). */
+int32_t t2r_im2col_small_cin(const T2RConvDesc* d, const void* x, void* a, int32_t Kpad,
+                             void* stream);
+
+/* ---- fp32 CUDA-core GEMM for the tiny action-context / logit layers -------------------- */
+/* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, op = transpose if flag set.
+ * Replaces slim.fully_connected on grasp params and logits (networks.py:488-503,566-573). */
+int32_t t2r_sgemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, float alpha,
+                  const float* A, int32_t lda, const float* B, int32_t ldb, float beta, float* C,
+                  int32_t ldc, void* stream);
+int32_t t2r_bias_add_f32(float* y, const float* bias, int64_t rows, int32_t C, void* stream);
+int32_t t2r_colsum_f32(const float* x, float* out, int64_t rows, int32_t C, void* stream);
+int32_t t2r_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int32_t t2r_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+
+/* ---- batch norm (slim.batch_norm / tf.layers.batch_normalization, training + inference) - */
+/* x: bf16 [rows, C].  stats: fp64 [2*C] workspace (sum, sumsq), zeroed by the call.
+ * Reference: film_resnet_model.py:50-57 (momentum .997 eps 1e-5), networks.py:396-410
+ * (decay .9997 eps .001); SURVEY §8c-4 (biased var to normalise, Bessel var into moving). */
+int32_t t2r_bn_stats(const void* x, int64_t rows, int32_t C, double* stats, void* stream);
+/* From stats: mean/var -> scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; saves
+ * mean and invstd (fp32 [C] each) for backward; updates moving stats in place with
+ * moving = moving*momentum + batch*(1-momentum) (variance Bessel-corrected).
+ * gamma may be NULL (scale=False).  moving_* may be NULL. */
+int32_t t2r_bn_finalize(const double* stats, int64_t rows, int32_t C, const float* gamma,
+                        const float* beta, float eps, float momentum, float* moving_mean,
+                        float* moving_var, float* mean, float* invstd, float* scale,
+                        float* shift, void* stream);
+/* Inference: scale/shift from moving statistics. */
+int32_t t2r_bn_infer_params(int32_t C, const float* gamma, const float* beta,
+                            const float* moving_mean, const float* moving_var, float eps,
+                            float* scale, float* shift, void* stream);
+/* y = act(x*scale[c] + shift[c]); optional FiLM per image (film [N, 2C] fp32: gamma|beta,
+ * applied as (1+g)*v + b before the ReLU, film_resnet_model.py:108-115); rows_per_image
+ * = H*W of that tensor.  relu != 0 applies ReLU. */
+int32_t t2r_bn_apply(const void* x, void* y, int64_t rows, int32_t C, const float* scale,
+                     const float* shift, const float* film, int64_t rows_per_image,
+                     int32_t relu, void* stream);
+/* Backward of y = relu?(bn(x)) w.r.t. x, gamma, beta.  dy, x: bf16 [rows,C].
+ * red: fp64 [2*C] workspace.  dgamma/dbeta: fp32 [C] written (dgamma may be NULL).
+ * dres (optional, bf16 [rows,C]) is added to dx (residual-branch gradient). */
+int32_t t2r_bn_backward(const void* dy, const void* x, const void* dres, void* dx, int64_t rows,
+                        int32_t C, const float* gamma, const float* mean, const float* invstd,
+                        const float* scale, const float* shift, int32_t relu, double* red,
+                        float* dgamma, float* dbeta, void* stream);
+
+/* ---- pooling / reductions / elementwise ------------------------------------------------ */
+/* slim.max_pool2d SAME/VALID (networks.py:452,459,528; film_resnet_model.py:575-579).
+ * argmax: uint8 [N,Ho,Wo,C] window-relative index of the first maximum (TF tie rule). */
+int32_t t2r_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t N, int32_t H, int32_t W,
+                        int32_t C, int32_t k, int32_t stride, int32_t pad_top, int32_t pad_left,
+                        int32_t Ho, int32_t Wo, void* stream);
+int32_t t2r_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int32_t N, int32_t H,
+                        int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_top,
+                        int32_t pad_left, int32_t Ho, int32_t Wo, void* stream);
+/* tf.reduce_mean over H,W (film_resnet_model.py:611-613): bf16 [N,HW,C] -> bf16 [N,C]. */
+int32_t t2r_global_mean_fwd(const void* x, void* y, int32_t N, int32_t HW, int32_t C,
+                            void* stream);
+int32_t t2r_global_mean_bwd(const void* dy, void* dx, int32_t N, int32_t HW, int32_t C,
+                            void* stream);
+/* Tile + broadcast add of the action context (networks.py:513-522, tile_batch + tf.add):
+ * y[(b*A+a), p, c] = x[b, p, c] + ctx[(b*A+a), c]; never materialises the tile of x. */
+int32_t t2r_add_context_fwd(const void* x, const void* ctx, void* y, int32_t B, int32_t A,
+                            int32_t HW, int32_t C, void* stream);
+/* dx[b,p,c] = sum_a dy[(b*A+a),p,c]; dctx[(b*A+a),c] = sum_p dy[(b*A+a),p,c]. */
+int32_t t2r_add_context_bwd(const void* dy, void* dx, void* dctx, int32_t B, int32_t A,
+                            int32_t HW, int32_t C, void* stream);
+/* y = a + b (bf16), used for gradient fan-in. */
+int32_t t2r_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+int32_t t2r_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+
+/* ---- image preprocessing (HBM-bound) --------------------------------------------------- */
+/* Fused crop + uint8->float (x * (1/255)) + photometric distortion + clip.
+ * Reference: research/qtopt/t2r_models.py:277-308, preprocessors/image_transformations.py:
+ * 25-101 (crops), :176-264 (ApplyPhotometricImageDistortions).  One parameter set per image
+ * (the reference draws one per batch; replicate the scalar to reproduce it). */
+typedef struct T2RDistortParams {   /* per image, fp32 */
+  float brightness_delta;  /* added after conversion; 0 = off                             */
+  float saturation_scale;  /* HSV saturation multiplier; 1 = off                          */
+  float hue_delta;         /* HSV hue shift in [-1,1] turns; 0 = off                      */
+  float contrast_scale;    /* (x-mean_c)*c+mean_c with per-image per-channel mean; 1 = off */
+  float noise_stddev;      /* gaussian noise level; 0 = off                               */
+  int32_t crop_y, crop_x;  /* crop offsets into the source image                          */
+  int32_t reserved;
+} T2RDistortParams;
+/* src u8 [N,H,W,3]; dst bf16 or fp32 [N,h,w,3] (out_f32 selects).  chan_mean: fp32 [N,3]
+ * workspace used when any contrast_scale != 1 (computed by the call).  seed/offset: Philox
+ * stream for the noise. */
+int32_t t2r_crop_convert_distort(const uint8_t* src, void* dst, const T2RDistortParams* params,
+                                 float* chan_mean, int32_t N, int32_t H, int32_t W, int32_t h,
+                                 int32_t w, int32_t out_f32, int32_t use_contrast,
+                                 uint64_t seed, uint64_t offset, void* stream);
+/* tf.image.resize_images bilinear, TF1 legacy sampling (align_corners=False, no half-pixel
+ * centres: src = dst * in/out), preprocessors/distortion.py:56-107.  fp32 NHWC. */
+int32_t t2r_resize_bilinear_legacy(const float* src, float* dst, int32_t N, int32_t H, int32_t W,
+                                   int32_t C, int32_t h, int32_t w, void* stream);
+
+/* ---- losses ---------------------------------------------------------------------------- */
+/* q = sigmoid(logit); loss = mean(-(y log(q+eps) + (1-y) log(1-q+eps))), eps = 1e-7
+ * (tf.losses.log_loss; research/qtopt/t2r_models.py:229-239, models/critic_model.py:171-192).
+ * Writes q [n], loss [1] (accumulated: caller zeroes), dlogit [n] = dloss/dlogit. */
+int32_t t2r_sigmoid_logloss(const float* logit, const float* label, float* q, float* loss,
+                            float* dlogit, int64_t n, void* stream);
+int32_t t2r_sigmoid_f32(const float* logit, float* q, int64_t n, void* stream);
+
+/* ---- CEM + Bellman target (utils/cross_entropy.py:30-154, policies/policies.py:105-184) - */
+/* samples[b,a,d] = mean[b,d] + std[b,d] * N(0,1) (Philox4x32-10 + Box-Muller). */
+int32_t t2r_cem_sample(const float* mean, const float* stddev, float* samples, int32_t B,
+                       int32_t A, int32_t D, uint64_t seed, uint64_t offset, void* stream);
+/* Per row b: stable ascending sort of values[b,:], elites = last num_elites; writes
+ * mean[b,:], std[b,:] (ddof=1) of the elite samples, best_value[b] = max, best_index[b] =
+ * first argmax (np.argmax).  A <= 1024. */
+int32_t t2r_cem_refit(const float* samples, const float* values, float* mean, float* stddev,
+                      float* best_value, int32_t* best_index, int32_t B, int32_t A, int32_t D,
+                      int32_t num_elites, void* stream);
+/* y[b] = r[b] + gamma * (1 - done[b]) * max_q[b]   (QT-Opt target; SURVEY A-23: absent from
+ * the reference, parity unpinned). */
+int32_t t2r_bellman_target(const float* reward, const float* done, const float* max_q,
+                           float gamma, float* target, int64_t n, void* stream);
+
+/* ---- optimizers (models/optimizers.py:61-146, research/qtopt/optimizer_builder.py:25-96) */
+/* All state fp32, flat contiguous buffers of n elements.  grad_scale multiplies the raw
+ * gradient (1/world_size after the NCCL sum).  Elements [0, n_decay) additionally receive
+ * the slim l2_regularizer gradient l2 * w.  ema (optional) is updated as
+ * ema = d*ema + (1-d)*w with the *new* w.  w_bf16 (optional) receives the bf16 copy. */
+int32_t t2r_momentum_step(float* w, const float* g, float* accum, float* ema, void* w_bf16,
+                          int64_t n, int64_t n_decay, float lr, float momentum, float l2,
+                          float grad_scale, float ema_decay, void* stream);
+/* TF Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updates; w -= lr_t*m/(sqrt(v)+eps). */
+int32_t t2r_adam_step(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16,
+                      int64_t n, int64_t n_decay, float lr, float beta1, float beta2, float eps,
+                      int64_t step, float l2, float grad_scale, float ema_decay, void* stream);
+
+/* ---- host-side record path (no GPU): TFRecord framing + tf.Example wire format ---------- */
+/* Reference: utils/tfdata.py:174-210,629-689 (reader), :273-424 (tf.parse_example). */
+uint32_t t2r_crc32c(const uint8_t* data, uint64_t n);
+uint32_t t2r_masked_crc32c(const uint8_t* data, uint64_t n);
+/* Index an in-memory TFRecord file: writes up to max_records (offset,length) pairs of the
+ * record payloads; returns the record count or a negative error (CRC mismatch => PARSE). */
+int64_t t2r_tfrecord_index(const uint8_t* file, uint64_t file_len, uint64_t* offsets,
+                           uint64_t* lengths, int64_t max_records, int32_t verify_crc);
+/* A parse plan: for each feature key, a dtype, element count and destination. */
+#define T2R_DT_FLOAT 1
+#define T2R_DT_INT64 2
+#define T2R_DT_BYTES 3
+typedef struct T2RFeaturePlan {
+  const char* key;
+  int32_t dtype;     /* T2R_DT_*                                                         */
+  int32_t count;     /* fixed element count (FixedLenFeature); <0 => varlen, |count|=max */
+  int32_t required;  /* missing key => error when non-zero                               */
+  void* dst;         /* FLOAT: float[B*count]; INT64: int64[B*count];
+                        BYTES: (const uint8_t*)[B*count] pointers into the record        */
+  uint64_t* dst_len; /* BYTES: byte length per element; varlen: element count per row    */
+  float pad_float;   /* varlen default                                                   */
+  int64_t pad_int64;
+} T2RFeaturePlan;
+int32_t t2r_example_parse_batch(const uint8_t* const* records, const uint64_t* lengths,
+                                int32_t B, T2RFeaturePlan* plan, int32_t n_features);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2R_B200_H_ */

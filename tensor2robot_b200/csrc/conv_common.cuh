@@ -1,0 +1,23 @@
+// conv_common.cuh — declarations shared by the tcgen05 convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace t2r {
+
+// One filter tap of an implicit-GEMM convolution.
+struct ConvTap {
+  int8_t map;       // which activation tensor map (stride phase)
+  int8_t dh, dw;    // coordinate offset inside that map
+  int8_t pad;
+  int32_t kchunk0;  // first 64-wide K chunk of this tap in the weight matrix
+};
+constexpr int kMaxTaps = 32;
+
+// Pick the TW x TH = `pixels` rectangle that wastes the fewest padded pixels.
+void pick_tile(int Ho, int Wo, int pixels, int* TW, int* TH);
+// Tensor maps (box 64 x TW x TH x 1, 128B swizzle) for the stride*stride phases of a
+// [N,H,W,C] bf16 tensor; unused slots are filled with map 0.
+int make_phase_maps(CUtensorMap* maps, const void* x, int N, int H, int W, int C, int stride,
+                    int TW, int TH);
+
+}  // namespace t2r

@@ -1,0 +1,483 @@
+// conv_igemm.cu — implicit-GEMM convolution forward / data-gradient on tcgen05 (sm_100a).
+//
+// One persistent, warp-specialised kernel serves conv fprop, conv dgrad and plain GEMM
+// (a 1x1 "conv" over a [1,1,M,K] image).  The convolution is expressed as a *tap table*:
+// for every filter tap the producer issues one 4-D TMA tile load of the activation tensor
+// at a shifted coordinate (out-of-bounds rows/columns are zero-filled by TMA, which is the
+// zero padding), plus one 2-D TMA load of the matching weight slice.  Strided convolutions
+// read through per-phase tensor maps (even/odd rows x even/odd columns of the same buffer,
+// expressed with doubled strides), so stride 2 costs nothing extra.
+//
+//   A (activations): 128 output pixels (a TW x TH rectangle of one image) x 64 channels,
+//                    K-major, 128B-swizzled  -> 16 KB per stage
+//   B (weights)    : BLOCK_N output channels x 64, K-major, 128B-swizzled
+//   D (accumulator): 128 lanes x BLOCK_N fp32 columns in TMEM, double buffered
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/residual/ReLU -> global).
+//
+// Replaces: slim.conv2d / tf.layers.conv2d (research/qtopt/networks.py:443-591,
+// layers/film_resnet_model.py:89-105) and their autodiff data gradients.
+#include <algorithm>
+#include <vector>
+
+#include "conv_common.cuh"
+
+namespace t2r {
+
+
+struct IgemmParams {
+  CUtensorMap tmap_a[4];
+  CUtensorMap tmap_b;
+  ConvTap taps[kMaxTaps];
+  int n_taps;
+  int chunks_per_tap;  // Cin / 64
+  int TW, TH;          // tile rectangle, TW*TH == 128
+  int tiles_w, tiles_h;
+  int N, Ho, Wo;       // output iteration space (a strided view for dgrad phases)
+  int Cout;
+  int n_tiles_n;
+  int total_tiles;
+  long long os_n, os_h, os_w;  // output element strides of the view
+  void* out;
+  const void* residual;
+  const float* bias;
+  int flags;
+};
+
+template <int BLOCK_N>
+struct IgemmCfg {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: all powers of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmap_a[i]);
+    tma_prefetch_desc(&p.tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int k_iters = p.n_taps * p.chunks_per_tap;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        const int mt = tile / p.n_tiles_n;
+        const int img = mt / tiles_per_img;
+        const int rem = mt - img * tiles_per_img;
+        const int oh0 = (rem / p.tiles_w) * p.TH;
+        const int ow0 = (rem % p.tiles_w) * p.TW;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const ConvTap tap = p.taps[t];
+          for (int c = 0; c < p.chunks_per_tap; ++c) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t sb = sa + Cfg::kABytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_4d(sa, &p.tmap_a[tap.map], full_bar(stage), c * 64, ow0 + tap.dw,
+                        oh0 + tap.dh, img);
+            tma_load_2d(sb, &p.tmap_b, full_bar(stage), (tap.kchunk0 + c) * 64, nt * BLOCK_N);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(as));
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int th = row / p.TW;
+    const int tw = row - th * p.TW;
+    const bool out_f32 = (p.flags & T2R_EPI_OUT_F32) != 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      const int mt = tile / p.n_tiles_n;
+      const int img = mt / tiles_per_img;
+      const int rem = mt - img * tiles_per_img;
+      const int oh = (rem / p.tiles_w) * p.TH + th;
+      const int ow = (rem % p.tiles_w) * p.TW + tw;
+      const bool valid = (oh < p.Ho) && (ow < p.Wo);
+      const long long pix_off = img * p.os_n + oh * p.os_h + ow * p.os_w;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BLOCK_N + c0, v);
+        tmem_ld_wait();
+        const int ch = nt * BLOCK_N + c0;
+        if (valid && ch < p.Cout) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.flags & T2R_EPI_BIAS) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + ch + j);
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (p.flags & T2R_EPI_RESIDUAL) {
+            const uint4* r = reinterpret_cast<const uint4*>(
+                static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = r[j];
+              f[8 * j + 0] += bf16_lo(q.x); f[8 * j + 1] += bf16_hi(q.x);
+              f[8 * j + 2] += bf16_lo(q.y); f[8 * j + 3] += bf16_hi(q.y);
+              f[8 * j + 4] += bf16_lo(q.z); f[8 * j + 5] += bf16_hi(q.z);
+              f[8 * j + 6] += bf16_lo(q.w); f[8 * j + 7] += bf16_hi(q.w);
+            }
+          }
+          if (p.flags & T2R_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (out_f32) {
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix_off + ch);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix_off + ch);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+              q.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              o[j] = q;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Zero a strided [N,Hv,Wv,C] view (C in uint4 = 8 bf16 units).
+__global__ void zero_view_kernel(uint4* out, int N, int Hv, int Wv, int C8, long long os_n,
+                                 long long os_h, long long os_w) {
+  const long long total = (long long)N * Hv * Wv * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8);
+    long long r = i / C8;
+    const int w = int(r % Wv); r /= Wv;
+    const int h = int(r % Hv);
+    const int n = int(r / Hv);
+    out[n * os_n + h * os_h + w * os_w + c] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+// Pick the TW x TH = `pixels` rectangle that wastes the fewest padded pixels.
+void pick_tile(int Ho, int Wo, int pixels, int* TW, int* TH) {
+  long long best = -1;
+  for (int tw = pixels; tw >= 1; tw >>= 1) {
+    const int th = pixels / tw;
+    if (tw > 256 || th > 256) continue;
+    const long long cover = ceil_div(Wo, tw) * tw * ceil_div(Ho, th) * th;
+    // prefer wider tiles on ties (longer contiguous runs per TMA row)
+    if (best < 0 || cover < best) {
+      best = cover;
+      *TW = tw;
+      *TH = th;
+    }
+  }
+}
+
+// Activation tensor maps for reading input coordinate (s*o + k - pad): phase (ph, pw) of a
+// [N,H,W,C] bf16 tensor is the sub-image of rows ph, ph+s, ... and columns pw, pw+s, ...
+int make_phase_maps(CUtensorMap* maps, const void* x, int N, int H, int W, int C, int stride,
+                    int TW, int TH) {
+  const char* base = static_cast<const char*>(x);
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      const int Hd = (H - ph + stride - 1) / stride;
+      const int Wd = (W - pw + stride - 1) / stride;
+      uint64_t dims[4] = {uint64_t(C), uint64_t(std::max(Wd, 1)), uint64_t(std::max(Hd, 1)),
+                          uint64_t(N)};
+      uint64_t strides[3] = {uint64_t(stride) * C * 2, uint64_t(stride) * W * C * 2,
+                             uint64_t(H) * W * C * 2};
+      uint32_t box[4] = {64, uint32_t(TW), uint32_t(TH), 1};
+      const void* addr = base + (size_t(ph) * W + pw) * C * 2;
+      if (Hd <= 0 || Wd <= 0) addr = base;  // degenerate phase: never referenced by a tap
+      if (encode_tmap_bf16(&maps[ph * stride + pw], addr, 4, dims, strides, box) != 0) return -1;
+    }
+  // fill unused slots with a valid descriptor so prefetch is harmless
+  for (int i = stride * stride; i < 4; ++i) maps[i] = maps[0];
+  return 0;
+}
+
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int BLOCK_N>
+static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = std::min(p.total_tiles, num_sms());
+  conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+static int dispatch_igemm(IgemmParams& p, int block_n, cudaStream_t stream) {
+  p.n_tiles_n = int(ceil_div(p.Cout, block_n));
+  p.total_tiles = p.N * p.tiles_w * p.tiles_h * p.n_tiles_n;
+  if (p.total_tiles <= 0) return T2R_OK;
+  switch (block_n) {
+    case 64: return launch_igemm<64>(p, stream);
+    case 128: return launch_igemm<128>(p, stream);
+    default: return launch_igemm<256>(p, stream);
+  }
+}
+
+static int pick_block_n(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  return 64;
+}
+
+static int check_desc(const T2RConvDesc* d) {
+  T2R_CHECK_ARG(d != nullptr && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc size");
+  T2R_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2 (got %d)", d->stride);
+  T2R_CHECK_ARG(d->KH * d->KW <= kMaxTaps && d->KH >= 1 && d->KW >= 1, "filter %dx%d unsupported",
+                d->KH, d->KW);
+  T2R_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "empty tensor");
+  T2R_CHECK_ARG(d->Cin % 64 == 0 && d->Cin > 0, "Cin=%d must be a multiple of 64", d->Cin);
+  T2R_CHECK_ARG(d->Cout % 64 == 0 && d->Cout > 0, "Cout=%d must be a multiple of 64", d->Cout);
+  return T2R_OK;
+}
+
+}  // namespace t2r
+
+using namespace t2r;
+
+extern "C" int32_t t2r_conv_same_padding(int32_t in, int32_t k, int32_t stride, int32_t* out,
+                                         int32_t* pad_before) {
+  T2R_CHECK_ARG(in > 0 && k > 0 && stride > 0, "bad same-padding args");
+  const int o = (in + stride - 1) / stride;
+  const int total = std::max((o - 1) * stride + k - in, 0);
+  if (out) *out = o;
+  if (pad_before) *pad_before = total / 2;
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const void* w,
+                                    const float* bias, const void* residual, void* y,
+                                    void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  T2R_CHECK_ARG(x && w && y, "null pointer");
+  T2R_CHECK_ARG(!(d->flags & T2R_EPI_BIAS) || bias, "bias flag without bias");
+  T2R_CHECK_ARG(!(d->flags & T2R_EPI_RESIDUAL) || residual, "residual flag without residual");
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  pick_tile(d->Ho, d->Wo, 128, &p.TW, &p.TH);
+  if (make_phase_maps(p.tmap_a, x, d->N, d->H, d->W, d->Cin, d->stride, p.TW, p.TH) != 0)
+    return T2R_ERR_CUDA;
+  const int block_n = pick_block_n(d->Cout);
+  const uint64_t Ktot = uint64_t(d->KH) * d->KW * d->Cin;
+  {
+    uint64_t dims[2] = {Ktot, uint64_t(d->Cout)};
+    uint64_t strides[1] = {Ktot * 2};
+    uint32_t box[2] = {64, uint32_t(block_n)};
+    if (encode_tmap_bf16(&p.tmap_b, w, 2, dims, strides, box) != 0) return T2R_ERR_CUDA;
+  }
+  p.chunks_per_tap = d->Cin / 64;
+  int t = 0;
+  for (int kh = 0; kh < d->KH; ++kh)
+    for (int kw = 0; kw < d->KW; ++kw, ++t) {
+      const int ih = kh - d->pad_top, iw = kw - d->pad_left;  // input = s*o + ih
+      const int ph = ((ih % d->stride) + d->stride) % d->stride;
+      const int pw = ((iw % d->stride) + d->stride) % d->stride;
+      p.taps[t].map = int8_t(ph * d->stride + pw);
+      p.taps[t].dh = int8_t(floor_div(ih, d->stride));
+      p.taps[t].dw = int8_t(floor_div(iw, d->stride));
+      p.taps[t].kchunk0 = t * p.chunks_per_tap;
+    }
+  p.n_taps = t;
+  p.tiles_w = int(ceil_div(d->Wo, p.TW));
+  p.tiles_h = int(ceil_div(d->Ho, p.TH));
+  p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
+  p.os_w = d->Cout;
+  p.os_h = (long long)d->Wo * d->Cout;
+  p.os_n = (long long)d->Ho * d->Wo * d->Cout;
+  p.out = y; p.residual = residual; p.bias = bias; p.flags = d->flags;
+  return dispatch_igemm(p, block_n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const void* w_dgrad,
+                                    void* dx, int32_t accumulate, void* stream) {
+  if (int rc = check_desc(d)) return rc;
+  T2R_CHECK_ARG(dy && w_dgrad && dx, "null pointer");
+  const int s = d->stride;
+  const int taps_total = d->KH * d->KW;
+  const int block_n = pick_block_n(d->Cin);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // dx[n,h,w,ci] = sum_{kh,kw,co} dy[n,(h+pt-kh)/s,(w+pl-kw)/s,co] * w[co,kh,kw,ci]
+  // One launch per output phase (h%s, w%s): inside a phase the contributing taps are fixed and
+  // the access is a stride-1 convolution over dy.
+  for (int ph = 0; ph < s; ++ph)
+    for (int pw = 0; pw < s; ++pw) {
+      const int Hv = (d->H - ph + s - 1) / s, Wv = (d->W - pw + s - 1) / s;
+      if (Hv <= 0 || Wv <= 0) continue;
+      IgemmParams p;
+      memset(&p, 0, sizeof(p));
+      int t = 0;
+      for (int kh = 0; kh < d->KH; ++kh) {
+        if (((ph + d->pad_top - kh) % s + s) % s != 0) continue;
+        for (int kw = 0; kw < d->KW; ++kw) {
+          if (((pw + d->pad_left - kw) % s + s) % s != 0) continue;
+          p.taps[t].map = 0;
+          p.taps[t].dh = int8_t(floor_div(ph + d->pad_top - kh, s));
+          p.taps[t].dw = int8_t(floor_div(pw + d->pad_left - kw, s));
+          p.taps[t].kchunk0 = (kh * d->KW + kw) * (d->Cout / 64);
+          ++t;
+        }
+      }
+      p.n_taps = t;
+      char* out = static_cast<char*>(dx) + (size_t(ph) * d->W + pw) * d->Cin * 2;
+      pick_tile(Hv, Wv, 128, &p.TW, &p.TH);
+      if (make_phase_maps(p.tmap_a, dy, d->N, d->Ho, d->Wo, d->Cout, 1, p.TW, p.TH) != 0)
+        return T2R_ERR_CUDA;
+      const uint64_t Ktot = uint64_t(taps_total) * d->Cout;
+      uint64_t dims[2] = {Ktot, uint64_t(d->Cin)};
+      uint64_t strides[1] = {Ktot * 2};
+      uint32_t box[2] = {64, uint32_t(block_n)};
+      if (encode_tmap_bf16(&p.tmap_b, w_dgrad, 2, dims, strides, box) != 0) return T2R_ERR_CUDA;
+      p.chunks_per_tap = d->Cout / 64;
+      p.tiles_w = int(ceil_div(Wv, p.TW));
+      p.tiles_h = int(ceil_div(Hv, p.TH));
+      p.N = d->N; p.Ho = Hv; p.Wo = Wv; p.Cout = d->Cin;
+      p.os_w = (long long)s * d->Cin;
+      p.os_h = (long long)s * d->W * d->Cin;
+      p.os_n = (long long)d->H * d->W * d->Cin;
+      p.out = out;
+      p.residual = accumulate ? out : nullptr;
+      p.flags = accumulate ? T2R_EPI_RESIDUAL : 0;
+      if (t == 0) {
+        // No tap reaches this phase (e.g. 1x1 stride-2): the gradient there is zero.
+        if (!accumulate) {
+          const long long total = (long long)d->N * Hv * Wv * (d->Cin / 8);
+          const int blocks = int(std::min<long long>(ceil_div(total, 256), 148 * 16));
+          zero_view_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(out), d->N, Hv, Wv,
+                                                   d->Cin / 8, p.os_n / 8, p.os_h / 8, p.os_w / 8);
+          T2R_LAUNCH_OK();
+        }
+        continue;
+      }
+      if (int rc = dispatch_igemm(p, block_n, st)) return rc;
+    }
+  return T2R_OK;
+}

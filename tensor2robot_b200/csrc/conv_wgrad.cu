@@ -1,0 +1,269 @@
+// conv_wgrad.cu — convolution weight gradient on tcgen05 (sm_100a).
+//
+//   dW[co, tap, ci] = sum over output pixels  dY[pix, co] * X[pix shifted by tap, ci]
+//
+// The reduction dimension (K of the GEMM) is the pixel index, which is the *slow* dimension of
+// both NHWC operands, so both operands are fed to the tensor core as MN-major tiles: a TMA box
+// of [64 pixels x 64 channels] lands in shared memory as 64 rows of 128 bytes (128B swizzle),
+// which is exactly the canonical MN-major SW128 UMMA layout (8-row atoms, SBO = 1024 B), and
+// several 64-channel tiles side by side form the M / N extent (LBO = tile size).
+//
+//   A: two X tiles  -> M = 128 rows = 128 consecutive columns of the OHWI weight row
+//        (k = tap*Cin + ci; for Cin = 64 the two tiles are two filter taps)
+//   B: BLOCK_N/64 dY tiles -> N = BLOCK_N output channels
+//   D: [128 x BLOCK_N] fp32 per "group" in TMEM; a CTA owns up to 512/BLOCK_N groups and a
+//      range of pixel tiles (split-K), and flushes with fp32 atomics (red.global.add.f32).
+//
+// Replaces the autodiff filter gradients of slim.conv2d / tf.layers.conv2d
+// (research/qtopt/networks.py:443-591, layers/film_resnet_model.py:89-105).
+#include <algorithm>
+
+#include "conv_common.cuh"
+
+namespace t2r {
+
+
+struct WgradParams {
+  CUtensorMap tmap_x[4];
+  CUtensorMap tmap_dy;
+  ConvTap taps[kMaxTaps];
+  int chunks_per_tap;  // Cin / 64
+  int n_slots;         // taps * chunks_per_tap (64-wide column blocks of the weight row)
+  int n_groups;        // ceil(n_slots / 2)
+  int groups_per_cta;  // G
+  int n_gsets;         // ceil(n_groups / G)
+  int n_chunks_n;      // Cout / BLOCK_N
+  int ksplits;
+  int TW, TH, tiles_w, tiles_h;
+  int total_ptiles;    // N * tiles_w * tiles_h
+  int Ktot;            // taps * Cin
+  int Cout;
+  float* dw;
+};
+
+template <int BLOCK_N>
+struct WgradCfg {
+  static constexpr int kTileBytes = 64 * 128;  // 64 pixels x 64 channels bf16
+  static constexpr int kNB = BLOCK_N / 64;
+  static constexpr int kStageBytes = (2 + kNB) * kTileBytes;
+  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kMaxGroups = 512 / BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 1);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmap_x[i]);
+    tma_prefetch_desc(&p.tmap_dy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // work item: (group set, output-channel chunk, pixel-tile range)
+  int item = blockIdx.x;
+  const int ks = item % p.ksplits; item /= p.ksplits;
+  const int nc = item % p.n_chunks_n; item /= p.n_chunks_n;
+  const int gs = item;
+  const int g0 = gs * p.groups_per_cta;
+  const int g1 = min(g0 + p.groups_per_cta, p.n_groups);
+  const int pt0 = int((long long)p.total_ptiles * ks / p.ksplits);
+  const int pt1 = int((long long)p.total_ptiles * (ks + 1) / p.ksplits);
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int n0 = nc * BLOCK_N;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        const int img = pt / tiles_per_img;
+        const int rem = pt - img * tiles_per_img;
+        const int oh0 = (rem / p.tiles_w) * p.TH;
+        const int ow0 = (rem % p.tiles_w) * p.TW;
+        for (int g = g0; g < g1; ++g) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int slot = 2 * g + h;
+            if (slot >= p.n_slots) slot = p.n_slots - 1;  // duplicate: rows are never stored
+            const int t = slot / p.chunks_per_tap;
+            const int c = slot - t * p.chunks_per_tap;
+            const ConvTap tap = p.taps[t];
+            tma_load_4d(sa + h * Cfg::kTileBytes, &p.tmap_x[tap.map], full_bar(stage), c * 64,
+                        ow0 + tap.dw, oh0 + tap.dh, img);
+          }
+#pragma unroll
+          for (int j = 0; j < Cfg::kNB; ++j)
+            tma_load_4d(sa + (2 + j) * Cfg::kTileBytes, &p.tmap_dy, full_bar(stage), n0 + j * 64,
+                        ow0, oh0, img);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        for (int g = g0; g < g1; ++g) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + 2 * Cfg::kTileBytes;
+          const uint32_t d_tmem = tmem_base + (g - g0) * BLOCK_N;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 64 pixels = 4 x (K = 16)
+            const uint64_t adesc =
+                make_smem_desc_sw128(sa + kk * 2048, Cfg::kTileBytes, 1024);
+            const uint64_t bdesc =
+                make_smem_desc_sw128(sb + kk * 2048, Cfg::kTileBytes, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int quad = warp - 4;
+    const int row = quad * 32 + lane;
+    if (pt1 > pt0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      for (int g = g0; g < g1; ++g) {
+        const int k = g * 128 + row;  // column of the OHWI weight row
+        const bool kvalid = k < p.Ktot;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + (g - g0) * BLOCK_N + c0, v);
+          tmem_ld_wait();
+          if (kvalid) {
+            float* dst = p.dw + (long long)(n0 + c0) * p.Ktot + k;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < p.Cout) atomicAdd(dst + (long long)j * p.Ktot, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int BLOCK_N>
+static int launch_wgrad(WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  p.groups_per_cta = std::min(p.n_groups, Cfg::kMaxGroups);
+  p.n_gsets = int(ceil_div(p.n_groups, p.groups_per_cta));
+  p.n_chunks_n = int(ceil_div(p.Cout, BLOCK_N));
+  const int base_items = p.n_gsets * p.n_chunks_n;
+  // split the pixel range so that ~2 waves of CTAs are in flight, each with >= 4 pixel tiles
+  int ks = int(ceil_div(2 * num_sms(), base_items));
+  ks = std::max(1, std::min(ks, std::max(1, p.total_ptiles / 4)));
+  p.ksplits = ks;
+  const int grid = base_items * ks;
+  conv_wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+}  // namespace t2r
+
+using namespace t2r;
+
+extern "C" int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const void* dy,
+                                    float* dw, void* stream) {
+  T2R_CHECK_ARG(d != nullptr && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc size");
+  T2R_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+  T2R_CHECK_ARG(d->KH * d->KW <= kMaxTaps, "filter too large");
+  T2R_CHECK_ARG(d->Cin % 64 == 0 && d->Cout % 64 == 0, "Cin/Cout must be multiples of 64");
+  T2R_CHECK_ARG(x && dy && dw, "null pointer");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  pick_tile(d->Ho, d->Wo, 64, &p.TW, &p.TH);
+  if (make_phase_maps(p.tmap_x, x, d->N, d->H, d->W, d->Cin, d->stride, p.TW, p.TH) != 0)
+    return T2R_ERR_CUDA;
+  CUtensorMap dy_maps[4];
+  if (make_phase_maps(dy_maps, dy, d->N, d->Ho, d->Wo, d->Cout, 1, p.TW, p.TH) != 0)
+    return T2R_ERR_CUDA;
+  p.tmap_dy = dy_maps[0];
+  p.chunks_per_tap = d->Cin / 64;
+  int t = 0;
+  for (int kh = 0; kh < d->KH; ++kh)
+    for (int kw = 0; kw < d->KW; ++kw, ++t) {
+      const int ih = kh - d->pad_top, iw = kw - d->pad_left;
+      const int ph = ((ih % d->stride) + d->stride) % d->stride;
+      const int pw = ((iw % d->stride) + d->stride) % d->stride;
+      p.taps[t].map = int8_t(ph * d->stride + pw);
+      p.taps[t].dh = int8_t(floor_div(ih, d->stride));
+      p.taps[t].dw = int8_t(floor_div(iw, d->stride));
+      p.taps[t].kchunk0 = t * p.chunks_per_tap;
+    }
+  p.n_slots = t * p.chunks_per_tap;
+  p.n_groups = (p.n_slots + 1) / 2;
+  p.tiles_w = int(ceil_div(d->Wo, p.TW));
+  p.tiles_h = int(ceil_div(d->Ho, p.TH));
+  p.total_ptiles = d->N * p.tiles_w * p.tiles_h;
+  p.Ktot = t * d->Cin;
+  p.Cout = d->Cout;
+  p.dw = dw;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->Cout % 256 == 0) return launch_wgrad<256>(p, st);
+  if (d->Cout % 128 == 0) return launch_wgrad<128>(p, st);
+  return launch_wgrad<64>(p, st);
+}

@@ -1,0 +1,341 @@
+// core.cu — library plumbing (errors, launch accounting, TMA descriptor encoding) and the small
+// utility kernels: weight packing, small-Cin im2col, casts, adds, fp32 SGEMM for tiny layers.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace t2r {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime so that the library loads (and its
+// symbol table can be checked) on machines without libcuda.so.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return -1;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box "
+              "[%u,%u,%u,%u] base %p",
+              int(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+    return -1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+
+// w fp32 [Cout][taps][Cin] -> wf bf16 same layout, wd bf16 [Cin][taps][Cout].
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd, int Cout, int taps, int Cin) {
+  const long long total = (long long)Cout * taps * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (wf) wf[i] = b;
+    if (wd) {
+      const int ci = int(i % Cin);
+      const long long r = i / Cin;
+      const int t = int(r % taps);
+      const int co = int(r / taps);
+      wd[((long long)ci * taps + t) * Cout + co] = b;
+    }
+  }
+}
+
+// x bf16 [N,H,W,Cin] -> a bf16 [N*Ho*Wo, Kpad]; one thread per (pixel, 8-column group).
+__global__ void im2col_small_cin_kernel(const __nv_bfloat16* __restrict__ x,
+                                        __nv_bfloat16* __restrict__ a, int N, int H, int W, int Cin,
+                                        int KH, int KW, int stride, int pad_top, int pad_left,
+                                        int Ho, int Wo, int Kpad) {
+  const int groups = Kpad / 8;
+  const long long total = (long long)N * Ho * Wo * groups;
+  const int Kreal = KH * KW * Cin;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % groups);
+    long long pix = i / groups;
+    const int ow = int(pix % Wo);
+    long long r = pix / Wo;
+    const int oh = int(r % Ho);
+    const int n = int(r / Ho);
+    unsigned short v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      unsigned short val = 0;
+      if (k < Kreal) {
+        const int c = k % Cin;
+        const int t = k / Cin;
+        const int kw = t % KW, kh = t / KW;
+        const int ih = oh * stride + kh - pad_top, iw = ow * stride + kw - pad_left;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          val = xs[(((long long)n * H + ih) * W + iw) * Cin + c];
+      }
+      v[j] = val;
+    }
+    uint4 q;
+    q.x = v[0] | (uint32_t(v[1]) << 16);
+    q.y = v[2] | (uint32_t(v[3]) << 16);
+    q.z = v[4] | (uint32_t(v[5]) << 16);
+    q.w = v[6] | (uint32_t(v[7]) << 16);
+    reinterpret_cast<uint4*>(a)[i] = q;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                     long long n) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                     long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                uint4* __restrict__ y, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 p = a[i], q = b[i];
+    uint4 o;
+    o.x = pack_bf16(bf16_lo(p.x) + bf16_lo(q.x), bf16_hi(p.x) + bf16_hi(q.x));
+    o.y = pack_bf16(bf16_lo(p.y) + bf16_lo(q.y), bf16_hi(p.y) + bf16_hi(q.y));
+    o.z = pack_bf16(bf16_lo(p.z) + bf16_lo(q.z), bf16_hi(p.z) + bf16_hi(q.z));
+    o.w = pack_bf16(bf16_lo(p.w) + bf16_lo(q.w), bf16_hi(p.w) + bf16_hi(q.w));
+    y[i] = o;
+  }
+}
+
+__global__ void add_bf16_tail_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b,
+                                     __nv_bfloat16* y, long long start, long long n) {
+  const long long i = start + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
+__global__ void relu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy,
+                                     const __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ dx, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dx[i] = (__bfloat162float(y[i]) > 0.f) ? dy[i] : __float2bfloat16_rn(0.f);
+}
+
+__global__ void bias_add_f32_kernel(float* y, const float* __restrict__ bias, long long total,
+                                    int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] += bias[i % C];
+}
+
+// out[c] = sum_r x[r,c]; one block per 32 columns, 8 row lanes.
+__global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                  long long rows, int C) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C)
+    for (long long r = threadIdx.y; r < rows; r += 8) acc += x[r * C + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+    for (int j = 0; j < 8; ++j) s += sm[j][threadIdx.x];
+    out[c] = s;
+  }
+}
+
+// Plain smem-tiled fp32 GEMM (CUDA cores).  Only used for layers whose inner dimension is not a
+// multiple of 64 (action context FC 10->256, logits 64->1): < 0.1 % of the step's FLOPs.
+template <bool TA, bool TB>
+__global__ void sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                             const float* __restrict__ B, int ldb, float beta, float* C, int ldc) {
+  __shared__ float As[16][17], Bs[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx, kb = k0 + ty;
+    As[ty][tx] = (row < M && ka < K) ? (TA ? A[(long long)ka * lda + row] : A[(long long)row * lda + ka]) : 0.f;
+    Bs[ty][tx] = (col < N && kb < K) ? (TB ? B[(long long)col * ldb + kb] : B[(long long)kb * ldb + col]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) {
+    float* c = C + (long long)row * ldc + col;
+    *c = alpha * acc + (beta == 0.f ? 0.f : beta * *c);
+  }
+}
+
+static inline int grid_for(long long n, int block = 256) {
+  return int(std::min<long long>(std::max<long long>((n + block - 1) / block, 1), 148LL * 32));
+}
+
+}  // namespace t2r
+
+using namespace t2r;
+
+extern "C" int32_t t2r_version(void) { return 100; }
+extern "C" const char* t2r_last_error(void) { return g_err; }
+extern "C" int64_t t2r_launch_count(void) { return g_launch_count.load(); }
+extern "C" void t2r_launch_count_reset(void) { g_launch_count.store(0); }
+
+extern "C" int32_t t2r_pack_weights(const float* w, void* w_fprop, void* w_dgrad, int32_t Cout,
+                                    int32_t taps, int32_t Cin, void* stream) {
+  T2R_CHECK_ARG(w && (w_fprop || w_dgrad), "null pointer");
+  const long long total = (long long)Cout * taps * Cin;
+  pack_weights_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), Cout, taps, Cin);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_im2col_small_cin(const T2RConvDesc* d, const void* x, void* a, int32_t Kpad,
+                                        void* stream) {
+  T2R_CHECK_ARG(d && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc");
+  T2R_CHECK_ARG(Kpad % 64 == 0 && Kpad >= d->KH * d->KW * d->Cin, "Kpad=%d invalid", Kpad);
+  const long long total = (long long)d->N * d->Ho * d->Wo * (Kpad / 8);
+  im2col_small_cin_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(a), d->N, d->H, d->W, d->Cin,
+      d->KH, d->KW, d->stride, d->pad_top, d->pad_left, d->Ho, d->Wo, Kpad);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_sgemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
+                             float alpha, const float* A, int32_t lda, const float* B, int32_t ldb,
+                             float beta, float* C, int32_t ldc, void* stream) {
+  T2R_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "bad sgemm args");
+  dim3 block(16, 16), grid((N + 15) / 16, (M + 15) / 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!transA && !transB) sgemm_kernel<false, false><<<grid, block, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (!transA && transB) sgemm_kernel<false, true><<<grid, block, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (transA && !transB) sgemm_kernel<true, false><<<grid, block, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else sgemm_kernel<true, true><<<grid, block, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_bias_add_f32(float* y, const float* bias, int64_t rows, int32_t C,
+                                    void* stream) {
+  T2R_CHECK_ARG(y && bias && rows > 0 && C > 0, "bad bias_add args");
+  bias_add_f32_kernel<<<grid_for(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, bias, rows * C, C);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_colsum_f32(const float* x, float* out, int64_t rows, int32_t C, void* stream) {
+  T2R_CHECK_ARG(x && out && rows > 0 && C > 0, "bad colsum args");
+  colsum_f32_kernel<<<(C + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows, C);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  T2R_CHECK_ARG(x && y && n > 0, "bad cast args");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+  T2R_CHECK_ARG(x && y && n > 0, "bad cast args");
+  cast_bf16_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, n);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) {
+  T2R_CHECK_ARG(a && b && y && n > 0, "bad add args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n8 = n / 8;
+  if (n8 > 0) {
+    add_bf16_kernel<<<grid_for(n8), 256, 0, st>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b),
+                                                  static_cast<uint4*>(y), n8);
+    T2R_LAUNCH_OK();
+  }
+  if (n % 8) {
+    add_bf16_tail_kernel<<<1, 32, 0, st>>>(static_cast<const __nv_bfloat16*>(a),
+                                           static_cast<const __nv_bfloat16*>(b),
+                                           static_cast<__nv_bfloat16*>(y), n8 * 8, n);
+    T2R_LAUNCH_OK();
+  }
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
+  T2R_CHECK_ARG(dy && y && dx && n > 0, "bad relu_bwd args");
+  relu_bwd_bf16_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+      static_cast<__nv_bfloat16*>(dx), n);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}

@@ -1,0 +1,211 @@
+// image.cu — fused crop + uint8->float + photometric distortion + clip, and legacy bilinear resize.
+//
+// Reference call sites: research/qtopt/t2r_models.py:297-308 (crop -> convert_image_dtype ->
+// ApplyPhotometricImageDistortions), preprocessors/image_transformations.py:176-264,
+// preprocessors/distortion.py:56-107.  TF op semantics restated (SURVEY §8c-3,8,9):
+//   convert_image_dtype(u8->f32): x * (1/255)
+//   adjust_brightness: x + delta
+//   adjust_saturation: RGB->HSV, s = clamp(s*f, 0, 1), HSV->RGB
+//   adjust_hue:        RGB->HSV, h = frac(h + delta), HSV->RGB
+//   adjust_contrast:   (x - mean_c) * f + mean_c, mean per image and channel
+//   noise:             x + N(0, sigma)
+//   clip_by_value(0, 1)
+// HBM-bound: one read of the cropped u8 window, one write of the bf16/f32 result.
+#include <algorithm>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace t2r {
+
+__device__ __forceinline__ void rgb_to_hsv(float r, float g, float b, float* h, float* s, float* v) {
+  const float mx = fmaxf(r, fmaxf(g, b)), mn = fminf(r, fminf(g, b));
+  const float range = mx - mn;
+  *v = mx;
+  *s = mx > 0.f ? range / mx : 0.f;
+  float hh = 0.f;
+  if (range > 0.f) {
+    const float norm = 1.0f / (6.0f * range);
+    if (r == mx) hh = norm * (g - b);
+    else if (g == mx) hh = norm * (b - r) + 2.0f / 6.0f;
+    else hh = norm * (r - g) + 4.0f / 6.0f;
+    if (hh < 0.f) hh += 1.0f;
+  }
+  *h = hh;
+}
+
+__device__ __forceinline__ void hsv_to_rgb(float h, float s, float v, float* r, float* g, float* b) {
+  const float c = s * v, m = v - c;
+  const float dh = h * 6.0f;
+  const int cat = int(dh);
+  float fm = dh;
+  while (fm <= 0.f) fm += 2.0f;
+  while (fm >= 2.0f) fm -= 2.0f;
+  const float x = c * (1.0f - fabsf(fm - 1.0f));
+  float rr = 0.f, gg = 0.f, bb = 0.f;
+  switch (cat) {
+    case 0: rr = c; gg = x; break;
+    case 1: rr = x; gg = c; break;
+    case 2: gg = c; bb = x; break;
+    case 3: gg = x; bb = c; break;
+    case 4: rr = x; bb = c; break;
+    case 5: rr = c; bb = x; break;
+    default: break;
+  }
+  *r = rr + m; *g = gg + m; *b = bb + m;
+}
+
+// Everything up to (not including) contrast.
+__device__ __forceinline__ void pre_contrast(const T2RDistortParams& pr, float& r, float& g, float& b) {
+  if (pr.brightness_delta != 0.f) {
+    r += pr.brightness_delta; g += pr.brightness_delta; b += pr.brightness_delta;
+  }
+  if (pr.saturation_scale != 1.f) {
+    float h, s, v;
+    rgb_to_hsv(r, g, b, &h, &s, &v);
+    s = fminf(fmaxf(s * pr.saturation_scale, 0.f), 1.f);
+    hsv_to_rgb(h, s, v, &r, &g, &b);
+  }
+  if (pr.hue_delta != 0.f) {
+    float h, s, v;
+    rgb_to_hsv(r, g, b, &h, &s, &v);
+    h += pr.hue_delta;
+    h -= floorf(h);
+    hsv_to_rgb(h, s, v, &r, &g, &b);
+  }
+}
+
+__global__ void __launch_bounds__(256) image_mean_kernel(const uint8_t* __restrict__ src,
+                                                         const T2RDistortParams* __restrict__ params,
+                                                         float* chan_mean, int H, int W, int h, int w) {
+  const int n = blockIdx.y;
+  const T2RDistortParams pr = params[n];
+  const uint8_t* img = src + (size_t)n * H * W * 3;
+  float acc[3] = {0.f, 0.f, 0.f};
+  const int total = h * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    const uint8_t* px = img + ((size_t)(y + pr.crop_y) * W + (x + pr.crop_x)) * 3;
+    float r = float(px[0]) * (1.0f / 255.0f), g = float(px[1]) * (1.0f / 255.0f),
+          b = float(px[2]) * (1.0f / 255.0f);
+    pre_contrast(pr, r, g, b);
+    acc[0] += r; acc[1] += g; acc[2] += b;
+  }
+  __shared__ float sm[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = acc[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[c][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int j = 0; j < 8; ++j) s += sm[threadIdx.x][j];
+    atomicAdd(chan_mean + n * 3 + threadIdx.x, s / float(total));
+  }
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) crop_convert_distort_kernel(
+    const uint8_t* __restrict__ src, void* __restrict__ dst, const T2RDistortParams* __restrict__ params,
+    const float* __restrict__ chan_mean, int H, int W, int h, int w, int use_contrast, uint64_t seed,
+    uint64_t offset) {
+  const int n = blockIdx.y;
+  const T2RDistortParams pr = params[n];
+  const uint8_t* img = src + (size_t)n * H * W * 3;
+  const int total = h * w;
+  float m[3] = {0.f, 0.f, 0.f};
+  if (use_contrast) { m[0] = chan_mean[n * 3]; m[1] = chan_mean[n * 3 + 1]; m[2] = chan_mean[n * 3 + 2]; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    const uint8_t* px = img + ((size_t)(y + pr.crop_y) * W + (x + pr.crop_x)) * 3;
+    float r = float(px[0]) * (1.0f / 255.0f), g = float(px[1]) * (1.0f / 255.0f),
+          b = float(px[2]) * (1.0f / 255.0f);
+    pre_contrast(pr, r, g, b);
+    if (use_contrast && pr.contrast_scale != 1.f) {
+      r = (r - m[0]) * pr.contrast_scale + m[0];
+      g = (g - m[1]) * pr.contrast_scale + m[1];
+      b = (b - m[2]) * pr.contrast_scale + m[2];
+    }
+    if (pr.noise_stddev != 0.f) {
+      const Philox4 rnd = philox4x32_10(seed, (uint64_t)n * total + i, offset);
+      float z0, z1, z2, z3;
+      box_muller(rnd.v[0], rnd.v[1], &z0, &z1);
+      box_muller(rnd.v[2], rnd.v[3], &z2, &z3);
+      r += pr.noise_stddev * z0; g += pr.noise_stddev * z1; b += pr.noise_stddev * z2;
+    }
+    r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); b = fminf(fmaxf(b, 0.f), 1.f);
+    const size_t o = ((size_t)n * total + i) * 3;
+    if (OUT_F32) {
+      float* d = static_cast<float*>(dst) + o;
+      d[0] = r; d[1] = g; d[2] = b;
+    } else {
+      __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + o;
+      d[0] = __float2bfloat16_rn(r); d[1] = __float2bfloat16_rn(g); d[2] = __float2bfloat16_rn(b);
+    }
+  }
+}
+
+// TF1 tf.image.resize_images(BILINEAR), align_corners=False, legacy sampling: src = dst * scale.
+__global__ void __launch_bounds__(256) resize_bilinear_legacy_kernel(const float* __restrict__ src,
+                                                                     float* __restrict__ dst, int N, int H,
+                                                                     int W, int C, int h, int w) {
+  const long long total = (long long)N * h * w * C;
+  const float sy = float(H) / float(h), sx = float(W) / float(w);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    long long r = i / C;
+    const int x = int(r % w); r /= w;
+    const int y = int(r % h);
+    const int n = int(r / h);
+    const float fy = y * sy, fx = x * sx;
+    const int y0 = int(floorf(fy)), x0 = int(floorf(fx));
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float* base = src + (size_t)n * H * W * C;
+    const float tl = base[((size_t)y0 * W + x0) * C + c], tr = base[((size_t)y0 * W + x1) * C + c];
+    const float bl = base[((size_t)y1 * W + x0) * C + c], br = base[((size_t)y1 * W + x1) * C + c];
+    const float top = tl + (tr - tl) * lx, bot = bl + (br - bl) * lx;
+    dst[i] = top + (bot - top) * ly;
+  }
+}
+
+}  // namespace t2r
+
+using namespace t2r;
+
+extern "C" int32_t t2r_crop_convert_distort(const uint8_t* src, void* dst, const T2RDistortParams* params,
+                                            float* chan_mean, int32_t N, int32_t H, int32_t W, int32_t h,
+                                            int32_t w, int32_t out_f32, int32_t use_contrast,
+                                            uint64_t seed, uint64_t offset, void* stream) {
+  T2R_CHECK_ARG(src && dst && params && N > 0 && h > 0 && w > 0 && h <= H && w <= W,
+                "crop_convert_distort: bad args");
+  T2R_CHECK_ARG(!use_contrast || chan_mean, "crop_convert_distort: contrast needs chan_mean workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int bx = std::max(1, std::min((h * w + 255) / 256, std::max(1, 148 * 8 / N)));
+  if (use_contrast) {
+    T2R_CUDA_OK(cudaMemsetAsync(chan_mean, 0, sizeof(float) * 3 * N, st));
+    image_mean_kernel<<<dim3(bx, N), 256, 0, st>>>(src, params, chan_mean, H, W, h, w);
+    T2R_LAUNCH_OK();
+  }
+  if (out_f32)
+    crop_convert_distort_kernel<true><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, h, w,
+                                                                   use_contrast, seed, offset);
+  else
+    crop_convert_distort_kernel<false><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, h, w,
+                                                                    use_contrast, seed, offset);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_resize_bilinear_legacy(const float* src, float* dst, int32_t N, int32_t H, int32_t W,
+                                              int32_t C, int32_t h, int32_t w, void* stream) {
+  T2R_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && h > 0 && w > 0, "resize: bad args");
+  const long long total = (long long)N * h * w * C;
+  const int grid = int(std::min<long long>((total + 255) / 256, 148LL * 16));
+  resize_bilinear_legacy_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, N, H, W, C, h, w);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}

@@ -1,0 +1,302 @@
+// pool.cu — max pooling, global spatial mean and the action-context broadcast add (bf16 NHWC).
+// All HBM-bound: 16-byte vectors over the channel dimension, grid-stride loops.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace t2r {
+
+__device__ __forceinline__ void unpack8(const uint4 q, float (&f)[8]) {
+  f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack_bf16(f[0], f[1]); q.y = pack_bf16(f[2], f[3]);
+  q.z = pack_bf16(f[4], f[5]); q.w = pack_bf16(f[6], f[7]);
+  return q;
+}
+
+// slim.max_pool2d: padding never wins (acts as -inf); first maximum in row-major window order
+// takes the gradient (TF MaxPoolGrad tie rule).
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                          uint2* __restrict__ argmax, int N, int H, int W,
+                                                          int cg, int k, int stride, int pt, int pl,
+                                                          int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    long long r = i / cg;
+    const int ow = int(r % Wo); r /= Wo;
+    const int oh = int(r % Ho);
+    const int n = int(r / Ho);
+    float best[8];
+    unsigned idx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; idx[j] = 0; }
+    for (int kh = 0; kh < k; ++kh) {
+      const int ih = oh * stride + kh - pt;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int iw = ow * stride + kw - pl;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        unpack8(x[(((long long)n * H + ih) * W + iw) * cg + g], f);
+        const unsigned code = unsigned(kh * k + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > best[j]) { best[j] = f[j]; idx[j] = code; }
+      }
+    }
+    y[i] = pack8(best);
+    if (argmax) {
+      uint2 a;
+      a.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+      a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+      argmax[i] = a;
+    }
+  }
+}
+
+// Gather form: every input pixel sums the dy of the (few) windows that selected it.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restrict__ dy,
+                                                          const uint2* __restrict__ argmax,
+                                                          uint4* __restrict__ dx, int N, int H, int W,
+                                                          int cg, int k, int stride, int pt, int pl,
+                                                          int Ho, int Wo) {
+  const long long total = (long long)N * H * W * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    long long r = i / cg;
+    const int iw = int(r % W); r /= W;
+    const int ih = int(r % H);
+    const int n = int(r / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows (oh, kh) with oh*stride + kh - pt == ih
+    for (int kh = 0; kh < k; ++kh) {
+      const int num = ih + pt - kh;
+      if (num < 0 || num % stride != 0) continue;
+      const int oh = num / stride;
+      if (oh >= Ho) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int numw = iw + pl - kw;
+        if (numw < 0 || numw % stride != 0) continue;
+        const int ow = numw / stride;
+        if (ow >= Wo) continue;
+        const long long o = (((long long)n * Ho + oh) * Wo + ow) * cg + g;
+        const uint2 a = argmax[o];
+        float f[8];
+        unpack8(dy[o], f);
+        const unsigned code = unsigned(kh * k + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned sel = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xFFu;
+          if (sel == code) acc[j] += f[j];
+        }
+      }
+    }
+    dx[i] = pack8(acc);
+  }
+}
+
+// x [N, HW, C] -> y [N, C]: one block per (image, 32 column groups), 8 row lanes.
+__global__ void __launch_bounds__(256) global_mean_fwd_kernel(const uint4* __restrict__ x,
+                                                              uint4* __restrict__ y, int HW, int cg) {
+  __shared__ float sm[8][32][9];
+  const int n = blockIdx.x;
+  const int g = blockIdx.y * 32 + threadIdx.x;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (g < cg)
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      float f[8];
+      unpack8(x[((long long)n * HW + p) * cg + g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && g < cg) {
+    float o[8];
+    const float inv = 1.f / float(HW);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int r = 0; r < 8; ++r) s += sm[r][threadIdx.x][j];
+      o[j] = s * inv;
+    }
+    y[(long long)n * cg + g] = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256) global_mean_bwd_kernel(const uint4* __restrict__ dy,
+                                                              uint4* __restrict__ dx, long long total8,
+                                                              int HW, int cg) {
+  const float inv = 1.f / float(HW);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    const long long n = (i / cg) / HW;
+    float f[8];
+    unpack8(dy[n * cg + g], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    dx[i] = pack8(f);
+  }
+}
+
+// y[(b*A+a), p, :] = x[b, p, :] + ctx[(b*A+a), :]
+__global__ void __launch_bounds__(256) add_context_fwd_kernel(const uint4* __restrict__ x,
+                                                              const uint4* __restrict__ ctx,
+                                                              uint4* __restrict__ y, long long total8,
+                                                              int A, int HW, int cg) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    long long r = i / cg;
+    const int p = int(r % HW);
+    const long long ba = r / HW;
+    const long long b = ba / A;
+    float fx[8], fc[8];
+    unpack8(x[(b * HW + p) * cg + g], fx);
+    unpack8(ctx[ba * cg + g], fc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fx[j] += fc[j];
+    y[i] = pack8(fx);
+  }
+}
+
+// dx[b,p,:] = sum_a dy[(b*A+a),p,:]
+__global__ void __launch_bounds__(256) add_context_bwd_x_kernel(const uint4* __restrict__ dy,
+                                                                uint4* __restrict__ dx, long long total8,
+                                                                int A, int HW, int cg) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    long long r = i / cg;
+    const int p = int(r % HW);
+    const long long b = r / HW;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < A; ++a) {
+      float f[8];
+      unpack8(dy[((b * A + a) * HW + p) * cg + g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    dx[i] = pack8(acc);
+  }
+}
+
+// dctx[(b*A+a),:] = sum_p dy[(b*A+a),p,:]   (same shape of work as global mean without the 1/HW)
+__global__ void __launch_bounds__(256) add_context_bwd_ctx_kernel(const uint4* __restrict__ dy,
+                                                                  uint4* __restrict__ dctx, int HW, int cg) {
+  __shared__ float sm[8][32][9];
+  const long long n = blockIdx.x;
+  const int g = blockIdx.y * 32 + threadIdx.x;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (g < cg)
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      float f[8];
+      unpack8(dy[(n * HW + p) * cg + g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && g < cg) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int r = 0; r < 8; ++r) s += sm[r][threadIdx.x][j];
+      o[j] = s;
+    }
+    dctx[n * cg + g] = pack8(o);
+  }
+}
+
+static inline int grid_for(long long n) {
+  return int(std::min<long long>(std::max<long long>((n + 255) / 256, 1), 148LL * 16));
+}
+
+}  // namespace t2r
+
+using namespace t2r;
+
+extern "C" int32_t t2r_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t N, int32_t H,
+                                   int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_top,
+                                   int32_t pad_left, int32_t Ho, int32_t Wo, void* stream) {
+  T2R_CHECK_ARG(x && y && C % 8 == 0 && k >= 1 && k * k <= 255 && stride >= 1, "maxpool_fwd: bad args");
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), reinterpret_cast<uint2*>(argmax), N, H, W,
+      C / 8, k, stride, pad_top, pad_left, Ho, Wo);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int32_t N,
+                                   int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                                   int32_t pad_top, int32_t pad_left, int32_t Ho, int32_t Wo,
+                                   void* stream) {
+  T2R_CHECK_ARG(dy && argmax && dx && C % 8 == 0, "maxpool_bwd: bad args");
+  const long long total = (long long)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(argmax), static_cast<uint4*>(dx), N,
+      H, W, C / 8, k, stride, pad_top, pad_left, Ho, Wo);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_global_mean_fwd(const void* x, void* y, int32_t N, int32_t HW, int32_t C,
+                                       void* stream) {
+  T2R_CHECK_ARG(x && y && N > 0 && HW > 0 && C % 8 == 0, "global_mean_fwd: bad args");
+  const int cg = C / 8;
+  global_mean_fwd_kernel<<<dim3(N, (cg + 31) / 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), HW, cg);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_global_mean_bwd(const void* dy, void* dx, int32_t N, int32_t HW, int32_t C,
+                                       void* stream) {
+  T2R_CHECK_ARG(dy && dx && N > 0 && HW > 0 && C % 8 == 0, "global_mean_bwd: bad args");
+  const long long total8 = (long long)N * HW * (C / 8);
+  global_mean_bwd_kernel<<<grid_for(total8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), static_cast<uint4*>(dx), total8, HW, C / 8);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_add_context_fwd(const void* x, const void* ctx, void* y, int32_t B, int32_t A,
+                                       int32_t HW, int32_t C, void* stream) {
+  T2R_CHECK_ARG(x && ctx && y && B > 0 && A > 0 && HW > 0 && C % 8 == 0, "add_context_fwd: bad args");
+  const long long total8 = (long long)B * A * HW * (C / 8);
+  add_context_fwd_kernel<<<grid_for(total8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(ctx), static_cast<uint4*>(y), total8, A, HW,
+      C / 8);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_add_context_bwd(const void* dy, void* dx, void* dctx, int32_t B, int32_t A,
+                                       int32_t HW, int32_t C, void* stream) {
+  T2R_CHECK_ARG(dy && (dx || dctx) && B > 0 && A > 0 && HW > 0 && C % 8 == 0, "add_context_bwd: bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cg = C / 8;
+  if (dx) {
+    const long long total8 = (long long)B * HW * cg;
+    add_context_bwd_x_kernel<<<grid_for(total8), 256, 0, st>>>(static_cast<const uint4*>(dy),
+                                                               static_cast<uint4*>(dx), total8, A, HW, cg);
+    T2R_LAUNCH_OK();
+  }
+  if (dctx) {
+    add_context_bwd_ctx_kernel<<<dim3(B * A, (cg + 31) / 32), dim3(32, 8), 0, st>>>(
+        static_cast<const uint4*>(dy), static_cast<uint4*>(dctx), HW, cg);
+    T2R_LAUNCH_OK();
+  }
+  return T2R_OK;
+}
