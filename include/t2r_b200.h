@@ -92,6 +92,8 @@ int32_t t2r_sgemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t 
                   int32_t ldc, void* stream);
 int32_t t2r_bias_add_f32(float* y, const float* bias, int64_t rows, int32_t C, void* stream);
 int32_t t2r_colsum_f32(const float* x, float* out, int64_t rows, int32_t C, void* stream);
+/* out[0] += scale * sum(x^2): the slim l2_regularizer loss term. */
+int32_t t2r_sumsq_f32(const float* x, float* out, int64_t n, float scale, void* stream);
 int32_t t2r_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int32_t t2r_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 
@@ -119,7 +121,7 @@ int32_t t2r_bn_apply(const void* x, void* y, int64_t rows, int32_t C, const floa
                      const float* shift, const float* film, int64_t rows_per_image,
                      int32_t relu, void* stream);
 /* Backward of y = relu?(bn(x)) w.r.t. x, gamma, beta.  dy, x: bf16 [rows,C].
- * red: fp64 [2*C] workspace.  dgamma/dbeta: fp32 [C] written (dgamma may be NULL).
+ * red: fp64 [2*C] workspace.  dgamma/dbeta: fp32 [C], both written (required).
  * dres (optional, bf16 [rows,C]) is added to dx (residual-branch gradient). */
 int32_t t2r_bn_backward(const void* dy, const void* x, const void* dres, void* dx, int64_t rows,
                         int32_t C, const float* gamma, const float* mean, const float* invstd,

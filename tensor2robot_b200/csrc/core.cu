@@ -339,3 +339,31 @@ extern "C" int32_t t2r_relu_bwd_bf16(const void* dy, const void* y, void* dx, in
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
+
+// sum of squares of a flat fp32 buffer (slim l2_regularizer term: l2 * sum(w^2) / 2), accumulated
+// into out[0] (caller zeroes).
+namespace t2r {
+__global__ void __launch_bounds__(256) sumsq_f32_kernel(const float* __restrict__ x, float* out, long long n,
+                                                        float scale) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    acc += x[i] * x[i];
+  __shared__ float sm[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int j = 0; j < 8; ++j) s += sm[j];
+    atomicAdd(out, s * scale);
+  }
+}
+}  // namespace t2r
+
+extern "C" int32_t t2r_sumsq_f32(const float* x, float* out, int64_t n, float scale, void* stream) {
+  T2R_CHECK_ARG(x && out && n > 0, "bad sumsq args");
+  t2r::sumsq_f32_kernel<<<t2r::grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n, scale);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}

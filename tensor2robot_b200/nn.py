@@ -1,0 +1,849 @@
+"""Functional layer library of the B200 engine: torch tensors in, hand-written sm_100a kernels underneath.
+
+This is the layer vocabulary the reference models are written in (slim.conv2d, slim.batch_norm,
+slim.max_pool2d, slim.fully_connected, tf.layers.*; see research/qtopt/networks.py:343-615 and
+layers/film_resnet_model.py:39-340), re-expressed over:
+
+  * `VariableStore`  - TF-style named variables ("scope/conv1_1/weights") living in flat fp32
+    buffers (parameters, gradients, optimizer slots, EMA) so the optimizer and the NCCL gradient
+    all-reduce are each ONE pass over one contiguous buffer.
+  * `torch.autograd.Function`s whose forward/backward call the C-ABI (tensor2robot_b200/_lib.py).
+    PyTorch supplies device memory, streams and the autograd tape only; parameter gradients are
+    written by the kernels straight into the flat gradient buffer (wgrad accumulates with atomics),
+    never through autograd.
+
+Activations are NHWC bf16; the tiny action-context / logit layers run in fp32.
+All functions fail loudly without a CUDA device or without libt2r_b200.so.
+"""
+import collections
+import contextlib
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from tensor2robot_b200 import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+  return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _require_cuda(t, what):
+  if not t.is_cuda:
+    raise _lib.T2RError('%s: tensor is on %s; the B200 engine has no CPU path' % (what, t.device))
+
+
+# ---------------------------------------------------------------------------------------------
+# variables
+# ---------------------------------------------------------------------------------------------
+class Variable(object):
+  """A named parameter.  `data`/`grad` are fp32 views into the store's flat buffers."""
+
+  def __init__(self, name, shape, trainable, regularize, kind, tf_layout):
+    self.name = name
+    self.shape = tuple(int(s) for s in shape)
+    self.trainable = trainable
+    self.regularize = regularize  # receives the slim l2_regularizer gradient
+    self.kind = kind              # 'conv' (OHWI weights), 'fc32', 'other'
+    self.tf_layout = tf_layout    # how to_tf / from_tf permute: 'hwio', 'io', 'fcgrasp', None
+    self.data = None
+    self.grad = None
+    self.bf16 = None    # bf16 copy in compute layout (conv: OHWI)
+    self.dgrad = None   # bf16 [Cin][taps][Cout] for conv layers that need a data gradient
+    self.needs_dgrad = False
+
+  @property
+  def numel(self):
+    return int(np.prod(self.shape)) if self.shape else 1
+
+  def to_tf(self):
+    """numpy array in the reference's (TensorFlow) variable layout."""
+    a = self.data.detach().float().cpu().numpy().reshape(self.shape)
+    if self.tf_layout == 'hwio':      # ours [Cout,KH,KW,Cin] -> [KH,KW,Cin,Cout]
+      return np.ascontiguousarray(a.transpose(1, 2, 3, 0))
+    if self.tf_layout == 'io':        # ours [out,in] -> [in,out]
+      return np.ascontiguousarray(a.T)
+    if self.tf_layout == 'io_hwc':    # ours [out,1,1,in] -> [in,out]
+      return np.ascontiguousarray(a.reshape(self.shape[0], -1).T)
+    if len(self.shape) == 2 and self.shape[0] == 1 and self.name.endswith(('biases', 'bias')):
+      return a[0].copy()            # stored [1, units], the reference has [units]
+    return a.copy()
+
+  def from_tf(self, a):
+    a = np.asarray(a, dtype=np.float32)
+    if self.tf_layout == 'hwio':
+      a = a.transpose(3, 0, 1, 2)
+    elif self.tf_layout == 'io':
+      a = a.T
+    elif self.tf_layout == 'io_hwc':
+      a = a.T.reshape(self.shape)
+    elif a.size == self.numel and len(self.shape) == 2 and self.shape[0] == 1:
+      a = a.reshape(self.shape)
+    if tuple(a.shape) != self.shape:
+      raise ValueError('variable %s: expected shape %s (our layout), got %s' % (self.name, self.shape, a.shape))
+    self.data.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(self.data.device))
+
+
+class VariableStore(object):
+  """Named variables with TF-style scopes, consolidated into flat buffers by `finalize()`."""
+
+  def __init__(self, device='cuda', seed=0):
+    self.device = torch.device(device)
+    self.vars = collections.OrderedDict()
+    self._scope = []
+    self._finalized = False
+    self._rng = np.random.RandomState(seed)
+    self.flat = None        # trainable fp32 params  [decay | no-decay]
+    self.flat_grad = None
+    self.flat_bf16 = None
+    self.n_decay = 0
+    self.state_flat = None  # non-trainable (moving statistics)
+    self.workspace = {}
+    # A leaf that requires grad: fed to the first layers so that autograd runs their backward
+    # (parameters live outside autograd, and images / actions are constants).
+    self.anchor = torch.zeros((), dtype=F32, device=self.device, requires_grad=True)
+
+  # -- scopes ---------------------------------------------------------------------------------
+  @contextlib.contextmanager
+  def scope(self, name):
+    if name:
+      self._scope.append(name)
+    try:
+      yield
+    finally:
+      if name:
+        self._scope.pop()
+
+  def full_name(self, name):
+    return '/'.join(self._scope + [name])
+
+  # -- creation -------------------------------------------------------------------------------
+  def get_variable(self, name, shape, init, trainable=True, regularize=False, kind='other',
+                   tf_layout=None):
+    full = self.full_name(name)
+    if full in self.vars:
+      v = self.vars[full]
+      if v.shape != tuple(shape):
+        raise ValueError('variable %s exists with shape %s, requested %s' % (full, v.shape, tuple(shape)))
+      return v
+    if self._finalized:
+      raise ValueError('variable %s requested after finalize(); build the model first' % full)
+    v = Variable(full, shape, trainable, regularize, kind, tf_layout)
+    value = init(v.shape, self._rng) if callable(init) else np.full(v.shape, init, np.float32)
+    v.data = torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32)).to(self.device)
+    self.vars[full] = v
+    return v
+
+  @property
+  def finalized(self):
+    return self._finalized
+
+  def trainable_variables(self):
+    return [v for v in self.vars.values() if v.trainable]
+
+  def finalize(self):
+    """Moves every variable into flat buffers: trainable = [regularised | rest], state = rest."""
+    if self._finalized:
+      return
+    train = [v for v in self.vars.values() if v.trainable]
+    decay = [v for v in train if v.regularize]
+    nodecay = [v for v in train if not v.regularize]
+    state = [v for v in self.vars.values() if not v.trainable]
+    align = 64  # elements: keeps every view 256-byte aligned (TMA needs 16 B)
+
+    def layout(vs):
+      off, table = 0, []
+      for v in vs:
+        table.append((v, off))
+        off += (v.numel + align - 1) // align * align
+      return table, off
+
+    t1, n1 = layout(decay)
+    t2, n2 = layout(nodecay)
+    total = n1 + n2
+    self.n_decay = n1
+    self.flat = torch.zeros(max(total, align), dtype=F32, device=self.device)
+    self.flat_grad = torch.zeros_like(self.flat)
+    self.flat_bf16 = torch.zeros(self.flat.numel(), dtype=BF16, device=self.device)
+    for table, base in ((t1, 0), (t2, n1)):
+      for v, off in table:
+        sl = slice(base + off, base + off + v.numel)
+        self.flat[sl].copy_(v.data.reshape(-1))
+        v.data = self.flat[sl].view(v.shape)
+        v.grad = self.flat_grad[sl].view(v.shape)
+        v.bf16 = self.flat_bf16[sl].view(v.shape)
+        v.offset = base + off
+    t3, n3 = layout(state)
+    self.state_flat = torch.zeros(max(n3, align), dtype=F32, device=self.device)
+    for v, off in t3:
+      sl = slice(off, off + v.numel)
+      self.state_flat[sl].copy_(v.data.reshape(-1))
+      v.data = self.state_flat[sl].view(v.shape)
+      v.offset = off
+    self._finalized = True
+    self.sync_compute_copies()
+
+  def sync_compute_copies(self, after_optimizer=False):
+    """Refreshes the bf16 compute copies of the weights from the fp32 masters.
+
+    after_optimizer=True: the optimizer kernel already wrote the flat bf16 buffer, only the
+    transposed data-gradient packs remain."""
+    st = _stream()
+    if not self._finalized:
+      raise ValueError('finalize() first')
+    if not after_optimizer:
+      _lib.call('t2r_cast_f32_to_bf16', _p(self.flat), _p(self.flat_bf16), self.flat.numel(), st)
+    for v in self.vars.values():
+      if v.kind == 'conv' and not v.trainable:   # frozen weights live outside the flat buffer
+        if v.bf16 is None:
+          v.bf16 = torch.empty(v.shape, dtype=BF16, device=self.device)
+        _lib.call('t2r_cast_f32_to_bf16', _p(v.data), _p(v.bf16), v.numel, st)
+      if v.kind == 'conv' and v.needs_dgrad:
+        cout, kh, kw, cin = v.shape
+        if v.dgrad is None:
+          v.dgrad = torch.empty(cin * kh * kw * cout, dtype=BF16, device=self.device)
+        _lib.call('t2r_pack_weights', _p(v.data), None, _p(v.dgrad), cout, kh * kw, cin, st)
+
+  def zero_grad(self):
+    self.flat_grad.zero_()
+
+  def scratch(self, key, numel, dtype):
+    """Persistent small workspaces (BN statistics etc.), keyed by use site."""
+    t = self.workspace.get(key)
+    if t is None or t.numel() < numel or t.dtype != dtype:
+      t = torch.zeros(numel, dtype=dtype, device=self.device)
+      self.workspace[key] = t
+    return t
+
+  # -- checkpoints in the reference's naming/layout ---------------------------------------------
+  def export_tf_grads(self):
+    """Gradients of the trainable variables, keyed and laid out like export_tf()."""
+    saved = {}
+    for n, v in self.vars.items():
+      if v.trainable and v.grad is not None:
+        saved[n] = v.data
+        v.data = v.grad
+    try:
+      out = self.export_tf()
+    finally:
+      for n, d in saved.items():
+        self.vars[n].data = d
+    keep = set()
+    for n in saved:
+      parts = getattr(self.vars[n], 'tf_parts', None)
+      keep.update([p[0] for p in parts] if parts else [n])
+    return collections.OrderedDict((k, a) for k, a in out.items() if k in keep)
+
+  def export_tf(self):
+    """{reference variable name: numpy array in the reference (TF) layout}.
+
+    A variable with `tf_parts = [(tf_name, row_start, row_stop, squeeze)]` is the row-wise
+    concatenation of several reference variables (the fcgrasp_* blocks)."""
+    out = collections.OrderedDict()
+    for n, v in self.vars.items():
+      parts = getattr(v, 'tf_parts', None)
+      if parts is None:
+        out[n] = v.to_tf()
+        continue
+      a = v.to_tf()
+      for tf_name, r0, r1, squeeze in parts:
+        out[tf_name] = a[r0] if squeeze else a[r0:r1]
+    return out
+
+  def import_tf(self, arrays, strict=True):
+    for n, v in self.vars.items():
+      parts = getattr(v, 'tf_parts', None)
+      if parts is None:
+        if n in arrays:
+          v.from_tf(arrays[n])
+        elif strict:
+          raise ValueError('checkpoint lacks variable %s' % n)
+        continue
+      if not all(p[0] in arrays for p in parts):
+        if strict:
+          raise ValueError('checkpoint lacks parts of %s' % n)
+        continue
+      a = np.zeros(v.shape, np.float32)
+      for tf_name, r0, r1, squeeze in parts:
+        a[r0:r1] = np.asarray(arrays[tf_name], np.float32).reshape(a[r0:r1].shape)
+      v.from_tf(a)
+    if self._finalized:
+      self.sync_compute_copies()
+
+
+_STORE_STACK = []
+# When a list is installed here every layer call appends (op, scope, output): used by the
+# layer-by-layer parity tests (tests/parity_trace.py).  None in production.
+TRACE = None
+
+
+def _trace(op, scope, y):
+  if TRACE is not None:
+    TRACE.append((op, current_store().full_name(scope) if scope else '', y))
+  return y
+
+
+
+@contextlib.contextmanager
+def variable_store(vs):
+  """Makes `vs` the store layer functions create/look up variables in (cf. tf.Graph.as_default)."""
+  _STORE_STACK.append(vs)
+  try:
+    yield vs
+  finally:
+    _STORE_STACK.pop()
+
+
+def current_store():
+  if not _STORE_STACK:
+    raise ValueError('no active VariableStore: wrap the network call in `with nn.variable_store(vs):`')
+  return _STORE_STACK[-1]
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+  with current_store().scope(name):
+    yield
+
+
+# ---------------------------------------------------------------------------------------------
+# initialisers (numpy, seeded by the store)
+# ---------------------------------------------------------------------------------------------
+def truncated_normal(stddev):
+  def init(shape, rng):
+    a = rng.normal(0.0, stddev, size=shape)
+    bad = np.abs(a) > 2 * stddev
+    while bad.any():
+      a[bad] = rng.normal(0.0, stddev, size=int(bad.sum()))
+      bad = np.abs(a) > 2 * stddev
+    return a.astype(np.float32)
+  return init
+
+
+def variance_scaling(fan_in):
+  """tf.variance_scaling_initializer() defaults: scale 1, fan_in, truncated normal."""
+  std = math.sqrt(1.0 / max(1.0, fan_in)) / .87962566103423978
+  return truncated_normal(std)
+
+
+def glorot_uniform(fan_in, fan_out):
+  lim = math.sqrt(6.0 / (fan_in + fan_out))
+  return lambda shape, rng: rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------
+def _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, flags=0):
+  d = _lib.ConvDesc()
+  d.struct_size = C.sizeof(_lib.ConvDesc)
+  d.N, d.H, d.W, d.Cin, d.Cout, d.KH, d.KW = n, h, w, cin, cout, kh, kw
+  d.stride, d.pad_top, d.pad_left, d.Ho, d.Wo, d.flags = stride, pt, pl, ho, wo, flags
+  return d
+
+
+def conv_geometry(h, w, kh, kw, stride, padding):
+  """padding: 'SAME' | 'VALID' | ('EXPLICIT', pad_begin) -> (Ho, Wo, pad_top, pad_left)."""
+  if padding == 'SAME':
+    ho, pt = _lib.same_padding(h, kh, stride)
+    wo, pl = _lib.same_padding(w, kw, stride)
+  elif padding == 'VALID':
+    ho, wo, pt, pl = (h - kh) // stride + 1, (w - kw) // stride + 1, 0, 0
+  else:  # fixed_padding (film_resnet_model.py:60-86): pad_beg=(k-1)//2, pad_end=k-1-pad_beg, then VALID
+    pb_h, pb_w = (kh - 1) // 2, (kw - 1) // 2
+    ho = (h + (kh - 1) - kh) // stride + 1
+    wo = (w + (kw - 1) - kw) // stride + 1
+    pt, pl = pb_h, pb_w
+  return ho, wo, pt, pl
+
+
+class _Conv2dFn(torch.autograd.Function):
+  """y = conv(x, W) [+bias] [+residual] [relu] on the tcgen05 implicit-GEMM kernels."""
+
+  @staticmethod
+  def forward(ctx, x, residual, var, bias_var, geom, relu, out_f32):
+    n, h, w, cin = x.shape
+    cout, kh, kw, _ = var.shape
+    stride, ho, wo, pt, pl = geom
+    flags = 0
+    if bias_var is not None:
+      flags |= _lib.T2R_EPI_BIAS
+    if residual is not None:
+      flags |= _lib.T2R_EPI_RESIDUAL
+    if relu:
+      flags |= _lib.T2R_EPI_RELU
+    if out_f32:
+      flags |= _lib.T2R_EPI_OUT_F32
+    d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, flags)
+    y = torch.empty((n, ho, wo, cout), dtype=F32 if out_f32 else BF16, device=x.device)
+    _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(var.bf16), _p(bias_var.data if bias_var is not None else None),
+              _p(residual), _p(y), _stream())
+    ctx.var, ctx.bias_var, ctx.desc, ctx.relu, ctx.out_f32 = var, bias_var, d, relu, out_f32
+    ctx.has_res = residual is not None
+    ctx.save_for_backward(x, y if relu else None)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, y = ctx.saved_tensors
+    var, d = ctx.var, ctx.desc
+    st = _stream()
+    if ctx.out_f32:
+      dyb = torch.empty(dy.shape, dtype=BF16, device=dy.device)
+      _lib.call('t2r_cast_f32_to_bf16', _p(dy.contiguous()), _p(dyb), dy.numel(), st)
+      dy = dyb
+    dy = dy.contiguous()
+    if ctx.relu:
+      dz = torch.empty_like(dy)
+      _lib.call('t2r_relu_bwd_bf16', _p(dy), _p(y), _p(dz), dy.numel(), st)
+      dy = dz
+    if ctx.bias_var is not None and ctx.bias_var.trainable:
+      rows = dy.numel() // dy.shape[-1]
+      dyf = torch.empty(dy.shape, dtype=F32, device=dy.device)
+      _lib.call('t2r_cast_bf16_to_f32', _p(dy), _p(dyf), dy.numel(), st)
+      _lib.call('t2r_colsum_f32', _p(dyf), _p(ctx.bias_var.grad), rows, dy.shape[-1], st)
+    if var.trainable:
+      _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(x), _p(dy), _p(var.grad), st)
+    dx = None
+    if ctx.needs_input_grad[0]:
+      if var.dgrad is None:
+        raise _lib.T2RError('conv %s needs a data gradient but was built with needs_dgrad=False' % var.name)
+      dx = torch.empty_like(x)
+      _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 0, st)
+    dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
+    return dx, dres, None, None, None, None, None
+
+
+class _StemConvFn(torch.autograd.Function):
+  """Small-Cin convolution (image stem): explicit im2col to a K-padded matrix + GEMM."""
+
+  @staticmethod
+  def forward(ctx, x, anchor, var, bias_var, geom, kpad):
+    n, h, w, cin = x.shape
+    cout = var.shape[0]
+    kh, kw, stride, ho, wo, pt, pl = geom
+    d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo)
+    st = _stream()
+    a = torch.empty((n * ho * wo, kpad), dtype=BF16, device=x.device)
+    _lib.call('t2r_im2col_small_cin', C.byref(d), _p(x), _p(a), kpad, st)
+    g = _conv_desc(1, 1, n * ho * wo, kpad, cout, 1, 1, 1, 0, 0, 1, n * ho * wo,
+                   _lib.T2R_EPI_BIAS if bias_var is not None else 0)
+    y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+    _lib.call('t2r_conv2d_fprop', C.byref(g), _p(a), _p(var.bf16), _p(bias_var.data if bias_var is not None else None),
+              None, _p(y), st)
+    ctx.var, ctx.bias_var, ctx.desc, ctx.gdesc, ctx.kpad = var, bias_var, d, g, kpad
+    # The im2col matrix is recomputed in backward instead of being kept alive (it is ~50x the image).
+    ctx.save_for_backward(x)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (x,) = ctx.saved_tensors
+    st = _stream()
+    dy = dy.contiguous()
+    if ctx.bias_var is not None and ctx.bias_var.trainable:
+      rows = dy.numel() // dy.shape[-1]
+      dyf = torch.empty(dy.shape, dtype=F32, device=dy.device)
+      _lib.call('t2r_cast_bf16_to_f32', _p(dy), _p(dyf), dy.numel(), st)
+      _lib.call('t2r_colsum_f32', _p(dyf), _p(ctx.bias_var.grad), rows, dy.shape[-1], st)
+    if ctx.var.trainable:
+      a = torch.empty((ctx.gdesc.W, ctx.kpad), dtype=BF16, device=x.device)
+      _lib.call('t2r_im2col_small_cin', C.byref(ctx.desc), _p(x), _p(a), ctx.kpad, st)
+      _lib.call('t2r_conv2d_wgrad', C.byref(ctx.gdesc), _p(a), _p(dy), _p(ctx.var.grad), st)
+    if ctx.needs_input_grad[0]:
+      raise _lib.T2RError('stem convolution %s has no data gradient (image inputs are leaves)' % ctx.var.name)
+    return None, None, None, None, None, None
+
+
+def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, scope='conv',
+           initializer=None, regularize=True, residual=None, relu=False, needs_dgrad=True,
+           trainable=True, out_f32=False, names=('weights', 'biases')):
+  """slim.conv2d / tf.layers.conv2d without normaliser or activation (compose with batch_norm)."""
+  _require_cuda(x, 'conv2d')
+  vs = current_store()
+  kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+  n, h, w, cin = x.shape
+  ho, wo, pt, pl = conv_geometry(h, w, kh, kw, stride, padding)
+  small = cin % 64 != 0
+  kpad = (kh * kw * cin + 63) // 64 * 64 if small else 0
+  with vs.scope(scope):
+    if small:
+      # stored as [Cout, 1, 1, Kpad] (K-padded OHWI, flattened taps); TF layout handled by to_tf
+      wv = vs.get_variable(names[0], (filters, 1, 1, kpad),
+                           _padded_init(initializer or variance_scaling(kh * kw * cin), filters, kh, kw, cin, kpad),
+                           trainable, regularize, 'conv', None)
+      wv.stem_geom = (kh, kw, cin)
+      _install_stem_tf(wv)
+    else:
+      wv = vs.get_variable(names[0], (filters, kh, kw, cin), initializer or variance_scaling(kh * kw * cin),
+                           trainable, regularize, 'conv', 'hwio')
+      wv.needs_dgrad = wv.needs_dgrad or needs_dgrad
+    bv = vs.get_variable(names[1], (filters,), 0.0, trainable, False) if use_bias else None
+  if not vs.finalized:
+    _ensure_bf16(wv)
+  if small:
+    return _trace('conv', scope, _StemConvFn.apply(x, vs.anchor, wv, bv, (kh, kw, stride, ho, wo, pt, pl), kpad))
+  return _trace('conv', scope, _Conv2dFn.apply(x, residual, wv, bv, (stride, ho, wo, pt, pl), relu, out_f32))
+
+
+def _padded_init(init, filters, kh, kw, cin, kpad):
+  def f(shape, rng):
+    w = init((filters, kh, kw, cin), rng).reshape(filters, kh * kw * cin)
+    out = np.zeros((filters, kpad), np.float32)
+    out[:, :kh * kw * cin] = w
+    return out.reshape(shape)
+  return f
+
+
+def _install_stem_tf(v):
+  kh, kw, cin = v.stem_geom
+  k = kh * kw * cin
+
+  def to_tf():
+    a = v.data.detach().float().cpu().numpy().reshape(v.shape[0], -1)[:, :k]
+    return np.ascontiguousarray(a.reshape(v.shape[0], kh, kw, cin).transpose(1, 2, 3, 0))
+
+  def from_tf(a):
+    a = np.asarray(a, np.float32).transpose(3, 0, 1, 2).reshape(v.shape[0], k)
+    full = np.zeros((v.shape[0], v.shape[-1]), np.float32)
+    full[:, :k] = a
+    v.data.copy_(torch.from_numpy(full.reshape(v.shape)).to(v.data.device))
+  v.to_tf, v.from_tf = to_tf, from_tf
+
+
+def _ensure_bf16(v):
+  """Before finalize() (the build pass) variables are stand-alone tensors: give them compute copies."""
+  st = _stream()
+  if v.bf16 is None or v.bf16.numel() != v.numel:
+    v.bf16 = torch.empty(v.shape, dtype=BF16, device=v.data.device)
+  _lib.call('t2r_cast_f32_to_bf16', _p(v.data), _p(v.bf16), v.numel, st)
+  if v.kind == 'conv' and v.needs_dgrad and len(v.shape) == 4:
+    cout, kh, kw, cin = v.shape
+    v.dgrad = torch.empty(v.numel, dtype=BF16, device=v.data.device)
+    _lib.call('t2r_pack_weights', _p(v.data), None, _p(v.dgrad), cout, kh * kw, cin, st)
+  if v.grad is None:
+    v.grad = torch.zeros(v.shape, dtype=F32, device=v.data.device)
+
+
+def dense(x, units, scope='fc', use_bias=False, initializer=None, regularize=True, relu=False,
+          needs_dgrad=True, trainable=True, out_f32=False, names=('weights', 'biases')):
+  """slim.fully_connected on a [rows, K] bf16 matrix through the tensor-core path (K % 64 == 0)."""
+  vs = current_store()
+  rows, k = x.shape
+  y = conv2d(x.view(1, 1, rows, k), units, 1, 1, 'VALID', use_bias, scope,
+             initializer or glorot_uniform(k, units), regularize, None, relu, needs_dgrad, trainable, out_f32,
+             names)
+  v = vs.vars[vs.full_name(scope + '/' + names[0])]
+  v.tf_layout = 'io_hwc'
+  return y.view(rows, units)
+
+
+# ---------------------------------------------------------------------------------------------
+# batch norm (+ReLU, +FiLM)
+# ---------------------------------------------------------------------------------------------
+class _BatchNormFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, film, bn, training, relu, vs):
+    c = x.shape[-1]
+    rows = x.numel() // c
+    st = _stream()
+    y = torch.empty_like(x)
+    scale = torch.empty(c, dtype=F32, device=x.device)
+    shift = torch.empty(c, dtype=F32, device=x.device)
+    rows_per_image = rows // x.shape[0]
+    if training:
+      stats = vs.scratch('bn_stats', 2 * 4096, torch.float64)
+      mean = torch.empty(c, dtype=F32, device=x.device)
+      invstd = torch.empty(c, dtype=F32, device=x.device)
+      _lib.call('t2r_bn_stats', _p(x), rows, c, _p(stats), st)
+      _lib.call('t2r_bn_finalize', _p(stats), rows, c, _p(bn['gamma'].data if bn['gamma'] is not None else None),
+                _p(bn['beta'].data), bn['eps'], bn['momentum'], _p(bn['moving_mean'].data),
+                _p(bn['moving_variance'].data), _p(mean), _p(invstd), _p(scale), _p(shift), st)
+      ctx.save_for_backward(x, mean, invstd, scale, shift, film)
+    else:
+      _lib.call('t2r_bn_infer_params', c, _p(bn['gamma'].data if bn['gamma'] is not None else None),
+                _p(bn['beta'].data), _p(bn['moving_mean'].data), _p(bn['moving_variance'].data), bn['eps'],
+                _p(scale), _p(shift), st)
+    _lib.call('t2r_bn_apply', _p(x), _p(y), rows, c, _p(scale), _p(shift), _p(film), rows_per_image,
+              1 if relu else 0, st)
+    ctx.bn, ctx.relu, ctx.training, ctx.vs = bn, relu, training, vs
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    if not ctx.training:
+      raise _lib.T2RError('backward through inference-mode batch norm is not supported')
+    x, mean, invstd, scale, shift, film = ctx.saved_tensors
+    if film is not None:
+      raise _lib.T2RError('FiLM backward is not implemented yet')
+    bn = ctx.bn
+    c = x.shape[-1]
+    rows = x.numel() // c
+    st = _stream()
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    red = ctx.vs.scratch('bn_red', 2 * 4096, torch.float64)
+    gamma = bn['gamma']
+    dgamma = gamma.grad if (gamma is not None and gamma.trainable) else ctx.vs.scratch('bn_dgamma', 4096, F32)
+    dbeta = bn['beta'].grad if bn['beta'].trainable else ctx.vs.scratch('bn_dbeta', 4096, F32)
+    _lib.call('t2r_bn_backward', _p(dy), _p(x), None, _p(dx), rows, c, _p(gamma.data if gamma is not None else None),
+              _p(mean), _p(invstd), _p(scale), _p(shift), 1 if ctx.relu else 0, _p(red), _p(dgamma), _p(dbeta), st)
+    return dx, None, None, None, None, None
+
+
+def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=0.997, eps=1e-5,
+               film=None, trainable=True):
+  """slim.batch_norm / tf.layers.batch_normalization(fused=True) followed by an optional ReLU."""
+  _require_cuda(x, 'batch_norm')
+  vs = current_store()
+  c = x.shape[-1]
+  if c > 4096:
+    raise ValueError('batch_norm supports up to 4096 channels')
+  with vs.scope(scope):
+    bn = {
+        'gamma': vs.get_variable('gamma', (c,), 1.0, trainable, False) if scale else None,
+        'beta': vs.get_variable('beta', (c,), 0.0, trainable, False),
+        'moving_mean': vs.get_variable('moving_mean', (c,), 0.0, False, False),
+        'moving_variance': vs.get_variable('moving_variance', (c,), 1.0, False, False),
+        'eps': float(eps), 'momentum': float(momentum),
+    }
+  if not vs.finalized:
+    for k in ('gamma', 'beta'):
+      if bn[k] is not None and bn[k].grad is None:
+        bn[k].grad = torch.zeros(bn[k].shape, dtype=F32, device=x.device)
+  return _trace('bn', scope, _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs))
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling / reshaping
+# ---------------------------------------------------------------------------------------------
+class _MaxPoolFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, k, stride, geom):
+    n, h, w, c = x.shape
+    ho, wo, pt, pl = geom
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    arg = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+    _lib.call('t2r_maxpool_fwd', _p(x), _p(y), _p(arg), n, h, w, c, k, stride, pt, pl, ho, wo, _stream())
+    ctx.save_for_backward(arg)
+    ctx.geom = (n, h, w, c, k, stride, pt, pl, ho, wo)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (arg,) = ctx.saved_tensors
+    n, h, w, c, k, stride, pt, pl, ho, wo = ctx.geom
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    _lib.call('t2r_maxpool_bwd', _p(dy.contiguous()), _p(arg), _p(dx), n, h, w, c, k, stride, pt, pl, ho, wo, _stream())
+    return dx, None, None, None
+
+
+def max_pool2d(x, kernel_size, stride, padding='SAME'):
+  """slim.max_pool2d / tf.layers.max_pooling2d."""
+  _require_cuda(x, 'max_pool2d')
+  _, h, w, _ = x.shape
+  geom = conv_geometry(h, w, kernel_size, kernel_size, stride, padding)
+  return _trace('pool', None, _MaxPoolFn.apply(x.contiguous(), kernel_size, stride, geom))
+
+
+class _GlobalMeanFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=BF16, device=x.device)
+    _lib.call('t2r_global_mean_fwd', _p(x), _p(y), n, h * w, c, _stream())
+    ctx.shape = (n, h, w, c)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    n, h, w, c = ctx.shape
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    _lib.call('t2r_global_mean_bwd', _p(dy.contiguous()), _p(dx), n, h * w, c, _stream())
+    return dx
+
+
+def global_mean(x):
+  """tf.reduce_mean over the spatial axes (film_resnet_model.py:611-616)."""
+  _require_cuda(x, 'global_mean')
+  return _GlobalMeanFn.apply(x.contiguous())
+
+
+class _AddContextFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, context, a):
+    b, h, w, c = x.shape
+    y = torch.empty((b * a, h, w, c), dtype=BF16, device=x.device)
+    _lib.call('t2r_add_context_fwd', _p(x), _p(context), _p(y), b, a, h * w, c, _stream())
+    ctx.geom = (b, a, h, w, c)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    b, a, h, w, c = ctx.geom
+    dy = dy.contiguous()
+    dx = torch.empty((b, h, w, c), dtype=BF16, device=dy.device) if ctx.needs_input_grad[0] else None
+    dctx = torch.empty((b * a, c), dtype=BF16, device=dy.device) if ctx.needs_input_grad[1] else None
+    _lib.call('t2r_add_context_bwd', _p(dy), _p(dx), _p(dctx), b, a, h * w, c, _stream())
+    return dx, dctx, None
+
+
+def add_context(x, context, action_batch_size=1):
+  """tile_batch(x, A) + context[:, None, None, :] without materialising the tile
+  (research/qtopt/networks.py:513-522; research/dql_grasping_lib/tf_modules.py:74-93)."""
+  _require_cuda(x, 'add_context')
+  if context.shape[0] != x.shape[0] * action_batch_size:
+    raise ValueError('context rows %d != batch %d * action_batch %d' % (context.shape[0], x.shape[0], action_batch_size))
+  return _trace('add_context', None, _AddContextFn.apply(x.contiguous(), context.contiguous(), action_batch_size))
+
+
+class _CastFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, to_bf16):
+    y = torch.empty(x.shape, dtype=BF16 if to_bf16 else F32, device=x.device)
+    _lib.call('t2r_cast_f32_to_bf16' if to_bf16 else 't2r_cast_bf16_to_f32', _p(x), _p(y), x.numel(), _stream())
+    ctx.to_bf16 = to_bf16
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    dy = dy.contiguous()
+    dx = torch.empty(dy.shape, dtype=F32 if ctx.to_bf16 else BF16, device=dy.device)
+    _lib.call('t2r_cast_bf16_to_f32' if ctx.to_bf16 else 't2r_cast_f32_to_bf16', _p(dy), _p(dx), dy.numel(), _stream())
+    return dx, None
+
+
+def to_bf16(x):
+  return x if x.dtype == BF16 else _CastFn.apply(x.contiguous(), True)
+
+
+def to_f32(x):
+  return x if x.dtype == F32 else _CastFn.apply(x.contiguous(), False)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 fully connected (tiny layers: action context input, logits)
+# ---------------------------------------------------------------------------------------------
+class _Fc32Fn(torch.autograd.Function):
+  """y[M,N] = x[M,K] @ W[K,N] + sum_rows(bias[R,N]); W is stored in the TF [in,out] layout."""
+
+  @staticmethod
+  def forward(ctx, x, anchor, wv, bv):
+    m, k = x.shape
+    n = wv.shape[1]
+    st = _stream()
+    y = torch.empty((m, n), dtype=F32, device=x.device)
+    _lib.call('t2r_sgemm', 0, 0, m, n, k, 1.0, _p(x), k, _p(wv.data), n, 0.0, _p(y), n, st)
+    if bv is not None:
+      r = bv.shape[0]
+      if r == 1:
+        bias = bv.data
+      else:
+        bias = torch.empty(n, dtype=F32, device=x.device)
+        _lib.call('t2r_colsum_f32', _p(bv.data), _p(bias), r, n, st)
+      _lib.call('t2r_bias_add_f32', _p(y), _p(bias), m, n, st)
+    ctx.wv, ctx.bv = wv, bv
+    ctx.save_for_backward(x)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (x,) = ctx.saved_tensors
+    wv, bv = ctx.wv, ctx.bv
+    m, k = x.shape
+    n = wv.shape[1]
+    st = _stream()
+    dy = dy.contiguous()
+    if wv.trainable:   # dW[K,N] = x^T dy
+      _lib.call('t2r_sgemm', 1, 0, k, n, m, 1.0, _p(x), k, _p(dy), n, 0.0, _p(wv.grad), n, st)
+    if bv is not None and bv.trainable:
+      db = torch.empty(n, dtype=F32, device=x.device)
+      _lib.call('t2r_colsum_f32', _p(dy), _p(db), m, n, st)
+      r = bv.shape[0]
+      ones = torch.ones(r, dtype=F32, device=x.device)   # every summed bias row receives db
+      _lib.call('t2r_sgemm', 0, 0, r, n, 1, 1.0, _p(ones), 1, _p(db), n, 0.0, _p(bv.grad), n, st)
+    dx = None
+    if ctx.needs_input_grad[0]:   # dx[M,K] = dy W^T
+      dx = torch.empty((m, k), dtype=F32, device=x.device)
+      _lib.call('t2r_sgemm', 0, 1, m, k, n, 1.0, _p(dy), n, _p(wv.data), n, 0.0, _p(dx), k, st)
+    return dx, None, None, None
+
+
+def dense_f32(x, units, scope='fc', bias_rows=1, initializer=None, regularize=True, trainable=True,
+              names=('weights', 'biases')):
+  """fp32 slim.fully_connected for inner dimensions that are not multiples of 64.
+
+  bias_rows > 1 models `tf.add_n` of several FC blocks that share the output (the reference's
+  fcgrasp_* blocks, networks.py:481-501): their weights are the row blocks of W, their biases the
+  rows of a [bias_rows, units] matrix that is summed."""
+  _require_cuda(x, 'dense_f32')
+  vs = current_store()
+  k = x.shape[1]
+  with vs.scope(scope):
+    wv = vs.get_variable(names[0], (k, units), initializer or glorot_uniform(k, units), trainable, regularize,
+                         'fc32', None)
+    bv = vs.get_variable(names[1], (bias_rows, units), 0.0, trainable, False, 'fc32', None) if bias_rows else None
+  if not vs.finalized:
+    for v in (wv, bv):
+      if v is not None and v.grad is None:
+        v.grad = torch.zeros(v.shape, dtype=F32, device=x.device)
+  return _trace('fc32', scope, _Fc32Fn.apply(x.contiguous(), vs.anchor, wv, bv))
+
+
+# ---------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------
+class _SigmoidLogLossFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, logit, label):
+    n = logit.numel()
+    q = torch.empty_like(logit)
+    dlogit = torch.empty_like(logit)
+    loss = torch.zeros(1, dtype=F32, device=logit.device)
+    _lib.call('t2r_sigmoid_logloss', _p(logit), _p(label), _p(q), _p(loss), _p(dlogit), n, _stream())
+    ctx.save_for_backward(dlogit)
+    ctx.mark_non_differentiable(q)
+    return loss[0], q
+
+  @staticmethod
+  def backward(ctx, dloss, _dq):
+    (dlogit,) = ctx.saved_tensors
+    return dlogit * dloss, None
+
+
+def sigmoid_log_loss(logit, label):
+  """tf.losses.log_loss(label, sigmoid(logit)) computed with the reference's eps=1e-7; returns
+  (loss, q_predicted)."""
+  _require_cuda(logit, 'sigmoid_log_loss')
+  return _SigmoidLogLossFn.apply(to_f32(logit).contiguous(), label.to(F32).contiguous())
+
+
+def sigmoid(logit):
+  logit = to_f32(logit).contiguous()
+  q = torch.empty_like(logit)
+  _lib.call('t2r_sigmoid_f32', _p(logit), _p(q), logit.numel(), _stream())
+  return q
+
+
+def l2_regularization_loss(l2, vs=None):
+  """slim.l2_regularizer(l2)(w) summed over regularised weights = l2 * sum(w^2) / 2."""
+  vs = vs or current_store()
+  out = torch.zeros(1, dtype=F32, device=vs.device)
+  if vs.finalized and vs.n_decay > 0:
+    _lib.call('t2r_sumsq_f32', _p(vs.flat), _p(out), vs.n_decay, 0.5 * l2, _stream())
+  return out[0]

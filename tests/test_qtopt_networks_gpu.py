@@ -1,0 +1,189 @@
+"""GPU parity: the engine's Grasping44 critic (tcgen05 convs, fused BN, ...) against the torch-CPU
+oracle restatement of research/qtopt/networks.py:343-615, on identical weights and inputs.
+
+Two oracles are used (oracle/tf_ops.py STORAGE_DTYPE):
+  * bf16-storage oracle: fp32 arithmetic, every stored activation / tensor-core weight rounded to
+    bf16 exactly where the engine stores bf16.  The engine must match it tightly - this is the
+    correctness gate.
+  * fp32 oracle (the reference's precision): measures what bf16 storage costs end to end.  The
+    16-layer random-weight network with batch-statistics BN amplifies rounding noise, so this bound
+    is loose and the measured value is printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# A randomly initialised 16-layer BatchNorm-ReLU network in training mode is ill-conditioned
+# (perturbations and gradients grow ~1.2x per layer at init: mean-field theory of batch norm,
+# Yang et al. 2019), so rounding differences are amplified end to end.  The train-step criterion is
+# therefore *relative to the conditioning*: the engine must be as close to the bf16-storage oracle
+# as that oracle is to the fp32 oracle (two legitimate precision choices of the same algorithm),
+# within COND_FACTOR, plus the absolute floors below.  The tight per-op gates are in
+# tests/test_ops_parity_gpu.py.
+COND_FACTOR = 1.5
+Q_TOL_FP32_ORACLE = 1e-1      # |q_engine - q_fp32_oracle|, absolute cap
+GRAD_FLOOR = 0.05             # relative-L2 floor per gradient tensor
+Q_TOL_PREDICT = 2e-3          # inference mode (moving statistics): no amplification
+
+
+def _inputs(b, a=None, seed=0, size=472):
+  rng = np.random.RandomState(seed)
+  yy, xx = np.mgrid[0:size, 0:size].astype(np.float32) / size
+  img = np.zeros((b, size, size, 3), np.float32)
+  for i in range(b):   # distinct smooth scenes: a few random blobs per image on a random background
+    img[i] = rng.uniform(0.1, 0.9, size=(1, 1, 3))
+    for _ in range(6):
+      cy, cx, r = rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(0.05, 0.3)
+      col = rng.uniform(0, 1, size=3)
+      m = np.exp(-((yy - cy)**2 + (xx - cx)**2) / (2 * r * r))[..., None]
+      img[i] = img[i] * (1 - m) + col * m
+  img += rng.uniform(-0.03, 0.03, size=img.shape).astype(np.float32)
+  img = np.clip(img, 0, 1)
+  shape = (b, 10) if a is None else (b, a, 10)
+  grasp = rng.uniform(-1, 1, size=shape).astype(np.float32)
+  reward = (rng.uniform(size=(b, 1)) < 0.3).astype(np.float32)
+  return img, grasp, reward
+
+
+def _rel_l2(a, b):
+  a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+  return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+def _variables(seed, scale=8.0):
+  from oracle import qtopt_networks as oracle
+  variables = oracle.init_variables(seed=seed)
+  rng = np.random.RandomState(seed + 100)
+  for k in variables:
+    if k.endswith('gamma'):
+      variables[k] = (1 + 0.2 * rng.randn(*variables[k].shape)).astype(np.float32)
+    if k.endswith('beta'):
+      variables[k] = (0.1 * rng.randn(*variables[k].shape)).astype(np.float32)
+    if k.endswith('/weights'):
+      variables[k] = (variables[k] * scale).astype(np.float32)
+    if k.endswith('moving_variance'):
+      variables[k] = (0.5 + rng.uniform(size=variables[k].shape)).astype(np.float32)
+    if k.endswith('moving_mean'):
+      variables[k] = (0.1 * rng.randn(*variables[k].shape)).astype(np.float32)
+  return variables
+
+
+def _build_engine(img_bf16, grasp, variables):
+  from tensor2robot_b200 import nn
+  from tensor2robot_b200.research.qtopt import networks
+  vs = nn.VariableStore('cuda', seed=1)
+  net = networks.Grasping44E2EOpenCloseTerminateGripperStatusHeightToBottom()
+  with torch.no_grad(), nn.variable_store(vs):
+    net.model((None, img_bf16[:2]), grasp[:2], is_training=False)
+  vs.finalize()
+  vs.import_tf(variables)
+  return vs, net
+
+
+def _oracle_step(variables, img_o, grasp, reward, storage):
+  from oracle import qtopt_networks as oracle
+  from oracle import tf_ops
+  tf_ops.STORAGE_DTYPE = storage
+  try:
+    ov = oracle.to_torch(variables)
+    updates = {}
+    logits = oracle.model(ov, img_o, torch.from_numpy(grasp), True, updates=updates)
+    q = torch.sigmoid(logits)
+    loss = tf_ops.log_loss(torch.from_numpy(reward), q)
+    loss.backward()
+  finally:
+    tf_ops.STORAGE_DTYPE = None
+  return ov, updates, q.detach().numpy().reshape(-1), float(loss.detach())
+
+
+def test_grasping44_train_step_matches_oracle():
+  from tensor2robot_b200 import nn
+  b = 16
+  img, grasp, reward = _inputs(b)
+  variables = _variables(3)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  grasp_t = torch.from_numpy(grasp).cuda()
+  reward_t = torch.from_numpy(reward).cuda()
+  vs, net = _build_engine(img_t, grasp_t, variables)
+
+  with nn.variable_store(vs):
+    logits, _ = net.model((None, img_t), grasp_t, is_training=True)
+    loss, q = nn.sigmoid_log_loss(logits, reward_t)
+    vs.zero_grad()
+    loss.backward()
+  torch.cuda.synchronize()
+  grads = vs.export_tf_grads()
+  new_vars = vs.export_tf()
+  q_e = q.float().cpu().numpy().reshape(-1)
+  loss_e = float(loss.detach())
+
+  img_o = img_t.float().cpu()          # the oracles see the same bf16-rounded pixels
+  ov, updates, q_b, loss_b = _oracle_step(variables, img_o, grasp, reward, torch.bfloat16)
+  ov_f, _, q_f, loss_f = _oracle_step(variables, img_o, grasp, reward, None)
+
+  err_b, err_f = np.abs(q_e - q_b).max(), np.abs(q_e - q_f).max()
+  print('q engine     ', q_e[:6])
+  print('q bf16 oracle', q_b[:6])
+  print('q fp32 oracle', q_f[:6])
+  print('loss engine %.6f  bf16-oracle %.6f  fp32-oracle %.6f' % (loss_e, loss_b, loss_f))
+  print('max|dq| vs bf16-storage oracle %.3e (rel %.3e); vs fp32 oracle %.3e (rel %.3e); bf16 vs fp32 oracle %.3e'
+        % (err_b, (np.abs(q_e - q_b) / q_b).max(), err_f, (np.abs(q_e - q_f) / q_f).max(), np.abs(q_b - q_f).max()))
+  failures = []
+  gmax = max(float(np.linalg.norm(ov[k].grad.numpy())) for k in grads if ov[k].grad is not None)
+  for k, g in grads.items():
+    go = ov[k].grad
+    if go is None:
+      continue
+    gn = float(np.linalg.norm(go.numpy()))
+    if gn < 1e-4 * gmax:      # biases in front of a batch norm: the true gradient is zero
+      assert np.linalg.norm(g) < 1e-2 * gmax, k
+      continue
+    e = _rel_l2(g, go.numpy())
+    cond = _rel_l2(ov_f[k].grad.numpy(), go.numpy())
+    print('grad %-40s engine-vs-bf16 %.3e   fp32-vs-bf16 %.3e  |g| %.3e' % (k.split('/', 1)[1], e, cond, gn))
+    if not e < COND_FACTOR * cond + GRAD_FLOOR:
+      failures.append((k, e, cond))
+  for k, u in updates.items():
+    e = _rel_l2(new_vars[k], u.numpy())
+    if not e < 2e-2:
+      failures.append((k, e))
+  cond_q = np.abs(q_b - q_f).max()
+  assert err_b < COND_FACTOR * cond_q + 2e-3
+  assert err_f < Q_TOL_FP32_ORACLE
+  assert abs(loss_e - loss_b) < COND_FACTOR * abs(loss_b - loss_f) + 2e-3
+  assert not failures, failures
+
+
+def test_grasping44_predict_action_batch_matches_oracle():
+  """PREDICT mode with an action batch: the state tower runs once, Q is [B, A] (networks.py:583-590)."""
+  from oracle import qtopt_networks as oracle
+  from oracle import tf_ops
+  from tensor2robot_b200 import nn
+  b, a = 2, 16
+  img, grasp, _ = _inputs(b, a, seed=7)
+  variables = _variables(4, scale=5.0)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  grasp_t = torch.from_numpy(grasp).cuda()
+  vs, net = _build_engine(img_t, grasp_t[:, 0], variables)
+  with torch.no_grad(), nn.variable_store(vs):
+    _, ep = net.model((None, img_t), grasp_t, is_training=False)
+  q_e = ep['predictions'].float().cpu().numpy()
+  assert q_e.shape == (b, a)
+  res = {}
+  for name, storage in (('bf16', torch.bfloat16), ('fp32', None)):
+    tf_ops.STORAGE_DTYPE = storage
+    try:
+      ep_o = {}
+      with torch.no_grad():
+        oracle.model(oracle.to_torch(variables, False), img_t.float().cpu(), torch.from_numpy(grasp), False,
+                     end_points=ep_o)
+      res[name] = ep_o['predictions'].numpy()
+    finally:
+      tf_ops.STORAGE_DTYPE = None
+  print('q engine', q_e[0, :4], 'bf16 oracle', res['bf16'][0, :4], 'fp32 oracle', res['fp32'][0, :4])
+  print('max|dq| vs bf16-storage oracle %.3e, vs fp32 oracle %.3e' %
+        (np.abs(q_e - res['bf16']).max(), np.abs(q_e - res['fp32']).max()))
+  assert np.abs(q_e - res['bf16']).max() < Q_TOL_PREDICT
+  assert np.abs(q_e - res['fp32']).max() < Q_TOL_FP32_ORACLE
