@@ -102,6 +102,8 @@ int32_t t2r_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
  * Reference: film_resnet_model.py:50-57 (momentum .997 eps 1e-5), networks.py:396-410
  * (decay .9997 eps .001); SURVEY §8c-4 (biased var to normalise, Bessel var into moving). */
 int32_t t2r_bn_stats(const void* x, int64_t rows, int32_t C, double* stats, void* stream);
+/* out[c] = sum_r x[r,c] for bf16 x (bias gradients); stats: fp64 [2*C] workspace. */
+int32_t t2r_colsum_bf16(const void* x, int64_t rows, int32_t C, double* stats, float* out, void* stream);
 /* From stats: mean/var -> scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; saves
  * mean and invstd (fp32 [C] each) for backward; updates moving stats in place with
  * moving = moving*momentum + batch*(1-momentum) (variance Bessel-corrected).

@@ -60,6 +60,7 @@ _PROTOS = {
     't2r_cast_f32_to_bf16': (_I32, [_P, _P, _I64, _P]),
     't2r_cast_bf16_to_f32': (_I32, [_P, _P, _I64, _P]),
     't2r_bn_stats': (_I32, [_P, _I64, _I32, _P, _P]),
+    't2r_colsum_bf16': (_I32, [_P, _I64, _I32, _P, _P, _P]),
     't2r_bn_finalize': (_I32, [_P, _I64, _I32, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     't2r_bn_infer_params': (_I32, [_I32, _P, _P, _P, _P, _F, _P, _P, _P]),
     't2r_bn_apply': (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P]),

@@ -97,9 +97,27 @@ __global__ void im2col_small_cin_kernel(const __nv_bfloat16* __restrict__ x,
                                         __nv_bfloat16* __restrict__ a, int N, int H, int W, int Cin,
                                         int KH, int KW, int stride, int pad_top, int pad_left,
                                         int Ho, int Wo, int Kpad) {
+  // Per-k lookup table (shared memory) instead of a div/mod chain per element:
+  //   tab_hw[k] = kh << 16 | kw (or -1 for the zero padding columns), tab_d[k] = element offset of
+  //   (kh, kw, c) relative to the window origin.
+  extern __shared__ int im2col_tab[];
+  int* tab_hw = im2col_tab;
+  int* tab_d = im2col_tab + Kpad;
+  const int Kreal = KH * KW * Cin;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    if (k < Kreal) {
+      const int c = k % Cin, t = k / Cin;
+      const int kw = t % KW, kh = t / KW;
+      tab_hw[k] = (kh << 16) | kw;
+      tab_d[k] = (kh * W + kw) * Cin + c;
+    } else {
+      tab_hw[k] = -1;
+      tab_d[k] = 0;
+    }
+  }
+  __syncthreads();
   const int groups = Kpad / 8;
   const long long total = (long long)N * Ho * Wo * groups;
-  const int Kreal = KH * KW * Cin;
   const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -109,18 +127,17 @@ __global__ void im2col_small_cin_kernel(const __nv_bfloat16* __restrict__ x,
     long long r = pix / Wo;
     const int oh = int(r % Ho);
     const int n = int(r / Ho);
+    const int ih0 = oh * stride - pad_top, iw0 = ow * stride - pad_left;
+    const long long base = (((long long)n * H + ih0) * W + iw0) * Cin;
     unsigned short v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = g * 8 + j;
+      const int hw = tab_hw[k];
       unsigned short val = 0;
-      if (k < Kreal) {
-        const int c = k % Cin;
-        const int t = k / Cin;
-        const int kw = t % KW, kh = t / KW;
-        const int ih = oh * stride + kh - pad_top, iw = ow * stride + kw - pad_left;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-          val = xs[(((long long)n * H + ih) * W + iw) * Cin + c];
+      if (hw >= 0) {
+        const int ih = ih0 + (hw >> 16), iw = iw0 + (hw & 0xFFFF);
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = xs[base + tab_d[k]];
       }
       v[j] = val;
     }
@@ -261,7 +278,7 @@ extern "C" int32_t t2r_im2col_small_cin(const T2RConvDesc* d, const void* x, voi
   T2R_CHECK_ARG(d && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc");
   T2R_CHECK_ARG(Kpad % 64 == 0 && Kpad >= d->KH * d->KW * d->Cin, "Kpad=%d invalid", Kpad);
   const long long total = (long long)d->N * d->Ho * d->Wo * (Kpad / 8);
-  im2col_small_cin_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  im2col_small_cin_kernel<<<grid_for(total), 256, 2 * Kpad * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(a), d->N, d->H, d->W, d->Cin,
       d->KH, d->KW, d->stride, d->pad_top, d->pad_left, d->Ho, d->Wo, Kpad);
   T2R_LAUNCH_OK();

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__
   if (cgi < cg) {
     const long long r0 = blockIdx.x * rows_per_block;
     const long long r1 = min(r0 + rows_per_block, rows);
+#pragma unroll 4
     for (long long r = r0 + rl; r < r1; r += lanes_r) {
       float f[8];
       unpack8(x[r * cg + cgi], f);
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
     }
     const long long r0 = blockIdx.x * rows_per_block;
     const long long r1 = min(r0 + rows_per_block, rows);
+#pragma unroll 2
     for (long long r = r0 + rl; r < r1; r += lanes_r) {
       float fx[8], fd[8];
       unpack8(x[r * cg + cgi], fx);
@@ -206,35 +208,86 @@ __global__ void bn_bwd_finalize_kernel(const double* red, int C, float* dgamma, 
 }
 
 // pass 2: dx = scale * (dz - sum(dz)/rows - xhat * sum(dz*xhat)/rows) (+ dres)
+//            = scale*dz + kb*x + kc   with per-channel kb, kc.
+// Row-partitioned like the reductions: a thread owns one 8-channel group, so the coefficients
+// stay in registers and the loop body is 2-3 16-byte loads and one 16-byte store per 8 elements.
 template <bool RES>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ dres,
-    uint4* __restrict__ dx, long long total8, int cg, float inv_rows, const float* __restrict__ mean,
-    const float* __restrict__ invstd, const float* __restrict__ scale,
-    const float* __restrict__ shift, const float* __restrict__ dgamma,
+    uint4* __restrict__ dx, long long rows, int C, int cgb, int lanes_r, long long rows_per_block,
+    float inv_rows, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ dgamma,
     const float* __restrict__ dbeta, int relu) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = int(i % cg);
+  const int cg = C / 8;
+  const int g = threadIdx.x % cgb, rl = threadIdx.x / cgb;
+  const int cgi = blockIdx.y * cgb + g;
+  if (cgi >= cg) return;
+  float sc[8], sh[8], kb[8], kc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cgi * 8 + j;
+    sc[j] = scale[c];
+    sh[j] = shift[c];
+    const float t = sc[j] * dgamma[c] * inv_rows * invstd[c];
+    kb[j] = -t;
+    kc[j] = t * mean[c] - sc[j] * dbeta[c] * inv_rows;
+  }
+  const long long r0 = blockIdx.x * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, rows);
+#pragma unroll 2
+  for (long long r = r0 + rl; r < r1; r += lanes_r) {
+    const long long i = r * cg + cgi;
     float fx[8], fd[8], fo[8];
-    unpack8(x[i], fx);
-    unpack8(dy[i], fd);
+    const uint4 qx = x[i], qd = dy[i];
+    uint4 qr;
+    if (RES) qr = dres[i];
+    unpack8(qx, fx);
+    unpack8(qd, fd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float sc = __ldg(scale + c);
-      const float z = fmaf(fx[j], sc, __ldg(shift + c));
+      const float z = fmaf(fx[j], sc[j], sh[j]);
       const float dz = (relu && !(z > 0.f)) ? 0.f : fd[j];
-      const float xhat = (fx[j] - __ldg(mean + c)) * __ldg(invstd + c);
-      fo[j] = sc * (dz - __ldg(dbeta + c) * inv_rows - xhat * __ldg(dgamma + c) * inv_rows);
+      fo[j] = fmaf(sc[j], dz, fmaf(kb[j], fx[j], kc[j]));
     }
     if (RES) {
       float fr[8];
-      unpack8(dres[i], fr);
+      unpack8(qr, fr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) fo[j] += fr[j];
     }
     dx[i] = pack8(fo);
+  }
+}
+
+// y = relu?(x*scale + shift), row-partitioned (no FiLM).
+__global__ void __launch_bounds__(256) bn_apply_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                            long long rows, int C, int cgb, int lanes_r,
+                                                            long long rows_per_block,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int relu) {
+  const int cg = C / 8;
+  const int g = threadIdx.x % cgb, rl = threadIdx.x / cgb;
+  const int cgi = blockIdx.y * cgb + g;
+  if (cgi >= cg) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cgi * 8 + j];
+    sh[j] = shift[cgi * 8 + j];
+  }
+  const long long r0 = blockIdx.x * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, rows);
+#pragma unroll 4
+  for (long long r = r0 + rl; r < r1; r += lanes_r) {
+    const long long i = r * cg + cgi;
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    y[i] = pack8(f);
   }
 }
 
@@ -288,9 +341,12 @@ extern "C" int32_t t2r_bn_apply(const void* x, void* y, int64_t rows, int32_t C,
   if (film)
     bn_apply_kernel<true><<<grid_for(total8), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
                                                             total8, C / 8, scale, shift, film, rows_per_image, relu);
-  else
-    bn_apply_kernel<false><<<grid_for(total8), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
-                                                             total8, C / 8, scale, shift, nullptr, 1, relu);
+  else {
+    const RowPartition p = partition(rows, C);
+    bn_apply_rows_kernel<<<dim3(p.row_blocks, p.col_blocks), 256, 0, st>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), rows, C, p.cgb, p.lanes_r, p.rows_per_block, scale,
+        shift, relu);
+  }
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
@@ -313,16 +369,35 @@ extern "C" int32_t t2r_bn_backward(const void* dy, const void* x, const void* dr
   T2R_LAUNCH_OK();
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, C, dgamma, dbeta);
   T2R_LAUNCH_OK();
-  const long long total8 = rows * (C / 8);
   const float inv_rows = 1.f / float(rows);
+  const dim3 grid(p.row_blocks, p.col_blocks);
   if (dres)
-    bn_bwd_apply_kernel<true><<<grid_for(total8), 256, 0, st>>>(
+    bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(
         static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<const uint4*>(dres),
-        static_cast<uint4*>(dx), total8, C / 8, inv_rows, mean, invstd, scale, shift, dgamma, dbeta, relu);
+        static_cast<uint4*>(dx), rows, C, p.cgb, p.lanes_r, p.rows_per_block, inv_rows, mean, invstd, scale,
+        shift, dgamma, dbeta, relu);
   else
-    bn_bwd_apply_kernel<false><<<grid_for(total8), 256, 0, st>>>(
-        static_cast<const uint4*>(dy), static_cast<const uint4*>(x), nullptr, static_cast<uint4*>(dx),
-        total8, C / 8, inv_rows, mean, invstd, scale, shift, dgamma, dbeta, relu);
+    bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(
+        static_cast<const uint4*>(dy), static_cast<const uint4*>(x), nullptr, static_cast<uint4*>(dx), rows, C,
+        p.cgb, p.lanes_r, p.rows_per_block, inv_rows, mean, invstd, scale, shift, dgamma, dbeta, relu);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+// Column sums of a bf16 [rows, C] matrix (bias gradients): the bn_stats partition (fills every SM)
+// followed by a fp64 -> fp32 conversion.
+namespace t2r {
+__global__ void colsum_finalize_kernel(const double* stats, int C, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = float(stats[c]);
+}
+}  // namespace t2r
+
+extern "C" int32_t t2r_colsum_bf16(const void* x, int64_t rows, int32_t C, double* stats, float* out,
+                                   void* stream) {
+  T2R_CHECK_ARG(out != nullptr, "colsum_bf16: null output");
+  if (int32_t rc = t2r_bn_stats(x, rows, C, stats, stream)) return rc;
+  t2r::colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, C, out);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

@@ -1,0 +1,111 @@
+"""The per-replay-batch training step of the B200 engine (replaces the TF-Estimator train op).
+
+Reference decomposition being replaced (models/abstract_model.py:694-755): validate_and_pack ->
+inference_network_fn -> model_train_fn -> create_optimizer -> create_train_op, run by the Estimator's
+Session.run loop (utils/train_eval.py:424-613).  Here one `CriticTrainStep.step` issues, on the
+current CUDA stream and without any host synchronisation:
+
+  crop + uint8->bf16 (+distortion)      1 HBM kernel         (t2r_models.py:297-308)
+  critic forward                         tcgen05 convs ...    (networks.py:343-615)
+  sigmoid + log loss (+ l2 term)         1 kernel             (t2r_models.py:229-239)
+  backward                               dgrad/wgrad/BN kernels writing the flat gradient buffer
+  gradient all-reduce (world_size > 1)   ONE NCCL all-reduce over the flat buffer
+  optimizer + EMA + bf16 refresh         1 fused kernel       (optimizer_builder.py:25-96)
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from tensor2robot_b200 import nn
+from tensor2robot_b200.preprocessors import image_ops
+
+
+class CriticTrainStep(object):
+  """Owns the variables, optimizer state and RNG of one data-parallel replica of a Q-critic."""
+
+  def __init__(self, critic, optimizer, input_hw=(512, 640), target_hw=(472, 472), device='cuda', seed=0,
+               world_size=1, rank=0, distort=None):
+    self.critic = critic
+    self.optimizer = optimizer
+    self.optimizer.l2_regularization = critic.l2_regularization
+    self.vs = nn.VariableStore(device, seed=seed)
+    self.input_hw, self.target_hw = input_hw, target_hw
+    self.world_size, self.rank = world_size, rank
+    self.global_step = 0
+    self.distort = distort or {}
+    self._rng = np.random.RandomState(seed * 9973 + rank)
+    self._built = False
+
+  # -- preprocessing (DefaultGrasping44ImagePreprocessor._preprocess_fn, t2r_models.py:277-308) ----
+  def preprocess(self, images_u8, training=True):
+    n = images_u8.shape[0]
+    (ih, iw), (th, tw) = images_u8.shape[1:3], self.target_hw
+    if training:   # RandomCropImages: ONE offset pair per batch (image_transformations.py:25-59)
+      oy, ox = int(self._rng.randint(0, ih - th + 1)), int(self._rng.randint(0, iw - tw + 1))
+    else:          # CenterCropImages (image_transformations.py:62-101)
+      oy, ox = (ih - th) // 2, (iw - tw) // 2
+    params = image_ops.identity_params(n, oy, ox)
+    seed = offset = 0
+    if training and self.distort:
+      d = self.distort
+      if d.get('random_brightness'):
+        params['brightness_delta'] = self._rng.uniform(-d.get('max_delta_brightness', 0.125),
+                                                       d.get('max_delta_brightness', 0.125))
+      if d.get('random_saturation'):
+        params['saturation_scale'] = self._rng.uniform(d.get('lower_saturation', 0.5), d.get('upper_saturation', 1.5))
+      if d.get('random_hue'):
+        params['hue_delta'] = self._rng.uniform(-d.get('max_delta_hue', 0.2), d.get('max_delta_hue', 0.2))
+      if d.get('random_contrast'):
+        params['contrast_scale'] = self._rng.uniform(d.get('lower_contrast', 0.5), d.get('upper_contrast', 1.5))
+      level = d.get('random_noise_level', 0.0)
+      if level and not self._rng.uniform() > d.get('random_noise_apply_probability', 0.5):
+        params['noise_stddev'] = level
+        seed, offset = int(self._rng.randint(0, 2**31 - 1)), self.global_step
+    return image_ops.crop_convert_distort(images_u8, (th, tw), params, torch.bfloat16, seed, offset)
+
+  # -- build -------------------------------------------------------------------------------------
+  def build(self, images_u8, actions):
+    """Creates the variables with a 2-sample inference pass, consolidates them into flat buffers and
+    (world_size > 1) broadcasts rank 0's initial values."""
+    if self._built:
+      return
+    with torch.no_grad(), nn.variable_store(self.vs):
+      x = self.preprocess(images_u8[:2], training=False)
+      self.critic.model((None, x), actions[:2], is_training=False)
+    self.vs.finalize()
+    if self.world_size > 1:
+      dist.broadcast(self.vs.flat, src=0)
+      dist.broadcast(self.vs.state_flat, src=0)
+      self.vs.sync_compute_copies()
+    self._built = True
+
+  # -- one step ----------------------------------------------------------------------------------
+  def step(self, images_u8, actions, reward):
+    """images_u8 [B,H,W,3] uint8, actions [B,10] f32, reward [B,1] f32 - all CUDA.  Returns the
+    device scalar loss = log_loss + l2 regularisation (no host sync)."""
+    if not self._built:
+      self.build(images_u8, actions)
+    vs = self.vs
+    with nn.variable_store(vs):
+      x = self.preprocess(images_u8, training=True)
+      logits, _ = self.critic.model((None, x), actions, is_training=True)
+      loss, _ = nn.sigmoid_log_loss(logits, reward)
+      vs.zero_grad()
+      loss.backward()
+      total = loss.detach() + nn.l2_regularization_loss(self.critic.l2_regularization, vs)
+    grad_scale = 1.0
+    if self.world_size > 1:
+      dist.all_reduce(vs.flat_grad, op=dist.ReduceOp.SUM)
+      grad_scale = 1.0 / self.world_size
+    self.optimizer.apply_gradients(vs, self.global_step, grad_scale)
+    vs.sync_compute_copies(after_optimizer=True)
+    self.global_step += 1
+    return total
+
+  @torch.no_grad()
+  def predict(self, images_u8, actions):
+    """PREDICT mode: centre crop, moving-average BN, q_predicted [B] or [B, A]."""
+    with nn.variable_store(self.vs):
+      x = self.preprocess(images_u8, training=False)
+      _, end_points = self.critic.model((None, x), actions, is_training=False)
+    return end_points['predictions']

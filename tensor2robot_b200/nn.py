@@ -286,6 +286,40 @@ _STORE_STACK = []
 TRACE = None
 
 
+# When a list is installed here, every tensor-core kernel launch is bracketed by CUDA events on the
+# launching stream and (kind, algorithmic_flops, start_event, end_event) is appended: bench.py's
+# live roofline measurement.  None in production.
+PROFILE = None
+
+
+class _prof(object):
+  """with _prof('fprop', flops): <one kernel launch>"""
+
+  def __init__(self, kind, flops):
+    if not isinstance(flops, float):     # a ConvDesc: algorithmic flops + a shape tag
+      d = flops
+      flops = _conv_flops(d)
+      kind = '%s|%dx%dx%dx%d->%d k%d s%d' % (kind, d.N, d.H, d.W, d.Cin, d.Cout, d.KH, d.stride)
+    self.kind, self.flops = kind, flops
+
+  def __enter__(self):
+    if PROFILE is not None:
+      self.start = torch.cuda.Event(enable_timing=True)
+      self.end = torch.cuda.Event(enable_timing=True)
+      self.start.record()
+    return self
+
+  def __exit__(self, *exc):
+    if PROFILE is not None:
+      self.end.record()
+      PROFILE.append((self.kind, self.flops, self.start, self.end))
+    return False
+
+
+def _conv_flops(d):
+  return 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
+
+
 def _trace(op, scope, y):
   if TRACE is not None:
     TRACE.append((op, current_store().full_name(scope) if scope else '', y))
@@ -385,8 +419,9 @@ class _Conv2dFn(torch.autograd.Function):
       flags |= _lib.T2R_EPI_OUT_F32
     d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, flags)
     y = torch.empty((n, ho, wo, cout), dtype=F32 if out_f32 else BF16, device=x.device)
-    _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(var.bf16), _p(bias_var.data if bias_var is not None else None),
-              _p(residual), _p(y), _stream())
+    with _prof('fprop', d):
+      _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(var.bf16),
+                _p(bias_var.data if bias_var is not None else None), _p(residual), _p(y), _stream())
     ctx.var, ctx.bias_var, ctx.desc, ctx.relu, ctx.out_f32 = var, bias_var, d, relu, out_f32
     ctx.has_res = residual is not None
     ctx.save_for_backward(x, y if relu else None)
@@ -408,17 +443,18 @@ class _Conv2dFn(torch.autograd.Function):
       dy = dz
     if ctx.bias_var is not None and ctx.bias_var.trainable:
       rows = dy.numel() // dy.shape[-1]
-      dyf = torch.empty(dy.shape, dtype=F32, device=dy.device)
-      _lib.call('t2r_cast_bf16_to_f32', _p(dy), _p(dyf), dy.numel(), st)
-      _lib.call('t2r_colsum_f32', _p(dyf), _p(ctx.bias_var.grad), rows, dy.shape[-1], st)
+      ws = torch.empty(2 * dy.shape[-1], dtype=torch.float64, device=dy.device)
+      _lib.call('t2r_colsum_bf16', _p(dy), rows, dy.shape[-1], _p(ws), _p(ctx.bias_var.grad), st)
     if var.trainable:
-      _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(x), _p(dy), _p(var.grad), st)
+      with _prof('wgrad', d):
+        _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(x), _p(dy), _p(var.grad), st)
     dx = None
     if ctx.needs_input_grad[0]:
       if var.dgrad is None:
         raise _lib.T2RError('conv %s needs a data gradient but was built with needs_dgrad=False' % var.name)
       dx = torch.empty_like(x)
-      _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 0, st)
+      with _prof('dgrad', d):
+        _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 0, st)
     dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
     return dx, dres, None, None, None, None, None
 
@@ -438,8 +474,9 @@ class _StemConvFn(torch.autograd.Function):
     g = _conv_desc(1, 1, n * ho * wo, kpad, cout, 1, 1, 1, 0, 0, 1, n * ho * wo,
                    _lib.T2R_EPI_BIAS if bias_var is not None else 0)
     y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
-    _lib.call('t2r_conv2d_fprop', C.byref(g), _p(a), _p(var.bf16), _p(bias_var.data if bias_var is not None else None),
-              None, _p(y), st)
+    with _prof('fprop', d):   # algorithmic flops of the real (unpadded) convolution
+      _lib.call('t2r_conv2d_fprop', C.byref(g), _p(a), _p(var.bf16),
+                _p(bias_var.data if bias_var is not None else None), None, _p(y), st)
     ctx.var, ctx.bias_var, ctx.desc, ctx.gdesc, ctx.kpad = var, bias_var, d, g, kpad
     # The im2col matrix is recomputed in backward instead of being kept alive (it is ~50x the image).
     ctx.save_for_backward(x)
@@ -452,13 +489,13 @@ class _StemConvFn(torch.autograd.Function):
     dy = dy.contiguous()
     if ctx.bias_var is not None and ctx.bias_var.trainable:
       rows = dy.numel() // dy.shape[-1]
-      dyf = torch.empty(dy.shape, dtype=F32, device=dy.device)
-      _lib.call('t2r_cast_bf16_to_f32', _p(dy), _p(dyf), dy.numel(), st)
-      _lib.call('t2r_colsum_f32', _p(dyf), _p(ctx.bias_var.grad), rows, dy.shape[-1], st)
+      ws = torch.empty(2 * dy.shape[-1], dtype=torch.float64, device=dy.device)
+      _lib.call('t2r_colsum_bf16', _p(dy), rows, dy.shape[-1], _p(ws), _p(ctx.bias_var.grad), st)
     if ctx.var.trainable:
       a = torch.empty((ctx.gdesc.W, ctx.kpad), dtype=BF16, device=x.device)
       _lib.call('t2r_im2col_small_cin', C.byref(ctx.desc), _p(x), _p(a), ctx.kpad, st)
-      _lib.call('t2r_conv2d_wgrad', C.byref(ctx.gdesc), _p(a), _p(dy), _p(ctx.var.grad), st)
+      with _prof('wgrad', ctx.desc):
+        _lib.call('t2r_conv2d_wgrad', C.byref(ctx.gdesc), _p(a), _p(dy), _p(ctx.var.grad), st)
     if ctx.needs_input_grad[0]:
       raise _lib.T2RError('stem convolution %s has no data gradient (image inputs are leaves)' % ctx.var.name)
     return None, None, None, None, None, None
