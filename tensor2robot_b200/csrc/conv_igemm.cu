@@ -13,8 +13,9 @@
 //   B (weights)    : BLOCK_N output channels x 64, K-major, 128B-swizzled
 //   D (accumulator): 128 lanes x BLOCK_N fp32 columns in TMEM, double buffered
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/residual/ReLU -> global).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..11 = epilogue (TMEM -> registers -> bias/residual/ReLU -> global), two
+// warpgroups splitting the BLOCK_N accumulator columns.
 //
 // Replaces: slim.conv2d / tf.layers.conv2d (research/qtopt/networks.py:443-591,
 // layers/film_resnet_model.py:89-105) and their autodiff data gradients.
@@ -56,7 +57,7 @@ struct IgemmCfg {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     fence_mbar_init();
   }
@@ -167,12 +168,21 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    // ===================== epilogue: 8 warps =====================
+    // Warp w may read TMEM lanes 32*(w%4)..+31 (one output pixel per thread); the two warpgroups
+    // split the BLOCK_N columns.  The residual (bf16, same addressing as the output) of the next
+    // 32-column chunk is prefetched into registers before the accumulator wait / while the current
+    // chunk is converted, so its DRAM latency is off the critical path.
+    const int ew = warp - 4;
+    const int quad = ew & 3;
+    const int half = ew >> 2;
+    constexpr int kColsPerWG = BLOCK_N / 2;
+    constexpr int kChunks = kColsPerWG / 32;
     const int row = quad * 32 + lane;
     const int th = row / p.TW;
     const int tw = row - th * p.TW;
     const bool out_f32 = (p.flags & T2R_EPI_OUT_F32) != 0;
+    const bool has_res = (p.flags & T2R_EPI_RESIDUAL) != 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -184,14 +194,29 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int ow = (rem % p.tiles_w) * p.TW + tw;
       const bool valid = (oh < p.Ho) && (ow < p.Wo);
       const long long pix_off = img * p.os_n + oh * p.os_h + ow * p.os_w;
+      const int ch0 = nt * BLOCK_N + half * kColsPerWG;
+      uint4 rnext[4];
+      if (has_res && valid && ch0 < p.Cout) {
+        const uint4* r = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = r[j];
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int ch = ch0 + c * 32;
+        uint4 rcur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        if (c + 1 < kChunks && has_res && valid && ch + 32 < p.Cout) {
+          const uint4* r = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch + 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = r[j];
+        }
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BLOCK_N + c0, v);
+        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BLOCK_N + half * kColsPerWG + c * 32, v);
         tmem_ld_wait();
-        const int ch = nt * BLOCK_N + c0;
         if (valid && ch < p.Cout) {
           float f[32];
 #pragma unroll
@@ -203,12 +228,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
               f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
             }
           }
-          if (p.flags & T2R_EPI_RESIDUAL) {
-            const uint4* r = reinterpret_cast<const uint4*>(
-                static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch);
+          if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 q = r[j];
+              const uint4 q = rcur[j];
               f[8 * j + 0] += bf16_lo(q.x); f[8 * j + 1] += bf16_hi(q.x);
               f[8 * j + 2] += bf16_lo(q.y); f[8 * j + 3] += bf16_hi(q.y);
               f[8 * j + 4] += bf16_lo(q.z); f[8 * j + 5] += bf16_hi(q.z);
@@ -327,7 +350,7 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = std::min(p.total_tiles, num_sms());
-  conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  conv_igemm_kernel<BLOCK_N><<<grid, 384, Cfg::kSmemBytes, stream>>>(p);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
