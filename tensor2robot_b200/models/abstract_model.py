@@ -1,0 +1,259 @@
+"""AbstractT2RModel on the B200 engine.
+
+Keeps the reference's model decomposition (models/abstract_model.py:162-981):
+  get_feature_specification / get_label_specification (no batch dim)  -> preprocessor
+  inference_network_fn(features, labels, mode, config, params) -> dict | (dict, update_ops)   :405-451
+  model_train_fn(features, labels, inference_outputs, mode, ...) -> loss | (loss, dict)       :454-504
+  model_eval_fn(...) -> metrics dict                                                           :506-565
+  create_optimizer(params) / create_train_op(...)                                              :335-381, :836-871
+  model_fn(features, labels, mode, config, params)                                             :662-834
+and replaces what TensorFlow did underneath: there is no graph / EstimatorSpec.  `model_fn` executes
+eagerly on the current CUDA stream inside the model's VariableStore and returns a `ModelOutput`;
+`train_step` = model_fn(TRAIN) + backward + (all-reduce) + fused optimizer kernel, i.e. one
+Session.run of the reference's train_op.
+"""
+import abc
+import collections
+
+import torch
+import torch.distributed as dist
+
+from tensor2robot_b200 import nn
+from tensor2robot_b200.models import model_interface
+from tensor2robot_b200.models import optimizers
+from tensor2robot_b200.utils import tensorspec_utils
+
+TRAIN, EVAL, PREDICT = model_interface.TRAIN, model_interface.EVAL, model_interface.PREDICT
+DEVICE_TYPE_CPU, DEVICE_TYPE_GPU, DEVICE_TYPE_TPU = 'cpu', 'gpu', 'tpu'
+
+ModelOutput = collections.namedtuple('ModelOutput', ['mode', 'loss', 'train_outputs', 'predictions', 'eval_metrics'])
+
+
+class AbstractT2RModel(model_interface.ModelInterface):
+  """Base class encapsulating a model_fn and metadata about input/output sizes."""
+
+  def __init__(self, preprocessor_cls=None, create_optimizer_fn=optimizers.default_create_optimizer_fn,
+               device_type=DEVICE_TYPE_GPU, summarize_gradients=True, use_sync_replicas_optimizer=False,
+               use_avg_model_params=False, init_from_checkpoint_fn=None, device=None, seed=0):
+    self._preprocessor_cls = preprocessor_cls
+    self._create_optimizer_fn = create_optimizer_fn
+    self._device_type = device_type
+    self._summarize_gradients = summarize_gradients
+    self._use_sync_replicas_optimizer = use_sync_replicas_optimizer
+    self._use_avg_model_params = use_avg_model_params
+    self._init_from_checkpoint_fn = init_from_checkpoint_fn
+    self._optimizer = None
+    self._device = device
+    self._seed = seed
+    self._vs = None
+    self.global_step = 0
+
+  # -- engine state ---------------------------------------------------------------------------
+  @property
+  def variable_store(self):
+    """The model's variables (created lazily on the model's CUDA device)."""
+    if self._vs is None:
+      device = self._device or torch.device('cuda', torch.cuda.current_device())
+      self._vs = nn.VariableStore(device, seed=self._seed)
+    return self._vs
+
+  def l2_regularization(self):
+    """slim l2_regularizer scale applied to the regularised weights (0 = none)."""
+    return 0.0
+
+  # -- specs / preprocessor (abstract_model.py:220-276) -----------------------------------------
+  def create_pack_features(self, feature_spec, label_spec):
+    raise NotImplementedError()
+
+  def get_feature_specification_for_packing(self, mode):
+    return self.preprocessor.get_in_feature_specification(mode)
+
+  def get_label_specification_for_packing(self, mode):
+    return self.preprocessor.get_in_label_specification(mode)
+
+  @property
+  def default_preprocessor_cls(self):
+    from tensor2robot_b200.preprocessors import noop_preprocessor
+    return noop_preprocessor.NoOpPreprocessor
+
+  @property
+  def preprocessor(self):
+    preprocessor_cls = self._preprocessor_cls
+    if preprocessor_cls is None:
+      preprocessor_cls = self.default_preprocessor_cls
+    return preprocessor_cls(model_feature_specification_fn=self.get_feature_specification,
+                            model_label_specification_fn=self.get_label_specification,
+                            is_model_device_tpu=self.is_device_tpu)
+
+  @abc.abstractmethod
+  def get_feature_specification(self, mode):
+    """Required features for the model_fn / inference_network_fn (no batch dimension)."""
+
+  @abc.abstractmethod
+  def get_label_specification(self, mode):
+    """Required labels for the model_fn / model_train_fn / model_eval_fn."""
+
+  # -- the model decomposition ------------------------------------------------------------------
+  @abc.abstractmethod
+  def inference_network_fn(self, features, labels, mode, config=None, params=None):
+    """The inference network; returns a dict of outputs or (dict, update_ops)."""
+
+  @abc.abstractmethod
+  def model_train_fn(self, features, labels, inference_outputs, mode, config=None, params=None):
+    """The training loss; returns loss or (loss, train_outputs dict)."""
+
+  def model_eval_fn(self, features, labels, inference_outputs, train_loss, train_outputs, mode, config=None,
+                    params=None):
+    """Evaluation metrics (abstract_model.py:506-565): by default the loss."""
+    del features, labels, inference_outputs, train_outputs, mode, config, params
+    return {'loss': train_loss}
+
+  def add_summaries(self, features, labels, inference_outputs, train_loss, train_outputs, mode, config=None,
+                    params=None):
+    del features, labels, inference_outputs, train_loss, train_outputs, mode, config, params
+
+  def create_export_outputs_fn(self, features, inference_outputs, mode, config=None, params=None):
+    """Predictions exposed by predictors (abstract_model.py:610-660): the inference outputs."""
+    del features, mode, config, params
+    return inference_outputs
+
+  def create_optimizer(self, params=None):
+    """abstract_model.py:836-871; sync-replica / tower wrappers are replaced by the single NCCL
+    all-reduce in train_step."""
+    optimizer = self._create_optimizer_fn(self.use_summaries(params))
+    if self._use_avg_model_params and not isinstance(optimizer, optimizers.MovingAverageOptimizer):
+      optimizer = optimizers.create_moving_average_optimizer(optimizer)
+    optimizer.l2_regularization = self.l2_regularization()
+    return optimizer
+
+  @property
+  def optimizer(self):
+    if self._optimizer is None:
+      self._optimizer = self.create_optimizer()
+    return self._optimizer
+
+  def use_summaries(self, params=None):
+    if params is None:
+      return True
+    return params.get('use_summaries', True) if isinstance(params, dict) else True
+
+  def maybe_init_from_checkpoint(self):
+    if self._init_from_checkpoint_fn is not None:
+      self._init_from_checkpoint_fn(self)
+
+  # -- model_fn (abstract_model.py:662-834) -----------------------------------------------------
+  def model_fn(self, features, labels, mode, config=None, params=None):
+    feature_spec = self.get_feature_specification(mode)
+    with tensorspec_utils.device_bf16_as_float32():
+      features = tensorspec_utils.validate_and_pack(feature_spec, features, ignore_batch=True)
+      if labels is not None:
+        labels = tensorspec_utils.validate_and_pack(self.get_label_specification(mode), labels, ignore_batch=True)
+    vs = self.variable_store
+    grad = torch.enable_grad() if mode == TRAIN else torch.no_grad()
+    with grad, nn.variable_store(vs):
+      inference_outputs = self.inference_network_fn(features, labels, mode, config, params)
+      if isinstance(inference_outputs, tuple):
+        inference_outputs = inference_outputs[0]   # update ops run inside the fused BN kernels
+      if mode == PREDICT:
+        predictions = self.create_export_outputs_fn(features, inference_outputs, mode, config, params)
+        return ModelOutput(mode, None, None, predictions, None)
+      train_fn_result = self.model_train_fn(features, labels, inference_outputs, mode, config, params)
+      if isinstance(train_fn_result, tuple):
+        train_loss, train_outputs = train_fn_result
+      else:
+        train_loss, train_outputs = train_fn_result, {}
+      if mode == TRAIN:
+        return ModelOutput(mode, train_loss, train_outputs, inference_outputs, None)
+      metrics = self.model_eval_fn(features, labels, inference_outputs, train_loss, train_outputs, mode, config,
+                                   params)
+      return ModelOutput(mode, train_loss, train_outputs, inference_outputs, metrics)
+
+  def build(self, features, labels=None, mode=EVAL):
+    """Creates the variables with an inference pass over the first two examples and consolidates
+    them into the flat parameter / gradient buffers (nn.VariableStore.finalize)."""
+    vs = self.variable_store
+    if vs.finalized:
+      return
+    def first_two(struct):
+      return tensorspec_utils.TensorSpecStruct(
+          [(k, v[:2]) for k, v in tensorspec_utils.flatten_spec_structure(struct).items()])
+
+    # An inference-mode pass creates every variable (graph structure does not depend on the mode;
+    # batch norm merely reads its moving statistics instead of updating them).
+    with tensorspec_utils.device_bf16_as_float32():
+      head = tensorspec_utils.validate_and_pack(self.get_feature_specification(mode), first_two(features),
+                                                ignore_batch=True)
+    with torch.no_grad(), nn.variable_store(vs):
+      self.inference_network_fn(head, first_two(labels) if labels is not None else None, mode, None, None)
+    vs.finalize()
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if world > 1:
+      dist.broadcast(vs.flat, src=0)
+      dist.broadcast(vs.state_flat, src=0)
+      vs.sync_compute_copies()
+    self.maybe_init_from_checkpoint()
+
+  def _build_mode_is_predict(self):
+    """PREDICT feature specs may differ from TRAIN ones (tiled actions): build with EVAL-shaped
+    features unless a subclass says the PREDICT graph has the same variables."""
+    return False
+
+  # -- one optimisation step (the reference's train_op: create_train_op :335-381) ---------------
+  def train_step(self, features, labels, config=None, params=None):
+    """features/labels: (flat or packed) structures of batched CUDA tensors as produced by the
+    preprocessor.  Returns the device scalar loss; never synchronises."""
+    vs = self.variable_store
+    if not vs.finalized:
+      self.build(features, labels)
+    out = self.model_fn(features, labels, TRAIN, config, params)
+    vs.zero_grad()
+    out.loss.backward()
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    grad_scale = 1.0
+    if world > 1:
+      dist.all_reduce(vs.flat_grad, op=dist.ReduceOp.SUM)
+      grad_scale = 1.0 / world
+    self.optimizer.apply_gradients(vs, self.global_step, grad_scale)
+    vs.sync_compute_copies(after_optimizer=True)
+    self.global_step += 1
+    total = out.loss.detach()
+    l2 = self.l2_regularization()
+    if l2:
+      total = total + nn.l2_regularization_loss(l2, vs)
+    return total
+
+  def predict(self, features, config=None, params=None):
+    return self.model_fn(features, None, PREDICT, config, params).predictions
+
+  # -- checkpoints (TF variable names / layouts) --------------------------------------
+  def state_dict(self):
+    vs = self.variable_store
+    return {'variables': vs.export_tf(), 'optimizer': self.optimizer.state_dict() if self._optimizer else {},
+            'global_step': self.global_step}
+
+  def load_state_dict(self, state):
+    vs = self.variable_store
+    vs.import_tf(state['variables'])
+    if state.get('optimizer'):
+      self.optimizer.load_state_dict(state['optimizer'], vs)
+    self.global_step = int(state.get('global_step', 0))
+
+  # -- run config / device ----------------------------------------------------------------------
+  def get_run_config(self):
+    return {'save_checkpoints_steps': 1000, 'keep_checkpoint_max': 5}
+
+  @property
+  def is_device_tpu(self):
+    return self._device_type == DEVICE_TYPE_TPU
+
+  @property
+  def is_device_gpu(self):
+    return self._device_type == DEVICE_TYPE_GPU
+
+  @property
+  def device_type(self):
+    return self._device_type
+
+  @device_type.setter
+  def device_type(self, device_type):
+    self._device_type = device_type

@@ -20,6 +20,7 @@ Spec/index work is exact: nothing here touches floating point values.
 """
 import collections
 import collections.abc
+import contextlib
 import logging
 import pickle
 import pprint
@@ -533,13 +534,32 @@ def maybe_ignore_batch(spec_or_tensors, ignore_batch=False):
   return _map_structure(map_fn, spec_or_tensors)
 
 
+_DEVICE_BF16_AS_F32 = [False]
+
+
+@contextlib.contextmanager
+def device_bf16_as_float32():
+  """Inside this context a CUDA bfloat16 *tensor* satisfies a float32 spec.
+
+  The engine stores activations in bf16 on the device while model specs stay float32, the same
+  arrangement the reference makes for TPUs (preprocessors/tpu_preprocessor_wrapper.py rewrites
+  float32 specs to bfloat16, models/tpu_model_wrapper.py casts back)."""
+  _DEVICE_BF16_AS_F32.append(True)
+  try:
+    yield
+  finally:
+    _DEVICE_BF16_AS_F32.pop()
+
+
 def assert_equal_spec_or_tensor(expected_spec_or_tensor, actual_spec_or_tensor):
   """dtype, rank and every non-None dimension must agree (utils/tensorspec_utils.py:1099-1139)."""
   expected_spec = ExtendedTensorSpec.to_spec(expected_spec_or_tensor)
   actual_spec = ExtendedTensorSpec.to_spec(actual_spec_or_tensor)
   if expected_spec.is_sequence and actual_spec.is_extracted:
     actual_spec = maybe_ignore_batch(actual_spec, ignore_batch=True)
-  if expected_spec.dtype != actual_spec.dtype:
+  device_bf16 = (_DEVICE_BF16_AS_F32[-1] and expected_spec.dtype == dtypes.float32 and
+                 actual_spec.dtype == dtypes.bfloat16 and actual_spec.is_extracted)
+  if expected_spec.dtype != actual_spec.dtype and not device_bf16:
     raise ValueError('TensorSpec.dtype {} does not match TensorSpec.dtype {} in specs\n expected: {}\n actual: {}'
                      .format(expected_spec.dtype, actual_spec.dtype, expected_spec, actual_spec))
   if len(expected_spec.shape) != len(actual_spec.shape):

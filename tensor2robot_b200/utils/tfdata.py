@@ -1,0 +1,392 @@
+"""The record input path: TFRecord files -> tf.Example parsing -> image decode -> batches.
+
+Replaces the tf.data pipeline of the reference (utils/tfdata.py:64-138 file patterns, :174-210
+readers, :273-543 create_parse_tf_example_fn, :629-689 default_input_fn_tmpl) with:
+
+  * TFRecord framing + CRC-32C and the tf.Example wire format walked by the host C++ side of
+    libt2r_b200.so (csrc/host_io.cc, no protobuf/TensorFlow), values copied bit-exactly into numpy
+    buffers described by a parse plan compiled from the specs;
+  * JPEG/PNG decode through libjpeg-turbo / libpng (PIL) on a host thread pool - the same decoder
+    family TensorFlow links, bit-identical on the reference fixture.  A GPU JPEG
+    decoder is the listed next step;
+  * shuffle / repeat / batch(drop_remainder) with the reference's structure and buffer sizes.
+
+Semantics kept (SURVEY A-3..A-6): features are looked up by `dataset_key + name` and returned keyed
+by spec *path*; specs without a name are not parsed; bfloat16 specs are parsed as float32 and cast;
+varlen specs are padded/clipped to shape[0]; encoded images arrive as bytes, '' decodes to zeros, a
+decoded size different from the spec raises; only uint8/uint16 image specs are accepted.
+"""
+import concurrent.futures
+import ctypes as C
+import glob
+import io
+import itertools
+import mmap
+import os
+
+import numpy as np
+
+from tensor2robot_b200 import _lib
+from tensor2robot_b200.models import model_interface
+from tensor2robot_b200.utils import dtypes
+from tensor2robot_b200.utils import tensorspec_utils
+
+ModeKeys = model_interface.ModeKeys
+DATA_FORMAT = {'tfrecord': 'tfrecord'}    # recordio / sstable are Google-internal containers
+SUPPORTED_PIXEL_ENCODINGS = (dtypes.uint8, dtypes.uint16)
+SHUFFLE_BUFFER_SIZE = 500                 # utils/tfdata.py:665
+
+
+def get_batch_size(params, batch_size):
+  """params['batch_size'] overrides the configured batch size (utils/tfdata.py:38-61)."""
+  params_batch_size = params.get('batch_size') if params else None
+  if params_batch_size is None and batch_size is None:
+    raise ValueError('Both params["batch_size"] and batch_size are None, one of them has to be set.')
+  if params_batch_size is not None:
+    return params_batch_size
+  return batch_size
+
+
+def infer_data_format(file_patterns):
+  """The container format named inside the pattern string (utils/tfdata.py:64-89)."""
+  data_format = None
+  for key in ('tfrecord', 'recordio', 'sstable'):
+    if key in file_patterns:
+      if data_format is not None:
+        raise ValueError('More than one data_format {} and {} have been found in {}.'.format(
+            key, data_format, file_patterns))
+      data_format = key
+  if data_format is None:
+    raise ValueError('Could not infer file record type from extension of pattern "%s"' % file_patterns)
+  return data_format
+
+
+def get_data_format_and_filenames_list(file_patterns):
+  """Comma-separated patterns (optional '<format>:' prefix) -> (format, [files per pattern])."""
+  data_format = infer_data_format(file_patterns)
+  file_patterns = file_patterns.replace('{}:'.format(data_format), '')
+  filenames_list = [sorted(glob.glob(pattern)) for pattern in file_patterns.split(',')]
+  for filenames in filenames_list:
+    if not filenames:
+      raise ValueError('File list for some pattern in {} is empty'.format(file_patterns))
+  return data_format, filenames_list
+
+
+def get_data_format_and_filenames(file_patterns):
+  data_format, filenames_list = get_data_format_and_filenames_list(file_patterns)
+  return data_format, list(itertools.chain.from_iterable(filenames_list))
+
+
+# ---------------------------------------------------------------------------------------------
+# TFRecord files
+# ---------------------------------------------------------------------------------------------
+class TFRecordFile(object):
+  """A memory-mapped TFRecord file indexed by the C++ reader (CRC-32C verified)."""
+
+  def __init__(self, filename, verify_crc=True):
+    self.filename = filename
+    size = os.path.getsize(filename)
+    self._file = open(filename, 'rb')
+    self._map = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ) if size else b''
+    self._buf = (C.c_char * size).from_buffer_copy(self._map) if size else (C.c_char * 0)()
+    self._base = C.addressof(self._buf)
+    n = _lib.lib().t2r_tfrecord_index(self._base, size, None, None, 0, 1 if verify_crc else 0)
+    if n < 0:
+      raise ValueError('%s: %s' % (filename, _lib.last_error()))
+    self.offsets = np.zeros(n, np.uint64)
+    self.lengths = np.zeros(n, np.uint64)
+    if n:
+      _lib.lib().t2r_tfrecord_index(self._base, size, self.offsets.ctypes.data, self.lengths.ctypes.data, n, 0)
+
+  def __len__(self):
+    return len(self.offsets)
+
+  def pointer(self, i):
+    return self._base + int(self.offsets[i]), int(self.lengths[i])
+
+  def record(self, i):
+    off, n = int(self.offsets[i]), int(self.lengths[i])
+    return bytes(self._buf[off:off + n])
+
+  def __iter__(self):
+    for i in range(len(self)):
+      yield self.record(i)
+
+
+def read_records(filename, verify_crc=True):
+  """All serialized records of a TFRecord file."""
+  return list(TFRecordFile(filename, verify_crc))
+
+
+# ---------------------------------------------------------------------------------------------
+# tf.Example parsing
+# ---------------------------------------------------------------------------------------------
+def _decode_one(image_bytes, single_img_dims, np_dtype, name):
+  if not image_bytes:
+    return np.zeros(single_img_dims, np_dtype)          # '' -> zeros (utils/tfdata.py:465-473)
+  from PIL import Image
+  with Image.open(io.BytesIO(image_bytes)) as im:
+    channels = single_img_dims[2]
+    if np_dtype == np.uint16:
+      arr = np.asarray(im)
+      if arr.dtype != np.uint16:
+        arr = arr.astype(np.uint16)
+    else:
+      im = im.convert('L' if channels == 1 else 'RGB')
+      arr = np.asarray(im, dtype=np.uint8)
+  if arr.ndim == 2:
+    arr = arr[:, :, None]
+  if tuple(arr.shape) != tuple(single_img_dims):
+    raise ValueError('InvalidArgument: decoded image "%s" has shape %s, the spec requires %s' % (
+        name, tuple(arr.shape), tuple(single_img_dims)))
+  return arr
+
+
+_POOL = None
+
+
+def _pool():
+  global _POOL
+  if _POOL is None:
+    _POOL = concurrent.futures.ThreadPoolExecutor(max_workers=min(32, (os.cpu_count() or 4)))
+  return _POOL
+
+
+def _decode_images(tensor_spec, byte_rows):
+  """byte_rows: nested list [B][k] of bytes.  Returns [B, (k,) h, w, c]."""
+  if len(tensor_spec.shape) < 3:
+    raise ValueError('Shape of tensor spec for image feature "%s" must be 3 dimensional (h, w, c), but is %s' % (
+        tensor_spec.name, tensor_spec.shape))
+  dims = tuple(tensor_spec.shape[-3:])
+  if dims[2] not in (1, 3):
+    raise ValueError('Last dimension of shape of tensor spec for image feature "%s" must 1 or 3, but the shape '
+                     'is %s' % (tensor_spec.name, tensor_spec.shape))
+  if tensor_spec.dtype not in SUPPORTED_PIXEL_ENCODINGS:
+    raise ValueError('Decoding an image requires tensorspec.data_type to be uint8 or uint16.')
+  np_dtype = tensor_spec.dtype.as_numpy_dtype
+  flat = [b for row in byte_rows for b in row]
+  if len(flat) >= 8:
+    decoded = list(_pool().map(lambda b: _decode_one(b, dims, np_dtype, tensor_spec.name), flat))
+  else:
+    decoded = [_decode_one(b, dims, np_dtype, tensor_spec.name) for b in flat]
+  out = np.stack(decoded) if decoded else np.zeros((0,) + dims, np_dtype)
+  per_row = len(byte_rows[0]) if byte_rows else 0
+  if len(tensor_spec.shape) > 3 or tensor_spec.varlen_default_value is not None:
+    out = out.reshape((len(byte_rows), per_row) + dims)
+  return out
+
+
+def _records_as_pointers(serialized):
+  """list of bytes -> (keep-alive list, pointer array, length array)."""
+  n = len(serialized)
+  ptrs = (C.c_void_p * n)()
+  lens = (C.c_uint64 * n)()
+  keep = []
+  for i, rec in enumerate(serialized):
+    if isinstance(rec, tuple):           # (address, length) from TFRecordFile.pointer
+      ptrs[i], lens[i] = rec
+    else:
+      buf = C.create_string_buffer(rec, len(rec))
+      keep.append(buf)
+      ptrs[i], lens[i] = C.addressof(buf), len(rec)
+  return keep, ptrs, lens
+
+
+def _parse_examples(serialized, tensor_spec_dict, decode_images):
+  """The tf.parse_example equivalent: {dataset_key+name: spec} -> {same key: numpy [B, ...]}."""
+  b = len(serialized)
+  keep, ptrs, lens = _records_as_pointers(serialized)
+  plans = (_lib.FeaturePlan * len(tensor_spec_dict))()
+  buffers = {}
+  for i, (key, spec) in enumerate(tensor_spec_dict.items()):
+    if getattr(spec, 'is_sequence', False):
+      raise NotImplementedError('SequenceExample parsing (is_sequence specs) is not on the QT-Opt hot path yet')
+    plan = plans[i]
+    plan.key = spec.name.encode('utf-8')
+    keep.append(plan.key)
+    encoded = decode_images and tensorspec_utils.is_encoded_image_spec(spec)
+    varlen = spec.varlen_default_value is not None
+    if encoded:
+      count = int(spec.shape[0]) if (len(spec.shape) > 3 or varlen) else 1
+      dst = np.zeros(b * count, np.uint64)
+      dst_len = np.zeros(b * count, np.uint64)
+      plan.dtype, plan.count = _lib.T2R_DT_BYTES, (-count if varlen else count)
+      buffers[key] = ('bytes', dst, dst_len, count)
+    else:
+      shape = tuple(spec.shape)
+      count = int(np.prod(shape)) if shape else 1
+      if varlen:
+        count = int(spec.shape[0])
+      if spec.dtype == dtypes.string:
+        dst, dst_len = np.zeros(b * count, np.uint64), np.zeros(b * count, np.uint64)
+        plan.dtype = _lib.T2R_DT_BYTES
+        buffers[key] = ('strings', dst, dst_len, count)
+      elif spec.dtype.is_floating:
+        dst, dst_len = np.zeros(b * count, np.float32), np.zeros(b, np.uint64)
+        plan.dtype = _lib.T2R_DT_FLOAT
+        plan.pad_float = float(spec.varlen_default_value) if varlen else 0.0
+        buffers[key] = ('float', dst, dst_len, count)
+      elif spec.dtype.is_integer or spec.dtype == dtypes.bool_:
+        dst, dst_len = np.zeros(b * count, np.int64), np.zeros(b, np.uint64)
+        plan.dtype = _lib.T2R_DT_INT64
+        plan.pad_int64 = int(spec.varlen_default_value) if varlen else 0
+        buffers[key] = ('int', dst, dst_len, count)
+      else:
+        raise ValueError('unsupported dtype %s for feature %s' % (spec.dtype, spec.name))
+      plan.count = -count if varlen else count
+    plan.required = 0 if (getattr(spec, 'is_optional', False) or varlen) else 1
+    plan.dst = dst.ctypes.data
+    plan.dst_len = dst_len.ctypes.data
+  rc = _lib.lib().t2r_example_parse_batch(ptrs, lens, b, plans, len(tensor_spec_dict))
+  if rc != 0:
+    raise ValueError('tf.Example parsing failed: %s' % _lib.last_error())
+  parsed = {}
+  for key, spec in tensor_spec_dict.items():
+    kind, dst, dst_len, count = buffers[key]
+    if kind in ('bytes', 'strings'):
+      rows = [[C.string_at(int(dst[r * count + j]), int(dst_len[r * count + j])) if dst[r * count + j] else b''
+               for j in range(count)] for r in range(b)]
+      if kind == 'bytes':
+        parsed[key] = _decode_images(spec, rows)
+      else:
+        arr = np.array(rows, dtype=object)
+        parsed[key] = arr.reshape((b,) + tuple(spec.shape)) if spec.shape else arr.reshape(b)
+    else:
+      shape = (int(spec.shape[0]),) if spec.varlen_default_value is not None else tuple(spec.shape)
+      arr = dst.reshape((b,) + shape)
+      if spec.dtype == dtypes.bfloat16:
+        import torch
+        parsed[key] = torch.from_numpy(arr).to(torch.bfloat16)      # parsed as f32 then cast (:326-346)
+      else:
+        parsed[key] = arr.astype(spec.dtype.as_numpy_dtype, copy=False)
+  del keep
+  return parsed
+
+
+def create_parse_tf_example_fn(feature_tspec, label_tspec=None, decode_images=True):
+  """Returns parse_tf_example_fn(serialized) -> features | (features, labels).
+
+  `serialized` is a list of serialized tf.Example protos (bytes, or (address, length) pairs from
+  TFRecordFile.pointer) or a {dataset_key: list} dict when specs carry dataset keys."""
+
+  def parse_tf_example_fn(*input_values):
+    serialized = input_values[-1]
+    if not isinstance(serialized, dict):
+      serialized = {'': serialized}
+    parsed_tensors = {}
+    for dataset_key, records in serialized.items():
+      spec_dict = {}
+      for tspec in (feature_tspec, label_tspec):
+        if tspec is None:
+          continue
+        subset = tensorspec_utils.filter_spec_structure_by_dataset(tspec, dataset_key)
+        _, tensor_spec_dict = tensorspec_utils.tensorspec_to_feature_dict(subset, decode_images=decode_images)
+        for name, spec in tensor_spec_dict.items():
+          if name in spec_dict:
+            tensorspec_utils.assert_equal_spec_or_tensor(spec_dict[name], spec)
+          spec_dict[name] = spec
+      for name, value in _parse_examples(records, spec_dict, decode_images).items():
+        parsed_tensors[dataset_key + name] = value
+
+    def pack(tspec):
+      flat = tensorspec_utils.TensorSpecStruct(sorted(tensorspec_utils.flatten_spec_structure(tspec).items()))
+      out = tensorspec_utils.TensorSpecStruct()
+      for key, value in flat.items():
+        if value.name is None:
+          continue
+        lookup = value.dataset_key + value.name
+        if lookup in parsed_tensors:
+          out[key] = parsed_tensors[lookup]
+      return tensorspec_utils.validate_and_pack(flat, out, ignore_batch=True)
+
+    features = pack(feature_tspec)
+    if label_tspec is not None:
+      return features, pack(label_tspec)
+    return features
+
+  return parse_tf_example_fn
+
+
+# ---------------------------------------------------------------------------------------------
+# the input pipeline
+# ---------------------------------------------------------------------------------------------
+def record_stream(filenames, mode, seed=None, shard=(0, 1), verify_crc=True):
+  """Yields (address, length) record pointers: files shuffled and repeated forever in TRAIN, a single
+  ordered pass otherwise; `shard=(rank, world)` keeps every world-th file (or record when there are
+  fewer files than ranks)."""
+  rank, world = shard
+  rng = np.random.RandomState(seed)
+  files = list(filenames)
+  by_record = len(files) < world
+  if not by_record:
+    files = files[rank::world]
+  opened = {}
+  while True:
+    order = list(range(len(files)))
+    if mode == ModeKeys.TRAIN:
+      rng.shuffle(order)
+    for fi in order:
+      f = opened.get(fi)
+      if f is None:
+        f = opened[fi] = TFRecordFile(files[fi], verify_crc)
+      idx = range(rank, len(f), world) if by_record else range(len(f))
+      for i in idx:
+        yield f.pointer(i)
+    if mode != ModeKeys.TRAIN:
+      return
+
+
+def shuffled(stream, buffer_size, seed=None):
+  """tf.data shuffle(buffer_size)."""
+  rng = np.random.RandomState(seed)
+  buf = []
+  for item in stream:
+    if len(buf) < buffer_size:
+      buf.append(item)
+      continue
+    j = rng.randint(0, buffer_size)
+    yield buf[j]
+    buf[j] = item
+  rng.shuffle(buf)
+  for item in buf:
+    yield item
+
+
+def default_input_fn_tmpl(file_patterns, batch_size, feature_spec, label_spec, num_parallel_calls=4,
+                          is_training=False, preprocess_fn=None, shuffle_filenames=True,
+                          shuffle_buffer_size=SHUFFLE_BUFFER_SIZE, mode=ModeKeys.TRAIN, seed=None, shard=(0, 1),
+                          **unused):
+  """Generator of (features, labels) batches: list files -> shuffle -> repeat -> batch(drop_remainder)
+  -> parse -> preprocess (utils/tfdata.py:629-689)."""
+  del num_parallel_calls, shuffle_filenames, unused
+  if isinstance(file_patterns, dict):
+    streams = {}
+    for key, patterns in file_patterns.items():
+      _, filenames = get_data_format_and_filenames(patterns)
+      streams[key] = record_stream(filenames, mode, seed, shard)
+  else:
+    _, filenames = get_data_format_and_filenames(file_patterns)
+    streams = {'': record_stream(filenames, mode, seed, shard)}
+  if is_training or mode == ModeKeys.TRAIN:
+    streams = {k: shuffled(s, shuffle_buffer_size, seed) for k, s in streams.items()}
+  parse_fn = create_parse_tf_example_fn(feature_spec, label_spec)
+  while True:
+    batch = {k: list(itertools.islice(s, batch_size)) for k, s in streams.items()}
+    if any(len(v) < batch_size for v in batch.values()):
+      return                                   # drop_remainder=True
+    parsed = parse_fn(batch if len(batch) > 1 or '' not in batch else batch[''])
+    features, labels = parsed if label_spec is not None else (parsed, None)
+    if preprocess_fn is not None:
+      features, labels = preprocess_fn(features, labels)
+    yield features, labels
+
+
+def get_input_fn(feature_spec, label_spec, file_patterns, mode, batch_size, preprocess_fn=None, **kwargs):
+  """Returns input_fn(params) -> iterator of (features, labels) (utils/tfdata.py:692-718)."""
+
+  def input_fn(params=None):
+    return default_input_fn_tmpl(file_patterns=file_patterns, batch_size=get_batch_size(params, batch_size),
+                                 feature_spec=feature_spec, label_spec=label_spec,
+                                 is_training=(mode == ModeKeys.TRAIN), preprocess_fn=preprocess_fn, mode=mode,
+                                 **kwargs)
+  return input_fn

@@ -1,0 +1,189 @@
+"""train_eval_model: the training / evaluation driver of the B200 engine.
+
+Keeps the entry point of the reference (utils/train_eval.py:424-613,
+`train_eval_model(t2r_model, input_generator_train, input_generator_eval, max_train_steps, model_dir,
+eval_steps, ...)`) and replaces tf.estimator.Estimator with a CUDA-stream driver:
+
+  host batch (numpy) -> pinned staging buffers -> async H2D on a copy stream (double buffered,
+  overlapping the previous step's compute) -> model.preprocessor.preprocess on the GPU ->
+  model.train_step (forward, backward, NCCL all-reduce, fused optimizer) -> checkpoint cadence.
+
+Checkpoints are torch files of {reference variable name: array in TF layout} + optimizer slots +
+global_step, written as model_dir/model.ckpt-<step>.pt; training resumes from the newest.
+"""
+import glob
+import logging
+import os
+import re
+
+import torch
+
+from tensor2robot_b200.models import model_interface
+from tensor2robot_b200.utils import tensorspec_utils
+
+ModeKeys = model_interface.ModeKeys
+
+
+def print_spec(tensor_spec):
+  for key, value in tensorspec_utils.flatten_spec_structure(tensor_spec).items():
+    logging.info('%s: %s', key, value)
+
+
+def print_specification(t2r_model):
+  """Logs the model / preprocessor specifications for all modes (:73-94)."""
+  for mode in (ModeKeys.TRAIN, ModeKeys.EVAL, ModeKeys.PREDICT):
+    logging.info('Preprocessor in feature specification (%s):', mode)
+    print_spec(t2r_model.preprocessor.get_in_feature_specification(mode))
+    logging.info('Model feature specification (%s):', mode)
+    print_spec(t2r_model.get_feature_specification(mode))
+
+
+def provide_input_generator_with_model_information(input_generator_or_generators, t2r_model, mode):
+  """Sets the specifications and preprocess function on the input generator(s) (:97-129)."""
+  if isinstance(input_generator_or_generators, (list, tuple)):
+    for g in input_generator_or_generators:
+      g.set_specification_from_model(t2r_model, mode)
+  else:
+    input_generator_or_generators.set_specification_from_model(t2r_model, mode)
+  return input_generator_or_generators
+
+
+class DeviceStager(object):
+  """Pinned host staging + async H2D on a dedicated copy stream, double buffered."""
+
+  def __init__(self, device, depth=2):
+    self.device = torch.device(device)
+    self.stream = torch.cuda.Stream(device=self.device)
+    self.depth = depth
+    self._pinned = [dict() for _ in range(depth)]
+    self._slot = 0
+
+  def stage(self, struct):
+    """struct: flat {path: numpy | torch CPU tensor}.  Returns (device struct, ready event)."""
+    slot = self._pinned[self._slot]
+    self._slot = (self._slot + 1) % self.depth
+    out = tensorspec_utils.TensorSpecStruct()
+    with torch.cuda.stream(self.stream):
+      for key, value in struct.items():
+        t = value if isinstance(value, torch.Tensor) else torch.from_numpy(value)
+        if t.dtype == torch.float64:
+          t = t.float()
+        buf = slot.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+          buf = slot[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        buf.copy_(t)
+        out[key] = buf.to(self.device, non_blocking=True)
+      ready = torch.cuda.Event()
+      ready.record(self.stream)
+    return out, ready
+
+
+def latest_checkpoint(model_dir):
+  best, best_step = None, -1
+  for path in glob.glob(os.path.join(model_dir, 'model.ckpt-*.pt')):
+    m = re.search(r'model\.ckpt-(\d+)\.pt$', path)
+    if m and int(m.group(1)) > best_step:
+      best, best_step = path, int(m.group(1))
+  return best
+
+
+def save_checkpoint(t2r_model, model_dir, keep_checkpoint_max=5):
+  os.makedirs(model_dir, exist_ok=True)
+  path = os.path.join(model_dir, 'model.ckpt-%d.pt' % t2r_model.global_step)
+  torch.save(t2r_model.state_dict(), path)
+  existing = sorted(glob.glob(os.path.join(model_dir, 'model.ckpt-*.pt')),
+                    key=lambda p: int(re.search(r'-(\d+)\.pt$', p).group(1)))
+  for old in existing[:-keep_checkpoint_max]:
+    os.remove(old)
+  return path
+
+
+def _batches(input_generator, t2r_model, mode, device):
+  """Host batches -> staged device batches -> preprocessed (features, labels)."""
+  stager = DeviceStager(device)
+  preprocessor = t2r_model.preprocessor
+  for features, labels in input_generator.create_dataset(mode):
+    flat = tensorspec_utils.flatten_spec_structure(features)
+    n_feat = len(flat)
+    merged = tensorspec_utils.TensorSpecStruct([('f/' + k, v) for k, v in flat.items()])
+    if labels is not None:
+      for k, v in tensorspec_utils.flatten_spec_structure(labels).items():
+        merged['l/' + k] = v
+    staged, ready = stager.stage(merged)
+    torch.cuda.current_stream(device).wait_event(ready)
+    dev_features = tensorspec_utils.TensorSpecStruct([(k[2:], v) for k, v in staged.items() if k.startswith('f/')])
+    dev_labels = tensorspec_utils.TensorSpecStruct([(k[2:], v) for k, v in staged.items() if k.startswith('l/')])
+    del n_feat
+    yield preprocessor.preprocess(dev_features, dev_labels if len(dev_labels) else None, mode)
+
+
+def train_eval_model(t2r_model=None, input_generator_train=None, input_generator_eval=None, max_train_steps=1000,
+                     model_dir='/tmp/t2r_b200', eval_steps=100, eval_throttle_secs=600, create_exporters_fn=None,
+                     export_generator=None, use_continuous_eval=True, train_hook_builders=None,
+                     chief_train_hook_builders=None, eval_hook_builders=None, device=None, log_every_n_steps=100):
+  """Trains (and evaluates) a T2R model.  Returns {'global_step', 'loss', 'eval'}.
+
+  Hooks / exporters of the Estimator world have no analogue here and must be None."""
+  del eval_throttle_secs, use_continuous_eval
+  if any(x is not None for x in (create_exporters_fn, export_generator, train_hook_builders,
+                                 chief_train_hook_builders, eval_hook_builders)):
+    raise NotImplementedError('Estimator hooks / SavedModel exporters are outside the B200 engine (SURVEY 2)')
+  if t2r_model is None:
+    raise ValueError('t2r_model is required')
+  device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+  print_specification(t2r_model)
+  result = {'global_step': t2r_model.global_step, 'loss': None, 'eval': None}
+  run_config = t2r_model.get_run_config()
+  if input_generator_train is not None:
+    provide_input_generator_with_model_information(input_generator_train, t2r_model, ModeKeys.TRAIN)
+    resumed = False
+    last_loss = None
+    for features, labels in _batches(input_generator_train, t2r_model, ModeKeys.TRAIN, device):
+      if not resumed:
+        t2r_model.build(features, labels)
+        ckpt = latest_checkpoint(model_dir)
+        if ckpt:
+          t2r_model.load_state_dict(torch.load(ckpt, weights_only=False))
+        else:
+          save_checkpoint(t2r_model, model_dir, run_config.get('keep_checkpoint_max', 5))   # model.ckpt-0
+        resumed = True
+      if t2r_model.global_step >= max_train_steps:
+        break
+      last_loss = t2r_model.train_step(features, labels)
+      step = t2r_model.global_step
+      if step % log_every_n_steps == 0:
+        logging.info('step %d loss %.5f', step, float(last_loss))
+      if step % run_config.get('save_checkpoints_steps', 1000) == 0:
+        save_checkpoint(t2r_model, model_dir, run_config.get('keep_checkpoint_max', 5))
+    if resumed:
+      save_checkpoint(t2r_model, model_dir, run_config.get('keep_checkpoint_max', 5))
+    result['global_step'] = t2r_model.global_step
+    result['loss'] = float(last_loss) if last_loss is not None else None
+  if input_generator_eval is not None:
+    provide_input_generator_with_model_information(input_generator_eval, t2r_model, ModeKeys.EVAL)
+    losses = []
+    for i, (features, labels) in enumerate(_batches(input_generator_eval, t2r_model, ModeKeys.EVAL, device)):
+      if eval_steps is not None and i >= eval_steps:
+        break
+      if not t2r_model.variable_store.finalized:
+        t2r_model.build(features, labels)
+      out = t2r_model.model_fn(features, labels, ModeKeys.EVAL)
+      losses.append(out.loss.detach())
+    if losses:
+      result['eval'] = {'loss': float(torch.stack(losses).mean()), 'steps': len(losses)}
+  return result
+
+
+def predict_from_model(t2r_model=None, input_generator_predict=None, model_dir=None, device=None):
+  """Yields predictions for every batch of the generator (:390-421)."""
+  device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+  provide_input_generator_with_model_information(input_generator_predict, t2r_model, ModeKeys.PREDICT)
+  loaded = False
+  for features, _ in _batches(input_generator_predict, t2r_model, ModeKeys.PREDICT, device):
+    if not loaded:
+      t2r_model.build(features, mode=ModeKeys.PREDICT)
+      ckpt = latest_checkpoint(model_dir) if model_dir else None
+      if ckpt:
+        t2r_model.load_state_dict(torch.load(ckpt, weights_only=False))
+      loaded = True
+    yield t2r_model.predict(features)

@@ -1,0 +1,216 @@
+"""Record-path parity (CPU): TFRecord framing / CRC-32C / tf.Example parsing / image decode of the
+host side of libt2r_b200.so against the pure-Python oracle and the golden values of the reference's
+own fixture test_data/pose_env_test_data.tfrecord (tests/golden/pose_env_golden.npz).
+
+Mirrors the assertions of the reference's utils/tfdata_test.py: fixture shapes (:65-88), PNG
+uint8/uint16 (:143-179), unsupported dtype raises (:181-202), varlen ints (:230-248), wrong image
+size raises (:311-344), file-pattern inference (:398-433), get_batch_size (:436-444).
+"""
+import ctypes as C
+import io
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import tfrecord as oracle
+from tensor2robot_b200 import _lib
+from tensor2robot_b200.utils import dtypes
+from tensor2robot_b200.utils import tensorspec_utils as utils
+from tensor2robot_b200.utils import tfdata
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURE = os.path.join(HERE, 'golden', 'pose_env_test_data.tfrecord')
+GOLDEN = np.load(os.path.join(HERE, 'golden', 'pose_env_golden.npz'))
+TSPEC = utils.ExtendedTensorSpec
+
+
+def test_library_exports_every_declared_symbol():
+  lib = _lib.lib()
+  header = open(os.path.join(os.path.dirname(HERE), 'include', 't2r_b200.h')).read()
+  import re
+  declared = set(re.findall(r'\b(t2r_[a-z0-9_]+)\s*\(', header))
+  assert declared, 'no declarations found'
+  for name in sorted(declared):
+    assert hasattr(lib, name), name
+  assert set(_lib.EXPORTED_SYMBOLS) <= declared | {'t2r_version'}
+  assert lib.t2r_version() >= 100
+
+
+def test_crc32c_known_answers():
+  lib = _lib.lib()
+  vectors = [(b'', 0x00000000), (b'a', 0xC1D04330), (b'123456789', 0xE3069283), (bytes(32), 0x8A9136AA),
+             (bytes([0xFF] * 32), 0x62A8AB43), (bytes(range(32)), 0x46DD794E)]   # RFC 3720 B.4 vectors
+  for data, expected in vectors:
+    buf = C.create_string_buffer(data, len(data))
+    assert lib.t2r_crc32c(C.addressof(buf), len(data)) == expected, data
+    assert oracle.crc32c(data) == expected
+    assert lib.t2r_masked_crc32c(C.addressof(buf), len(data)) == oracle.masked_crc32c(data)
+  try:
+    from tensorboard.compat.tensorflow_stub.pywrap_tensorflow import masked_crc32c
+  except Exception:  # pragma: no cover
+    return
+  rng = np.random.RandomState(0)
+  for n in (1, 7, 8, 9, 63, 64, 1000):
+    data = rng.bytes(n)
+    buf = C.create_string_buffer(data, n)
+    assert lib.t2r_masked_crc32c(C.addressof(buf), n) == masked_crc32c(data)
+
+
+def test_fixture_framing_matches_oracle():
+  f = tfdata.TFRecordFile(FIXTURE, verify_crc=True)
+  ref = oracle.read_tfrecords(FIXTURE)
+  assert len(f) == len(ref) == 100
+  np.testing.assert_array_equal(f.lengths, GOLDEN['record_length'])
+  assert list(f) == ref
+
+
+def test_corrupt_record_is_rejected(tmp_path):
+  data = bytearray(open(FIXTURE, 'rb').read())
+  data[40] ^= 0x01
+  bad = tmp_path / 'bad.tfrecord'
+  bad.write_bytes(bytes(data))
+  with pytest.raises(ValueError):
+    tfdata.TFRecordFile(str(bad), verify_crc=True)
+  assert len(tfdata.TFRecordFile(str(bad), verify_crc=False)) == 100
+  bad.write_bytes(bytes(data[:-3]))
+  with pytest.raises(ValueError):
+    tfdata.TFRecordFile(str(bad), verify_crc=False)
+
+
+def _pose_env_specs():
+  features = utils.TensorSpecStruct(
+      state=utils.TensorSpecStruct(image=TSPEC((64, 64, 3), dtypes.uint8, 'state/image', data_format='jpeg')),
+      action=utils.TensorSpecStruct(pose=TSPEC((2,), dtypes.float32, 'pose')))
+  labels = utils.TensorSpecStruct(reward=TSPEC((1,), dtypes.float32, 'reward'),
+                                  target_pose=TSPEC((2,), dtypes.float32, 'target_pose'))
+  return features, labels
+
+
+def test_fixture_parses_bit_exact():
+  feature_spec, label_spec = _pose_env_specs()
+  records = tfdata.read_records(FIXTURE)
+  parse = tfdata.create_parse_tf_example_fn(feature_spec, label_spec)
+  features, labels = parse(records)
+  assert features.state.image.shape == (100, 64, 64, 3) and features.state.image.dtype == np.uint8
+  np.testing.assert_array_equal(features.action.pose.view(np.uint32), GOLDEN['pose'].view(np.uint32))
+  np.testing.assert_array_equal(labels.reward.view(np.uint32), GOLDEN['reward'].view(np.uint32))
+  np.testing.assert_array_equal(labels.target_pose.view(np.uint32), GOLDEN['target_pose'].view(np.uint32))
+  np.testing.assert_array_equal(features.state.image.astype(np.int64).sum((1, 2, 3)), GOLDEN['image_sum'])
+  np.testing.assert_array_equal(features.state.image[:, :2, :2], GOLDEN['image_corner'])
+  # the oracle parser agrees record by record
+  for i in (0, 17, 99):
+    ex = oracle.parse_example(records[i])
+    np.testing.assert_array_equal(np.float32(ex['pose'][1]), features.action.pose[i])
+  # zero-copy pointers from the mmap index give the same result
+  f = tfdata.TFRecordFile(FIXTURE)
+  f2, _ = parse([f.pointer(i) for i in range(5)])
+  np.testing.assert_array_equal(f2.action.pose, features.action.pose[:5])
+
+
+def _png(arr):
+  buf = io.BytesIO()
+  Image.fromarray(arr.squeeze() if arr.shape[-1] == 1 else arr).save(buf, format='PNG')
+  return buf.getvalue()
+
+
+def test_png_uint8_uint16_and_unsupported_dtype():
+  rng = np.random.RandomState(1)
+  img8 = rng.randint(0, 255, (12, 10, 1)).astype(np.uint8)
+  img16 = rng.randint(0, 65535, (12, 10, 1)).astype(np.uint16)
+  rec = oracle.make_example({'a': _png(img8), 'b': _png(img16)})
+  spec = utils.TensorSpecStruct(a=TSPEC((12, 10, 1), dtypes.uint8, 'a', data_format='png'),
+                                b=TSPEC((12, 10, 1), dtypes.uint16, 'b', data_format='png'))
+  out = tfdata.create_parse_tf_example_fn(spec)([rec, rec])
+  np.testing.assert_array_equal(out.a[1], img8)
+  np.testing.assert_array_equal(out.b[0], img16)
+  bad = utils.TensorSpecStruct(a=TSPEC((12, 10, 1), dtypes.uint32, 'a', data_format='png'))
+  with pytest.raises(ValueError):
+    tfdata.create_parse_tf_example_fn(bad)([rec])
+
+
+def test_varlen_optional_missing_and_wrong_size():
+  rec1 = oracle.make_example({'ids': [1, 2], 'x': [0.5, 1.5, 2.5]})
+  rec2 = oracle.make_example({'ids': [1, 2, 3, 4, 5], 'x': [1.0, 2.0, 3.0]})
+  spec = utils.TensorSpecStruct(ids=TSPEC((3,), dtypes.int64, 'ids', varlen_default_value=3.0),
+                                x=TSPEC((3,), dtypes.float32, 'x'),
+                                opt=TSPEC((2,), dtypes.float32, 'opt', is_optional=True))
+  out = tfdata.create_parse_tf_example_fn(spec)([rec1, rec2])
+  np.testing.assert_array_equal(out.ids, [[1, 2, 3], [1, 2, 3]])       # padded with 3, clipped to 3
+  np.testing.assert_array_equal(out.x, [[0.5, 1.5, 2.5], [1, 2, 3]])
+  with pytest.raises(ValueError):                                        # required key missing
+    tfdata.create_parse_tf_example_fn(utils.TensorSpecStruct(y=TSPEC((1,), dtypes.float32, 'y')))([rec1])
+  with pytest.raises(ValueError):                                        # wrong number of values
+    tfdata.create_parse_tf_example_fn(utils.TensorSpecStruct(x=TSPEC((2,), dtypes.float32, 'x')))([rec1])
+  img = np.zeros((8, 8, 3), np.uint8)
+  buf = io.BytesIO()
+  Image.fromarray(img).save(buf, format='JPEG')
+  rec = oracle.make_example({'im': buf.getvalue()})
+  with pytest.raises(ValueError):                                        # decoded size != spec
+    tfdata.create_parse_tf_example_fn(utils.TensorSpecStruct(
+        im=TSPEC((8, 9, 3), dtypes.uint8, 'im', data_format='jpeg')))([rec])
+  empty = oracle.make_example({'im': b''})
+  out = tfdata.create_parse_tf_example_fn(utils.TensorSpecStruct(
+      im=TSPEC((8, 8, 3), dtypes.uint8, 'im', data_format='jpeg')))([empty])
+  assert out.im.shape == (1, 8, 8, 3) and not out.im.any()               # '' -> black image
+
+
+def test_same_name_feeds_several_paths_and_dataset_keys():
+  rec_a = oracle.make_example({'v': [1.0]})
+  rec_b = oracle.make_example({'v': [2.0]})
+  spec = utils.TensorSpecStruct(first=TSPEC((1,), dtypes.float32, 'v', dataset_key='a'),
+                                second=TSPEC((1,), dtypes.float32, 'v', dataset_key='b'),
+                                third=TSPEC((1,), dtypes.float32, 'v', dataset_key='a'))
+  out = tfdata.create_parse_tf_example_fn(spec)({'a': [rec_a], 'b': [rec_b]})
+  assert out.first[0, 0] == 1.0 and out.second[0, 0] == 2.0 and out.third[0, 0] == 1.0
+
+
+def test_file_patterns_and_batch_size(tmp_path):
+  assert tfdata.infer_data_format('a/b.tfrecord') == 'tfrecord'
+  with pytest.raises(ValueError):
+    tfdata.infer_data_format('a/b.tfrecord,c.recordio')
+  with pytest.raises(ValueError):
+    tfdata.infer_data_format('a/b.txt')
+  p = tmp_path / 'x.tfrecord'
+  oracle.write_tfrecords(str(p), [oracle.make_example({'v': [float(i)]}) for i in range(10)])
+  fmt, files = tfdata.get_data_format_and_filenames('tfrecord:%s,%s' % (p, FIXTURE))
+  assert fmt == 'tfrecord' and files == [str(p), FIXTURE]
+  with pytest.raises(ValueError):
+    tfdata.get_data_format_and_filenames(str(tmp_path / 'missing*.tfrecord'))
+  assert tfdata.get_batch_size({'batch_size': 4}, 8) == 4 and tfdata.get_batch_size({}, 8) == 8
+  with pytest.raises(ValueError):
+    tfdata.get_batch_size({}, None)
+  # written records round-trip through the C++ reader
+  assert [oracle.parse_example(r)['v'][1][0] for r in tfdata.read_records(str(p))] == [float(i) for i in range(10)]
+
+
+def test_record_input_generator_batches_and_shards():
+  from tensor2robot_b200.input_generators import default_input_generator as gens
+  feature_spec, label_spec = _pose_env_specs()
+  g = gens.DefaultRecordInputGenerator(file_patterns=FIXTURE, batch_size=32, seed=0)
+  g.set_feature_specifications(feature_spec, feature_spec)
+  g.set_label_specifications(label_spec, label_spec)
+  batches = list(g.create_dataset('eval'))
+  assert len(batches) == 3                                   # 100 records, drop_remainder
+  f, l = batches[0]
+  assert f.state.image.shape == (32, 64, 64, 3) and l.reward.shape == (32, 1)
+  np.testing.assert_array_equal(f.action.pose, GOLDEN['pose'][:32])     # eval: file order
+  it = g.create_dataset('train')                             # train: shuffled, repeats forever
+  seen = [next(it)[0].action.pose for _ in range(5)]
+  assert not np.array_equal(seen[0], GOLDEN['pose'][:32])
+  # rank sharding by record when there are fewer files than ranks
+  g0 = gens.DefaultRecordInputGenerator(file_patterns=FIXTURE, batch_size=10, shard=(0, 2))
+  g1 = gens.DefaultRecordInputGenerator(file_patterns=FIXTURE, batch_size=10, shard=(1, 2))
+  for g_ in (g0, g1):
+    g_.set_feature_specifications(feature_spec, feature_spec)
+    g_.set_label_specifications(label_spec, label_spec)
+  a = np.concatenate([b[0].action.pose for b in g0.create_dataset('eval')])
+  b = np.concatenate([b[0].action.pose for b in g1.create_dataset('eval')])
+  np.testing.assert_array_equal(a, GOLDEN['pose'][0::2])
+  np.testing.assert_array_equal(b, GOLDEN['pose'][1::2])
+  rnd = gens.DefaultRandomInputGenerator(batch_size=3)
+  rnd.set_feature_specifications(feature_spec, feature_spec)
+  rnd.set_label_specifications(label_spec, label_spec)
+  f, l = next(rnd.create_dataset('train'))
+  assert f.state.image.shape == (3, 64, 64, 3) and f.state.image.dtype == np.uint8
