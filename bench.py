@@ -40,6 +40,8 @@ def parse_args():
   p.add_argument('--cpu-batch', type=int, default=8)
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
+  p.add_argument('--no-cem', action='store_true')
+  p.add_argument('--cem-batch', type=int, default=64, help='transitions per GPU for the CEM measurement')
   return p.parse_args()
 
 
@@ -314,6 +316,38 @@ def run_b200(args):
     e2e = {'value': b * world * args.steps / e2e_s, 'unit': 'transitions/s', 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / args.steps * 1e3}
 
+  # ---- CEM action maximisation (BASELINE metric "CEM Q-evals/sec"): 64 samples x 2 iterations per
+  # transition against the staged state features, + Bellman target ----
+  cem_line = None
+  if not args.no_cem:
+    cb = min(b, args.cem_batch)
+    cem = engine.CEMTargetComputer(critic, step.vs, action_size=10, cem_samples=64, cem_iters=2, num_elites=10,
+                                   seed=rank, chunk=16 if args.model == 'resnet50' else None)
+    frames = dev_batches[0][0][:cb]
+    reward, done = dev_batches[0][2][:cb, 0].contiguous(), torch.zeros(cb, device=dev)
+
+    def cem_once():
+      x = step.preprocess(frames, training=False)
+      _, max_q, _ = cem.maximize(x)
+      return cem.bellman_target(reward, done, max_q, 0.9)
+
+    cem_once()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(2):
+      target = cem_once()
+    c1.record()
+    barrier()
+    cem_ms = c0.elapsed_time(c1) / 2
+    if world > 1:
+      t = torch.tensor([cem_ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      cem_ms = float(t.item())
+    cem_line = {'q_evals_per_sec': cb * world * 64 * 2 * 1000.0 / cem_ms, 'transitions_per_sec': cb * world * 1000.0 / cem_ms,
+                'per_gpu_batch': cb, 'samples': 64, 'iterations': 2, 'elites': 10, 'ms': cem_ms,
+                'target_mean': float(target.mean())}
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -331,7 +365,7 @@ def run_b200(args):
       'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
       'config': workload_config(args, b), 'clocks': clocks, 'gpu_launches': int(launches),
-      'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'loss': loss_value,
+      'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'cem': cem_line, 'loss': loss_value,
       'model_tflops': value * TRAIN_GFLOP_PER_TRANSITION[args.model] / 1e3,
       'peak_mem_gb': torch.cuda.max_memory_allocated(dev) / 1e9,
   }

@@ -20,6 +20,26 @@ from tensor2robot_b200 import nn
 from tensor2robot_b200.preprocessors import image_ops
 
 
+def reduce_gradients(flat_grad, world_size=None, group=None):
+  """The ONE collective of a data-parallel step: sum the flat gradient buffer over the
+  replicas (NCCL on GPU tensors, gloo on CPU tensors in the tests) and return the factor the fused
+  optimizer kernel multiplies the gradient with (1 / world_size).  BatchNorm statistics stay
+  per-replica, like the reference's towers."""
+  if world_size is None:
+    world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+  if world_size <= 1:
+    return 1.0
+  dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+  return 1.0 / world_size
+
+
+def shard_for_rank():
+  """(rank, world_size) of this process for record sharding (files[rank::world])."""
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(), dist.get_world_size()
+  return 0, 1
+
+
 class CriticTrainStep(object):
   """Owns the variables, optimizer state and RNG of one data-parallel replica of a Q-critic."""
 
@@ -93,10 +113,7 @@ class CriticTrainStep(object):
       vs.zero_grad()
       loss.backward()
       total = loss.detach() + nn.l2_regularization_loss(self.critic.l2_regularization, vs)
-    grad_scale = 1.0
-    if self.world_size > 1:
-      dist.all_reduce(vs.flat_grad, op=dist.ReduceOp.SUM)
-      grad_scale = 1.0 / self.world_size
+    grad_scale = reduce_gradients(vs.flat_grad, self.world_size)
     self.optimizer.apply_gradients(vs, self.global_step, grad_scale)
     vs.sync_compute_copies(after_optimizer=True)
     self.global_step += 1
