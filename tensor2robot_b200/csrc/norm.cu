@@ -19,14 +19,17 @@ struct RowPartition {
   int row_blocks;   // grid.x
 };
 
-static RowPartition partition(long long rows, int C) {
+// blocks_per_sm: resident CTAs per SM of the kernel that uses the partition (register limited), so
+// that the grid is exactly one full wave: a 4/SM grid on a kernel that fits 3/SM runs a second,
+// third-full wave and loses a third of the bandwidth.
+static RowPartition partition(long long rows, int C, int blocks_per_sm = 4) {
   RowPartition p;
   const int cg = C / 8;
   p.cgb = std::min(cg, 256);
   while (256 % p.cgb != 0) --p.cgb;  // keep 256 % cgb == 0 (C = 192 -> cg 24 -> cgb 16)
   p.col_blocks = (cg + p.cgb - 1) / p.cgb;
   p.lanes_r = 256 / p.cgb;
-  const long long target_blocks = std::max(1LL, 148LL * 4 / p.col_blocks);
+  const long long target_blocks = std::max(1LL, (long long)num_sms() * blocks_per_sm / p.col_blocks);
   long long rpb = (rows + target_blocks - 1) / target_blocks;
   rpb = std::max<long long>(rpb, p.lanes_r);
   rpb = (rpb + p.lanes_r - 1) / p.lanes_r * p.lanes_r;
@@ -362,11 +365,12 @@ extern "C" int32_t t2r_bn_backward(const void* dy, const void* x, const void* dr
   T2R_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_backward: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   T2R_CUDA_OK(cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st));
-  const RowPartition p = partition(rows, C);
-  bn_bwd_reduce_kernel<<<dim3(p.row_blocks, p.col_blocks), 256, 0, st>>>(
-      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), rows, C, p.cgb, p.lanes_r,
-      p.rows_per_block, mean, invstd, scale, shift, relu, red);
+  const RowPartition pr = partition(rows, C, 3);   // 80 registers/thread: 3 CTAs per SM
+  bn_bwd_reduce_kernel<<<dim3(pr.row_blocks, pr.col_blocks), 256, 0, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), rows, C, pr.cgb, pr.lanes_r,
+      pr.rows_per_block, mean, invstd, scale, shift, relu, red);
   T2R_LAUNCH_OK();
+  const RowPartition p = partition(rows, C, 4);    // 64 registers/thread: 4 CTAs per SM
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, C, dgamma, dbeta);
   T2R_LAUNCH_OK();
   const float inv_rows = 1.f / float(rows);

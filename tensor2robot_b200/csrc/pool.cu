@@ -74,17 +74,15 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restric
     const int ih = int(r % H);
     const int n = int(r / H);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // windows (oh, kh) with oh*stride + kh - pt == ih
-    for (int kh = 0; kh < k; ++kh) {
-      const int num = ih + pt - kh;
-      if (num < 0 || num % stride != 0) continue;
-      const int oh = num / stride;
-      if (oh >= Ho) continue;
-      for (int kw = 0; kw < k; ++kw) {
-        const int numw = iw + pl - kw;
-        if (numw < 0 || numw % stride != 0) continue;
-        const int ow = numw / stride;
-        if (ow >= Wo) continue;
+    // windows oh with 0 <= ih + pt - oh*stride < k  (and likewise ow): at most ceil(k/stride)^2
+    const int oh_hi = min((ih + pt) / stride, Ho - 1);
+    const int oh_lo = max(0, (ih + pt - k + stride) / stride);   // ceil((ih+pt-k+1)/stride), arg >= 0 when used
+    const int ow_hi = min((iw + pl) / stride, Wo - 1);
+    const int ow_lo = max(0, (iw + pl - k + stride) / stride);
+    for (int oh = (ih + pt - k + 1 > 0 ? oh_lo : 0); oh <= oh_hi; ++oh) {
+      const int kh = ih + pt - oh * stride;
+      for (int ow = (iw + pl - k + 1 > 0 ? ow_lo : 0); ow <= ow_hi; ++ow) {
+        const int kw = iw + pl - ow * stride;
         const long long o = (((long long)n * Ho + oh) * Wo + ow) * cg + g;
         const uint2 a = argmax[o];
         float f[8];

@@ -31,10 +31,44 @@ class _Namer(object):
     return base if n == 0 else '%s_%d' % (base, n)
 
 
-def batch_norm(inputs, training, namer, relu=False, film=None):
-  """tf.layers.batch_normalization(momentum=.997, eps=1e-5, fused=True) [+FiLM] [+ReLU]."""
+def batch_norm(inputs, training, namer, relu=False, film=None, passthrough=False):
+  """tf.layers.batch_normalization(momentum=.997, eps=1e-5, fused=True) [+FiLM] [+ReLU].
+  passthrough=True additionally returns `inputs` routed through the same autograd node (used for
+  the identity shortcut, whose gradient the BN backward kernel then adds for free)."""
   return nn.batch_norm(inputs, training, scope=namer('batch_normalization'), scale=True, relu=relu,
-                       momentum=_BATCH_NORM_DECAY, eps=_BATCH_NORM_EPSILON, film=film)
+                       momentum=_BATCH_NORM_DECAY, eps=_BATCH_NORM_EPSILON, film=film, passthrough=passthrough)
+
+
+def _conv_spec(filters, kernel_size, strides, namer, weight_decay):
+  return dict(filters=filters, kernel_size=kernel_size, stride=strides,
+              padding='SAME' if strides == 1 else 'FIXED', scope=namer('conv2d'),
+              regularize=weight_decay is not None, names=('kernel', 'bias'))
+
+
+def _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters, kernel_size, strides,
+                           weight_decay):
+  """BN+ReLU, then the (optional) projection shortcut and the block's first convolution.
+
+  Identity shortcut: `inputs` is returned through the BN node (gradient fan-in fused into the BN
+  backward kernel).  Projection shortcut: both convolutions read the pre-activation, so they run as
+  one autograd node whose second data gradient accumulates into the first (nn.conv2d_pair)."""
+  if projection_shortcut is None:
+    if training and torch.is_grad_enabled():
+      preact, shortcut = batch_norm(inputs, training, namer, relu=True, passthrough=True)
+    else:
+      preact, shortcut = batch_norm(inputs, training, namer, relu=True), inputs
+    first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay)
+    return shortcut, first
+  preact = batch_norm(inputs, training, namer, relu=True)
+  fused = getattr(projection_shortcut, 'fused_args', None)
+  if fused is None or not training:
+    shortcut = projection_shortcut(preact)
+    first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay)
+    return shortcut, first
+  proj_filters, proj_strides = fused
+  shortcut, first = nn.conv2d_pair(preact, _conv_spec(proj_filters, 1, proj_strides, namer, weight_decay),
+                                   _conv_spec(filters, kernel_size, strides, namer, weight_decay))
+  return shortcut, first
 
 
 def conv2d_fixed_padding(inputs, filters, kernel_size, strides, namer, weight_decay=None, residual=None,
@@ -55,11 +89,8 @@ def _film_tensor(film_gamma_beta):
 def _building_block_v2(inputs, filters, training, projection_shortcut, strides, namer, weight_decay,
                        film_gamma_beta=None):
   """BN-ReLU-conv3x3-BN-[FiLM]-ReLU-conv3x3 + shortcut (film_resnet_model.py:166-223)."""
-  shortcut = inputs
-  inputs = batch_norm(inputs, training, namer, relu=True)
-  if projection_shortcut is not None:
-    shortcut = projection_shortcut(inputs)
-  inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay)
+  shortcut, inputs = _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters, 3, strides,
+                                            weight_decay)
   inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta))
   return conv2d_fixed_padding(inputs, filters, 3, 1, namer, weight_decay, residual=shortcut)
 
@@ -67,11 +98,8 @@ def _building_block_v2(inputs, filters, training, projection_shortcut, strides, 
 def _bottleneck_block_v2(inputs, filters, training, projection_shortcut, strides, namer, weight_decay,
                          film_gamma_beta=None):
   """BN-ReLU-1x1-BN-ReLU-3x3(stride)-BN-[FiLM]-ReLU-1x1(4x) + shortcut (film_resnet_model.py:283-340)."""
-  shortcut = inputs
-  inputs = batch_norm(inputs, training, namer, relu=True)
-  if projection_shortcut is not None:
-    shortcut = projection_shortcut(inputs)
-  inputs = conv2d_fixed_padding(inputs, filters, 1, 1, namer, weight_decay)
+  shortcut, inputs = _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters, 1, 1,
+                                            weight_decay)
   inputs = batch_norm(inputs, training, namer, relu=True)
   inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay)
   inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta))
@@ -88,6 +116,7 @@ def block_layer(inputs, filters, bottleneck, block_fn, blocks, strides, training
 
   def projection_shortcut(x):
     return conv2d_fixed_padding(x, filters_out, 1, strides, namer, weight_decay)
+  projection_shortcut.fused_args = (filters_out, strides)
 
   inputs = block_fn(inputs, filters, training, projection_shortcut, strides, namer, weight_decay,
                     film_gamma_betas[0])

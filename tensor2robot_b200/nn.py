@@ -459,6 +459,72 @@ class _Conv2dFn(torch.autograd.Function):
     return dx, dres, None, None, None, None, None
 
 
+class _DualConvFn(torch.autograd.Function):
+  """Two convolutions reading the same input (ResNet projection shortcut + first block conv):
+  one autograd node, so the two data gradients are accumulated by the second dgrad's epilogue
+  instead of a separate elementwise add."""
+
+  @staticmethod
+  def forward(ctx, x, var1, geom1, var2, geom2):
+    n, h, w, cin = x.shape
+    descs, ys = [], []
+    for var, (stride, ho, wo, pt, pl) in ((var1, geom1), (var2, geom2)):
+      cout, kh, kw, _ = var.shape
+      d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, 0)
+      y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+      with _prof('fprop', d):
+        _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(var.bf16), None, None, _p(y), _stream())
+      descs.append(d)
+      ys.append(y)
+    ctx.vars, ctx.descs = (var1, var2), descs
+    ctx.save_for_backward(x)
+    return ys[0], ys[1]
+
+  @staticmethod
+  def backward(ctx, dy1, dy2):
+    (x,) = ctx.saved_tensors
+    st = _stream()
+    dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+    wrote = False
+    for var, d, dy in zip(ctx.vars, ctx.descs, (dy1, dy2)):
+      if dy is None:
+        continue
+      dy = dy.contiguous()
+      if var.trainable:
+        with _prof('wgrad', d):
+          _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(x), _p(dy), _p(var.grad), st)
+      if dx is not None:
+        with _prof('dgrad', d):
+          _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 1 if wrote else 0, st)
+        wrote = True
+    if dx is not None and not wrote:
+      dx.zero_()
+    return dx, None, None, None, None
+
+
+def conv2d_pair(x, spec1, spec2):
+  """spec = dict(filters, kernel_size, stride, padding, scope, names, regularize).  Returns (y1, y2);
+  variables are created in the order (spec1, spec2)."""
+  _require_cuda(x, 'conv2d_pair')
+  vs = current_store()
+  n, h, w, cin = x.shape
+  out = []
+  for spec in (spec1, spec2):
+    k = spec['kernel_size']
+    stride, padding = spec.get('stride', 1), spec.get('padding', 'SAME')
+    ho, wo, pt, pl = conv_geometry(h, w, k, k, stride, padding)
+    with vs.scope(spec['scope']):
+      wv = vs.get_variable(spec.get('names', ('weights', 'biases'))[0], (spec['filters'], k, k, cin),
+                           spec.get('initializer') or variance_scaling(k * k * cin), True,
+                           spec.get('regularize', True), 'conv', 'hwio')
+      wv.needs_dgrad = True
+    if not vs.finalized:
+      _ensure_bf16(wv)
+    out.append((wv, (stride, ho, wo, pt, pl)))
+  y1, y2 = _DualConvFn.apply(x, out[0][0], out[0][1], out[1][0], out[1][1])
+  return _trace('conv', spec1['scope'], y1), _trace('conv', spec2['scope'], y2)
+
+
 class _StemConvFn(torch.autograd.Function):
   """Small-Cin convolution (image stem): explicit im2col to a K-padded matrix + GEMM."""
 
@@ -590,7 +656,7 @@ def dense(x, units, scope='fc', use_bias=False, initializer=None, regularize=Tru
 class _BatchNormFn(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, x, film, bn, training, relu, vs):
+  def forward(ctx, x, film, bn, training, relu, vs, passthrough=False):
     c = x.shape[-1]
     rows = x.numel() // c
     st = _stream()
@@ -614,10 +680,14 @@ class _BatchNormFn(torch.autograd.Function):
     _lib.call('t2r_bn_apply', _p(x), _p(y), rows, c, _p(scale), _p(shift), _p(film), rows_per_image,
               1 if relu else 0, st)
     ctx.bn, ctx.relu, ctx.training, ctx.vs = bn, relu, training, vs
+    if passthrough:
+      # `x` is also consumed elsewhere (the residual branch): returning it as a second output routes
+      # that branch's gradient into THIS backward, where the kernel adds it for free (dres).
+      return y, x.view_as(x)
     return y
 
   @staticmethod
-  def backward(ctx, dy):
+  def backward(ctx, dy, dpass=None):
     if not ctx.training:
       raise _lib.T2RError('backward through inference-mode batch norm is not supported')
     x, mean, invstd, scale, shift, film = ctx.saved_tensors
@@ -633,13 +703,16 @@ class _BatchNormFn(torch.autograd.Function):
     gamma = bn['gamma']
     dgamma = gamma.grad if (gamma is not None and gamma.trainable) else ctx.vs.scratch('bn_dgamma', 4096, F32)
     dbeta = bn['beta'].grad if bn['beta'].trainable else ctx.vs.scratch('bn_dbeta', 4096, F32)
-    _lib.call('t2r_bn_backward', _p(dy), _p(x), None, _p(dx), rows, c, _p(gamma.data if gamma is not None else None),
-              _p(mean), _p(invstd), _p(scale), _p(shift), 1 if ctx.relu else 0, _p(red), _p(dgamma), _p(dbeta), st)
-    return dx, None, None, None, None, None
+    if dpass is not None:
+      dpass = dpass.contiguous()
+    _lib.call('t2r_bn_backward', _p(dy), _p(x), _p(dpass), _p(dx), rows, c,
+              _p(gamma.data if gamma is not None else None), _p(mean), _p(invstd), _p(scale), _p(shift),
+              1 if ctx.relu else 0, _p(red), _p(dgamma), _p(dbeta), st)
+    return dx, None, None, None, None, None, None
 
 
 def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=0.997, eps=1e-5,
-               film=None, trainable=True):
+               film=None, trainable=True, passthrough=False):
   """slim.batch_norm / tf.layers.batch_normalization(fused=True) followed by an optional ReLU."""
   _require_cuda(x, 'batch_norm')
   vs = current_store()
@@ -658,6 +731,9 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
     for k in ('gamma', 'beta'):
       if bn[k] is not None and bn[k].grad is None:
         bn[k].grad = torch.zeros(bn[k].shape, dtype=F32, device=x.device)
+  if passthrough:
+    y, x_pass = _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs, True)
+    return _trace('bn', scope, y), x_pass
   return _trace('bn', scope, _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs))
 
 

@@ -1,0 +1,162 @@
+"""GPU parity of the ResNet v2 tower (layers/film_resnet_model.py) and of the ResNet-50 Q-critic
+composition against the oracle restatement (oracle/resnet.py), on identical weights / inputs.
+
+Inference mode (moving statistics) is well conditioned and asserted tightly against the
+bf16-storage oracle.  The training step uses the conditioning-relative criterion explained in
+tests/test_qtopt_networks_gpu.py (random-init BN-ReLU nets amplify rounding differences)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+COND_FACTOR, GRAD_FLOOR = 1.5, 0.05
+
+
+def _rel_l2(a, b):
+  a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+  return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+def _images(b, size, seed):
+  rng = np.random.RandomState(seed)
+  yy, xx = np.mgrid[0:size, 0:size].astype(np.float32) / size
+  img = np.zeros((b, size, size, 3), np.float32)
+  for i in range(b):
+    img[i] = rng.uniform(0.1, 0.9, size=(1, 1, 3))
+    for _ in range(5):
+      cy, cx, r = rng.uniform(0, 1, 3) * [1, 1, 0.3] + [0, 0, 0.05]
+      m = np.exp(-((yy - cy)**2 + (xx - cx)**2) / (2 * r * r))[..., None]
+      img[i] = img[i] * (1 - m) + rng.uniform(0, 1, 3) * m
+  return np.clip(img + rng.uniform(-.03, .03, img.shape), 0, 1).astype(np.float32)
+
+
+def _oracle_variables(img, grasp, resnet_size, seed):
+  from oracle import resnet as oracle
+  variables = {}
+  with torch.no_grad():
+    oracle.critic(variables, torch.from_numpy(img[:2]), torch.from_numpy(grasp[:2]), False, resnet_size=resnet_size,
+                  rng=np.random.RandomState(seed))
+  rng = np.random.RandomState(seed + 1)
+  for k in list(variables):
+    v = variables[k]
+    if k.endswith('gamma'):
+      variables[k] = (1 + 0.2 * torch.from_numpy(rng.randn(*v.shape).astype(np.float32)))
+    elif k.endswith('beta'):
+      variables[k] = 0.1 * torch.from_numpy(rng.randn(*v.shape).astype(np.float32))
+    elif k.endswith('moving_variance'):
+      variables[k] = torch.from_numpy(rng.uniform(0.5, 1.5, v.shape).astype(np.float32))
+    elif k.endswith('moving_mean'):
+      variables[k] = 0.1 * torch.from_numpy(rng.randn(*v.shape).astype(np.float32))
+    elif k.endswith('/weights'):
+      variables[k] = v * 8.0
+  return variables
+
+
+def _engine(img_t, grasp_t, variables, resnet_size):
+  from tensor2robot_b200 import nn
+  from tensor2robot_b200.research.qtopt import resnet_critic
+  vs = nn.VariableStore('cuda', seed=2)
+  net = resnet_critic.ResNet50QCritic(resnet_size=resnet_size)
+  with torch.no_grad(), nn.variable_store(vs):
+    net.model((None, img_t[:2]), grasp_t[:2], is_training=False)
+  vs.finalize()
+  assert sorted(vs.export_tf().keys()) == sorted(variables.keys())      # identical reference variable names
+  vs.import_tf({k: v.numpy() for k, v in variables.items()})
+  return vs, net
+
+
+@pytest.mark.parametrize('resnet_size', [50, 18])
+def test_resnet_critic_inference_matches_oracle(resnet_size):
+  from oracle import resnet as oracle, tf_ops
+  from tensor2robot_b200 import nn
+  b, a, size = 2, 8, 96
+  img = _images(b, size, 0)
+  grasp = np.random.RandomState(1).uniform(-1, 1, (b, a, 10)).astype(np.float32)
+  variables = _oracle_variables(img, grasp[:, 0], resnet_size, 3)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  grasp_t = torch.from_numpy(grasp).cuda()
+  vs, net = _engine(img_t, grasp_t[:, 0], variables, resnet_size)
+  with torch.no_grad(), nn.variable_store(vs):
+    logits, ep = net.model((None, img_t), grasp_t, is_training=False)
+  q = ep['predictions'].float().cpu().numpy()
+  assert q.shape == (b, a)
+  res = {}
+  for name, storage in (('bf16', torch.bfloat16), ('fp32', None)):
+    tf_ops.STORAGE_DTYPE = storage
+    try:
+      ep_o = {}
+      with torch.no_grad():
+        lo = oracle.critic(dict(variables), img_t.float().cpu(), torch.from_numpy(grasp), False, resnet_size=resnet_size,
+                           end_points=ep_o)
+      res[name] = (lo.numpy().reshape(-1), ep_o['predictions'].numpy())
+    finally:
+      tf_ops.STORAGE_DTYPE = None
+  le = logits.float().cpu().numpy().reshape(-1)
+  print('resnet%d logits engine %s\n         bf16 oracle %s' % (resnet_size, le[:4], res['bf16'][0][:4]))
+  print('rel_l2(logits) vs bf16-storage oracle %.3e, vs fp32 oracle %.3e; max|dq| %.3e / %.3e' % (
+      _rel_l2(le, res['bf16'][0]), _rel_l2(le, res['fp32'][0]), np.abs(q - res['bf16'][1]).max(),
+      np.abs(q - res['fp32'][1]).max()))
+  assert _rel_l2(le, res['bf16'][0]) < 2e-2
+  assert np.abs(q - res['bf16'][1]).max() < 1e-2
+  assert np.abs(q - res['fp32'][1]).max() < 2e-2
+
+
+def test_resnet50_critic_train_step_matches_oracle():
+  from oracle import resnet as oracle, tf_ops
+  from tensor2robot_b200 import nn
+  b, size = 8, 96
+  img = _images(b, size, 5)
+  rng = np.random.RandomState(6)
+  grasp = rng.uniform(-1, 1, (b, 10)).astype(np.float32)
+  reward = (rng.uniform(size=(b, 1)) < 0.4).astype(np.float32)
+  variables = _oracle_variables(img, grasp, 50, 7)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  grasp_t, reward_t = torch.from_numpy(grasp).cuda(), torch.from_numpy(reward).cuda()
+  vs, net = _engine(img_t, grasp_t, variables, 50)
+  with nn.variable_store(vs):
+    logits, _ = net.model((None, img_t), grasp_t, is_training=True)
+    loss, q = nn.sigmoid_log_loss(logits, reward_t)
+    vs.zero_grad()
+    loss.backward()
+  torch.cuda.synchronize()
+  grads = vs.export_tf_grads()
+  new_vars = vs.export_tf()
+
+  def oracle_step(storage):
+    tf_ops.STORAGE_DTYPE = storage
+    try:
+      ov = {k: v.clone().requires_grad_(not k.endswith(('moving_mean', 'moving_variance'))) for k, v in variables.items()}
+      updates = {}
+      lo = oracle.critic(ov, img_t.float().cpu(), torch.from_numpy(grasp), True, updates=updates)
+      qo = torch.sigmoid(lo)
+      l = tf_ops.log_loss(torch.from_numpy(reward), qo)
+      l.backward()
+    finally:
+      tf_ops.STORAGE_DTYPE = None
+    return ov, updates, qo.detach().numpy().reshape(-1), float(l.detach())
+
+  ov, updates, q_b, loss_b = oracle_step(torch.bfloat16)
+  ov_f, _, q_f, loss_f = oracle_step(None)
+  q_e = q.float().cpu().numpy().reshape(-1)
+  err_b, cond_q = np.abs(q_e - q_b).max(), np.abs(q_b - q_f).max()
+  print('loss engine %.5f bf16-oracle %.5f fp32-oracle %.5f; max|dq| engine-vs-bf16 %.3e, bf16-vs-fp32 %.3e' % (
+      float(loss.detach()), loss_b, loss_f, err_b, cond_q))
+  failures, worst = [], 0.0
+  gmax = max(float(v.grad.norm()) for v in ov.values() if v.grad is not None)
+  for k, g in grads.items():
+    go = ov[k].grad
+    if go is None or float(go.norm()) < 1e-4 * gmax:
+      continue
+    # tensors whose true gradient nearly cancels (e.g. the logit bias = sum(q - y)/n) are measured
+    # against 1 % of the largest gradient norm instead of their own tiny norm
+    den = max(float(go.norm()), 1e-2 * gmax)
+    e = float(np.linalg.norm(np.asarray(g, np.float64) - go.numpy())) / den
+    cond = float((ov_f[k].grad - go).norm()) / den
+    worst = max(worst, e)
+    if not e < COND_FACTOR * cond + GRAD_FLOOR:
+      failures.append((k, e, cond))
+  print('worst gradient rel_l2 vs bf16-storage oracle: %.3e over %d tensors' % (worst, len(grads)))
+  for k, u in updates.items():
+    assert _rel_l2(new_vars[k], u.numpy()) < 3e-2, k
+  assert err_b < COND_FACTOR * cond_q + 2e-3
+  assert not failures, failures[:5]
