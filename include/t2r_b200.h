@@ -84,6 +84,21 @@ int32_t t2r_pack_weights(const float* w, void* w_fprop, void* w_dgrad, int32_t C
 int32_t t2r_im2col_small_cin(const T2RConvDesc* d, const void* x, void* a, int32_t Kpad,
                              void* stream);
 
+/* Stem convolution (Cin = 3) WITHOUT im2col: the image lives in a zero-padded NHWC4 bf16 buffer
+ * x4p[N][Hp][Wp][4] (channel 3 = 0; logical pixel (ih,iw) at (ih+pad_top, iw+pad_left); Wp >=
+ * stride*(Wo-1)+16, Hp >= stride*(Ho-1)+KH).  Overlapping-window TMA maps deliver, per filter row,
+ * the 64 contiguous values (16 pixels x 4 channels) under each output pixel, so the weights are
+ * stored as w_stem bf16 [Cout][KH][16][4] (zero where kw >= KW or c == 3).  Same reference call sites
+ * as t2r_im2col_small_cin. */
+int32_t t2r_pad_nhwc3_c4(const void* x_nhwc3, void* x4p, int32_t N, int32_t H, int32_t W, int32_t Hp,
+                         int32_t Wp, int32_t pad_top, int32_t pad_left, void* stream);
+int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, int32_t Hp, int32_t Wp,
+                            const void* w_stem, const float* bias, void* y, void* stream);
+int32_t t2r_stem_conv_wgrad(const T2RConvDesc* d, const void* x4p, int32_t Hp, int32_t Wp, const void* dy,
+                            float* dw_stem, void* stream);
+/* Clears the padded slots of dw_stem fp32 [Cout][KH][16][4] after t2r_stem_conv_wgrad. */
+int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, void* stream);
+
 /* ---- fp32 CUDA-core GEMM for the tiny action-context / logit layers -------------------- */
 /* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, op = transpose if flag set.
  * Replaces slim.fully_connected on grasp params and logits (networks.py:488-503,566-573). */

@@ -53,6 +53,10 @@ _PROTOS = {
     't2r_conv2d_wgrad': (_I32, [_CD, _P, _P, _P, _P]),
     't2r_pack_weights': (_I32, [_P, _P, _P, _I32, _I32, _I32, _P]),
     't2r_im2col_small_cin': (_I32, [_CD, _P, _P, _I32, _P]),
+    't2r_pad_nhwc3_c4': (_I32, [_P, _P] + [_I32] * 7 + [_P]),
+    't2r_stem_conv_fprop': (_I32, [_CD, _P, _I32, _I32, _P, _P, _P, _P]),
+    't2r_stem_conv_wgrad': (_I32, [_CD, _P, _I32, _I32, _P, _P, _P]),
+    't2r_stem_mask_grad': (_I32, [_P, _I32, _I32, _I32, _P]),
     't2r_sgemm': (_I32, [_I32, _I32, _I32, _I32, _I32, _F, _P, _I32, _P, _I32, _F, _P, _I32, _P]),
     't2r_bias_add_f32': (_I32, [_P, _P, _I64, _I32, _P]),
     't2r_colsum_f32': (_I32, [_P, _P, _I64, _I32, _P]),

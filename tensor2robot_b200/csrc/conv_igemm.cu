@@ -504,3 +504,66 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
     }
   return T2R_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Stem convolution (Cin = 3) without im2col.
+//
+// The image is held as a zero-padded NHWC4 buffer x4p[N][Hp][Wp][4] (channel 3 = 0, logical pixel
+// (ih, iw) at (ih + pad_top, iw + pad_left)).  For one filter row kh, the K slice of output pixel
+// (oh, ow) is the 64 *contiguous* bf16 values x4p[n, s*oh + kh, s*ow : s*ow + 16, 0:4]: 16 pixels x
+// 4 channels, of which the first KW pixels x 3 channels carry non-zero weights.  A TMA tensor map
+// with OVERLAPPING windows (dim1 = ow with a byte stride of s*8, smaller than the 128-byte inner
+// extent) delivers exactly that tile, so the tap-table kernel runs unchanged with KH "taps" of one
+// 64-wide chunk each.  K is padded 147 -> 448 (7x7) / 108 -> 384 (6x6): the stem is ~3 % of the
+// model's FLOPs and this removes the 10.9 GB im2col matrix and two HBM passes over it.
+namespace t2r {
+int make_stem_maps(CUtensorMap* maps, const void* x4p, int N, int Hp, int Wp, int stride, int Ho, int Wo, int TW,
+                   int TH) {
+  const char* base = static_cast<const char*>(x4p);
+  for (int ph = 0; ph < stride; ++ph) {
+    const int rows = (Hp - ph + stride - 1) / stride;
+    uint64_t dims[4] = {64, uint64_t(Wo), uint64_t(std::max(rows, 1)), uint64_t(N)};
+    uint64_t strides[3] = {uint64_t(stride) * 8, uint64_t(stride) * Wp * 8, uint64_t(Hp) * Wp * 8};
+    uint32_t box[4] = {64, uint32_t(TW), uint32_t(TH), 1};
+    if (encode_tmap_bf16(&maps[ph], base + size_t(ph) * Wp * 8, 4, dims, strides, box) != 0) return -1;
+  }
+  for (int i = stride; i < 4; ++i) maps[i] = maps[0];
+  (void)Ho;
+  return 0;
+}
+}  // namespace t2r
+
+extern "C" int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, int32_t Hp, int32_t Wp,
+                                       const void* w_stem, const float* bias, void* y, void* stream) {
+  T2R_CHECK_ARG(d && d->struct_size == sizeof(T2RConvDesc) && x4p && w_stem && y, "stem_conv_fprop: bad args");
+  T2R_CHECK_ARG(d->Cin == 3 && d->KW <= 16 && d->KH <= kMaxTaps && d->Cout % 64 == 0 && d->stride >= 1 &&
+                    d->stride <= 2, "stem_conv_fprop: unsupported geometry");
+  T2R_CHECK_ARG(Wp >= d->stride * (d->Wo - 1) + 16 && Hp >= d->stride * (d->Ho - 1) + d->KH,
+                "stem_conv_fprop: padded image %dx%d too small", Hp, Wp);
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  pick_tile(d->Ho, d->Wo, 128, &p.TW, &p.TH);
+  if (make_stem_maps(p.tmap_a, x4p, d->N, Hp, Wp, d->stride, d->Ho, d->Wo, p.TW, p.TH) != 0) return T2R_ERR_CUDA;
+  const int block_n = pick_block_n(d->Cout);
+  const uint64_t Ktot = uint64_t(d->KH) * 64;
+  uint64_t dims[2] = {Ktot, uint64_t(d->Cout)};
+  uint64_t strides[1] = {Ktot * 2};
+  uint32_t box[2] = {64, uint32_t(block_n)};
+  if (encode_tmap_bf16(&p.tmap_b, w_stem, 2, dims, strides, box) != 0) return T2R_ERR_CUDA;
+  p.chunks_per_tap = 1;
+  for (int kh = 0; kh < d->KH; ++kh) {
+    p.taps[kh].map = int8_t(kh % d->stride);
+    p.taps[kh].dh = int8_t(kh / d->stride);
+    p.taps[kh].dw = 0;
+    p.taps[kh].kchunk0 = kh;
+  }
+  p.n_taps = d->KH;
+  p.tiles_w = int(ceil_div(d->Wo, p.TW));
+  p.tiles_h = int(ceil_div(d->Ho, p.TH));
+  p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
+  p.os_w = d->Cout;
+  p.os_h = (long long)d->Wo * d->Cout;
+  p.os_n = (long long)d->Ho * d->Wo * d->Cout;
+  p.out = y; p.bias = bias; p.flags = bias ? T2R_EPI_BIAS : 0;
+  return dispatch_igemm(p, block_n, static_cast<cudaStream_t>(stream));
+}

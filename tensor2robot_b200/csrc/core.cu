@@ -384,3 +384,53 @@ extern "C" int32_t t2r_sumsq_f32(const float* x, float* out, int64_t n, float sc
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
+
+namespace t2r {
+// x bf16 [N,H,W,3] -> interior of the zero-padded x4p bf16 [N,Hp,Wp,4] (channel 3 = 0).  The border
+// of x4p is never written: the caller zeroes the buffer once and reuses it.
+__global__ void __launch_bounds__(256) pad_nhwc3_c4_kernel(const unsigned short* __restrict__ x,
+                                                           uint2* __restrict__ x4p, int N, int H, int W, int Hp,
+                                                           int Wp, int pad_top, int pad_left) {
+  const long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = int(i % W);
+    const long long r = i / W;
+    const int h = int(r % H);
+    const int n = int(r / H);
+    const unsigned short* px = x + i * 3;
+    uint2 o;
+    o.x = uint32_t(px[0]) | (uint32_t(px[1]) << 16);
+    o.y = uint32_t(px[2]);
+    x4p[((long long)n * Hp + h + pad_top) * Wp + w + pad_left] = o;
+  }
+}
+
+// Clears the padded slots of a stem weight gradient [Cout][KH][16 pixels][4 channels].
+__global__ void stem_mask_grad_kernel(float* dw, long long total, int KW) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int slot = int(i & 63);
+    if ((slot >> 2) >= KW || (slot & 3) == 3) dw[i] = 0.f;
+  }
+}
+}  // namespace t2r
+
+extern "C" int32_t t2r_pad_nhwc3_c4(const void* x, void* x4p, int32_t N, int32_t H, int32_t W, int32_t Hp,
+                                    int32_t Wp, int32_t pad_top, int32_t pad_left, void* stream) {
+  T2R_CHECK_ARG(x && x4p && N > 0 && H + pad_top <= Hp && W + pad_left <= Wp, "pad_nhwc3_c4: bad args");
+  const long long total = (long long)N * H * W;
+  t2r::pad_nhwc3_c4_kernel<<<t2r::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned short*>(x), static_cast<uint2*>(x4p), N, H, W, Hp, Wp, pad_top, pad_left);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, void* stream) {
+  T2R_CHECK_ARG(dw_stem && Cout > 0 && KH > 0 && KW > 0 && KW <= 16, "stem_mask_grad: bad args");
+  const long long total = (long long)Cout * KH * 64;
+  t2r::stem_mask_grad_kernel<<<t2r::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_stem, total,
+                                                                                                  KW);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}

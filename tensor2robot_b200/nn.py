@@ -526,26 +526,34 @@ def conv2d_pair(x, spec1, spec2):
 
 
 class _StemConvFn(torch.autograd.Function):
-  """Small-Cin convolution (image stem): explicit im2col to a K-padded matrix + GEMM."""
+  """Small-Cin convolution (image stem) without im2col: the bf16 NHWC3 image is repacked into a
+  persistent zero-padded NHWC4 buffer and read through overlapping-window TMA maps
+  (t2r_stem_conv_fprop / _wgrad).  Weights live as [Cout, 1, 1, KH*64] = [Cout][kh][16 px][4 ch]."""
 
   @staticmethod
-  def forward(ctx, x, anchor, var, bias_var, geom, kpad):
+  def _padded(vs, x, geom):
+    kh, kw, stride, ho, wo, pt, pl = geom
+    n, h, w, _ = x.shape
+    hp = max(h + pt, stride * (ho - 1) + kh)
+    wp = max(w + pl, stride * (wo - 1) + 16)
+    wp = (wp + 1) // 2 * 2                       # row pitch multiple of 16 bytes
+    buf = vs.scratch(('stem_x4p', n, hp, wp), n * hp * wp * 4, BF16)   # zero-initialised once
+    _lib.call('t2r_pad_nhwc3_c4', _p(x), _p(buf), n, h, w, hp, wp, pt, pl, _stream())
+    return buf, hp, wp
+
+  @staticmethod
+  def forward(ctx, x, anchor, var, bias_var, geom, vs):
     n, h, w, cin = x.shape
     cout = var.shape[0]
     kh, kw, stride, ho, wo, pt, pl = geom
     d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo)
-    st = _stream()
-    a = torch.empty((n * ho * wo, kpad), dtype=BF16, device=x.device)
-    _lib.call('t2r_im2col_small_cin', C.byref(d), _p(x), _p(a), kpad, st)
-    g = _conv_desc(1, 1, n * ho * wo, kpad, cout, 1, 1, 1, 0, 0, 1, n * ho * wo,
-                   _lib.T2R_EPI_BIAS if bias_var is not None else 0)
+    x4p, hp, wp = _StemConvFn._padded(vs, x, geom)
     y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
     with _prof('fprop', d):   # algorithmic flops of the real (unpadded) convolution
-      _lib.call('t2r_conv2d_fprop', C.byref(g), _p(a), _p(var.bf16),
-                _p(bias_var.data if bias_var is not None else None), None, _p(y), st)
-    ctx.var, ctx.bias_var, ctx.desc, ctx.gdesc, ctx.kpad = var, bias_var, d, g, kpad
-    # The im2col matrix is recomputed in backward instead of being kept alive (it is ~50x the image).
-    ctx.save_for_backward(x)
+      _lib.call('t2r_stem_conv_fprop', C.byref(d), _p(x4p), hp, wp, _p(var.bf16),
+                _p(bias_var.data if bias_var is not None else None), _p(y), _stream())
+    ctx.var, ctx.bias_var, ctx.desc, ctx.geom, ctx.vs = var, bias_var, d, geom, vs
+    ctx.save_for_backward(x)   # the padded copy is rebuilt in backward (0.3 ms) rather than kept alive
     return y
 
   @staticmethod
@@ -558,10 +566,11 @@ class _StemConvFn(torch.autograd.Function):
       ws = torch.empty(2 * dy.shape[-1], dtype=torch.float64, device=dy.device)
       _lib.call('t2r_colsum_bf16', _p(dy), rows, dy.shape[-1], _p(ws), _p(ctx.bias_var.grad), st)
     if ctx.var.trainable:
-      a = torch.empty((ctx.gdesc.W, ctx.kpad), dtype=BF16, device=x.device)
-      _lib.call('t2r_im2col_small_cin', C.byref(ctx.desc), _p(x), _p(a), ctx.kpad, st)
+      kh, kw = ctx.geom[0], ctx.geom[1]
+      x4p, hp, wp = _StemConvFn._padded(ctx.vs, x, ctx.geom)
       with _prof('wgrad', ctx.desc):
-        _lib.call('t2r_conv2d_wgrad', C.byref(ctx.gdesc), _p(a), _p(dy), _p(ctx.var.grad), st)
+        _lib.call('t2r_stem_conv_wgrad', C.byref(ctx.desc), _p(x4p), hp, wp, _p(dy), _p(ctx.var.grad), st)
+      _lib.call('t2r_stem_mask_grad', _p(ctx.var.grad), ctx.var.shape[0], kh, kw, st)
     if ctx.needs_input_grad[0]:
       raise _lib.T2RError('stem convolution %s has no data gradient (image inputs are leaves)' % ctx.var.name)
     return None, None, None, None, None, None
@@ -577,7 +586,9 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   n, h, w, cin = x.shape
   ho, wo, pt, pl = conv_geometry(h, w, kh, kw, stride, padding)
   small = cin % 64 != 0
-  kpad = (kh * kw * cin + 63) // 64 * 64 if small else 0
+  if small and (cin != 3 or kw > 16 or stride > 2):
+    raise _lib.T2RError('conv2d: Cin=%d is supported only as the 3-channel image stem' % cin)
+  kpad = kh * 64 if small else 0   # [kh][16 pixels][4 channels]
   with vs.scope(scope):
     if small:
       # stored as [Cout, 1, 1, Kpad] (K-padded OHWI, flattened taps); TF layout handled by to_tf
@@ -594,32 +605,35 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   if not vs.finalized:
     _ensure_bf16(wv)
   if small:
-    return _trace('conv', scope, _StemConvFn.apply(x, vs.anchor, wv, bv, (kh, kw, stride, ho, wo, pt, pl), kpad))
+    return _trace('conv', scope, _StemConvFn.apply(x.contiguous(), vs.anchor, wv, bv,
+                                                   (kh, kw, stride, ho, wo, pt, pl), vs))
   return _trace('conv', scope, _Conv2dFn.apply(x, residual, wv, bv, (stride, ho, wo, pt, pl), relu, out_f32))
+
+
+def _stem_pack(w_ohwi):
+  """[Cout, KH, KW, 3] -> [Cout, KH*64] in the stem layout [kh][16 pixels][4 channels]."""
+  cout, kh, kw, cin = w_ohwi.shape
+  out = np.zeros((cout, kh, 16, 4), np.float32)
+  out[:, :, :kw, :cin] = w_ohwi
+  return out.reshape(cout, kh * 64)
 
 
 def _padded_init(init, filters, kh, kw, cin, kpad):
   def f(shape, rng):
-    w = init((filters, kh, kw, cin), rng).reshape(filters, kh * kw * cin)
-    out = np.zeros((filters, kpad), np.float32)
-    out[:, :kh * kw * cin] = w
-    return out.reshape(shape)
+    return _stem_pack(init((filters, kh, kw, cin), rng)).reshape(shape)
   return f
 
 
 def _install_stem_tf(v):
   kh, kw, cin = v.stem_geom
-  k = kh * kw * cin
 
   def to_tf():
-    a = v.data.detach().float().cpu().numpy().reshape(v.shape[0], -1)[:, :k]
-    return np.ascontiguousarray(a.reshape(v.shape[0], kh, kw, cin).transpose(1, 2, 3, 0))
+    a = v.data.detach().float().cpu().numpy().reshape(v.shape[0], kh, 16, 4)[:, :, :kw, :cin]
+    return np.ascontiguousarray(a.transpose(1, 2, 3, 0))          # HWIO
 
   def from_tf(a):
-    a = np.asarray(a, np.float32).transpose(3, 0, 1, 2).reshape(v.shape[0], k)
-    full = np.zeros((v.shape[0], v.shape[-1]), np.float32)
-    full[:, :k] = a
-    v.data.copy_(torch.from_numpy(full.reshape(v.shape)).to(v.data.device))
+    a = np.asarray(a, np.float32).transpose(3, 0, 1, 2)            # OHWI
+    v.data.copy_(torch.from_numpy(_stem_pack(a).reshape(v.shape)).to(v.data.device))
   v.to_tf, v.from_tf = to_tf, from_tf
 
 
