@@ -53,7 +53,8 @@ struct IgemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: all powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStoreStageBytes = 8 * 2048;   // one 32 rows x 64 B tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStoreStageBytes;
 };
 
 template <int BLOCK_N>
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 4);
+  const uint32_t store_stage_base = bar_base + 256u;
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
@@ -195,6 +197,18 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
       const bool valid = (oh < p.Ho) && (ow < p.Wo);
       const long long pix_off = img * p.os_n + oh * p.os_h + ow * p.os_w;
       const int ch0 = nt * BLOCK_N + half * kColsPerWG;
+      // rows this lane STORES: instruction i of a chunk writes rows 8i + lane/4 of the warp's 32
+      // (4 lanes x 16 B = the row's 64 contiguous bytes), see the staging below.
+      long long roff[4];
+      bool rvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = quad * 32 + 8 * i + (lane >> 2);
+        const int rth = r / p.TW, rtw = r - rth * p.TW;
+        const int roh = (rem / p.tiles_w) * p.TH + rth, row_w = (rem % p.tiles_w) * p.TW + rtw;
+        rvalid[i] = (roh < p.Ho) && (row_w < p.Wo);
+        roff[i] = img * p.os_n + roh * p.os_h + row_w * p.os_w;
+      }
       uint4 rnext[4];
       if (has_res && valid && ch0 < p.Cout) {
         const uint4* r = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch0);
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + as * BLOCK_N + half * kColsPerWG + c * 32, v);
         tmem_ld_wait();
-        if (valid && ch < p.Cout) {
+        if (out_f32 ? (valid && ch < p.Cout) : (ch < p.Cout)) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -228,7 +242,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
               f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
             }
           }
-          if (has_res) {
+          if (has_res && valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 q = rcur[j];
@@ -248,16 +262,34 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
             for (int j = 0; j < 8; ++j)
               o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix_off + ch);
+            // bf16 output.  A thread owns one pixel row, so direct stores would hit 32 different
+            // 32-byte sectors per instruction (16 B each, row pitch = Cout*2 B).  Stage the warp's
+            // 32 rows x 64 B through a swizzled shared tile instead: every store instruction then
+            // writes 8 rows x 64 contiguous bytes (16 fully written sectors).
+            const uint32_t wb = store_stage_base + uint32_t(ew) * 2048u;
+            const uint32_t sw = (uint32_t(lane) >> 1) & 3u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              q.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-              q.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              q.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-              q.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-              o[j] = q;
+              const uint32_t q0 = pack_bf16(f[8 * j + 0], f[8 * j + 1]), q1 = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              const uint32_t q2 = pack_bf16(f[8 * j + 4], f[8 * j + 5]), q3 = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wb + uint32_t(lane) * 64u + ((uint32_t(j) ^ sw) << 4)),
+                           "r"(q0), "r"(q1), "r"(q2), "r"(q3)
+                           : "memory");
             }
+            __syncwarp();
+            const uint32_t jj = uint32_t(lane) & 3u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t r = 8u * i + (uint32_t(lane) >> 2);
+              uint4 q;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                           : "r"(wb + r * 64u + ((jj ^ ((r >> 1) & 3u)) << 4))
+                           : "memory");
+              if (rvalid[i])
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + roff[i] + ch + jj * 8) = q;
+            }
+            __syncwarp();
           }
         }
       }
