@@ -20,4 +20,22 @@ void pick_tile(int Ho, int Wo, int pixels, int* TW, int* TH);
 int make_phase_maps(CUtensorMap* maps, const void* x, int N, int H, int W, int C, int stride,
                     int TW, int TH);
 
+// Stride-1 KxK convolution through the shared-memory halo kernel (conv_halo.cu).
+struct HaloRequest {
+  const void* x;       // [N,H,W,C] bf16, the tensor the taps slide over
+  int N, H, W, C;
+  const void* w;       // [Cout][Ktot] bf16, K-major
+  uint64_t Ktot;
+  ConvTap taps[kMaxTaps];
+  int n_taps;
+  int Ho, Wo, Cout;    // output iteration space and its channel count
+  long long os_n, os_h, os_w;
+  void* out;
+  const void* residual;
+  const float* bias;
+  int flags;
+};
+bool conv_halo_eligible(int stride, int n_taps, int k_channels, int n_channels);
+int conv_halo_launch(const HaloRequest& r, cudaStream_t stream);
+
 }  // namespace t2r

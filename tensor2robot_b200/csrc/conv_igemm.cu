@@ -462,6 +462,18 @@ extern "C" int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const v
       p.taps[t].kchunk0 = t * p.chunks_per_tap;
     }
   p.n_taps = t;
+  if (conv_halo_eligible(d->stride, t, d->Cin, d->Cout)) {
+    HaloRequest r;
+    memset(&r, 0, sizeof(r));
+    r.x = x; r.N = d->N; r.H = d->H; r.W = d->W; r.C = d->Cin;
+    r.w = w; r.Ktot = Ktot;
+    memcpy(r.taps, p.taps, sizeof(r.taps));
+    r.n_taps = t;
+    r.Ho = d->Ho; r.Wo = d->Wo; r.Cout = d->Cout;
+    r.os_w = d->Cout; r.os_h = (long long)d->Wo * d->Cout; r.os_n = (long long)d->Ho * d->Wo * d->Cout;
+    r.out = y; r.residual = residual; r.bias = bias; r.flags = d->flags;
+    return conv_halo_launch(r, static_cast<cudaStream_t>(stream));
+  }
   p.tiles_w = int(ceil_div(d->Wo, p.TW));
   p.tiles_h = int(ceil_div(d->Ho, p.TH));
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
@@ -503,6 +515,19 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
       }
       p.n_taps = t;
       char* out = static_cast<char*>(dx) + (size_t(ph) * d->W + pw) * d->Cin * 2;
+      if (conv_halo_eligible(s, t, d->Cout, d->Cin)) {
+        HaloRequest r;
+        memset(&r, 0, sizeof(r));
+        r.x = dy; r.N = d->N; r.H = d->Ho; r.W = d->Wo; r.C = d->Cout;
+        r.w = w_dgrad; r.Ktot = uint64_t(taps_total) * d->Cout;
+        memcpy(r.taps, p.taps, sizeof(r.taps));
+        r.n_taps = t;
+        r.Ho = Hv; r.Wo = Wv; r.Cout = d->Cin;
+        r.os_w = d->Cin; r.os_h = (long long)d->W * d->Cin; r.os_n = (long long)d->H * d->W * d->Cin;
+        r.out = out; r.residual = accumulate ? out : nullptr; r.flags = accumulate ? T2R_EPI_RESIDUAL : 0;
+        if (int rc = conv_halo_launch(r, st)) return rc;
+        continue;
+      }
       pick_tile(Hv, Wv, 128, &p.TW, &p.TH);
       if (make_phase_maps(p.tmap_a, dy, d->N, d->Ho, d->Wo, d->Cout, 1, p.TW, p.TH) != 0)
         return T2R_ERR_CUDA;

@@ -14,9 +14,14 @@
 //   D: [128 x BLOCK_N] fp32 per "group" in TMEM; a CTA owns up to 512/BLOCK_N groups and a
 //      range of pixel tiles (split-K), and flushes with fp32 atomics (red.global.add.f32).
 //
+// The dY tiles of a pixel tile are shared by all groups of the CTA, so they travel through their
+// own (shallow) ring and are loaded once per pixel tile; the X tiles stream through a deeper ring.
+// (L2 -> SMEM traffic per MMA drops from 12 KB to 8 KB at BLOCK_N = 256, 8 -> 5 KB at 128.)
+//
 // Replaces the autodiff filter gradients of slim.conv2d / tf.layers.conv2d
 // (research/qtopt/networks.py:443-591, layers/film_resnet_model.py:89-105).
 #include <algorithm>
+#include <cstdlib>
 
 #include "conv_common.cuh"
 
@@ -45,10 +50,12 @@ template <int BLOCK_N>
 struct WgradCfg {
   static constexpr int kTileBytes = 64 * 128;  // 64 pixels x 64 channels bf16
   static constexpr int kNB = BLOCK_N / 64;
-  static constexpr int kStageBytes = (2 + kNB) * kTileBytes;
-  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kXBytes = 2 * kTileBytes;     // one group's A operand
+  static constexpr int kDyBytes = kNB * kTileBytes;  // the pixel tile's B operand
+  static constexpr int kXStages = BLOCK_N == 64 ? 10 : (BLOCK_N == 128 ? 8 : 6);
+  static constexpr int kDyStages = 3;
   static constexpr int kMaxGroups = 512 / BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kXStages * kXBytes + kDyStages * kDyBytes + 1024 + 256;
 };
 
 template <int BLOCK_N>
@@ -56,11 +63,14 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
   using Cfg = WgradCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t dy_base = smem_base + Cfg::kXStages * Cfg::kXBytes;
+  const uint32_t bar_base = dy_base + Cfg::kDyStages * Cfg::kDyBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::kStages);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kXStages + s); };
+  auto dfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kXStages + s); };
+  auto dempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kXStages + Cfg::kDyStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::kXStages + 2 * Cfg::kDyStages);
+  const uint32_t tmem_ptr_addr = tfull_bar + 8u;
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
@@ -72,9 +82,13 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmap_dy);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < Cfg::kXStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < Cfg::kDyStages; ++s) {
+      mbar_init(dfull_bar(s), 1);
+      mbar_init(dempty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
@@ -102,17 +116,27 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ds = 0;
+      uint32_t phase = 0, dphase = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         const int img = pt / tiles_per_img;
         const int rem = pt - img * tiles_per_img;
         const int oh0 = (rem / p.tiles_w) * p.TH;
         const int ow0 = (rem % p.tiles_w) * p.TW;
+        mbar_wait(dempty_bar(ds), dphase ^ 1u);
+        mbar_expect_tx(dfull_bar(ds), Cfg::kDyBytes);
+#pragma unroll
+        for (int j = 0; j < Cfg::kNB; ++j)
+          tma_load_4d(dy_base + ds * Cfg::kDyBytes + j * Cfg::kTileBytes, &p.tmap_dy, dfull_bar(ds), n0 + j * 64,
+                      ow0, oh0, img);
+        if (++ds == Cfg::kDyStages) {
+          ds = 0;
+          dphase ^= 1u;
+        }
         for (int g = g0; g < g1; ++g) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + stage * Cfg::kXBytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kXBytes);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             int slot = 2 * g + h;
@@ -123,11 +147,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
             tma_load_4d(sa + h * Cfg::kTileBytes, &p.tmap_x[tap.map], full_bar(stage), c * 64,
                         ow0 + tap.dw, oh0 + tap.dh, img);
           }
-#pragma unroll
-          for (int j = 0; j < Cfg::kNB; ++j)
-            tma_load_4d(sa + (2 + j) * Cfg::kTileBytes, &p.tmap_dy, full_bar(stage), n0 + j * 64,
-                        ow0, oh0, img);
-          if (++stage == Cfg::kStages) {
+          if (++stage == Cfg::kXStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -137,14 +157,15 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ds = 0;
+      uint32_t phase = 0, dphase = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(dfull_bar(ds), dphase);
+        const uint32_t sb = dy_base + ds * Cfg::kDyBytes;
         for (int g = g0; g < g1; ++g) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + 2 * Cfg::kTileBytes;
+          const uint32_t sa = smem_base + stage * Cfg::kXBytes;
           const uint32_t d_tmem = tmem_base + (g - g0) * BLOCK_N;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // 64 pixels = 4 x (K = 16)
@@ -155,10 +176,15 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
             umma_bf16(d_tmem, adesc, bdesc, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == Cfg::kStages) {
+          if (++stage == Cfg::kXStages) {
             stage = 0;
             phase ^= 1u;
           }
+        }
+        umma_commit(dempty_bar(ds));
+        if (++ds == Cfg::kDyStages) {
+          ds = 0;
+          dphase ^= 1u;
         }
       }
       umma_commit(tfull_bar);
@@ -212,8 +238,10 @@ static int launch_wgrad(WgradParams& p, cudaStream_t stream) {
   p.n_gsets = int(ceil_div(p.n_groups, p.groups_per_cta));
   p.n_chunks_n = int(ceil_div(p.Cout, BLOCK_N));
   const int base_items = p.n_gsets * p.n_chunks_n;
-  // split the pixel range so that ~2 waves of CTAs are in flight, each with >= 4 pixel tiles
-  int ks = int(ceil_div(2 * num_sms(), base_items));
+  // Split the pixel range so that the grid fills the SMs `waves` times WITHOUT spilling into a partial
+  // extra wave (one CTA per SM: a 297-CTA grid costs three rounds, not two).
+  static const int waves = std::getenv("T2R_WGRAD_WAVES") ? atoi(std::getenv("T2R_WGRAD_WAVES")) : 1;
+  int ks = std::max(1, waves * num_sms() / base_items);
   ks = std::max(1, std::min(ks, std::max(1, p.total_ptiles / 4)));
   p.ksplits = ks;
   const int grid = base_items * ks;

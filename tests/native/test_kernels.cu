@@ -245,6 +245,11 @@ static void tests_conv() {
       {"1x1 256->512 f32 out", 2, 9, 9, 256, 512, 1, 1, 1, 0, 0, 9, 9, T2R_EPI_OUT_F32},
       {"fc 4096->64 rows=70", 1, 1, 70, 4096, 64, 1, 1, 1, 0, 0, 1, 70, T2R_EPI_BIAS},
       {"3x3 s2 even 16x16 64->128", 1, 16, 16, 64, 128, 3, 3, 2, 1, 1, 8, 8, 0},
+      // shared-memory halo kernel (conv_halo.cu): streaming 5x5, two K chunks, odd tile count, big image
+      {"halo 5x5 s1 SAME 19x23 64->64", 2, 19, 23, 64, 64, 5, 5, 1, 2, 2, 19, 23, T2R_EPI_BIAS | T2R_EPI_RELU},
+      {"halo 3x3 s1 SAME 37x21 128->64", 1, 37, 21, 128, 64, 3, 3, 1, 1, 1, 37, 21, 0},
+      {"halo 3x3 s1 SAME 16x8 64->64 odd tiles", 3, 16, 8, 64, 64, 3, 3, 1, 1, 1, 16, 8, T2R_EPI_RESIDUAL},
+      {"halo 3x3 s1 SAME 118x118 64->64", 1, 118, 118, 64, 64, 3, 3, 1, 1, 1, 118, 118, 0},
   };
   for (const auto& c : cases) {
     if (g_filter && !strstr(c.name, g_filter) && !strstr("conv", g_filter)) continue;
@@ -499,7 +504,53 @@ static void test_misc() {
   }
 }
 
+// `test_kernels bench N H W Cin Cout K stride [reps] [kinds]`: time fprop / dgrad / wgrad of one
+// SAME-padded convolution at full size with CUDA events (no CPU reference).  kinds = any of "fdw".
+#define TB(expr) do { int _rc = (expr); if (_rc != 0) { printf("[FAIL] %s rc=%d: %s\n", #expr, _rc, t2r_last_error()); return 1; } } while (0)
+static int bench_conv(int argc, char** argv) {
+  if (argc < 9) { fprintf(stderr, "usage: bench N H W Cin Cout K stride [reps] [fdw]\n"); return 2; }
+  const int N = atoi(argv[2]), H = atoi(argv[3]), W = atoi(argv[4]), Cin = atoi(argv[5]), Cout = atoi(argv[6]),
+            K = atoi(argv[7]), stride = atoi(argv[8]);
+  const int reps = argc > 9 ? atoi(argv[9]) : 5;
+  const char* kinds = argc > 10 ? argv[10] : "fdw";
+  int32_t Ho, Wo, pt, pl;
+  TB(t2r_conv_same_padding(H, K, stride, &Ho, &pt));
+  TB(t2r_conv_same_padding(W, K, stride, &Wo, &pl));
+  ConvCase c{"bench", N, H, W, Cin, Cout, K, K, stride, pt, pl, Ho, Wo, 0};
+  const T2RConvDesc d = mkdesc(c);
+  const size_t nx = size_t(N) * H * W * Cin, ny = size_t(N) * Ho * Wo * Cout, nw = size_t(Cout) * K * K * Cin;
+  Dev<__nv_bfloat16> x(nx), dx(nx), y(ny), dy(ny), wf(nw), wd(nw);
+  Dev<float> w32(nw), dw(nw);
+  CK(cudaMemset(x.p, 0x3c, nx * 2)); CK(cudaMemset(dy.p, 0x3c, ny * 2));
+  w32.up(randv(nw, 0.05f, false));
+  TB(t2r_pack_weights(w32.p, wf.p, wd.p, Cout, K * K, Cin, nullptr));
+  Dev<char> flush(256u << 20);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const double flops = 2.0 * N * Ho * Wo * double(Cout) * K * K * Cin;
+  for (const char* k = kinds; *k; ++k) {
+    float best = 1e30f, sum = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+      CK(cudaMemsetAsync(flush.p, r, flush.n));  // evict L2
+      CK(cudaEventRecord(e0));
+      if (*k == 'f') TB(t2r_conv2d_fprop(&d, x.p, wf.p, nullptr, nullptr, y.p, nullptr));
+      if (*k == 'd') TB(t2r_conv2d_dgrad(&d, dy.p, wd.p, dx.p, 0, nullptr));
+      if (*k == 'w') TB(t2r_conv2d_wgrad(&d, x.p, dy.p, dw.p, nullptr));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (r == 0) continue;  // warm-up
+      best = fminf(best, ms); sum += ms;
+    }
+    printf("%c %dx%dx%dx%d->%d k%d s%d  avg %.3f ms  best %.3f ms  %.1f TFLOP/s (avg)\n", *k, N, H, W, Cin, Cout, K,
+           stride, sum / reps, best, flops / (sum / reps) * 1e-9);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "bench")) return bench_conv(argc, argv);
   if (argc > 1) g_filter = argv[1];
   int dev_count = 0;
   CK(cudaGetDeviceCount(&dev_count));
