@@ -18,7 +18,7 @@
 // weight tile (N = 64), which halves the weight traffic per pixel; when all taps' weights fit
 // (<= 9 slots of 8 KB, e.g. 3x3 64->64) they stay resident in shared memory for the whole kernel.
 //
-// Warp roles as in conv_igemm.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// Warp roles as in conv_igemm.cu: warps 0 / 2 / 3 TMA producers, warp 1 MMA issuer, warp 2 also TMEM allocator,
 // warps 4..11 epilogue (warpgroup h handles tile h of the pair).
 //
 // Replaces: slim.conv2d 3x3 / 5x5 stride 1 (research/qtopt/networks.py:443-591) and
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(hfull_bar(s), 1);
+      mbar_init(hfull_bar(s), 2);  // one arrival (+tx bytes) per halo producer
       mbar_init(hempty_bar(s), 1);
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 8);
@@ -106,9 +106,13 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const uint32_t halo_tx = uint32_t(p.HW) * p.HH * 128u;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================== TMA producers =====================
+    // A TMA load costs its whole latency per issuing warp (profiles/r01_ncu_summary.md, 3.3), so the
+    // loads are spread over three warps: warp 0 -> halo of tile 0, warp 2 -> halo of tile 1,
+    // warp 3 -> weights.
     if (lane == 0) {
+      const int pid = warp == 0 ? 0 : warp - 1;
       int hs = 0, ws = 0;
       uint32_t hph = 0, wph = 0;
       bool first = true;
@@ -116,9 +120,10 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         const int nt = s % p.n_tiles_n;
         const int pair = s / p.n_tiles_n;
         for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(hempty_bar(hs), hph ^ 1u);
-          mbar_expect_tx(hfull_bar(hs), 2u * halo_tx);
-          for (int h = 0; h < 2; ++h) {
+          if (pid < 2) {
+            const int h = pid;
+            mbar_wait(hempty_bar(hs), hph ^ 1u);
+            mbar_expect_tx(hfull_bar(hs), halo_tx);
             const int m = pair * 2 + h;
             int img = p.N, oh0 = 0, ow0 = 0;  // image index N is out of bounds: zero fill
             if (m < p.total_halves) {
@@ -128,12 +133,11 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
               ow0 = (rem % p.tiles_w) * kHaloTW;
             }
             tma_load_4d(halo_addr(hs, h), &p.tmap_a, hfull_bar(hs), c * 64, ow0 + p.org_dw, oh0 + p.org_dh, img);
-          }
-          if (++hs == 2) {
-            hs = 0;
-            hph ^= 1u;
-          }
-          if (!kResident || first) {
+            if (++hs == 2) {
+              hs = 0;
+              hph ^= 1u;
+            }
+          } else if (!kResident || first) {
             for (int t = 0; t < p.n_taps; ++t) {
               const int slot = kResident ? (c * p.n_taps + t) : ws;
               if (!kResident) mbar_wait(wempty_bar(slot), wph ^ 1u);

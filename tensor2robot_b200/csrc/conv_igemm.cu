@@ -13,7 +13,7 @@
 //   B (weights)    : BLOCK_N output channels x 64, K-major, 128B-swizzled
 //   D (accumulator): 128 lanes x BLOCK_N fp32 columns in TMEM, double buffered
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// Warp roles (384 threads): warps 0, 2, 3 = TMA producers, warp 1 = MMA issuer, warp 2 also = TMEM
 // allocator, warps 4..11 = epilogue (TMEM -> registers -> bias/residual/ReLU -> global), two
 // warpgroups splitting the BLOCK_N accumulator columns.
 //
@@ -103,10 +103,15 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   const int k_iters = p.n_taps * p.chunks_per_tap;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================== TMA producers =====================
+    // A tile load costs its full latency (~280 cycles from L2, ~640 from DRAM) per *issuing warp*, no
+    // matter how many are queued (profiles/r01_ncu_summary.md, section 3.3): one producer thread caps
+    // the fill rate at box_bytes / latency.  Three warps on three different SM sub-partitions take
+    // the k-iterations round-robin; every ring slot still has exactly one producer per use.
     if (lane == 0) {
-      int stage = 0;
+      const int pid = warp == 0 ? 0 : warp - 1;
+      int stage = 0, turn = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles_n;
@@ -118,13 +123,16 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         for (int t = 0; t < p.n_taps; ++t) {
           const ConvTap tap = p.taps[t];
           for (int c = 0; c < p.chunks_per_tap; ++c) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-            const uint32_t sb = sa + Cfg::kABytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_4d(sa, &p.tmap_a[tap.map], full_bar(stage), c * 64, ow0 + tap.dw,
-                        oh0 + tap.dh, img);
-            tma_load_2d(sb, &p.tmap_b, full_bar(stage), (tap.kchunk0 + c) * 64, nt * BLOCK_N);
+            if (turn == pid) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+              const uint32_t sb = sa + Cfg::kABytes;
+              mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_4d(sa, &p.tmap_a[tap.map], full_bar(stage), c * 64, ow0 + tap.dw,
+                          oh0 + tap.dh, img);
+              tma_load_2d(sb, &p.tmap_b, full_bar(stage), (tap.kchunk0 + c) * 64, nt * BLOCK_N);
+            }
+            if (++turn == 3) turn = 0;
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1u;

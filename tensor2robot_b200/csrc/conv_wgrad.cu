@@ -114,39 +114,49 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int n0 = nc * BLOCK_N;
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // Three producer warps (one per free SM sub-partition) take the loads round-robin: a TMA tile
+    // load costs its whole latency per issuing warp, so one thread cannot keep the ring full
+    // (profiles/r01_ncu_summary.md, section 3.3).
     if (lane == 0) {
-      int stage = 0, ds = 0;
+      const int pid = warp == 0 ? 0 : warp - 1;
+      int stage = 0, ds = 0, turn = 0, dturn = 0;
       uint32_t phase = 0, dphase = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         const int img = pt / tiles_per_img;
         const int rem = pt - img * tiles_per_img;
         const int oh0 = (rem / p.tiles_w) * p.TH;
         const int ow0 = (rem % p.tiles_w) * p.TW;
-        mbar_wait(dempty_bar(ds), dphase ^ 1u);
-        mbar_expect_tx(dfull_bar(ds), Cfg::kDyBytes);
+        if (dturn == pid) {
+          mbar_wait(dempty_bar(ds), dphase ^ 1u);
+          mbar_expect_tx(dfull_bar(ds), Cfg::kDyBytes);
 #pragma unroll
-        for (int j = 0; j < Cfg::kNB; ++j)
-          tma_load_4d(dy_base + ds * Cfg::kDyBytes + j * Cfg::kTileBytes, &p.tmap_dy, dfull_bar(ds), n0 + j * 64,
-                      ow0, oh0, img);
+          for (int j = 0; j < Cfg::kNB; ++j)
+            tma_load_4d(dy_base + ds * Cfg::kDyBytes + j * Cfg::kTileBytes, &p.tmap_dy, dfull_bar(ds), n0 + j * 64,
+                        ow0, oh0, img);
+        }
+        if (++dturn == 3) dturn = 0;
         if (++ds == Cfg::kDyStages) {
           ds = 0;
           dphase ^= 1u;
         }
         for (int g = g0; g < g1; ++g) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * Cfg::kXBytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kXBytes);
+          if (turn == pid) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * Cfg::kXBytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kXBytes);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int slot = 2 * g + h;
-            if (slot >= p.n_slots) slot = p.n_slots - 1;  // duplicate: rows are never stored
-            const int t = slot / p.chunks_per_tap;
-            const int c = slot - t * p.chunks_per_tap;
-            const ConvTap tap = p.taps[t];
-            tma_load_4d(sa + h * Cfg::kTileBytes, &p.tmap_x[tap.map], full_bar(stage), c * 64,
-                        ow0 + tap.dw, oh0 + tap.dh, img);
+            for (int h = 0; h < 2; ++h) {
+              int slot = 2 * g + h;
+              if (slot >= p.n_slots) slot = p.n_slots - 1;  // duplicate: rows are never stored
+              const int t = slot / p.chunks_per_tap;
+              const int c = slot - t * p.chunks_per_tap;
+              const ConvTap tap = p.taps[t];
+              tma_load_4d(sa + h * Cfg::kTileBytes, &p.tmap_x[tap.map], full_bar(stage), c * 64,
+                          ow0 + tap.dw, oh0 + tap.dh, img);
+            }
           }
+          if (++turn == 3) turn = 0;
           if (++stage == Cfg::kXStages) {
             stage = 0;
             phase ^= 1u;
