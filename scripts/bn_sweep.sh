@@ -1,0 +1,2 @@
+cd tests/native
+for cfg in "7129088 256" "1782272 512" "460800 1024" "7129088 64"; do timeout 120 ./test_kernels benchbn $cfg 4 | head -2; done

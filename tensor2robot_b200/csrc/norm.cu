@@ -6,6 +6,7 @@
 // layers/film_resnet_model.py:50-57: normalise with the biased batch variance, feed the
 // Bessel-corrected variance into the moving average, epsilon inside the sqrt.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -35,6 +36,8 @@ static RowPartition partition(long long rows, int C, int blocks_per_sm = 4) {
   rpb = (rpb + p.lanes_r - 1) / p.lanes_r * p.lanes_r;
   p.rows_per_block = rpb;
   p.row_blocks = int((rows + rpb - 1) / rpb);
+  static const int interleave = std::getenv("T2R_BN_INTERLEAVE") ? atoi(std::getenv("T2R_BN_INTERLEAVE")) : 1;
+  if (interleave) p.rows_per_block = -1;
   return p;
 }
 
@@ -80,10 +83,13 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__
   const int cgi = blockIdx.y * cgb + g;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cgi < cg) {
-    const long long r0 = blockIdx.x * rows_per_block;
-    const long long r1 = min(r0 + rows_per_block, rows);
+    // rows_per_block < 0: interleaved mode, the blocks sweep the tensor together in chunks of lanes_r rows
+    const bool il = rows_per_block < 0;
+    const long long r0 = il ? blockIdx.x * (long long)lanes_r : blockIdx.x * rows_per_block;
+    const long long r1 = il ? rows : min(r0 + rows_per_block, rows);
+    const long long rstep = il ? (long long)gridDim.x * lanes_r : (long long)lanes_r;
 #pragma unroll 4
-    for (long long r = r0 + rl; r < r1; r += lanes_r) {
+    for (long long r = r0 + rl; r < r1; r += rstep) {
       float f[8];
       unpack8(x[r * cg + cgi], f);
 #pragma unroll
@@ -184,10 +190,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
       sc[j] = scale[cgi * 8 + j];
       sh[j] = shift[cgi * 8 + j];
     }
-    const long long r0 = blockIdx.x * rows_per_block;
-    const long long r1 = min(r0 + rows_per_block, rows);
+    // rows_per_block < 0: interleaved mode, the blocks sweep the tensor together in chunks of lanes_r rows
+    const bool il = rows_per_block < 0;
+    const long long r0 = il ? blockIdx.x * (long long)lanes_r : blockIdx.x * rows_per_block;
+    const long long r1 = il ? rows : min(r0 + rows_per_block, rows);
+    const long long rstep = il ? (long long)gridDim.x * lanes_r : (long long)lanes_r;
 #pragma unroll 2
-    for (long long r = r0 + rl; r < r1; r += lanes_r) {
+    for (long long r = r0 + rl; r < r1; r += rstep) {
       float fx[8], fd[8];
       unpack8(x[r * cg + cgi], fx);
       unpack8(dy[r * cg + cgi], fd);
@@ -235,10 +244,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     kb[j] = -t;
     kc[j] = t * mean[c] - sc[j] * dbeta[c] * inv_rows;
   }
-  const long long r0 = blockIdx.x * rows_per_block;
-  const long long r1 = min(r0 + rows_per_block, rows);
+  // rows_per_block < 0: interleaved mode, the blocks sweep the tensor together in chunks of lanes_r rows
+  const bool il = rows_per_block < 0;
+  const long long r0 = il ? blockIdx.x * (long long)lanes_r : blockIdx.x * rows_per_block;
+  const long long r1 = il ? rows : min(r0 + rows_per_block, rows);
+  const long long rstep = il ? (long long)gridDim.x * lanes_r : (long long)lanes_r;
 #pragma unroll 2
-  for (long long r = r0 + rl; r < r1; r += lanes_r) {
+  for (long long r = r0 + rl; r < r1; r += rstep) {
     const long long i = r * cg + cgi;
     float fx[8], fd[8], fo[8];
     const uint4 qx = x[i], qd = dy[i];
@@ -278,10 +290,13 @@ __global__ void __launch_bounds__(256) bn_apply_rows_kernel(const uint4* __restr
     sc[j] = scale[cgi * 8 + j];
     sh[j] = shift[cgi * 8 + j];
   }
-  const long long r0 = blockIdx.x * rows_per_block;
-  const long long r1 = min(r0 + rows_per_block, rows);
+  // rows_per_block < 0: interleaved mode, the blocks sweep the tensor together in chunks of lanes_r rows
+  const bool il = rows_per_block < 0;
+  const long long r0 = il ? blockIdx.x * (long long)lanes_r : blockIdx.x * rows_per_block;
+  const long long r1 = il ? rows : min(r0 + rows_per_block, rows);
+  const long long rstep = il ? (long long)gridDim.x * lanes_r : (long long)lanes_r;
 #pragma unroll 4
-  for (long long r = r0 + rl; r < r1; r += lanes_r) {
+  for (long long r = r0 + rl; r < r1; r += rstep) {
     const long long i = r * cg + cgi;
     float f[8];
     unpack8(x[i], f);

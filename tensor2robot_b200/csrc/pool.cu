@@ -19,71 +19,67 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // slim.max_pool2d: padding never wins (acts as -inf); first maximum in row-major window order
 // takes the gradient (TF MaxPoolGrad tie rule).
+// One block per output row (n, oh): all index arithmetic is 32-bit and per-row invariants are
+// hoisted (the 64-bit div/mod chain of a flat grid-stride loop cost 3x the memory time).
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                           uint2* __restrict__ argmax, int N, int H, int W,
                                                           int cg, int k, int stride, int pt, int pl,
                                                           int Ho, int Wo) {
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = int(i % cg);
-    long long r = i / cg;
-    const int ow = int(r % Wo); r /= Wo;
-    const int oh = int(r % Ho);
-    const int n = int(r / Ho);
+  const int n = blockIdx.x / Ho, oh = blockIdx.x - n * Ho;
+  const int kh_lo = max(0, pt - oh * stride), kh_hi = min(k, H + pt - oh * stride);
+  const uint4* xn = x + (long long)n * H * W * cg;
+  const long long orow = ((long long)n * Ho + oh) * Wo * cg;
+  for (int t = threadIdx.x; t < Wo * cg; t += blockDim.x) {
+    const int ow = t / cg, g = t - ow * cg;
+    const int kw_lo = max(0, pl - ow * stride), kw_hi = min(k, W + pl - ow * stride);
     float best[8];
     unsigned idx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; idx[j] = 0; }
-    for (int kh = 0; kh < k; ++kh) {
-      const int ih = oh * stride + kh - pt;
-      if (ih < 0 || ih >= H) continue;
-      for (int kw = 0; kw < k; ++kw) {
-        const int iw = ow * stride + kw - pl;
-        if (iw < 0 || iw >= W) continue;
+    for (int kh = kh_lo; kh < kh_hi; ++kh) {
+      const uint4* xr = xn + ((oh * stride + kh - pt) * W + (ow * stride - pl)) * cg + g;
+      for (int kw = kw_lo; kw < kw_hi; ++kw) {
         float f[8];
-        unpack8(x[(((long long)n * H + ih) * W + iw) * cg + g], f);
+        unpack8(xr[kw * cg], f);
         const unsigned code = unsigned(kh * k + kw);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (f[j] > best[j]) { best[j] = f[j]; idx[j] = code; }
       }
     }
-    y[i] = pack8(best);
+    y[orow + t] = pack8(best);
     if (argmax) {
       uint2 a;
       a.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
       a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
-      argmax[i] = a;
+      argmax[orow + t] = a;
     }
   }
 }
 
-// Gather form: every input pixel sums the dy of the (few) windows that selected it.
+// Gather form: every input pixel sums the dy of the (few) windows that selected it.  One block per
+// input row (n, ih); the candidate output rows are the same for the whole block.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restrict__ dy,
                                                           const uint2* __restrict__ argmax,
                                                           uint4* __restrict__ dx, int N, int H, int W,
                                                           int cg, int k, int stride, int pt, int pl,
                                                           int Ho, int Wo) {
-  const long long total = (long long)N * H * W * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = int(i % cg);
-    long long r = i / cg;
-    const int iw = int(r % W); r /= W;
-    const int ih = int(r % H);
-    const int n = int(r / H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // windows oh with 0 <= ih + pt - oh*stride < k  (and likewise ow): at most ceil(k/stride)^2
-    const int oh_hi = min((ih + pt) / stride, Ho - 1);
-    const int oh_lo = max(0, (ih + pt - k + stride) / stride);   // ceil((ih+pt-k+1)/stride), arg >= 0 when used
+  const int n = blockIdx.x / H, ih = blockIdx.x - n * H;
+  // windows oh with 0 <= ih + pt - oh*stride < k
+  const int oh_hi = min((ih + pt) / stride, Ho - 1);
+  const int oh_lo = (ih + pt - k + 1 > 0) ? (ih + pt - k + stride) / stride : 0;
+  const long long obase = (long long)n * Ho * Wo * cg;
+  const long long irow = ((long long)n * H + ih) * W * cg;
+  for (int t = threadIdx.x; t < W * cg; t += blockDim.x) {
+    const int iw = t / cg, g = t - iw * cg;
     const int ow_hi = min((iw + pl) / stride, Wo - 1);
-    const int ow_lo = max(0, (iw + pl - k + stride) / stride);
-    for (int oh = (ih + pt - k + 1 > 0 ? oh_lo : 0); oh <= oh_hi; ++oh) {
+    const int ow_lo = (iw + pl - k + 1 > 0) ? (iw + pl - k + stride) / stride : 0;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
       const int kh = ih + pt - oh * stride;
-      for (int ow = (iw + pl - k + 1 > 0 ? ow_lo : 0); ow <= ow_hi; ++ow) {
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
         const int kw = iw + pl - ow * stride;
-        const long long o = (((long long)n * Ho + oh) * Wo + ow) * cg + g;
+        const long long o = obase + (oh * Wo + ow) * cg + g;
         const uint2 a = argmax[o];
         float f[8];
         unpack8(dy[o], f);
@@ -95,7 +91,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restric
         }
       }
     }
-    dx[i] = pack8(acc);
+    dx[irow + t] = pack8(acc);
   }
 }
 
@@ -228,8 +224,8 @@ extern "C" int32_t t2r_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int3
                                    int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad_top,
                                    int32_t pad_left, int32_t Ho, int32_t Wo, void* stream) {
   T2R_CHECK_ARG(x && y && C % 8 == 0 && k >= 1 && k * k <= 255 && stride >= 1, "maxpool_fwd: bad args");
-  const long long total = (long long)N * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  T2R_CHECK_ARG((long long)N * Ho < (1LL << 31) && (long long)H * W * (C / 8) < (1LL << 31), "maxpool_fwd: too large");
+  maxpool_fwd_kernel<<<N * Ho, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), reinterpret_cast<uint2*>(argmax), N, H, W,
       C / 8, k, stride, pad_top, pad_left, Ho, Wo);
   T2R_LAUNCH_OK();
@@ -241,8 +237,8 @@ extern "C" int32_t t2r_maxpool_bwd(const void* dy, const uint8_t* argmax, void* 
                                    int32_t pad_top, int32_t pad_left, int32_t Ho, int32_t Wo,
                                    void* stream) {
   T2R_CHECK_ARG(dy && argmax && dx && C % 8 == 0, "maxpool_bwd: bad args");
-  const long long total = (long long)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  T2R_CHECK_ARG((long long)N * H < (1LL << 31) && (long long)Ho * Wo * (C / 8) < (1LL << 31), "maxpool_bwd: too large");
+  maxpool_bwd_kernel<<<N * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(argmax), static_cast<uint4*>(dx), N,
       H, W, C / 8, k, stride, pad_top, pad_left, Ho, Wo);
   T2R_LAUNCH_OK();

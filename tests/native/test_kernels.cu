@@ -549,8 +549,49 @@ static int bench_conv(int argc, char** argv) {
   return 0;
 }
 
+// `test_kernels benchbn rows C [reps]`: GB/s of the batch-norm passes (algorithmic bytes / time).
+static int bench_bn(int argc, char** argv) {
+  if (argc < 4) { fprintf(stderr, "usage: benchbn rows C [reps]\n"); return 2; }
+  const long long rows = atoll(argv[2]);
+  const int C = atoi(argv[3]);
+  const int reps = argc > 4 ? atoi(argv[4]) : 5;
+  const size_t n = size_t(rows) * C;
+  Dev<__nv_bfloat16> x(n), y(n), dy(n), dres(n), dx(n);
+  CK(cudaMemset(x.p, 0x3c, n * 2)); CK(cudaMemset(dy.p, 0x3c, n * 2)); CK(cudaMemset(dres.p, 0x3c, n * 2));
+  Dev<double> stats(2 * C), red(2 * C);
+  Dev<float> gamma(C), beta(C), mm(C), mv(C), mean(C), inv(C), scale(C), shift(C), dg(C), db(C);
+  Dev<char> flush(256u << 20);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const char* names[] = {"stats (2 B/el)", "apply+relu (4 B/el)", "backward (10 B/el)", "backward+dres (12 B/el)"};
+  const double bytes_per_el[] = {2, 4, 10, 12};
+  for (int k = 0; k < 4; ++k) {
+    float sum = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+      CK(cudaMemsetAsync(flush.p, r, flush.n));
+      CK(cudaEventRecord(e0));
+      if (k == 0) TB(t2r_bn_stats(x.p, rows, C, stats.p, nullptr));
+      if (k == 1) TB(t2r_bn_apply(x.p, y.p, rows, C, scale.p, shift.p, nullptr, 1, 1, nullptr));
+      if (k >= 2) TB(t2r_bn_backward(dy.p, x.p, k == 3 ? dres.p : nullptr, dx.p, rows, C, gamma.p, mean.p, inv.p, scale.p,
+                                     shift.p, 1, red.p, dg.p, db.p, nullptr));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (k == 0 && r == 0)
+        TB(t2r_bn_finalize(stats.p, rows, C, nullptr, nullptr, 1e-3f, 0.9f, mm.p, mv.p, mean.p, inv.p, scale.p, shift.p,
+                           nullptr));
+      if (r > 0) sum += ms;
+    }
+    printf("bn rows=%lld C=%d %-24s %.3f ms  %.0f GB/s\n", rows, C, names[k], sum / reps,
+           bytes_per_el[k] * n / (sum / reps) * 1e-6);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "bench")) return bench_conv(argc, argv);
+  if (argc > 1 && !strcmp(argv[1], "benchbn")) return bench_bn(argc, argv);
   if (argc > 1) g_filter = argv[1];
   int dev_count = 0;
   CK(cudaGetDeviceCount(&dev_count));
