@@ -37,7 +37,7 @@ def parse_args():
   p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   p.add_argument('--model', default='resnet50', choices=['resnet50', 'grasping44'])
   p.add_argument('--batch', type=int, default=512, help='transitions per GPU per step')
-  p.add_argument('--cpu-batch', type=int, default=8)
+  p.add_argument('--cpu-batch', type=int, default=16)
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
   p.add_argument('--no-cem', action='store_true')
@@ -109,11 +109,30 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the oracle restatement of the reference step (bench `cpu_baseline` / --impl reference)
 # ---------------------------------------------------------------------------------------------
+def usable_host_threads():
+  """Host threads this process can really run: the affinity mask capped by the cgroup CPU quota (a
+  128-core box with a 16-CPU quota runs a 128-thread torch step 70x slower than a 16-thread one)."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+  try:
+    quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+    if quota != 'max':
+      n = min(n, max(1, int(int(quota) / int(period))))
+  except (OSError, ValueError):
+    try:
+      quota = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+      period = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+      if quota > 0:
+        n = min(n, max(1, quota // period))
+    except (OSError, ValueError):
+      pass
+  return n
+
+
 def cpu_reference_step_rate(model, batch, steps, warmup, size=472):
   """Transitions/s of the torch-CPU fp32 restatement of the reference train step (forward, log loss
   + l2, backward, momentum update) on all host cores.  Executes oracle/ - allowed only here."""
   from oracle import qtopt_networks, resnet as oracle_resnet, tf_ops
-  threads = os.cpu_count() or 1
+  threads = usable_host_threads()
   torch.set_num_threads(threads)
   rng = np.random.RandomState(0)
   img = torch.from_numpy(rng.uniform(0, 1, (batch, size, size, 3)).astype(np.float32))
@@ -142,7 +161,7 @@ def cpu_reference_step_rate(model, batch, steps, warmup, size=472):
       for p, g, m in zip(params, grads, momentum):
         m.mul_(0.9).add_(g)
         p.sub_(1e-4 * m)
-    return float(loss)
+    return float(loss.detach())
 
   for _ in range(warmup):
     step()
@@ -157,7 +176,7 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+  steps, warmup = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))
   rate, threads, sec = cpu_reference_step_rate(args.model, args.cpu_batch, steps, warmup)
   sample = '%d timed steps (+%d warm-up) of batch %d, torch-CPU fp32 restatement of the reference step' % (
       steps, warmup, args.cpu_batch)
@@ -354,9 +373,9 @@ def run_b200(args):
     return
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
-    rate, threads, sec = cpu_reference_step_rate(args.model, args.cpu_batch, 2, 1)
+    rate, threads, sec = cpu_reference_step_rate(args.model, args.cpu_batch, 3, 1)
     cpu = {'value': rate, 'unit': 'transitions/s', 'cores': threads, 'kind': 'port',
-           'sample': '2 timed steps (+1 warm-up) of batch %d, torch-CPU fp32 restatement of the reference step '
+           'sample': '3 timed steps (+1 warm-up) of batch %d, torch-CPU fp32 restatement of the reference step '
                      '(%.1f s/step)' % (args.cpu_batch, sec)}
   ms_per_step = elapsed_ms / args.steps
   value = b * world * 1000.0 / ms_per_step

@@ -66,6 +66,14 @@ int32_t t2r_conv_same_padding(int32_t in, int32_t k, int32_t stride, int32_t* ou
 /* y = conv(x, w) (+bias)(+residual)(relu).  Requires Cin % 64 == 0, Cout % 64 == 0. */
 int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const void* w_ohwi,
                          const float* bias, const void* residual, void* y, void* stream);
+/* Same, and the epilogue also accumulates the batch-norm statistics of the bf16 output it writes:
+ * stats[c] += sum_rows y[.,c], stats[Cout + c] += sum_rows y[.,c]^2 (fp64, caller zeroes; the
+ * layout t2r_bn_stats produces, so t2r_bn_finalize consumes it directly).  Fuses the statistics
+ * pass of slim.batch_norm / tf.layers.batch_normalization that follows every convolution
+ * (research/qtopt/networks.py:443-448, layers/film_resnet_model.py:50-57).  stats may be NULL. */
+int32_t t2r_conv2d_fprop_stats(const T2RConvDesc* d, const void* x, const void* w_ohwi,
+                               const float* bias, const void* residual, void* y, double* stats,
+                               void* stream);
 /* dx = conv_transpose(dy, w).  w_dgrad is [Cin][KH*KW][Cout] bf16 (see t2r_pack_weights).
  * accumulate != 0: dx += result.  Requires Cout % 64 == 0, Cin % 64 == 0. */
 int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const void* w_dgrad, void* dx,

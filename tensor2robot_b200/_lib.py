@@ -49,6 +49,7 @@ _PROTOS = {
     't2r_launch_count_reset': (None, []),
     't2r_conv_same_padding': (_I32, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     't2r_conv2d_fprop': (_I32, [_CD, _P, _P, _P, _P, _P, _P]),
+    't2r_conv2d_fprop_stats': (_I32, [_CD, _P, _P, _P, _P, _P, _P, _P]),
     't2r_conv2d_dgrad': (_I32, [_CD, _P, _P, _P, _I32, _P]),
     't2r_conv2d_wgrad': (_I32, [_CD, _P, _P, _P, _P]),
     't2r_pack_weights': (_I32, [_P, _P, _P, _I32, _I32, _I32, _P]),

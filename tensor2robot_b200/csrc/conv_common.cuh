@@ -34,6 +34,7 @@ struct HaloRequest {
   const void* residual;
   const float* bias;
   int flags;
+  double* stats;       // optional fused bn_stats output, fp64 [2*Cout]
 };
 bool conv_halo_eligible(int stride, int n_taps, int k_channels, int n_channels);
 int conv_halo_launch(const HaloRequest& r, cudaStream_t stream);

@@ -52,6 +52,7 @@ struct HaloParams {
   const void* residual;
   const float* bias;
   int flags;
+  double* stats;
 };
 
 template <bool kResident>
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   auto wfull_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto wempty_bar = [&](int s) { return bar_base + 64u + 8u * kHaloWSlotsMax + 8u * s; };
   const uint32_t tmem_ptr_addr = bar_base + 64u + 16u * kHaloWSlotsMax;
+  float* stat_acc = reinterpret_cast<float*>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));  // [2][Cout <= 128]
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
   constexpr int kTmemCols = 256;  // 2 accumulator stages x 2 tiles x 64 columns
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
     tmem_alloc(tmem_ptr_addr, kTmemCols);
     tmem_relinquish();
   }
+  if (p.stats != nullptr)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) stat_acc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -294,13 +298,28 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
           const uint32_t sw = (uint32_t(lane) >> 1) & 3u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t q0 = pack_bf16(f[8 * j + 0], f[8 * j + 1]), q1 = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-            const uint32_t q2 = pack_bf16(f[8 * j + 4], f[8 * j + 5]), q3 = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+            uint32_t q0 = pack_bf16(f[8 * j + 0], f[8 * j + 1]), q1 = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+            uint32_t q2 = pack_bf16(f[8 * j + 4], f[8 * j + 5]), q3 = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+            if (!valid) q0 = q1 = q2 = q3 = 0u;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wb + uint32_t(lane) * 64u + ((uint32_t(j) ^ sw) << 4)),
                          "r"(q0), "r"(q1), "r"(q2), "r"(q3)
                          : "memory");
           }
           __syncwarp();
+          if (p.stats != nullptr) {  // fused bn_stats, see conv_igemm.cu
+            float s1 = 0.f, s2 = 0.f;
+            const uint32_t cj = uint32_t(lane) >> 3, cb = (uint32_t(lane) & 7u) * 2u;
+#pragma unroll
+            for (uint32_t r = 0; r < 32; ++r) {
+              uint16_t h;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(wb + r * 64u + ((cj ^ ((r >> 1) & 3u)) << 4) + cb) : "memory");
+              const float v = __uint_as_float(uint32_t(h) << 16);
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+            atomicAdd(stat_acc + ch + lane, s1);
+            atomicAdd(stat_acc + p.Cout + ch + lane, s2);
+          }
           const uint32_t jj = uint32_t(lane) & 3u;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -321,6 +340,13 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += 256) {
+        const float v = stat_acc[i];
+        if (v != 0.f) atomicAdd(p.stats + i, double(v));
       }
     }
   }
@@ -380,9 +406,9 @@ int conv_halo_launch(const HaloRequest& r, cudaStream_t stream) {
   p.total_halves = r.N * p.tiles_w * p.tiles_h;
   p.total_super = int(ceil_div(p.total_halves, 2)) * p.n_tiles_n;
   p.os_n = r.os_n; p.os_h = r.os_h; p.os_w = r.os_w;
-  p.out = r.out; p.residual = r.residual; p.bias = r.bias; p.flags = r.flags;
+  p.out = r.out; p.residual = r.residual; p.bias = r.bias; p.flags = r.flags; p.stats = r.stats;
   if (p.total_super <= 0) return T2R_OK;
-  const int smem = 4 * p.halo_bytes + p.w_slots * 8192 + 8 * 2048 + 512 + 1024;
+  const int smem = 4 * p.halo_bytes + p.w_slots * 8192 + 8 * 2048 + 512 /*barriers*/ + 1024 /*stats*/ + 1024 /*align*/;
   T2R_CHECK_ARG(smem <= 227 * 1024, "halo conv needs %d B of shared memory", smem);
   const int grid = std::min(p.total_super, num_sms());
   static bool configured = false;

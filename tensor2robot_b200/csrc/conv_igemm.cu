@@ -27,6 +27,8 @@
 namespace t2r {
 
 
+constexpr int kMaxStatChannels = 2048;
+
 struct IgemmParams {
   CUtensorMap tmap_a[4];
   CUtensorMap tmap_b;
@@ -44,6 +46,7 @@ struct IgemmParams {
   const void* residual;
   const float* bias;
   int flags;
+  double* stats;  // optional fp64 [2*Cout]: per-channel sum / sum of squares of the bf16 output (fused bn_stats)
 };
 
 template <int BLOCK_N>
@@ -54,7 +57,9 @@ struct IgemmCfg {
   static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: all powers of two
   static constexpr int kStoreStageBytes = 8 * 2048;   // one 32 rows x 64 B tile per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStoreStageBytes;
+  static constexpr int kStatBytes = 2 * kMaxStatChannels * 4;  // per-CTA fp32 partials of the fused bn_stats
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStoreStageBytes + kStatBytes;
 };
 
 template <int BLOCK_N>
@@ -70,6 +75,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 4);
   const uint32_t store_stage_base = bar_base + 256u;
+  float* stat_acc = reinterpret_cast<float*>(smem_raw + (store_stage_base + Cfg::kStoreStageBytes - smem_u32(smem_raw)));
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
@@ -95,6 +101,8 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
     tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  if (p.stats != nullptr)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) stat_acc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -278,13 +286,30 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
             const uint32_t sw = (uint32_t(lane) >> 1) & 3u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t q0 = pack_bf16(f[8 * j + 0], f[8 * j + 1]), q1 = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              const uint32_t q2 = pack_bf16(f[8 * j + 4], f[8 * j + 5]), q3 = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              uint32_t q0 = pack_bf16(f[8 * j + 0], f[8 * j + 1]), q1 = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              uint32_t q2 = pack_bf16(f[8 * j + 4], f[8 * j + 5]), q3 = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              if (!valid) q0 = q1 = q2 = q3 = 0u;  // rows outside the image are never stored and must not count
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wb + uint32_t(lane) * 64u + ((uint32_t(j) ^ sw) << 4)),
                            "r"(q0), "r"(q1), "r"(q2), "r"(q3)
                            : "memory");
             }
             __syncwarp();
+            if (p.stats != nullptr) {
+              // fused bn_stats: lane l sums column l of the staged 32 x 32 tile (the bf16 values the
+              // next layer's batch norm will read), then one shared-memory atomic per statistic.
+              float s1 = 0.f, s2 = 0.f;
+              const uint32_t cj = uint32_t(lane) >> 3, cb = (uint32_t(lane) & 7u) * 2u;
+#pragma unroll
+              for (uint32_t r = 0; r < 32; ++r) {
+                uint16_t h;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(wb + r * 64u + ((cj ^ ((r >> 1) & 3u)) << 4) + cb) : "memory");
+                const float v = __uint_as_float(uint32_t(h) << 16);
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+              }
+              atomicAdd(stat_acc + ch + lane, s1);
+              atomicAdd(stat_acc + p.Cout + ch + lane, s2);
+            }
             const uint32_t jj = uint32_t(lane) & 3u;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -307,6 +332,13 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += 256) {
+        const float v = stat_acc[i];
+        if (v != 0.f) atomicAdd(p.stats + i, double(v));
       }
     }
   }
@@ -440,8 +472,16 @@ extern "C" int32_t t2r_conv_same_padding(int32_t in, int32_t k, int32_t stride, 
 extern "C" int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const void* w,
                                     const float* bias, const void* residual, void* y,
                                     void* stream) {
+  return t2r_conv2d_fprop_stats(d, x, w, bias, residual, y, nullptr, stream);
+}
+
+extern "C" int32_t t2r_conv2d_fprop_stats(const T2RConvDesc* d, const void* x, const void* w,
+                                          const float* bias, const void* residual, void* y,
+                                          double* stats, void* stream) {
   if (int rc = check_desc(d)) return rc;
   T2R_CHECK_ARG(x && w && y, "null pointer");
+  T2R_CHECK_ARG(stats == nullptr || (!(d->flags & T2R_EPI_OUT_F32) && d->Cout <= kMaxStatChannels),
+                "fused bn_stats needs a bf16 output with at most %d channels", kMaxStatChannels);
   T2R_CHECK_ARG(!(d->flags & T2R_EPI_BIAS) || bias, "bias flag without bias");
   T2R_CHECK_ARG(!(d->flags & T2R_EPI_RESIDUAL) || residual, "residual flag without residual");
   IgemmParams p;
@@ -479,7 +519,7 @@ extern "C" int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const v
     r.n_taps = t;
     r.Ho = d->Ho; r.Wo = d->Wo; r.Cout = d->Cout;
     r.os_w = d->Cout; r.os_h = (long long)d->Wo * d->Cout; r.os_n = (long long)d->Ho * d->Wo * d->Cout;
-    r.out = y; r.residual = residual; r.bias = bias; r.flags = d->flags;
+    r.out = y; r.residual = residual; r.bias = bias; r.flags = d->flags; r.stats = stats;
     return conv_halo_launch(r, static_cast<cudaStream_t>(stream));
   }
   p.tiles_w = int(ceil_div(d->Wo, p.TW));
@@ -488,7 +528,7 @@ extern "C" int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const v
   p.os_w = d->Cout;
   p.os_h = (long long)d->Wo * d->Cout;
   p.os_n = (long long)d->Ho * d->Wo * d->Cout;
-  p.out = y; p.residual = residual; p.bias = bias; p.flags = d->flags;
+  p.out = y; p.residual = residual; p.bias = bias; p.flags = d->flags; p.stats = stats;
   return dispatch_igemm(p, block_n, static_cast<cudaStream_t>(stream));
 }
 

@@ -19,6 +19,7 @@ import collections
 import contextlib
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -400,11 +401,25 @@ def conv_geometry(h, w, kh, kw, stride, padding):
   return ho, wo, pt, pl
 
 
+# Fused batch-norm statistics: in training, a bf16 convolution also accumulates the per-channel
+# sum / sum of squares of its output in the epilogue (t2r_conv2d_fprop_stats) and hangs the fp64
+# [2*C] buffer on the output tensor; batch_norm() on exactly that tensor then skips its statistics
+# pass (one full HBM read of the activation).  Any op in between creates a new tensor object
+# without the attribute, which falls back to t2r_bn_stats.
+FUSE_BN_STATS = os.environ.get('T2R_FUSE_BN_STATS', '1') != '0'
+
+
+def _new_bn_stats(channels, device):
+  if not (FUSE_BN_STATS and torch.is_grad_enabled()) or channels > 2048:
+    return None
+  return torch.zeros(2 * channels, dtype=torch.float64, device=device)
+
+
 class _Conv2dFn(torch.autograd.Function):
   """y = conv(x, W) [+bias] [+residual] [relu] on the tcgen05 implicit-GEMM kernels."""
 
   @staticmethod
-  def forward(ctx, x, residual, var, bias_var, geom, relu, out_f32):
+  def forward(ctx, x, residual, var, bias_var, geom, relu, out_f32, stats=None):
     n, h, w, cin = x.shape
     cout, kh, kw, _ = var.shape
     stride, ho, wo, pt, pl = geom
@@ -420,8 +435,8 @@ class _Conv2dFn(torch.autograd.Function):
     d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, flags)
     y = torch.empty((n, ho, wo, cout), dtype=F32 if out_f32 else BF16, device=x.device)
     with _prof('fprop', d):
-      _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(var.bf16),
-                _p(bias_var.data if bias_var is not None else None), _p(residual), _p(y), _stream())
+      _lib.call('t2r_conv2d_fprop_stats', C.byref(d), _p(x), _p(var.bf16),
+                _p(bias_var.data if bias_var is not None else None), _p(residual), _p(y), _p(stats), _stream())
     ctx.var, ctx.bias_var, ctx.desc, ctx.relu, ctx.out_f32 = var, bias_var, d, relu, out_f32
     ctx.has_res = residual is not None
     ctx.save_for_backward(x, y if relu else None)
@@ -456,7 +471,7 @@ class _Conv2dFn(torch.autograd.Function):
       with _prof('dgrad', d):
         _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 0, st)
     dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
-    return dx, dres, None, None, None, None, None
+    return dx, dres, None, None, None, None, None, None
 
 
 class _DualConvFn(torch.autograd.Function):
@@ -465,15 +480,15 @@ class _DualConvFn(torch.autograd.Function):
   instead of a separate elementwise add."""
 
   @staticmethod
-  def forward(ctx, x, var1, geom1, var2, geom2):
+  def forward(ctx, x, var1, geom1, var2, geom2, stats2=None):
     n, h, w, cin = x.shape
     descs, ys = [], []
-    for var, (stride, ho, wo, pt, pl) in ((var1, geom1), (var2, geom2)):
+    for var, (stride, ho, wo, pt, pl), stats in ((var1, geom1, None), (var2, geom2, stats2)):
       cout, kh, kw, _ = var.shape
       d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, 0)
       y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
       with _prof('fprop', d):
-        _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(var.bf16), None, None, _p(y), _stream())
+        _lib.call('t2r_conv2d_fprop_stats', C.byref(d), _p(x), _p(var.bf16), None, None, _p(y), _p(stats), _stream())
       descs.append(d)
       ys.append(y)
     ctx.vars, ctx.descs = (var1, var2), descs
@@ -499,7 +514,7 @@ class _DualConvFn(torch.autograd.Function):
         wrote = True
     if dx is not None and not wrote:
       dx.zero_()
-    return dx, None, None, None, None
+    return dx, None, None, None, None, None
 
 
 def conv2d_pair(x, spec1, spec2):
@@ -521,7 +536,10 @@ def conv2d_pair(x, spec1, spec2):
     if not vs.finalized:
       _ensure_bf16(wv)
     out.append((wv, (stride, ho, wo, pt, pl)))
-  y1, y2 = _DualConvFn.apply(x, out[0][0], out[0][1], out[1][0], out[1][1])
+  stats2 = _new_bn_stats(out[1][0].shape[0], x.device)
+  y1, y2 = _DualConvFn.apply(x, out[0][0], out[0][1], out[1][0], out[1][1], stats2)
+  if stats2 is not None:
+    y2._t2r_bn_stats = stats2
   return _trace('conv', spec1['scope'], y1), _trace('conv', spec2['scope'], y2)
 
 
@@ -607,7 +625,11 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   if small:
     return _trace('conv', scope, _StemConvFn.apply(x.contiguous(), vs.anchor, wv, bv,
                                                    (kh, kw, stride, ho, wo, pt, pl), vs))
-  return _trace('conv', scope, _Conv2dFn.apply(x, residual, wv, bv, (stride, ho, wo, pt, pl), relu, out_f32))
+  stats = None if (out_f32 or relu) else _new_bn_stats(filters, x.device)
+  y = _Conv2dFn.apply(x, residual, wv, bv, (stride, ho, wo, pt, pl), relu, out_f32, stats)
+  if stats is not None:
+    y._t2r_bn_stats = stats
+  return _trace('conv', scope, y)
 
 
 def _stem_pack(w_ohwi):
@@ -670,7 +692,7 @@ def dense(x, units, scope='fc', use_bias=False, initializer=None, regularize=Tru
 class _BatchNormFn(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, x, film, bn, training, relu, vs, passthrough=False):
+  def forward(ctx, x, film, bn, training, relu, vs, passthrough=False, fused_stats=None):
     c = x.shape[-1]
     rows = x.numel() // c
     st = _stream()
@@ -679,10 +701,13 @@ class _BatchNormFn(torch.autograd.Function):
     shift = torch.empty(c, dtype=F32, device=x.device)
     rows_per_image = rows // x.shape[0]
     if training:
-      stats = vs.scratch('bn_stats', 2 * 4096, torch.float64)
       mean = torch.empty(c, dtype=F32, device=x.device)
       invstd = torch.empty(c, dtype=F32, device=x.device)
-      _lib.call('t2r_bn_stats', _p(x), rows, c, _p(stats), st)
+      if fused_stats is not None:
+        stats = fused_stats
+      else:
+        stats = vs.scratch('bn_stats', 2 * 4096, torch.float64)
+        _lib.call('t2r_bn_stats', _p(x), rows, c, _p(stats), st)
       _lib.call('t2r_bn_finalize', _p(stats), rows, c, _p(bn['gamma'].data if bn['gamma'] is not None else None),
                 _p(bn['beta'].data), bn['eps'], bn['momentum'], _p(bn['moving_mean'].data),
                 _p(bn['moving_variance'].data), _p(mean), _p(invstd), _p(scale), _p(shift), st)
@@ -722,7 +747,7 @@ class _BatchNormFn(torch.autograd.Function):
     _lib.call('t2r_bn_backward', _p(dy), _p(x), _p(dpass), _p(dx), rows, c,
               _p(gamma.data if gamma is not None else None), _p(mean), _p(invstd), _p(scale), _p(shift),
               1 if ctx.relu else 0, _p(red), _p(dgamma), _p(dbeta), st)
-    return dx, None, None, None, None, None, None
+    return dx, None, None, None, None, None, None, None
 
 
 def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=0.997, eps=1e-5,
@@ -745,10 +770,11 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
     for k in ('gamma', 'beta'):
       if bn[k] is not None and bn[k].grad is None:
         bn[k].grad = torch.zeros(bn[k].shape, dtype=F32, device=x.device)
+  fused = getattr(x, '_t2r_bn_stats', None) if (training and x.is_contiguous()) else None
   if passthrough:
-    y, x_pass = _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs, True)
+    y, x_pass = _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs, True, fused)
     return _trace('bn', scope, y), x_pass
-  return _trace('bn', scope, _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs))
+  return _trace('bn', scope, _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs, False, fused))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -164,6 +164,21 @@ static void test_conv(const ConvCase& c) {
         }
   report(std::string(c.name) + " fprop", f32out ? dyo32.down() : from_bf16(dyo.down()), ref, f32out ? 1e-4f : 8e-3f,
          f32out ? 1e-4f : 4e-3f);
+  if (!f32out && c.Cout <= 2048) {
+    // fused bn_stats: column sums / sums of squares of exactly the bf16 values that were stored
+    Dev<double> dstats(2 * c.Cout);
+    CK(cudaMemset(dyo.p, 0, ny * 2));
+    T2R(t2r_conv2d_fprop_stats(&d, dx_.p, dwf.p, dbias.p, dres.p, dyo.p, dstats.p, nullptr));
+    sync_check((std::string(c.name) + " fprop+stats").c_str());
+    const std::vector<float> yv = from_bf16(dyo.down());
+    const std::vector<double> st = dstats.down();
+    std::vector<float> got(2 * c.Cout), want(2 * c.Cout);
+    std::vector<double> acc(2 * c.Cout, 0.0);
+    for (size_t i = 0; i < ny; ++i) { const int co = int(i % c.Cout); acc[co] += yv[i]; acc[c.Cout + co] += double(yv[i]) * yv[i]; }
+    double amax = 0;
+    for (int i = 0; i < 2 * c.Cout; ++i) { got[i] = float(st[i]); want[i] = float(acc[i]); amax = fmax(amax, fabs(acc[i])); }
+    report(std::string(c.name) + " fused bn_stats", got, want, 1e-4f, float(1e-5 * amax + 1e-4));
+  }
 
   // ---- dgrad ----
   CK(cudaMemset(dxg.p, 0x7f, nx * 2));  // poison
