@@ -20,6 +20,32 @@ void pick_tile(int Ho, int Wo, int pixels, int* TW, int* TH);
 int make_phase_maps(CUtensorMap* maps, const void* x, int N, int H, int W, int C, int stride,
                     int TW, int TH);
 
+constexpr int kMaxStatChannels = 2048;
+
+struct IgemmParams {
+  CUtensorMap tmap_a[4];
+  CUtensorMap tmap_b;
+  ConvTap taps[kMaxTaps];
+  int n_taps;
+  int chunks_per_tap;  // Cin / 64
+  int TW, TH;          // tile rectangle, TW*TH == 128
+  int tiles_w, tiles_h;
+  int N, Ho, Wo;       // output iteration space (a strided view for dgrad phases)
+  int Cout;
+  int n_tiles_n;
+  int total_tiles;
+  long long os_n, os_h, os_w;  // output element strides of the view
+  void* out;
+  const void* residual;
+  const float* bias;
+  int flags;
+  double* stats;  // optional fp64 [2*Cout]: per-channel sum / sum of squares of the bf16 output (fused bn_stats)
+};
+
+// The tap-table kernel with a TMA epilogue (conv_igemm_tma.cu): residual tile in by TMA, output tile
+// out by TMA.  block_n is 64 or 128; bf16 output only.
+int conv_igemm_tma_launch(const IgemmParams& p, int block_n, cudaStream_t stream);
+
 // Stride-1 KxK convolution through the shared-memory halo kernel (conv_halo.cu).
 struct HaloRequest {
   const void* x;       // [N,H,W,C] bf16, the tensor the taps slide over

@@ -20,34 +20,13 @@
 // Replaces: slim.conv2d / tf.layers.conv2d (research/qtopt/networks.py:443-591,
 // layers/film_resnet_model.py:89-105) and their autodiff data gradients.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "conv_common.cuh"
 
 namespace t2r {
 
-
-constexpr int kMaxStatChannels = 2048;
-
-struct IgemmParams {
-  CUtensorMap tmap_a[4];
-  CUtensorMap tmap_b;
-  ConvTap taps[kMaxTaps];
-  int n_taps;
-  int chunks_per_tap;  // Cin / 64
-  int TW, TH;          // tile rectangle, TW*TH == 128
-  int tiles_w, tiles_h;
-  int N, Ho, Wo;       // output iteration space (a strided view for dgrad phases)
-  int Cout;
-  int n_tiles_n;
-  int total_tiles;
-  long long os_n, os_h, os_w;  // output element strides of the view
-  void* out;
-  const void* residual;
-  const float* bias;
-  int flags;
-  double* stats;  // optional fp64 [2*Cout]: per-channel sum / sum of squares of the bf16 output (fused bn_stats)
-};
 
 template <int BLOCK_N>
 struct IgemmCfg {
@@ -233,7 +212,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
       }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int ch = ch0 + c * 32;
         uint4 rcur[4];
@@ -427,7 +406,23 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
   return T2R_OK;
 }
 
-static int dispatch_igemm(IgemmParams& p, int block_n, cudaStream_t stream) {
+// Tile width and epilogue flavour.  bf16 outputs with N <= 128 use the TMA epilogue
+// (conv_igemm_tma.cu); 256-multiple channel counts do so too (as two 128-wide tiles) when the GEMM K
+// is so small that the layer is bound by its output / residual traffic rather than by the MMA.
+static int pick_block_n(int Cout, long long k_total, int flags, bool* tma) {
+  static const bool no_tma = std::getenv("T2R_DISABLE_TMA_EPI") != nullptr;
+  int bn = 64;
+  if (Cout % 256 == 0) bn = 256;
+  else if (Cout % 128 == 0) bn = 128;
+  *tma = !no_tma && !(flags & T2R_EPI_OUT_F32);
+  if (*tma && bn == 256) {
+    if (k_total <= 256) bn = 128; else *tma = false;
+  }
+  return bn;
+}
+
+static int dispatch_igemm(IgemmParams& p, int block_n, bool tma, cudaStream_t stream) {
+  if (tma) return conv_igemm_tma_launch(p, block_n, stream);
   p.n_tiles_n = int(ceil_div(p.Cout, block_n));
   p.total_tiles = p.N * p.tiles_w * p.tiles_h * p.n_tiles_n;
   if (p.total_tiles <= 0) return T2R_OK;
@@ -436,12 +431,6 @@ static int dispatch_igemm(IgemmParams& p, int block_n, cudaStream_t stream) {
     case 128: return launch_igemm<128>(p, stream);
     default: return launch_igemm<256>(p, stream);
   }
-}
-
-static int pick_block_n(int Cout) {
-  if (Cout % 256 == 0) return 256;
-  if (Cout % 128 == 0) return 128;
-  return 64;
 }
 
 static int check_desc(const T2RConvDesc* d) {
@@ -489,8 +478,9 @@ extern "C" int32_t t2r_conv2d_fprop_stats(const T2RConvDesc* d, const void* x, c
   pick_tile(d->Ho, d->Wo, 128, &p.TW, &p.TH);
   if (make_phase_maps(p.tmap_a, x, d->N, d->H, d->W, d->Cin, d->stride, p.TW, p.TH) != 0)
     return T2R_ERR_CUDA;
-  const int block_n = pick_block_n(d->Cout);
   const uint64_t Ktot = uint64_t(d->KH) * d->KW * d->Cin;
+  bool tma = false;
+  const int block_n = pick_block_n(d->Cout, (long long)Ktot, d->flags, &tma);
   {
     uint64_t dims[2] = {Ktot, uint64_t(d->Cout)};
     uint64_t strides[1] = {Ktot * 2};
@@ -529,7 +519,7 @@ extern "C" int32_t t2r_conv2d_fprop_stats(const T2RConvDesc* d, const void* x, c
   p.os_h = (long long)d->Wo * d->Cout;
   p.os_n = (long long)d->Ho * d->Wo * d->Cout;
   p.out = y; p.residual = residual; p.bias = bias; p.flags = d->flags; p.stats = stats;
-  return dispatch_igemm(p, block_n, static_cast<cudaStream_t>(stream));
+  return dispatch_igemm(p, block_n, tma, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const void* w_dgrad,
@@ -538,7 +528,6 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
   T2R_CHECK_ARG(dy && w_dgrad && dx, "null pointer");
   const int s = d->stride;
   const int taps_total = d->KH * d->KW;
-  const int block_n = pick_block_n(d->Cin);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // dx[n,h,w,ci] = sum_{kh,kw,co} dy[n,(h+pt-kh)/s,(w+pl-kw)/s,co] * w[co,kh,kw,ci]
   // One launch per output phase (h%s, w%s): inside a phase the contributing taps are fixed and
@@ -562,6 +551,8 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
         }
       }
       p.n_taps = t;
+      bool tma = false;
+      const int block_n = pick_block_n(d->Cin, (long long)t * d->Cout, 0, &tma);
       char* out = static_cast<char*>(dx) + (size_t(ph) * d->W + pw) * d->Cin * 2;
       if (conv_halo_eligible(s, t, d->Cout, d->Cin)) {
         HaloRequest r;
@@ -605,7 +596,7 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
         }
         continue;
       }
-      if (int rc = dispatch_igemm(p, block_n, st)) return rc;
+      if (int rc = dispatch_igemm(p, block_n, tma, st)) return rc;
     }
   return T2R_OK;
 }
@@ -649,8 +640,9 @@ extern "C" int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, in
   memset(&p, 0, sizeof(p));
   pick_tile(d->Ho, d->Wo, 128, &p.TW, &p.TH);
   if (make_stem_maps(p.tmap_a, x4p, d->N, Hp, Wp, d->stride, d->Ho, d->Wo, p.TW, p.TH) != 0) return T2R_ERR_CUDA;
-  const int block_n = pick_block_n(d->Cout);
   const uint64_t Ktot = uint64_t(d->KH) * 64;
+  bool tma = false;
+  const int block_n = pick_block_n(d->Cout, (long long)Ktot, 0, &tma);
   uint64_t dims[2] = {Ktot, uint64_t(d->Cout)};
   uint64_t strides[1] = {Ktot * 2};
   uint32_t box[2] = {64, uint32_t(block_n)};
@@ -670,5 +662,5 @@ extern "C" int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, in
   p.os_h = (long long)d->Wo * d->Cout;
   p.os_n = (long long)d->Ho * d->Wo * d->Cout;
   p.out = y; p.bias = bias; p.flags = bias ? T2R_EPI_BIAS : 0;
-  return dispatch_igemm(p, block_n, static_cast<cudaStream_t>(stream));
+  return dispatch_igemm(p, block_n, tma, static_cast<cudaStream_t>(stream));
 }

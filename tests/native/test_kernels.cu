@@ -528,14 +528,15 @@ static int bench_conv(int argc, char** argv) {
             K = atoi(argv[7]), stride = atoi(argv[8]);
   const int reps = argc > 9 ? atoi(argv[9]) : 5;
   const char* kinds = argc > 10 ? argv[10] : "fdw";
+  const int flags = argc > 11 ? atoi(argv[11]) : 0;  // T2R_EPI_* for fprop; 2 = residual (also dgrad accumulate)
   int32_t Ho, Wo, pt, pl;
   TB(t2r_conv_same_padding(H, K, stride, &Ho, &pt));
   TB(t2r_conv_same_padding(W, K, stride, &Wo, &pl));
-  ConvCase c{"bench", N, H, W, Cin, Cout, K, K, stride, pt, pl, Ho, Wo, 0};
+  ConvCase c{"bench", N, H, W, Cin, Cout, K, K, stride, pt, pl, Ho, Wo, flags};
   const T2RConvDesc d = mkdesc(c);
   const size_t nx = size_t(N) * H * W * Cin, ny = size_t(N) * Ho * Wo * Cout, nw = size_t(Cout) * K * K * Cin;
-  Dev<__nv_bfloat16> x(nx), dx(nx), y(ny), dy(ny), wf(nw), wd(nw);
-  Dev<float> w32(nw), dw(nw);
+  Dev<__nv_bfloat16> x(nx), dx(nx), y(ny), dy(ny), wf(nw), wd(nw), res(flags & T2R_EPI_RESIDUAL ? ny : 1);
+  Dev<float> w32(nw), dw(nw), bias(Cout);
   CK(cudaMemset(x.p, 0x3c, nx * 2)); CK(cudaMemset(dy.p, 0x3c, ny * 2));
   w32.up(randv(nw, 0.05f, false));
   TB(t2r_pack_weights(w32.p, wf.p, wd.p, Cout, K * K, Cin, nullptr));
@@ -548,8 +549,8 @@ static int bench_conv(int argc, char** argv) {
     for (int r = 0; r < reps + 1; ++r) {
       CK(cudaMemsetAsync(flush.p, r, flush.n));  // evict L2
       CK(cudaEventRecord(e0));
-      if (*k == 'f') TB(t2r_conv2d_fprop(&d, x.p, wf.p, nullptr, nullptr, y.p, nullptr));
-      if (*k == 'd') TB(t2r_conv2d_dgrad(&d, dy.p, wd.p, dx.p, 0, nullptr));
+      if (*k == 'f') TB(t2r_conv2d_fprop(&d, x.p, wf.p, bias.p, res.p, y.p, nullptr));
+      if (*k == 'd') TB(t2r_conv2d_dgrad(&d, dy.p, wd.p, dx.p, (flags & T2R_EPI_RESIDUAL) ? 1 : 0, nullptr));
       if (*k == 'w') TB(t2r_conv2d_wgrad(&d, x.p, dy.p, dw.p, nullptr));
       CK(cudaEventRecord(e1));
       CK(cudaEventSynchronize(e1));
