@@ -92,20 +92,30 @@ int32_t t2r_pack_weights(const float* w, void* w_fprop, void* w_dgrad, int32_t C
 int32_t t2r_im2col_small_cin(const T2RConvDesc* d, const void* x, void* a, int32_t Kpad,
                              void* stream);
 
-/* Stem convolution (Cin = 3) WITHOUT im2col: the image lives in a zero-padded NHWC4 bf16 buffer
- * x4p[N][Hp][Wp][4] (channel 3 = 0; logical pixel (ih,iw) at (ih+pad_top, iw+pad_left); Wp >=
- * stride*(Wo-1)+16, Hp >= stride*(Ho-1)+KH).  Overlapping-window TMA maps deliver, per filter row,
- * the 64 contiguous values (16 pixels x 4 channels) under each output pixel, so the weights are
- * stored as w_stem bf16 [Cout][KH][16][4] (zero where kw >= KW or c == 3).  Same reference call sites
- * as t2r_im2col_small_cin. */
+/* Stem convolution (Cin = 3) WITHOUT im2col.  The image lives in a zero-padded bf16 buffer built by
+ * t2r_stem_pack_image (logical pixel (ih,iw) at padded (ih+pad_top, iw+pad_left)), in one of two layouts
+ * chosen by rows = (KW <= 8 && stride == 2) ? 2 : 1:
+ *   rows = 1: xp[N][Hp][Wp][4]    (channel 3 = 0)        K chunk = [16 px][4 ch] of one filter row
+ *   rows = 2: xp[N][Hp/2][Wp][8]  (row pair interleaved)  K chunk = [8 px][2 rows][4 ch]
+ * so that the 64 values under an output pixel are 128 contiguous bytes, which overlapping-window TMA
+ * maps deliver directly as the A operand (7x7/2: K = 256 instead of the 448 of rows = 1).  Weights:
+ * w_stem bf16 [Cout][chunks][64] in the same order, chunks = ceil(KH/rows), zero where kw >= KW,
+ * c == 3 or kh >= KH; K = t2r_stem_k(KH, KW, stride).  Requires Wp even, Hp % rows == 0,
+ * Wp >= stride*(Wo-1) + 16/rows, Hp >= stride*(Ho-1) + chunks*rows.
+ * Same reference call sites as t2r_im2col_small_cin. */
+int32_t t2r_stem_pack_image(const void* x_nhwc3, void* xp, int32_t N, int32_t H, int32_t W, int32_t Hp,
+                            int32_t Wp, int32_t pad_top, int32_t pad_left, int32_t KW, int32_t stride,
+                            void* stream);
+int32_t t2r_stem_k(int32_t KH, int32_t KW, int32_t stride);
 int32_t t2r_pad_nhwc3_c4(const void* x_nhwc3, void* x4p, int32_t N, int32_t H, int32_t W, int32_t Hp,
                          int32_t Wp, int32_t pad_top, int32_t pad_left, void* stream);
 int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, int32_t Hp, int32_t Wp,
                             const void* w_stem, const float* bias, void* y, void* stream);
 int32_t t2r_stem_conv_wgrad(const T2RConvDesc* d, const void* x4p, int32_t Hp, int32_t Wp, const void* dy,
                             float* dw_stem, void* stream);
-/* Clears the padded slots of dw_stem fp32 [Cout][KH][16][4] after t2r_stem_conv_wgrad. */
-int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, void* stream);
+/* Clears the padded slots of dw_stem fp32 [Cout][t2r_stem_k] after t2r_stem_conv_wgrad. */
+int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                           void* stream);
 
 /* ---- fp32 CUDA-core GEMM for the tiny action-context / logit layers -------------------- */
 /* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, op = transpose if flag set.

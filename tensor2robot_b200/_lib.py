@@ -57,7 +57,9 @@ _PROTOS = {
     't2r_pad_nhwc3_c4': (_I32, [_P, _P] + [_I32] * 7 + [_P]),
     't2r_stem_conv_fprop': (_I32, [_CD, _P, _I32, _I32, _P, _P, _P, _P]),
     't2r_stem_conv_wgrad': (_I32, [_CD, _P, _I32, _I32, _P, _P, _P]),
-    't2r_stem_mask_grad': (_I32, [_P, _I32, _I32, _I32, _P]),
+    't2r_stem_mask_grad': (_I32, [_P, _I32, _I32, _I32, _I32, _P]),
+    't2r_stem_k': (_I32, [_I32, _I32, _I32]),
+    't2r_stem_pack_image': (_I32, [_P, _P] + [_I32] * 9 + [_P]),
     't2r_sgemm': (_I32, [_I32, _I32, _I32, _I32, _I32, _F, _P, _I32, _P, _I32, _F, _P, _I32, _P]),
     't2r_bias_add_f32': (_I32, [_P, _P, _I64, _I32, _P]),
     't2r_colsum_f32': (_I32, [_P, _P, _I64, _I32, _P]),
@@ -94,7 +96,7 @@ _PROTOS = {
 }
 
 # Functions whose int return value is a status code (checked by `call`).
-_STATUS = {n for n, (r, _) in _PROTOS.items() if r is _I32 and n != 't2r_version'}
+_STATUS = {n for n, (r, _) in _PROTOS.items() if r is _I32 and n not in ('t2r_version', 't2r_stem_k')}
 
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOS))
 

@@ -46,6 +46,16 @@ struct IgemmParams {
 // out by TMA.  block_n is 64 or 128; bf16 output only.
 int conv_igemm_tma_launch(const IgemmParams& p, int block_n, cudaStream_t stream);
 
+// Stem (Cin = 3) K layout: a 64-wide chunk holds `rows` filter rows of 16/rows pixels x 4 channels
+// ([16 px][4 ch] for rows = 1, [8 px][2 rows][4 ch] over the row-pair image layout for rows = 2).
+// rows = 2 (K = ceil(KH/2)*64) when KW <= 8 and stride == 2, else 1 (K = KH*64).
+inline int stem_rows_per_chunk(int KW, int stride) { return (KW <= 8 && stride == 2) ? 2 : 1; }
+// Activation maps for the stem over the padded image (t2r_stem_pack_image layout); < 0 on error.
+int make_stem_maps(CUtensorMap* maps, const void* x4p, int N, int Hp, int Wp, int KW, int stride, int Ho, int Wo,
+                   int TW, int TH);
+// Tap table of the stem; returns the number of taps (= 64-wide K chunks).
+int make_stem_taps(ConvTap* taps, int KH, int KW, int stride);
+
 // Stride-1 KxK convolution through the shared-memory halo kernel (conv_halo.cu).
 struct HaloRequest {
   const void* x;       // [N,H,W,C] bf16, the tensor the taps slide over

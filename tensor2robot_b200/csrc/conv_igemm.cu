@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
               const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
               const uint32_t sb = sa + Cfg::kABytes;
               mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-              tma_load_4d(sa, &p.tmap_a[tap.map], full_bar(stage), c * 64, ow0 + tap.dw,
-                          oh0 + tap.dh, img);
+              tma_load_4d(sa, &p.tmap_a[tap.map], full_bar(stage), c * 64, ow0 + tap.dw, oh0 + tap.dh, img);
               tma_load_2d(sb, &p.tmap_b, full_bar(stage), (tap.kchunk0 + c) * 64, nt * BLOCK_N);
             }
             if (++turn == 3) turn = 0;
@@ -613,9 +612,20 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
 // 64-wide chunk each.  K is padded 147 -> 448 (7x7) / 108 -> 384 (6x6): the stem is ~3 % of the
 // model's FLOPs and this removes the 10.9 GB im2col matrix and two HBM passes over it.
 namespace t2r {
-int make_stem_maps(CUtensorMap* maps, const void* x4p, int N, int Hp, int Wp, int stride, int Ho, int Wo, int TW,
-                   int TH) {
+int make_stem_maps(CUtensorMap* maps, const void* x4p, int N, int Hp, int Wp, int KW, int stride, int Ho, int Wo,
+                   int TW, int TH) {
   const char* base = static_cast<const char*>(x4p);
+  (void)Ho;
+  if (stem_rows_per_chunk(KW, stride) == 2) {
+    // Row-pair image layout [N][Hp/2][Wp][8] (t2r_stem_pack_image): the window under output pixel
+    // (oh, ow) for filter rows (2j, 2j+1) is the 128 contiguous bytes at pair row oh + j, column 2*ow.
+    uint64_t dims[4] = {64, uint64_t(Wo), uint64_t(Hp / 2), uint64_t(N)};
+    uint64_t strides[3] = {uint64_t(stride) * 16, uint64_t(Wp) * 16, uint64_t(Hp / 2) * Wp * 16};
+    uint32_t box[4] = {64, uint32_t(TW), uint32_t(TH), 1};
+    if (encode_tmap_bf16(&maps[0], base, 4, dims, strides, box) != 0) return -1;
+    for (int i = 1; i < 4; ++i) maps[i] = maps[0];
+    return 0;
+  }
   for (int ph = 0; ph < stride; ++ph) {
     const int rows = (Hp - ph + stride - 1) / stride;
     uint64_t dims[4] = {64, uint64_t(Wo), uint64_t(std::max(rows, 1)), uint64_t(N)};
@@ -624,8 +634,20 @@ int make_stem_maps(CUtensorMap* maps, const void* x4p, int N, int Hp, int Wp, in
     if (encode_tmap_bf16(&maps[ph], base + size_t(ph) * Wp * 8, 4, dims, strides, box) != 0) return -1;
   }
   for (int i = stride; i < 4; ++i) maps[i] = maps[0];
-  (void)Ho;
   return 0;
+}
+
+int make_stem_taps(ConvTap* taps, int KH, int KW, int stride) {
+  const int rows = stem_rows_per_chunk(KW, stride);
+  const int n = (KH + rows - 1) / rows;
+  for (int j = 0; j < n; ++j) {
+    const int kh = j * rows;
+    taps[j].map = int8_t(rows == 2 ? 0 : kh % stride);
+    taps[j].dh = int8_t(kh / stride);
+    taps[j].dw = 0;
+    taps[j].kchunk0 = j;
+  }
+  return n;
 }
 }  // namespace t2r
 
@@ -634,13 +656,16 @@ extern "C" int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, in
   T2R_CHECK_ARG(d && d->struct_size == sizeof(T2RConvDesc) && x4p && w_stem && y, "stem_conv_fprop: bad args");
   T2R_CHECK_ARG(d->Cin == 3 && d->KW <= 16 && d->KH <= kMaxTaps && d->Cout % 64 == 0 && d->stride >= 1 &&
                     d->stride <= 2, "stem_conv_fprop: unsupported geometry");
-  T2R_CHECK_ARG(Wp >= d->stride * (d->Wo - 1) + 16 && Hp >= d->stride * (d->Ho - 1) + d->KH,
+  const int rpc = stem_rows_per_chunk(d->KW, d->stride);
+  const int n_chunks = (d->KH + rpc - 1) / rpc;
+  T2R_CHECK_ARG(Wp % 2 == 0 && Hp % rpc == 0 && Wp >= d->stride * (d->Wo - 1) + 16 / rpc &&
+                    Hp >= d->stride * (d->Ho - 1) + n_chunks * rpc,
                 "stem_conv_fprop: padded image %dx%d too small", Hp, Wp);
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   pick_tile(d->Ho, d->Wo, 128, &p.TW, &p.TH);
-  if (make_stem_maps(p.tmap_a, x4p, d->N, Hp, Wp, d->stride, d->Ho, d->Wo, p.TW, p.TH) != 0) return T2R_ERR_CUDA;
-  const uint64_t Ktot = uint64_t(d->KH) * 64;
+  if (make_stem_maps(p.tmap_a, x4p, d->N, Hp, Wp, d->KW, d->stride, d->Ho, d->Wo, p.TW, p.TH) < 0) return T2R_ERR_CUDA;
+  const uint64_t Ktot = uint64_t(n_chunks) * 64;
   bool tma = false;
   const int block_n = pick_block_n(d->Cout, (long long)Ktot, 0, &tma);
   uint64_t dims[2] = {Ktot, uint64_t(d->Cout)};
@@ -648,13 +673,7 @@ extern "C" int32_t t2r_stem_conv_fprop(const T2RConvDesc* d, const void* x4p, in
   uint32_t box[2] = {64, uint32_t(block_n)};
   if (encode_tmap_bf16(&p.tmap_b, w_stem, 2, dims, strides, box) != 0) return T2R_ERR_CUDA;
   p.chunks_per_tap = 1;
-  for (int kh = 0; kh < d->KH; ++kh) {
-    p.taps[kh].map = int8_t(kh % d->stride);
-    p.taps[kh].dh = int8_t(kh / d->stride);
-    p.taps[kh].dw = 0;
-    p.taps[kh].kchunk0 = kh;
-  }
-  p.n_taps = d->KH;
+  p.n_taps = make_stem_taps(p.taps, d->KH, d->KW, d->stride);
   p.tiles_w = int(ceil_div(d->Wo, p.TW));
   p.tiles_h = int(ceil_div(d->Ho, p.TH));
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;

@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
               const int t = slot / p.chunks_per_tap;
               const int c = slot - t * p.chunks_per_tap;
               const ConvTap tap = p.taps[t];
-              tma_load_4d(sa + h * Cfg::kTileBytes, &p.tmap_x[tap.map], full_bar(stage), c * 64,
-                          ow0 + tap.dw, oh0 + tap.dh, img);
+              tma_load_4d(sa + h * Cfg::kTileBytes, &p.tmap_x[tap.map], full_bar(stage), c * 64, ow0 + tap.dw,
+                          oh0 + tap.dh, img);
             }
           }
           if (++turn == 3) turn = 0;
@@ -306,11 +306,6 @@ extern "C" int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const v
   return launch_wgrad<64>(p, st);
 }
 
-namespace t2r {
-int make_stem_maps(CUtensorMap* maps, const void* x4p, int N, int Hp, int Wp, int stride, int Ho, int Wo, int TW,
-                   int TH);   // conv_igemm.cu
-}
-
 // Weight gradient of the stem convolution over the padded NHWC4 image (see t2r_stem_conv_fprop):
 // dw_stem fp32 [Cout][KH][64] += dy^T * windows; entries of padded slots (kw >= KW or c == 3) are
 // garbage by construction and must be cleared with t2r_stem_mask_grad.
@@ -322,23 +317,17 @@ extern "C" int32_t t2r_stem_conv_wgrad(const T2RConvDesc* d, const void* x4p, in
   WgradParams p;
   memset(&p, 0, sizeof(p));
   pick_tile(d->Ho, d->Wo, 64, &p.TW, &p.TH);
-  if (make_stem_maps(p.tmap_x, x4p, d->N, Hp, Wp, d->stride, d->Ho, d->Wo, p.TW, p.TH) != 0) return T2R_ERR_CUDA;
+  if (make_stem_maps(p.tmap_x, x4p, d->N, Hp, Wp, d->KW, d->stride, d->Ho, d->Wo, p.TW, p.TH) < 0) return T2R_ERR_CUDA;
   CUtensorMap dy_maps[4];
   if (make_phase_maps(dy_maps, dy, d->N, d->Ho, d->Wo, d->Cout, 1, p.TW, p.TH) != 0) return T2R_ERR_CUDA;
   p.tmap_dy = dy_maps[0];
   p.chunks_per_tap = 1;
-  for (int kh = 0; kh < d->KH; ++kh) {
-    p.taps[kh].map = int8_t(kh % d->stride);
-    p.taps[kh].dh = int8_t(kh / d->stride);
-    p.taps[kh].dw = 0;
-    p.taps[kh].kchunk0 = kh;
-  }
-  p.n_slots = d->KH;
+  p.n_slots = make_stem_taps(p.taps, d->KH, d->KW, d->stride);
   p.n_groups = (p.n_slots + 1) / 2;
   p.tiles_w = int(ceil_div(d->Wo, p.TW));
   p.tiles_h = int(ceil_div(d->Ho, p.TH));
   p.total_ptiles = d->N * p.tiles_w * p.tiles_h;
-  p.Ktot = d->KH * 64;
+  p.Ktot = p.n_slots * 64;
   p.Cout = d->Cout;
   p.dw = dw_stem;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

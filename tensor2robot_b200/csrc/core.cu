@@ -5,7 +5,7 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace t2r {
 
@@ -406,12 +406,38 @@ __global__ void __launch_bounds__(256) pad_nhwc3_c4_kernel(const unsigned short*
   }
 }
 
-// Clears the padded slots of a stem weight gradient [Cout][KH][16 pixels][4 channels].
-__global__ void stem_mask_grad_kernel(float* dw, long long total, int KW) {
+// Row-pair variant: x bf16 [N,H,W,3] -> x8p bf16 [N,Hp/2,Wp,8], where channels 0..3 of pair row p
+// hold padded image row 2p and channels 4..7 row 2p+1 (same column).  8 consecutive columns are then
+// 128 contiguous bytes = 2 filter rows x 8 pixels x 4 channels: one K chunk of a stride-2 stem.
+__global__ void __launch_bounds__(256) pad_nhwc3_pairs_kernel(const unsigned short* __restrict__ x,
+                                                              uint2* __restrict__ x8p, int N, int H, int W, int Hp2,
+                                                              int Wp, int pad_top, int pad_left) {
+  const long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = int(i % W);
+    const long long r = i / W;
+    const int h = int(r % H);
+    const int n = int(r / H);
+    const unsigned short* px = x + i * 3;
+    uint2 o;
+    o.x = uint32_t(px[0]) | (uint32_t(px[1]) << 16);
+    o.y = uint32_t(px[2]);
+    const int pr = h + pad_top;
+    x8p[(((long long)n * Hp2 + (pr >> 1)) * Wp + w + pad_left) * 2 + (pr & 1)] = o;
+  }
+}
+
+// Clears the padded slots of a stem weight gradient.  rows == 1: [Cout][KH][16 px][4 ch];
+// rows == 2: [Cout][chunks][8 px][2 rows][4 ch].
+__global__ void stem_mask_grad_kernel(float* dw, long long total, int KH, int KW, int rows, int chunks) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int slot = int(i & 63);
-    if ((slot >> 2) >= KW || (slot & 3) == 3) dw[i] = 0.f;
+    const int chunk = int((i >> 6) % chunks);
+    const int pxi = rows == 2 ? (slot >> 3) : (slot >> 2);
+    const int r = rows == 2 ? ((slot >> 2) & 1) : 0;
+    if (pxi >= KW || (slot & 3) == 3 || chunk * rows + r >= KH) dw[i] = 0.f;
   }
 }
 }  // namespace t2r
@@ -426,11 +452,31 @@ extern "C" int32_t t2r_pad_nhwc3_c4(const void* x, void* x4p, int32_t N, int32_t
   return T2R_OK;
 }
 
-extern "C" int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, void* stream) {
+extern "C" int32_t t2r_stem_pack_image(const void* x, void* xp, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                                       int32_t pad_top, int32_t pad_left, int32_t KW, int32_t stride, void* stream) {
+  if (t2r::stem_rows_per_chunk(KW, stride) == 1)
+    return t2r_pad_nhwc3_c4(x, xp, N, H, W, Hp, Wp, pad_top, pad_left, stream);
+  T2R_CHECK_ARG(x && xp && N > 0 && Hp % 2 == 0 && H + pad_top <= Hp && W + pad_left <= Wp, "stem_pack_image: bad args");
+  const long long total = (long long)N * H * W;
+  t2r::pad_nhwc3_pairs_kernel<<<t2r::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned short*>(x), static_cast<uint2*>(xp), N, H, W, Hp / 2, Wp, pad_top, pad_left);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_stem_k(int32_t KH, int32_t KW, int32_t stride) {
+  const int rows = t2r::stem_rows_per_chunk(KW, stride);
+  return ((KH + rows - 1) / rows) * 64;
+}
+
+extern "C" int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                                      void* stream) {
   T2R_CHECK_ARG(dw_stem && Cout > 0 && KH > 0 && KW > 0 && KW <= 16, "stem_mask_grad: bad args");
-  const long long total = (long long)Cout * KH * 64;
-  t2r::stem_mask_grad_kernel<<<t2r::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_stem, total,
-                                                                                                  KW);
+  const int rows = t2r::stem_rows_per_chunk(KW, stride);
+  const int chunks = (KH + rows - 1) / rows;
+  const long long total = (long long)Cout * chunks * 64;
+  t2r::stem_mask_grad_kernel<<<t2r::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_stem, total, KH,
+                                                                                                  KW, rows, chunks);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

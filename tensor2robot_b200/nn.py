@@ -552,11 +552,13 @@ class _StemConvFn(torch.autograd.Function):
   def _padded(vs, x, geom):
     kh, kw, stride, ho, wo, pt, pl = geom
     n, h, w, _ = x.shape
-    hp = max(h + pt, stride * (ho - 1) + kh)
-    wp = max(w + pl, stride * (wo - 1) + 16)
+    rows = _stem_rows(kw, stride)
+    hp = max(h + pt, stride * (ho - 1) + -(-kh // rows) * rows)
+    hp = -(-hp // rows) * rows
+    wp = max(w + pl, stride * (wo - 1) + 16 // rows)
     wp = (wp + 1) // 2 * 2                       # row pitch multiple of 16 bytes
     buf = vs.scratch(('stem_x4p', n, hp, wp), n * hp * wp * 4, BF16)   # zero-initialised once
-    _lib.call('t2r_pad_nhwc3_c4', _p(x), _p(buf), n, h, w, hp, wp, pt, pl, _stream())
+    _lib.call('t2r_stem_pack_image', _p(x), _p(buf), n, h, w, hp, wp, pt, pl, kw, stride, _stream())
     return buf, hp, wp
 
   @staticmethod
@@ -588,7 +590,7 @@ class _StemConvFn(torch.autograd.Function):
       x4p, hp, wp = _StemConvFn._padded(ctx.vs, x, ctx.geom)
       with _prof('wgrad', ctx.desc):
         _lib.call('t2r_stem_conv_wgrad', C.byref(ctx.desc), _p(x4p), hp, wp, _p(dy), _p(ctx.var.grad), st)
-      _lib.call('t2r_stem_mask_grad', _p(ctx.var.grad), ctx.var.shape[0], kh, kw, st)
+      _lib.call('t2r_stem_mask_grad', _p(ctx.var.grad), ctx.var.shape[0], kh, kw, ctx.geom[2], st)
     if ctx.needs_input_grad[0]:
       raise _lib.T2RError('stem convolution %s has no data gradient (image inputs are leaves)' % ctx.var.name)
     return None, None, None, None, None, None
@@ -606,14 +608,15 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   small = cin % 64 != 0
   if small and (cin != 3 or kw > 16 or stride > 2):
     raise _lib.T2RError('conv2d: Cin=%d is supported only as the 3-channel image stem' % cin)
-  kpad = kh * 64 if small else 0   # [kh][16 pixels][4 channels]
+  kpad = -(-kh // _stem_rows(kw, stride)) * 64 if small else 0   # [chunks][rows][16/rows pixels][4 ch]
   with vs.scope(scope):
     if small:
       # stored as [Cout, 1, 1, Kpad] (K-padded OHWI, flattened taps); TF layout handled by to_tf
       wv = vs.get_variable(names[0], (filters, 1, 1, kpad),
-                           _padded_init(initializer or variance_scaling(kh * kw * cin), filters, kh, kw, cin, kpad),
+                           _padded_init(initializer or variance_scaling(kh * kw * cin), filters, kh, kw, cin, kpad,
+                                        stride),
                            trainable, regularize, 'conv', None)
-      wv.stem_geom = (kh, kw, cin)
+      wv.stem_geom = (kh, kw, cin, stride)
       _install_stem_tf(wv)
     else:
       wv = vs.get_variable(names[0], (filters, kh, kw, cin), initializer or variance_scaling(kh * kw * cin),
@@ -632,30 +635,52 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   return _trace('conv', scope, y)
 
 
-def _stem_pack(w_ohwi):
-  """[Cout, KH, KW, 3] -> [Cout, KH*64] in the stem layout [kh][16 pixels][4 channels]."""
+def _stem_rows(kw, stride):
+  """Filter rows per 64-wide K chunk of the stem layout (t2r_b200.h: t2r_stem_k)."""
+  return 2 if (kw <= 8 and stride == 2) else 1
+
+
+def _stem_pack(w_ohwi, stride):
+  """[Cout, KH, KW, 3] -> [Cout, K] in the stem layout: [kh][16 px][4 ch] (rows = 1) or
+  [chunk][8 px][2 rows][4 ch] (rows = 2)."""
   cout, kh, kw, cin = w_ohwi.shape
-  out = np.zeros((cout, kh, 16, 4), np.float32)
-  out[:, :, :kw, :cin] = w_ohwi
-  return out.reshape(cout, kh * 64)
+  rows = _stem_rows(kw, stride)
+  chunks = -(-kh // rows)
+  out = np.zeros((cout, chunks * rows, 16 // rows, 4), np.float32)     # [co][kh][px][ch]
+  out[:, :kh, :kw, :cin] = w_ohwi
+  if rows == 2:
+    out = out.reshape(cout, chunks, 2, 8, 4).transpose(0, 1, 3, 2, 4)  # [co][chunk][px][row][ch]
+  return np.ascontiguousarray(out).reshape(cout, chunks * 64)
 
 
-def _padded_init(init, filters, kh, kw, cin, kpad):
+def _stem_unpack(w_packed, kh, kw, cin, stride):
+  """Inverse of _stem_pack: [Cout, K] -> [Cout, KH, KW, cin]."""
+  cout = w_packed.shape[0]
+  rows = _stem_rows(kw, stride)
+  chunks = -(-kh // rows)
+  a = w_packed.reshape(cout, chunks, 64)
+  if rows == 2:
+    a = a.reshape(cout, chunks, 8, 2, 4).transpose(0, 1, 3, 2, 4)      # [co][chunk][row][px][ch]
+  a = a.reshape(cout, chunks * rows, 16 // rows, 4)
+  return a[:, :kh, :kw, :cin]
+
+
+def _padded_init(init, filters, kh, kw, cin, kpad, stride):
   def f(shape, rng):
-    return _stem_pack(init((filters, kh, kw, cin), rng)).reshape(shape)
+    return _stem_pack(init((filters, kh, kw, cin), rng), stride).reshape(shape)
   return f
 
 
 def _install_stem_tf(v):
-  kh, kw, cin = v.stem_geom
+  kh, kw, cin, stride = v.stem_geom
 
   def to_tf():
-    a = v.data.detach().float().cpu().numpy().reshape(v.shape[0], kh, 16, 4)[:, :, :kw, :cin]
+    a = _stem_unpack(v.data.detach().float().cpu().numpy().reshape(v.shape[0], -1), kh, kw, cin, stride)
     return np.ascontiguousarray(a.transpose(1, 2, 3, 0))          # HWIO
 
   def from_tf(a):
     a = np.asarray(a, np.float32).transpose(3, 0, 1, 2)            # OHWI
-    v.data.copy_(torch.from_numpy(_stem_pack(a).reshape(v.shape)).to(v.data.device))
+    v.data.copy_(torch.from_numpy(_stem_pack(a, stride).reshape(v.shape)).to(v.data.device))
   v.to_tf, v.from_tf = to_tf, from_tf
 
 
