@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 }
 
 // pass 1 of backward: sum(dz), sum(dz * xhat) per channel, dz = dy * [relu mask]
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(
     const uint4* __restrict__ dy, const uint4* __restrict__ x, long long rows, int C, int cgb,
     int lanes_r, long long rows_per_block, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ scale,
@@ -182,11 +182,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
   const int cgi = blockIdx.y * cgb + g;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cgi < cg) {
-    float mu[8], is[8], sc[8], sh[8];
+    // q accumulates sum(dz * x) (raw); bn_bwd_finalize turns it into sum(dz * xhat) = invstd * (q - mean * s),
+    // which keeps mean / invstd out of the loop (16 registers -> one more resident CTA per SM).
+    float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      mu[j] = mean[cgi * 8 + j];
-      is[j] = invstd[cgi * 8 + j];
       sc[j] = scale[cgi * 8 + j];
       sh[j] = shift[cgi * 8 + j];
     }
@@ -205,18 +205,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
         const float z = fmaf(fx[j], sc[j], sh[j]);
         const float dz = (relu && !(z > 0.f)) ? 0.f : fd[j];
         s[j] += dz;
-        q[j] += dz * (fx[j] - mu[j]) * is[j];
+        q[j] = fmaf(dz, fx[j], q[j]);
       }
     }
   }
   block_reduce_16(s, q, cgb, lanes_r, cgi, C, red, red + C);
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* red, int C, float* dgamma, float* dbeta) {
+__global__ void bn_bwd_finalize_kernel(const double* red, int C, const float* mean, const float* invstd,
+                                       float* dgamma, float* dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   dbeta[c] = float(red[c]);
-  dgamma[c] = float(red[C + c]);
+  dgamma[c] = float((red[C + c] - double(mean[c]) * red[c]) * double(invstd[c]));
 }
 
 // pass 2: dx = scale * (dz - sum(dz)/rows - xhat * sum(dz*xhat)/rows) (+ dres)
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 }
 
 // y = relu?(x*scale + shift), row-partitioned (no FiLM).
-__global__ void __launch_bounds__(256) bn_apply_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+__global__ void __launch_bounds__(256, 6) bn_apply_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                             long long rows, int C, int cgb, int lanes_r,
                                                             long long rows_per_block,
                                                             const float* __restrict__ scale,
@@ -360,7 +361,7 @@ extern "C" int32_t t2r_bn_apply(const void* x, void* y, int64_t rows, int32_t C,
     bn_apply_kernel<true><<<grid_for(total8), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
                                                             total8, C / 8, scale, shift, film, rows_per_image, relu);
   else {
-    const RowPartition p = partition(rows, C);
+    const RowPartition p = partition(rows, C, 6);   // <= 40 registers/thread: 6 CTAs per SM
     bn_apply_rows_kernel<<<dim3(p.row_blocks, p.col_blocks), 256, 0, st>>>(
         static_cast<const uint4*>(x), static_cast<uint4*>(y), rows, C, p.cgb, p.lanes_r, p.rows_per_block, scale,
         shift, relu);
@@ -380,13 +381,13 @@ extern "C" int32_t t2r_bn_backward(const void* dy, const void* x, const void* dr
   T2R_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_backward: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   T2R_CUDA_OK(cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st));
-  const RowPartition pr = partition(rows, C, 3);   // 80 registers/thread: 3 CTAs per SM
+  const RowPartition pr = partition(rows, C, 4);   // <= 64 registers/thread: 4 CTAs per SM
   bn_bwd_reduce_kernel<<<dim3(pr.row_blocks, pr.col_blocks), 256, 0, st>>>(
       static_cast<const uint4*>(dy), static_cast<const uint4*>(x), rows, C, pr.cgb, pr.lanes_r,
       pr.rows_per_block, mean, invstd, scale, shift, relu, red);
   T2R_LAUNCH_OK();
   const RowPartition p = partition(rows, C, 4);    // 64 registers/thread: 4 CTAs per SM
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, C, mean, invstd, dgamma, dbeta);
   T2R_LAUNCH_OK();
   const float inv_rows = 1.f / float(rows);
   const dim3 grid(p.row_blocks, p.col_blocks);
