@@ -275,6 +275,15 @@ typedef struct T2RFeaturePlan {
 } T2RFeaturePlan;
 int32_t t2r_example_parse_batch(const uint8_t* const* records, const uint64_t* lengths,
                                 int32_t B, T2RFeaturePlan* plan, int32_t n_features);
+/* tf.SequenceExample feature_lists (tf.io.parse_sequence_example with FixedLenSequenceFeature(allow_missing),
+ * utils/tfdata.py:352-384).  The context part of a SequenceExample has the wire layout of an Example and is
+ * parsed by t2r_example_parse_batch.  plan[i].count = values per step; plan[i].dst = [B][max_steps][count]
+ * (BYTES: pointers, with dst_len of the same shape), zero-initialised by the caller = the padding.
+ * steps[i*B + b] receives the number of steps of feature i in record b; a missing key has 0 steps.
+ * max_steps == 0: only `steps` is produced (first pass, to size the dense batch). */
+int32_t t2r_sequence_example_parse_batch(const uint8_t* const* records, const uint64_t* lengths,
+                                         int32_t B, const T2RFeaturePlan* plan, int32_t n_features,
+                                         int32_t max_steps, int64_t* steps);
 
 #ifdef __cplusplus
 }

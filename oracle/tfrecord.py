@@ -156,6 +156,28 @@ def make_example(features):
   return _ld(1, entries)
 
 
+def _feature(value):
+  if isinstance(value, bytes):
+    value = [value]
+  if len(value) and isinstance(value[0], bytes):
+    return _ld(1, b''.join(_ld(1, v) for v in value))
+  if len(value) and isinstance(value[0], (int,)) and not isinstance(value[0], bool):
+    return _ld(3, _ld(1, b''.join(_enc_varint(int(v)) for v in value)))
+  return _ld(2, _ld(1, struct.pack('<%df' % len(value), *[float(v) for v in value])))
+
+
+def make_sequence_example(context, feature_lists):
+  """tf.train.SequenceExample{context = 1: Features, feature_lists = 2: FeatureLists{map<string,
+  FeatureList{repeated Feature feature = 1}>}} (tensorflow/core/example/example.proto).
+  context: {key: value}; feature_lists: {key: [value per step]} with values as in make_example."""
+  ctx = b''.join(_ld(1, _ld(1, k.encode('utf-8')) + _ld(2, _feature(v))) for k, v in context.items())
+  lists = b''
+  for key, steps in feature_lists.items():
+    fl = b''.join(_ld(1, _feature(v)) for v in steps)
+    lists += _ld(1, _ld(1, key.encode('utf-8')) + _ld(2, fl))
+  return _ld(1, ctx) + _ld(2, lists)
+
+
 def write_tfrecords(path, records):
   with open(path, 'wb') as f:
     for rec in records:

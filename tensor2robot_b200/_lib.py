@@ -93,6 +93,7 @@ _PROTOS = {
     't2r_masked_crc32c': (C.c_uint32, [_P, _U64]),
     't2r_tfrecord_index': (_I64, [_P, _U64, _P, _P, _I64, _I32]),
     't2r_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32]),
+    't2r_sequence_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32, _I32, _P]),
 }
 
 # Functions whose int return value is a status code (checked by `call`).

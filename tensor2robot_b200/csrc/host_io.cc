@@ -289,7 +289,104 @@ bool parse_one(const uint8_t* rec, uint64_t len, int b, T2RFeaturePlan* plan, in
   return true;
 }
 
+// tf.SequenceExample { Features context = 1; FeatureLists feature_lists = 2; }: walks feature_lists
+// and, for every planned key, decodes step t's Feature into dst[(b * max_steps + t) * count ...].
+bool parse_one_sequence(const uint8_t* rec, uint64_t len, int b, int B, const T2RFeaturePlan* plan, int nf,
+                        int max_steps, int64_t* steps, ParseError& err) {
+  for (int i = 0; i < nf; ++i) steps[(long long)i * B + b] = 0;
+  Cursor ex{rec, rec + len};
+  while (ex.p < ex.end) {
+    uint64_t tag;
+    if (!read_varint(ex, &tag)) { err.fail("record %d: bad SequenceExample tag", b); return false; }
+    if ((tag >> 3) != 2 || (tag & 7) != 2) {
+      if (!skip_field(ex, uint32_t(tag & 7))) { err.fail("record %d: bad SequenceExample field", b); return false; }
+      continue;
+    }
+    Cursor lists;
+    if (!read_len(ex, &lists)) { err.fail("record %d: truncated FeatureLists", b); return false; }
+    while (lists.p < lists.end) {
+      uint64_t t2;
+      if (!read_varint(lists, &t2)) { err.fail("record %d: bad FeatureLists tag", b); return false; }
+      if ((t2 >> 3) != 1 || (t2 & 7) != 2) {
+        if (!skip_field(lists, uint32_t(t2 & 7))) { err.fail("record %d: bad FeatureLists field", b); return false; }
+        continue;
+      }
+      Cursor entry;
+      if (!read_len(lists, &entry)) { err.fail("record %d: truncated feature_list entry", b); return false; }
+      Cursor key{nullptr, nullptr}, val{nullptr, nullptr};
+      while (entry.p < entry.end) {
+        uint64_t t3;
+        if (!read_varint(entry, &t3)) { err.fail("record %d: bad entry tag", b); return false; }
+        Cursor sub;
+        if ((t3 & 7) != 2) {
+          if (!skip_field(entry, uint32_t(t3 & 7))) { err.fail("record %d: bad entry field", b); return false; }
+          continue;
+        }
+        if (!read_len(entry, &sub)) { err.fail("record %d: truncated entry", b); return false; }
+        if ((t3 >> 3) == 1) key = sub;
+        else if ((t3 >> 3) == 2) val = sub;
+      }
+      if (!key.p || !val.p) continue;
+      const size_t klen = size_t(key.end - key.p);
+      for (int i = 0; i < nf; ++i) {
+        const T2RFeaturePlan& f = plan[i];
+        if (strlen(f.key) != klen || memcmp(f.key, key.p, klen) != 0) continue;
+        Cursor fl = val;   // FeatureList { repeated Feature feature = 1; }
+        int64_t t = 0;
+        while (fl.p < fl.end) {
+          uint64_t t4;
+          if (!read_varint(fl, &t4)) { err.fail("record %d: bad FeatureList tag in '%s'", b, f.key); return false; }
+          if ((t4 >> 3) != 1 || (t4 & 7) != 2) {
+            if (!skip_field(fl, uint32_t(t4 & 7))) { err.fail("record %d: bad FeatureList field", b); return false; }
+            continue;
+          }
+          Cursor feat;
+          if (!read_len(fl, &feat)) { err.fail("record %d: truncated step of '%s'", b, f.key); return false; }
+          if (max_steps > 0) {
+            if (t >= max_steps) { err.fail("record %d: '%s' has more than %d steps", b, f.key, max_steps); return false; }
+            T2RFeaturePlan step = f;
+            const long long off = ((long long)b * max_steps + t) * f.count;
+            if (f.dtype == T2R_DT_FLOAT) step.dst = static_cast<float*>(f.dst) + off;
+            else if (f.dtype == T2R_DT_INT64) step.dst = static_cast<int64_t*>(f.dst) + off;
+            else { step.dst = static_cast<const uint8_t**>(f.dst) + off; step.dst_len = f.dst_len + off; }
+            const long n = decode_feature(feat, step, 0, err);
+            if (n < 0) return false;
+            if (n != f.count) {
+              err.fail("record %d: step %lld of '%s' has %ld values, expected %d", b, (long long)t, f.key, n, f.count);
+              return false;
+            }
+          }
+          ++t;
+        }
+        steps[(long long)i * B + b] = t;
+      }
+    }
+  }
+  return true;
+}
+
 }  // namespace
+
+extern "C" int32_t t2r_sequence_example_parse_batch(const uint8_t* const* records, const uint64_t* lengths,
+                                                    int32_t B, const T2RFeaturePlan* plan, int32_t n_features,
+                                                    int32_t max_steps, int64_t* steps) {
+  if (!records || !lengths || !plan || !steps || B <= 0 || n_features <= 0 || max_steps < 0) {
+    t2r::set_error("sequence_example_parse_batch: bad args");
+    return T2R_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < n_features; ++i)
+    if (!plan[i].key || plan[i].count <= 0 || (max_steps > 0 && (!plan[i].dst || (plan[i].dtype == T2R_DT_BYTES && !plan[i].dst_len)))) {
+      t2r::set_error("sequence_example_parse_batch: bad plan entry %d", i);
+      return T2R_ERR_INVALID_ARG;
+    }
+  ParseError err;
+  for (int b = 0; b < B; ++b)
+    if (!parse_one_sequence(records[b], lengths[b], b, B, plan, n_features, max_steps, steps, err)) {
+      t2r::set_error("%s", err.msg);
+      return T2R_ERR_PARSE;
+    }
+  return T2R_OK;
+}
 
 extern "C" uint32_t t2r_crc32c(const uint8_t* data, uint64_t n) {
   static const bool hw = have_sse42();

@@ -16,6 +16,7 @@ by spec *path*; specs without a name are not parsed; bfloat16 specs are parsed a
 varlen specs are padded/clipped to shape[0]; encoded images arrive as bytes, '' decodes to zeros, a
 decoded size different from the spec raises; only uint8/uint16 image specs are accepted.
 """
+import collections
 import concurrent.futures
 import ctypes as C
 import glob
@@ -192,15 +193,102 @@ def _records_as_pointers(serialized):
   return keep, ptrs, lens
 
 
+def _parse_sequence_features(ptrs, lens, b, seq_specs, decode_images):
+  """tf.io.parse_sequence_example for FixedLenSequenceFeature(allow_missing=True) specs
+  (utils/tfdata.py:352-384): {name: spec} -> ({name: [B, T_max, ...]}, {name: int64 [B] lengths})."""
+  n = len(seq_specs)
+  plans = (_lib.FeaturePlan * n)()
+  keep, kinds = [], []
+  for i, (key, spec) in enumerate(seq_specs.items()):
+    plan = plans[i]
+    plan.key = spec.name.encode('utf-8')
+    keep.append(plan.key)
+    if decode_images and tensorspec_utils.is_encoded_image_spec(spec):
+      plan.dtype, plan.count = _lib.T2R_DT_BYTES, (int(spec.shape[0]) if len(spec.shape) > 3 else 1)
+      kinds.append('bytes')
+    elif spec.dtype == dtypes.string:
+      plan.dtype, plan.count = _lib.T2R_DT_BYTES, int(np.prod(tuple(spec.shape))) if spec.shape else 1
+      kinds.append('strings')
+    elif spec.dtype.is_floating:
+      plan.dtype, plan.count = _lib.T2R_DT_FLOAT, int(np.prod(tuple(spec.shape))) if spec.shape else 1
+      kinds.append('float')
+    elif spec.dtype.is_integer or spec.dtype == dtypes.bool_:
+      plan.dtype, plan.count = _lib.T2R_DT_INT64, int(np.prod(tuple(spec.shape))) if spec.shape else 1
+      kinds.append('int')
+    else:
+      raise ValueError('Feature specification with invalid data type for tf.Example parsing: "%s": %s' % (
+          key, spec.dtype))
+  steps = np.zeros((n, b), np.int64)
+  rc = _lib.lib().t2r_sequence_example_parse_batch(ptrs, lens, b, plans, n, 0, steps.ctypes.data)
+  if rc != 0:
+    raise ValueError('tf.SequenceExample parsing failed: %s' % _lib.last_error())
+  t_max = int(steps.max()) if steps.size else 0
+  bufs = []
+  for i, kind in enumerate(kinds):
+    count = plans[i].count
+    size = b * max(t_max, 1) * count
+    if kind in ('bytes', 'strings'):
+      dst, dst_len = np.zeros(size, np.uint64), np.zeros(size, np.uint64)
+      plans[i].dst_len = dst_len.ctypes.data
+    else:
+      dst, dst_len = np.zeros(size, np.float32 if kind == 'float' else np.int64), None
+    plans[i].dst = dst.ctypes.data
+    bufs.append((dst, dst_len))
+  if t_max > 0:
+    rc = _lib.lib().t2r_sequence_example_parse_batch(ptrs, lens, b, plans, n, t_max, steps.ctypes.data)
+    if rc != 0:
+      raise ValueError('tf.SequenceExample parsing failed: %s' % _lib.last_error())
+  parsed, lengths = {}, {}
+  for i, (key, spec) in enumerate(seq_specs.items()):
+    dst, dst_len = bufs[i]
+    count, kind = plans[i].count, kinds[i]
+    lengths[key] = steps[i].copy()
+    if kind in ('bytes', 'strings'):
+      rows = [[C.string_at(int(dst[(r * t_max + t) * count + j]), int(dst_len[(r * t_max + t) * count + j]))
+               if dst[(r * t_max + t) * count + j] else b'' for t in range(t_max) for j in range(count)]
+              for r in range(b)]
+      if kind == 'bytes':
+        dims = tuple(spec.shape[-3:])
+        lead = (t_max, count) if len(spec.shape) > 3 else (t_max,)
+        if t_max == 0:
+          parsed[key] = np.zeros((b,) + lead + dims, spec.dtype.as_numpy_dtype)
+        else:
+          step_spec = tensorspec_utils.ExtendedTensorSpec.from_spec(spec, shape=(t_max * count,) + dims)
+          parsed[key] = _decode_images(step_spec, rows).reshape((b,) + lead + dims)
+      else:
+        parsed[key] = np.array(rows, dtype=object).reshape((b, t_max) + tuple(spec.shape))
+    else:
+      arr = dst[:b * t_max * count].reshape((b, t_max) + tuple(spec.shape))
+      if spec.dtype == dtypes.bfloat16:
+        import torch
+        parsed[key] = torch.from_numpy(arr).to(torch.bfloat16)
+      else:
+        parsed[key] = arr.astype(spec.dtype.as_numpy_dtype, copy=False)
+  del keep
+  return parsed, lengths
+
+
 def _parse_examples(serialized, tensor_spec_dict, decode_images):
-  """The tf.parse_example equivalent: {dataset_key+name: spec} -> {same key: numpy [B, ...]}."""
+  """The tf.parse_example equivalent: {dataset_key+name: spec} -> {same key: numpy [B, ...]}.
+  Specs with is_sequence=True switch to tf.io.parse_sequence_example semantics: they are read from the
+  SequenceExample's feature_lists, `<name>_length` context specs are not parsed but produced from the
+  step counts (utils/tfdata.py:352-384)."""
   b = len(serialized)
   keep, ptrs, lens = _records_as_pointers(serialized)
+  seq_specs = collections.OrderedDict((k, v) for k, v in tensor_spec_dict.items() if getattr(v, 'is_sequence', False))
+  seq_parsed = {}
+  if seq_specs:
+    seq_parsed, seq_lengths = _parse_sequence_features(ptrs, lens, b, seq_specs, decode_images)
+    for k, v in seq_lengths.items():
+      seq_parsed[k + '_length'] = v
+    tensor_spec_dict = collections.OrderedDict(
+        (k, v) for k, v in tensor_spec_dict.items() if k not in seq_specs and k not in seq_parsed)
+    if not tensor_spec_dict:
+      del keep
+      return seq_parsed
   plans = (_lib.FeaturePlan * len(tensor_spec_dict))()
   buffers = {}
   for i, (key, spec) in enumerate(tensor_spec_dict.items()):
-    if getattr(spec, 'is_sequence', False):
-      raise NotImplementedError('SequenceExample parsing (is_sequence specs) is not on the QT-Opt hot path yet')
     plan = plans[i]
     plan.key = spec.name.encode('utf-8')
     keep.append(plan.key)
@@ -260,6 +348,7 @@ def _parse_examples(serialized, tensor_spec_dict, decode_images):
       else:
         parsed[key] = arr.astype(spec.dtype.as_numpy_dtype, copy=False)
   del keep
+  parsed.update(seq_parsed)
   return parsed
 
 

@@ -214,3 +214,42 @@ def test_record_input_generator_batches_and_shards():
   rnd.set_label_specifications(label_spec, label_spec)
   f, l = next(rnd.create_dataset('train'))
   assert f.state.image.shape == (3, 64, 64, 3) and f.state.image.dtype == np.uint8
+
+
+def test_sequence_example_parsing():
+  """utils/tfdata_test.py:346-395 (test_sequence_parsing): image + float sequences from
+  feature_lists, an int64 context feature, `<key>_length` outputs, zero padding to the longest
+  sequence of the batch (tf.io.parse_sequence_example)."""
+  base = (np.arange(8 * 8 * 3).reshape(8, 8, 3) % 7 * 30).astype(np.uint8)
+
+  def record(n_steps):
+    imgs, acts = [], []
+    for i in range(n_steps):
+      buf = io.BytesIO()
+      Image.fromarray((base * i % 251).astype(np.uint8)).save(buf, format='PNG')
+      imgs.append(buf.getvalue())
+      acts.append([3.0, 1.0 + i])
+    return oracle.make_sequence_example({'context_feature': [10]},
+                                        {'sequence_feature': acts, 'image_sequence_feature': imgs})
+
+  feature_tspec = utils.TensorSpecStruct(
+      state=TSPEC((8, 8, 3), dtypes.uint8, 'image_sequence_feature', is_sequence=True, data_format='png'),
+      action=TSPEC((2,), dtypes.float32, 'sequence_feature', is_sequence=True))
+  feature_tspec = utils.add_sequence_length_specs(feature_tspec)
+  label_tspec = utils.add_sequence_length_specs(
+      utils.TensorSpecStruct(reward=TSPEC((), dtypes.int64, 'context_feature')))
+  parse = tfdata.create_parse_tf_example_fn(feature_tspec, label_tspec)
+  for batch in ([record(3)], [record(3), record(3)], [record(3), record(1)]):
+    features, labels = parse(batch)
+    b = len(batch)
+    assert features.state.shape == (b, 3, 8, 8, 3) and features.state.dtype == np.uint8
+    assert features.action.shape == (b, 3, 2)
+    assert labels.reward.shape == (b,) and labels.reward.tolist() == [10] * b
+    for i in range(3):
+      np.testing.assert_array_equal(features.state[0, i], (base * i % 251).astype(np.uint8))
+      np.testing.assert_array_equal(features.action[0, i], [3.0, 1.0 + i])
+  assert features.state_length.tolist() == [3, 1] and features.action_length.tolist() == [3, 1]
+  assert not features.state[1, 1:].any() and not features.action[1, 1:].any()   # padding
+  # a record without the feature list is a zero-length sequence (allow_missing=True)
+  features, _ = parse([oracle.make_sequence_example({'context_feature': [10]}, {})])
+  assert features.action.shape == (1, 0, 2) and features.action_length.tolist() == [0]
