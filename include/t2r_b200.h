@@ -117,6 +117,16 @@ int32_t t2r_stem_conv_wgrad(const T2RConvDesc* d, const void* x4p, int32_t Hp, i
 int32_t t2r_stem_mask_grad(float* dw_stem, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
                            void* stream);
 
+/* Spatial softmax (layers/spatial_softmax.py:29-88): x bf16 [N,H,W,C] -> points fp32 [N,2C], the expected
+ * (x, y) position of every channel's softmax over H*W with x_j = 2j/(W-1)-1, y_i = 2i/(H-1)-1, laid out
+ * INTERLEAVED (x_1,y_1,x_2,y_2,...) as the reference's reshape of concat([x,y],1) produces; softmax
+ * (optional, bf16 [N,H,W,C]) is the heat map.  bwd: gradient w.r.t. x from dpoints (the softmax is
+ * recomputed). */
+int32_t t2r_spatial_softmax_fwd(const void* x, float* points, void* softmax, int32_t N, int32_t H, int32_t W,
+                                int32_t C, void* stream);
+int32_t t2r_spatial_softmax_bwd(const void* x, const float* points, const float* dpoints, void* dx, int32_t N,
+                                int32_t H, int32_t W, int32_t C, void* stream);
+
 /* ---- fp32 CUDA-core GEMM for the tiny action-context / logit layers -------------------- */
 /* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, op = transpose if flag set.
  * Replaces slim.fully_connected on grasp params and logits (networks.py:488-503,566-573). */
@@ -162,6 +172,14 @@ int32_t t2r_bn_backward(const void* dy, const void* x, const void* dres, void* d
                         int32_t C, const float* gamma, const float* mean, const float* invstd,
                         const float* scale, const float* shift, int32_t relu, double* red,
                         float* dgamma, float* dbeta, void* stream);
+
+/* Backward of y = relu?((1 + film_gamma[n,c]) * bn(x) + film_beta[n,c]) (FiLM-conditioned batch norm,
+ * layers/film_resnet_model.py:108-115): film fp32 [N][2C] (gamma part then beta part), dfilm same shape
+ * (written), sums_ws fp32 [N][2][C] workspace; other arguments as t2r_bn_backward. */
+int32_t t2r_bn_film_backward(const void* dy, const void* x, const float* film, const void* dres, void* dx,
+                             float* dfilm, int64_t rows, int32_t C, int64_t rows_per_image,
+                             const float* mean, const float* invstd, const float* scale, const float* shift,
+                             int32_t relu, float* sums_ws, float* dgamma, float* dbeta, void* stream);
 
 /* ---- pooling / reductions / elementwise ------------------------------------------------ */
 /* slim.max_pool2d SAME/VALID (networks.py:452,459,528; film_resnet_model.py:575-579).

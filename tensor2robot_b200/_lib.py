@@ -72,6 +72,9 @@ _PROTOS = {
     't2r_bn_infer_params': (_I32, [_I32, _P, _P, _P, _P, _F, _P, _P, _P]),
     't2r_bn_apply': (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P]),
     't2r_bn_backward': (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    't2r_spatial_softmax_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_spatial_softmax_bwd': (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_bn_film_backward': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     't2r_maxpool_fwd': (_I32, [_P, _P, _P] + [_I32] * 10 + [_P]),
     't2r_maxpool_bwd': (_I32, [_P, _P, _P] + [_I32] * 10 + [_P]),
     't2r_global_mean_fwd': (_I32, [_P, _P, _I32, _I32, _I32, _P]),

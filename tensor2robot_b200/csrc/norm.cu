@@ -314,6 +314,111 @@ static inline int grid_for(long long n) {
   return int(std::min<long long>(std::max<long long>((n + 255) / 256, 1), 148LL * 16));
 }
 
+// ---------------------------------------------------------------------------------------------
+// FiLM batch norm backward:  h = x*sc + sh,  z = (1 + g[n,c]) * h + b[n,c],  y = relu?(z)
+// (layers/film_resnet_model.py:108-115 after :50-57).  Per-image sums first:
+//   S1[n,c] = sum_pixels dz,  S3[n,c] = sum_pixels dz * x,   dz = dy * [z > 0]
+// from which d b = S1, d g = sc*S3 + sh*S1 and the batch-norm sums over dh = (1 + g) * dz follow.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_film_bwd_reduce_kernel(
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ film, int HW, int cg,
+    const float* __restrict__ scale, const float* __restrict__ shift, int relu, float* __restrict__ sums) {
+  __shared__ float sm[8][32][17];
+  const int n = blockIdx.x;
+  const int g = blockIdx.y * 32 + threadIdx.x;
+  const int C = cg * 8;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s3[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (g < cg) {
+    float sc[8], sh[8], fg[8], fb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale[g * 8 + j];
+      sh[j] = shift[g * 8 + j];
+      fg[j] = 1.f + film[(long long)n * 2 * C + g * 8 + j];
+      fb[j] = film[(long long)n * 2 * C + C + g * 8 + j];
+    }
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      const long long i = ((long long)n * HW + p) * cg + g;
+      float fx[8], fd[8];
+      unpack8(x[i], fx);
+      unpack8(dy[i], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(fg[j], fmaf(fx[j], sc[j], sh[j]), fb[j]);
+        const float dz = (relu && !(z > 0.f)) ? 0.f : fd[j];
+        s1[j] += dz;
+        s3[j] = fmaf(dz, fx[j], s3[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sm[threadIdx.y][threadIdx.x][j] = s1[j];
+    sm[threadIdx.y][threadIdx.x][8 + j] = s3[j];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && g < cg) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float s = 0.f;
+      for (int r = 0; r < 8; ++r) s += sm[r][threadIdx.x][j];
+      sums[((long long)n * 2 + (j >> 3)) * C + g * 8 + (j & 7)] = s;   // [N][2][C]
+    }
+  }
+}
+
+// dfilm [N][2C] (gamma part, beta part) and the batch-norm sums (fp64 over images).
+__global__ void bn_film_bwd_finalize_kernel(const float* sums, const float* film, int N, int C, const float* mean,
+                                            const float* invstd, const float* scale, const float* shift,
+                                            float* dfilm, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sdh = 0.0, sdhx = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const float s1 = sums[((long long)n * 2) * C + c], s3 = sums[((long long)n * 2 + 1) * C + c];
+    const float g1 = 1.f + film[(long long)n * 2 * C + c];
+    dfilm[(long long)n * 2 * C + c] = fmaf(scale[c], s3, shift[c] * s1);   // d gamma_film = sum dz * h
+    dfilm[(long long)n * 2 * C + C + c] = s1;                               // d beta_film  = sum dz
+    sdh += double(g1) * s1;
+    sdhx += double(g1) * s3;
+  }
+  dbeta[c] = float(sdh);
+  dgamma[c] = float((sdhx - double(mean[c]) * sdh) * double(invstd[c]));
+}
+
+__global__ void __launch_bounds__(256) bn_film_bwd_apply_kernel(
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ dres, uint4* __restrict__ dx,
+    const float* __restrict__ film, long long total8, int HW, int cg, float inv_rows, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int relu) {
+  const int C = cg * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    const long long n = (i / cg) / HW;
+    float fx[8], fd[8], fo[8];
+    unpack8(x[i], fx);
+    unpack8(dy[i], fd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const float sc = scale[c], sh = shift[c];
+      const float fg = 1.f + film[n * 2 * C + c], fb = film[n * 2 * C + C + c];
+      const float z = fmaf(fg, fmaf(fx[j], sc, sh), fb);
+      const float dh = ((relu && !(z > 0.f)) ? 0.f : fd[j]) * fg;
+      const float t = sc * dgamma[c] * inv_rows * invstd[c];
+      fo[j] = fmaf(sc, dh, fmaf(-t, fx[j], t * mean[c] - sc * dbeta[c] * inv_rows));
+    }
+    if (dres != nullptr) {
+      float fr[8];
+      unpack8(dres[i], fr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fo[j] += fr[j];
+    }
+    dx[i] = pack8(fo);
+  }
+}
+
 }  // namespace t2r
 
 using namespace t2r;
@@ -400,6 +505,31 @@ extern "C" int32_t t2r_bn_backward(const void* dy, const void* x, const void* dr
     bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(
         static_cast<const uint4*>(dy), static_cast<const uint4*>(x), nullptr, static_cast<uint4*>(dx), rows, C,
         p.cgb, p.lanes_r, p.rows_per_block, inv_rows, mean, invstd, scale, shift, dgamma, dbeta, relu);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_bn_film_backward(const void* dy, const void* x, const float* film, const void* dres, void* dx,
+                                        float* dfilm, int64_t rows, int32_t C, int64_t rows_per_image,
+                                        const float* mean, const float* invstd, const float* scale,
+                                        const float* shift, int32_t relu, float* sums_ws, float* dgamma,
+                                        float* dbeta, void* stream) {
+  T2R_CHECK_ARG(dy && x && film && dx && dfilm && mean && invstd && scale && shift && sums_ws && dgamma && dbeta,
+                "bn_film_backward: null pointer");
+  T2R_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && rows_per_image > 0 && rows % rows_per_image == 0 &&
+                    rows_per_image < (1LL << 31), "bn_film_backward: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = int(rows / rows_per_image), cg = C / 8, HW = int(rows_per_image);
+  bn_film_bwd_reduce_kernel<<<dim3(N, (cg + 31) / 32), dim3(32, 8), 0, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), film, HW, cg, scale, shift, relu, sums_ws);
+  T2R_LAUNCH_OK();
+  bn_film_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_ws, film, N, C, mean, invstd, scale, shift, dfilm,
+                                                               dgamma, dbeta);
+  T2R_LAUNCH_OK();
+  const long long total8 = rows * cg;
+  bn_film_bwd_apply_kernel<<<grid_for(total8), 256, 0, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<const uint4*>(dres),
+      static_cast<uint4*>(dx), film, total8, HW, cg, 1.f / float(rows), mean, invstd, scale, shift, dgamma, dbeta, relu);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

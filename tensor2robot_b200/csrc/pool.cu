@@ -216,6 +216,128 @@ static inline int grid_for(long long n) {
   return int(std::min<long long>(std::max<long long>((n + 255) / 256, 1), 148LL * 16));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spatial softmax (layers/spatial_softmax.py:29-88): per (image, channel) softmax over the H*W
+// positions and the expected coordinates x_j = 2j/(W-1) - 1, y_i = 2i/(H-1) - 1.  The reference
+// reshapes concat([x, y], 1) of shape [B*C, 2] to [B, 2C], i.e. the points come out INTERLEAVED
+// (x_1, y_1, x_2, y_2, ...) - the code, not its docstring, is restated here.
+// One block per (image, group of 8 channels); 256 threads stride over the positions.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_reduce8(float (&v)[8], float (*sm)[9], bool is_max) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[tid][j] = v[j];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sm[tid][j] = is_max ? fmaxf(sm[tid][j], sm[tid + s][j]) : sm[tid][j] + sm[tid + s][j];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = sm[0][j];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) spatial_softmax_fwd_kernel(const uint4* __restrict__ x, float* __restrict__ points,
+                                                                  uint4* __restrict__ softmax, int H, int W, int cg) {
+  __shared__ float sm[256][9];
+  const int n = blockIdx.x, g = blockIdx.y, HW = H * W, C = cg * 8;
+  const uint4* xn = x + (long long)n * HW * cg + g;
+  float mx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    float f[8];
+    unpack8(xn[(long long)p * cg], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], f[j]);
+  }
+  block_reduce8(mx, sm, true);
+  float se[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sx[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const float ax = W > 1 ? 2.f / float(W - 1) : 0.f, ay = H > 1 ? 2.f / float(H - 1) : 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const int i = p / W, j0 = p - i * W;
+    const float px = W > 1 ? ax * float(j0) - 1.f : NAN, py = H > 1 ? ay * float(i) - 1.f : NAN;  // 0/0 in the reference
+    float f[8];
+    unpack8(xn[(long long)p * cg], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = __expf(f[j] - mx[j]);
+      se[j] += e;
+      sx[j] = fmaf(e, px, sx[j]);
+      sy[j] = fmaf(e, py, sy[j]);
+    }
+  }
+  block_reduce8(se, sm, false);
+  block_reduce8(sx, sm, false);
+  block_reduce8(sy, sm, false);
+  if (threadIdx.x < 8) {
+    const int c = g * 8 + threadIdx.x;
+    points[(long long)n * 2 * C + 2 * c] = sx[threadIdx.x] / se[threadIdx.x];
+    points[(long long)n * 2 * C + 2 * c + 1] = sy[threadIdx.x] / se[threadIdx.x];
+  }
+  if (softmax != nullptr) {
+    uint4* sn = softmax + (long long)n * HW * cg + g;
+    for (int p = threadIdx.x; p < HW; p += 256) {
+      float f[8];
+      unpack8(xn[(long long)p * cg], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - mx[j]) / se[j];
+      sn[(long long)p * cg] = pack8(f);
+    }
+  }
+}
+
+// d logit_p = s_p * ((x_p - E[x]) * dEx + (y_p - E[y]) * dEy), recomputing the softmax from x.
+__global__ void __launch_bounds__(256) spatial_softmax_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ points,
+                                                                  const float* __restrict__ dpoints, uint4* __restrict__ dx,
+                                                                  int H, int W, int cg) {
+  __shared__ float sm[256][9];
+  const int n = blockIdx.x, g = blockIdx.y, HW = H * W, C = cg * 8;
+  const uint4* xn = x + (long long)n * HW * cg + g;
+  float mx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    float f[8];
+    unpack8(xn[(long long)p * cg], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], f[j]);
+  }
+  block_reduce8(mx, sm, true);
+  float se[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    float f[8];
+    unpack8(xn[(long long)p * cg], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) se[j] += __expf(f[j] - mx[j]);
+  }
+  block_reduce8(se, sm, false);
+  float ex[8], ey[8], gx[8], gy[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long o = (long long)n * 2 * C + 2 * (g * 8 + j);
+    ex[j] = points[o]; ey[j] = points[o + 1];
+    gx[j] = dpoints[o]; gy[j] = dpoints[o + 1];
+  }
+  const float ax = 2.f / float(W - 1), ay = 2.f / float(H - 1);
+  uint4* dn = dx + (long long)n * HW * cg + g;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const int i = p / W, j0 = p - i * W;
+    const float px = ax * float(j0) - 1.f, py = ay * float(i) - 1.f;
+    float f[8];
+    unpack8(xn[(long long)p * cg], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sft = __expf(f[j] - mx[j]) / se[j];
+      f[j] = sft * ((px - ex[j]) * gx[j] + (py - ey[j]) * gy[j]);
+    }
+    dn[(long long)p * cg] = pack8(f);
+  }
+}
+
 }  // namespace t2r
 
 using namespace t2r;
@@ -292,5 +414,23 @@ extern "C" int32_t t2r_add_context_bwd(const void* dy, void* dx, void* dctx, int
         static_cast<const uint4*>(dy), static_cast<uint4*>(dctx), HW, cg);
     T2R_LAUNCH_OK();
   }
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_spatial_softmax_fwd(const void* x, float* points, void* softmax, int32_t N, int32_t H,
+                                           int32_t W, int32_t C, void* stream) {
+  T2R_CHECK_ARG(x && points && N > 0 && H > 0 && W > 0 && C % 8 == 0, "spatial_softmax_fwd: bad args");
+  spatial_softmax_fwd_kernel<<<dim3(N, C / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), points, static_cast<uint4*>(softmax), H, W, C / 8);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_spatial_softmax_bwd(const void* x, const float* points, const float* dpoints, void* dx,
+                                           int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  T2R_CHECK_ARG(x && points && dpoints && dx && N > 0 && H > 1 && W > 1 && C % 8 == 0, "spatial_softmax_bwd: bad args");
+  spatial_softmax_bwd_kernel<<<dim3(N, C / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), points, dpoints, static_cast<uint4*>(dx), H, W, C / 8);
+  T2R_LAUNCH_OK();
   return T2R_OK;
 }

@@ -755,8 +755,6 @@ class _BatchNormFn(torch.autograd.Function):
     if not ctx.training:
       raise _lib.T2RError('backward through inference-mode batch norm is not supported')
     x, mean, invstd, scale, shift, film = ctx.saved_tensors
-    if film is not None:
-      raise _lib.T2RError('FiLM backward is not implemented yet')
     bn = ctx.bn
     c = x.shape[-1]
     rows = x.numel() // c
@@ -769,6 +767,13 @@ class _BatchNormFn(torch.autograd.Function):
     dbeta = bn['beta'].grad if bn['beta'].trainable else ctx.vs.scratch('bn_dbeta', 4096, F32)
     if dpass is not None:
       dpass = dpass.contiguous()
+    if film is not None:
+      n = x.shape[0]
+      dfilm = torch.empty_like(film)
+      sums = torch.empty((n, 2, c), dtype=F32, device=x.device)
+      _lib.call('t2r_bn_film_backward', _p(dy), _p(x), _p(film), _p(dpass), _p(dx), _p(dfilm), rows, c, rows // n,
+                _p(mean), _p(invstd), _p(scale), _p(shift), 1 if ctx.relu else 0, _p(sums), _p(dgamma), _p(dbeta), st)
+      return dx, (dfilm if ctx.needs_input_grad[1] else None), None, None, None, None, None, None
     _lib.call('t2r_bn_backward', _p(dy), _p(x), _p(dpass), _p(dx), rows, c,
               _p(gamma.data if gamma is not None else None), _p(mean), _p(invstd), _p(scale), _p(shift),
               1 if ctx.relu else 0, _p(red), _p(dgamma), _p(dbeta), st)
@@ -805,6 +810,40 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
 # ---------------------------------------------------------------------------------------------
 # pooling / reshaping
 # ---------------------------------------------------------------------------------------------
+class _SpatialSoftmaxFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, want_map):
+    n, h, w, c = x.shape
+    points = torch.empty((n, 2 * c), dtype=F32, device=x.device)
+    heat = torch.empty_like(x) if want_map else None
+    _lib.call('t2r_spatial_softmax_fwd', _p(x), _p(points), _p(heat), n, h, w, c, _stream())
+    ctx.save_for_backward(x, points)
+    if want_map:
+      ctx.mark_non_differentiable(heat)
+      return points, heat
+    return points
+
+  @staticmethod
+  def backward(ctx, dpoints, _dheat=None):
+    x, points = ctx.saved_tensors
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    _lib.call('t2r_spatial_softmax_bwd', _p(x), _p(points), _p(dpoints.contiguous().float()), _p(dx), n, h, w, c,
+              _stream())
+    return dx, None
+
+
+def spatial_softmax(features, return_softmax=False):
+  """layers/spatial_softmax.py:29-88 (BuildSpatialSoftmax, deterministic branch): bf16 [N,H,W,C] ->
+  fp32 expected feature points [N, 2C] (interleaved x, y per channel, as the reference's reshape
+  yields) and optionally the softmax heat map (no gradient flows through the map)."""
+  _require_cuda(features, 'spatial_softmax')
+  if features.shape[-1] % 8 != 0:
+    raise ValueError('spatial_softmax needs a multiple of 8 channels')
+  out = _SpatialSoftmaxFn.apply(features.contiguous(), return_softmax)
+  return out
+
 class _MaxPoolFn(torch.autograd.Function):
 
   @staticmethod

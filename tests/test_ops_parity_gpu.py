@@ -257,3 +257,76 @@ def test_optimizers_match_tf_formulas():
     np.testing.assert_allclose(v.data.cpu().numpy(), w, rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(opt.shadow(vs)[:v.numel].view(7, 13).cpu().numpy(), ema, rtol=2e-5, atol=2e-6)
     assert torch.equal(v.bf16.float().cpu(), v.data.to(torch.bfloat16).float().cpu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('relu', [True, False])
+def test_film_batch_norm_forward_backward_match_oracle(relu):
+  """FiLM-conditioned batch norm (layers/film_resnet_model.py:108-115 on top of :50-57): y, dx, dfilm,
+  dgamma, dbeta against torch autograd on the oracle's formula."""
+  from oracle import tf_ops
+  from tensor2robot_b200 import nn
+  n, hw, c = 6, 35, 64
+  rng = np.random.RandomState(7)
+  x = (_bf16_exact(rng, (n, hw, 1, c), 2.0) + _bf16_exact(rng, (1, 1, 1, c))).to(torch.bfloat16).float()
+  dy = _bf16_exact(rng, (n, hw, 1, c))
+  film = torch.from_numpy(rng.standard_normal((n, 2 * c)).astype(np.float32) * 0.5)
+  variables = {'bn/beta': torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.3).requires_grad_(True),
+               'bn/gamma': torch.from_numpy(1 + 0.3 * rng.standard_normal(c).astype(np.float32)).requires_grad_(True),
+               'bn/moving_mean': torch.zeros(c), 'bn/moving_variance': torch.ones(c)}
+  xo, fo = x.clone().requires_grad_(True), film.clone().requires_grad_(True)
+  yo = tf_ops.batch_norm(xo, variables, 'bn', True, 0.997, 1e-5, True, {})
+  yo = (1 + fo[:, None, None, :c]) * yo + fo[:, None, None, c:]
+  if relu:
+    yo = torch.relu(yo)
+  yo.backward(dy)
+  vs = nn.VariableStore('cuda')
+  with nn.variable_store(vs):
+    xg = x.cuda().to(torch.bfloat16).requires_grad_(True)
+    fg = film.cuda().requires_grad_(True)
+    nn.batch_norm(xg.detach(), False, scope='bn', scale=True, relu=relu, momentum=0.997, eps=1e-5, film=fg.detach())
+    vs.finalize()
+    vs.import_tf({k: v.detach().numpy() for k, v in variables.items()})
+    y = nn.batch_norm(xg, True, scope='bn', scale=True, relu=relu, momentum=0.997, eps=1e-5, film=fg)
+    vs.zero_grad()
+    y.backward(dy.cuda().to(torch.bfloat16))
+  torch.cuda.synchronize()
+  grads = vs.export_tf_grads()
+  _check('film bn y', y.detach().float().cpu(), yo.detach(), BF16_TOL)
+  _check('film bn dx', xg.grad.float().cpu(), xo.grad, BF16_TOL)
+  _check('film bn dfilm', fg.grad.cpu(), fo.grad, 2e-4)
+  _check('film bn dgamma', grads['bn/gamma'], variables['bn/gamma'].grad, 2e-4)
+  _check('film bn dbeta', grads['bn/beta'], variables['bn/beta'].grad, 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,h,w,c', [(3, 21, 17, 32), (2, 6, 6, 64), (1, 50, 64, 8)])
+def test_spatial_softmax_matches_oracle(n, h, w, c):
+  """layers/spatial_softmax.py:29-88: expected feature points (interleaved x, y), heat map, and the
+  gradient of a linear functional of the points against torch autograd on the same formula."""
+  from oracle import spatial_softmax as oracle
+  from tensor2robot_b200 import nn
+  rng = np.random.RandomState(n * 100 + h)
+  x = _bf16_exact(rng, (n, h, w, c), 3.0)
+  pts_o, heat_o = oracle.build_spatial_softmax(x.numpy())
+  xg = x.cuda().to(torch.bfloat16).requires_grad_(True)
+  pts, heat = nn.spatial_softmax(xg, return_softmax=True)
+  _check('spatial softmax points', pts.detach().cpu(), torch.from_numpy(pts_o), 2e-5)
+  _check('spatial softmax map', heat.float().cpu(), torch.from_numpy(heat_o), BF16_TOL)
+  # layout: x of channel k at 2k, y at 2k+1; a peak at the last column / first row gives (+1, -1)
+  peak = torch.full((1, h, w, 8), -30.0)
+  peak[0, 0, w - 1, :] = 30.0
+  p = nn.spatial_softmax(peak.cuda().to(torch.bfloat16)).cpu()
+  assert torch.allclose(p[0, 0::2], torch.ones(8), atol=1e-4) and torch.allclose(p[0, 1::2], -torch.ones(8), atol=1e-4)
+  # backward
+  wgt = torch.from_numpy(rng.standard_normal((n, 2 * c)).astype(np.float32))
+  (pts * wgt.cuda()).sum().backward()
+  xo = x.clone().requires_grad_(True)
+  f = xo.permute(0, 3, 1, 2).reshape(-1, h * w)
+  s = torch.softmax(f, 1)
+  jj, ii = torch.meshgrid(torch.arange(w), torch.arange(h), indexing='xy')
+  xp = (2.0 * jj.reshape(-1) / (w - 1.0) - 1.0).float()
+  yp = (2.0 * ii.reshape(-1) / (h - 1.0) - 1.0).float()
+  po = torch.cat([(s * xp).sum(1, keepdim=True), (s * yp).sum(1, keepdim=True)], 1).reshape(-1, 2 * c)
+  (po * wgt).sum().backward()
+  _check('spatial softmax dx', xg.grad.float().cpu(), xo.grad, BF16_TOL)

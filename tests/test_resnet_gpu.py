@@ -160,3 +160,80 @@ def test_resnet50_critic_train_step_matches_oracle():
     assert _rel_l2(new_vars[k], u.numpy()) < 3e-2, k
   assert err_b < COND_FACTOR * cond_q + 2e-3
   assert not failures, failures[:5]
+
+
+def test_film_resnet18_matches_oracle():
+  """BC-Z style FiLM-conditioned ResNet (layers/resnet.py:98-209 + film_resnet_model.py:108-115):
+  linear_film_generator -> per-block (gamma, beta) -> second batch norm of every block.  Inference
+  forward is asserted tightly; the training step (FiLM backward kernels, gradients into the
+  generator) against torch autograd on the oracle with the loose conditioning bound."""
+  from oracle import resnet as oracle, tf_ops
+  from tensor2robot_b200 import nn
+  from tensor2robot_b200.layers import resnet
+  b, size, classes, emb_dim = 4, 64, 64, 64
+  img = _images(b, size, 11)
+  emb = np.random.RandomState(12).standard_normal((b, emb_dim)).astype(np.float32)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  emb_t = torch.from_numpy(emb).cuda()
+  vs = nn.VariableStore('cuda', seed=4)
+
+  def run(training):
+    return resnet.resnet_model(img_t, training, classes, resnet_size=18,
+                               film_generator_fn=resnet.linear_film_generator, film_generator_input=emb_t)
+
+  with torch.no_grad(), nn.variable_store(vs):
+    run(False)
+  vs.finalize()
+  variables = {k: torch.from_numpy(np.array(v)) for k, v in vs.export_tf().items()}
+  rng = np.random.RandomState(13)
+  for k in list(variables):   # make the FiLM path matter: non-trivial generator weights / BN parameters
+    if k.startswith('film') and k.endswith('weights'):
+      variables[k] = torch.from_numpy(0.2 * rng.standard_normal(tuple(variables[k].shape)).astype(np.float32))
+    elif k.endswith('moving_variance'):
+      variables[k] = torch.from_numpy(rng.uniform(0.5, 1.5, tuple(variables[k].shape)).astype(np.float32))
+  vs.import_tf({k: v.numpy() for k, v in variables.items()})
+  film_keys = sorted(k for k in variables if k.startswith('film') and k.endswith('weights'))
+  assert len(film_keys) == 4
+
+  def oracle_films(v):
+    e = torch.from_numpy(emb).to(torch.bfloat16).float()
+    films = []
+    for i, nb in enumerate([2, 2, 2, 2]):
+      w = v['film%d/weights' % i]
+      out = e @ w.to(torch.bfloat16).float() + v['film%d/biases' % i]
+      films.append(list(tf_ops._store(out).split(out.shape[1] // nb, dim=-1)))
+    return films
+
+  # ---- inference ----
+  with torch.no_grad(), nn.variable_store(vs):
+    le = run(False).float().cpu().numpy()
+  tf_ops.STORAGE_DTYPE = torch.bfloat16
+  try:
+    with torch.no_grad():
+      lo = oracle.resnet_model(dict(variables), img_t.float().cpu(), False, classes, 18,
+                               films=oracle_films(variables)).numpy()
+  finally:
+    tf_ops.STORAGE_DTYPE = None
+  print('film resnet18 inference rel_l2 %.3e' % _rel_l2(le, lo))
+  assert _rel_l2(le, lo) < 2e-2
+
+  # ---- training step ----
+  target = torch.from_numpy(np.random.RandomState(14).standard_normal((b, classes)).astype(np.float32))
+  with nn.variable_store(vs):
+    logits = run(True)
+    vs.zero_grad()
+    (nn.to_f32(logits) * target.cuda()).sum().backward()
+  torch.cuda.synchronize()
+  grads = vs.export_tf_grads()
+  ov = {k: v.clone().requires_grad_(not k.endswith(('moving_mean', 'moving_variance'))) for k, v in variables.items()}
+  tf_ops.STORAGE_DTYPE = torch.bfloat16
+  try:
+    lo_t = oracle.resnet_model(ov, img_t.float().cpu(), True, classes, 18, films=oracle_films(ov), updates={})
+    (lo_t * target).sum().backward()
+  finally:
+    tf_ops.STORAGE_DTYPE = None
+  for k in film_keys + ['film0/biases']:
+    g, go = grads[k], ov[k].grad.numpy()
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    print('%-16s rel_l2 %.3e' % (k, _rel_l2(g, go)))
+    assert _rel_l2(g, go) < 0.25
