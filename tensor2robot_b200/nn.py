@@ -419,7 +419,7 @@ class _Conv2dFn(torch.autograd.Function):
   """y = conv(x, W) [+bias] [+residual] [relu] on the tcgen05 implicit-GEMM kernels."""
 
   @staticmethod
-  def forward(ctx, x, residual, var, bias_var, geom, relu, out_f32, stats=None):
+  def forward(ctx, x, residual, var, bias_var, geom, relu, out_f32, stats=None, anchor=None):
     n, h, w, cin = x.shape
     cout, kh, kw, _ = var.shape
     stride, ho, wo, pt, pl = geom
@@ -471,7 +471,7 @@ class _Conv2dFn(torch.autograd.Function):
       with _prof('dgrad', d):
         _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 0, st)
     dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
-    return dx, dres, None, None, None, None, None, None
+    return dx, dres, None, None, None, None, None, None, None
 
 
 class _DualConvFn(torch.autograd.Function):
@@ -629,7 +629,10 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
     return _trace('conv', scope, _StemConvFn.apply(x.contiguous(), vs.anchor, wv, bv,
                                                    (kh, kw, stride, ho, wo, pt, pl), vs))
   stats = None if (out_f32 or relu) else _new_bn_stats(filters, x.device)
-  y = _Conv2dFn.apply(x, residual, wv, bv, (stride, ho, wo, pt, pl), relu, out_f32, stats)
+  # a leaf input (e.g. the FiLM generator's embedding) would leave the node out of the autograd graph and
+  # its weights without a gradient: the store's anchor scalar keeps it in
+  anchor = vs.anchor if (torch.is_grad_enabled() and not x.requires_grad and trainable) else None
+  y = _Conv2dFn.apply(x, residual, wv, bv, (stride, ho, wo, pt, pl), relu, out_f32, stats, anchor)
   if stats is not None:
     y._t2r_bn_stats = stats
   return _trace('conv', scope, y)
