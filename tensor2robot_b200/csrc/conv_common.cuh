@@ -75,4 +75,10 @@ struct HaloRequest {
 bool conv_halo_eligible(int stride, int n_taps, int k_channels, int n_channels);
 int conv_halo_launch(const HaloRequest& r, cudaStream_t stream);
 
+// Weight gradient of stride-1 KxK convolutions with 64 input channels through the halo kernel
+// (conv_wgrad_halo.cu).
+bool conv_wgrad_halo_eligible(int stride, int n_taps, int Cin, int Cout);
+int conv_wgrad_halo_launch(const void* x, const void* dy, float* dw, int N, int H, int W, int Ho, int Wo, int Cout,
+                           const ConvTap* taps, int n_taps, cudaStream_t stream);
+
 }  // namespace t2r

@@ -292,6 +292,9 @@ extern "C" int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const v
       p.taps[t].dw = int8_t(floor_div(iw, d->stride));
       p.taps[t].kchunk0 = t * p.chunks_per_tap;
     }
+  if (conv_wgrad_halo_eligible(d->stride, t, d->Cin, d->Cout))
+    return conv_wgrad_halo_launch(x, dy, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->Cout, p.taps, t,
+                                  static_cast<cudaStream_t>(stream));
   p.n_slots = t * p.chunks_per_tap;
   p.n_groups = (p.n_slots + 1) / 2;
   p.tiles_w = int(ceil_div(d->Wo, p.TW));
