@@ -113,42 +113,58 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   if (warp == 0 || warp == 2 || warp == 3) {
     // ===================== TMA producers =====================
     // A TMA load costs its whole latency per issuing warp (profiles/r01_ncu_summary.md, 3.3), so the
-    // loads are spread over three warps: warp 0 -> halo of tile 0, warp 2 -> halo of tile 1,
-    // warp 3 -> weights.
+    // loads of a super tile - two halos and, when streaming, one 8 KB weight tile per tap - are dealt
+    // round-robin to three warps.  (With 25 taps a single weight warp was the bottleneck: 25 x ~1000
+    // cycles per super tile against 13.8 k cycles of MMA.)  Resident mode: warps 0 / 2 load the halos,
+    // warp 3 loads the weights once.
     if (lane == 0) {
       const int pid = warp == 0 ? 0 : warp - 1;
-      int hs = 0, ws = 0;
+      int hs = 0, ws = 0, turn = 0;
       uint32_t hph = 0, wph = 0;
       bool first = true;
       for (int s = blockIdx.x; s < p.total_super; s += gridDim.x) {
         const int nt = s % p.n_tiles_n;
         const int pair = s / p.n_tiles_n;
         for (int c = 0; c < p.chunks; ++c) {
-          if (pid < 2) {
-            const int h = pid;
-            mbar_wait(hempty_bar(hs), hph ^ 1u);
-            mbar_expect_tx(hfull_bar(hs), halo_tx);
-            const int m = pair * 2 + h;
-            int img = p.N, oh0 = 0, ow0 = 0;  // image index N is out of bounds: zero fill
-            if (m < p.total_halves) {
-              img = m / tiles_per_img;
-              const int rem = m - img * tiles_per_img;
-              oh0 = (rem / p.tiles_w) * kHaloTH;
-              ow0 = (rem % p.tiles_w) * kHaloTW;
+          for (int h = 0; h < 2; ++h) {
+            const bool mine = kResident ? (pid == h) : (turn == pid);
+            if (mine) {
+              mbar_wait(hempty_bar(hs), hph ^ 1u);
+              mbar_expect_tx(hfull_bar(hs), halo_tx);
+              const int m = pair * 2 + h;
+              int img = p.N, oh0 = 0, ow0 = 0;  // image index N is out of bounds: zero fill
+              if (m < p.total_halves) {
+                img = m / tiles_per_img;
+                const int rem = m - img * tiles_per_img;
+                oh0 = (rem / p.tiles_w) * kHaloTH;
+                ow0 = (rem % p.tiles_w) * kHaloTW;
+              }
+              tma_load_4d(halo_addr(hs, h), &p.tmap_a, hfull_bar(hs), c * 64, ow0 + p.org_dw, oh0 + p.org_dh, img);
             }
-            tma_load_4d(halo_addr(hs, h), &p.tmap_a, hfull_bar(hs), c * 64, ow0 + p.org_dw, oh0 + p.org_dh, img);
-            if (++hs == 2) {
-              hs = 0;
-              hph ^= 1u;
-            }
-          } else if (!kResident || first) {
+            if (!kResident && ++turn == 3) turn = 0;
+          }
+          if (++hs == 2) {
+            hs = 0;
+            hph ^= 1u;
+          }
+          if (kResident) {
+            if (pid == 2 && first)
+              for (int t = 0; t < p.n_taps; ++t) {
+                const int slot = c * p.n_taps + t;
+                mbar_expect_tx(wfull_bar(slot), 8192u);
+                tma_load_2d(w_base + uint32_t(slot) * 8192u, &p.tmap_b, wfull_bar(slot), (p.tap_kchunk0[t] + c) * 64,
+                            nt * 64);
+              }
+          } else {
             for (int t = 0; t < p.n_taps; ++t) {
-              const int slot = kResident ? (c * p.n_taps + t) : ws;
-              if (!kResident) mbar_wait(wempty_bar(slot), wph ^ 1u);
-              mbar_expect_tx(wfull_bar(slot), 8192u);
-              tma_load_2d(w_base + uint32_t(slot) * 8192u, &p.tmap_b, wfull_bar(slot), (p.tap_kchunk0[t] + c) * 64,
-                          nt * 64);
-              if (!kResident && ++ws == p.w_slots) {
+              if (turn == pid) {
+                mbar_wait(wempty_bar(ws), wph ^ 1u);
+                mbar_expect_tx(wfull_bar(ws), 8192u);
+                tma_load_2d(w_base + uint32_t(ws) * 8192u, &p.tmap_b, wfull_bar(ws), (p.tap_kchunk0[t] + c) * 64,
+                            nt * 64);
+              }
+              if (++turn == 3) turn = 0;
+              if (++ws == p.w_slots) {
                 ws = 0;
                 wph ^= 1u;
               }
@@ -160,9 +176,14 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this loop converged and an elected lane issues (umma_bf16_elect): descriptors
+    // are a precomputed 64-bit base plus a 16-byte-unit offset, all warp-uniform.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t sbo = uint32_t(p.HW) * 128u;
+      const uint64_t a_base = make_smem_desc_sw128(smem_base, 16, sbo, 0);   // + halo offset >> 4
+      const uint64_t b_base = make_smem_desc_sw128(w_base, 16, 1024, 0);     // + slot * 512
+      const uint32_t halo16 = uint32_t(p.halo_bytes) >> 4;
       int hs = 0, ws = 0, as = 0;
       uint32_t hph = 0, wph = 0, aphase = 0;
       for (int s = blockIdx.x; s < p.total_super; s += gridDim.x) {
@@ -172,37 +193,35 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(hfull_bar(hs), hph);
           tc_fence_after();
+          const uint64_t a_stage = a_base + uint64_t(uint32_t(hs * 2) * halo16);
           for (int t = 0; t < p.n_taps; ++t) {
             const int slot = kResident ? (c * p.n_taps + t) : ws;
             mbar_wait(wfull_bar(slot), kResident ? 0u : wph);
             tc_fence_after();
-            const uint32_t sb = w_base + uint32_t(slot) * 8192u;
-            const uint32_t aoff = (uint32_t(p.tap_dh[t]) * p.HW + p.tap_dw[t]) * 128u;
+            const uint64_t bt = b_base + uint64_t(uint32_t(slot) * 512u);
+            const uint64_t at = a_stage + uint64_t((uint32_t(p.tap_dh[t]) * p.HW + p.tap_dw[t]) * 8u);
             const uint32_t acc = (c > 0 || t > 0) ? 1u : 0u;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 32, 16, 1024, 0);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t adesc = make_smem_desc_sw128(halo_addr(hs, h) + aoff + kk * 32, 16, sbo, 0);
-                umma_bf16(d_tmem + h * 64, adesc, bdesc, idesc, (acc | uint32_t(kk > 0)));
-              }
+              umma_bf16_elect(d_tmem, at + uint64_t(kk * 2), bt + uint64_t(kk * 2), idesc, acc | uint32_t(kk > 0));
+              umma_bf16_elect(d_tmem + 64, at + uint64_t(halo16 + kk * 2), bt + uint64_t(kk * 2), idesc,
+                              acc | uint32_t(kk > 0));
             }
             if (!kResident) {
-              umma_commit(wempty_bar(slot));
+              umma_commit_elect(wempty_bar(slot));
               if (++ws == p.w_slots) {
                 ws = 0;
                 wph ^= 1u;
               }
             }
           }
-          umma_commit(hempty_bar(hs));
+          umma_commit_elect(hempty_bar(hs));
           if (++hs == 2) {
             hs = 0;
             hph ^= 1u;
           }
         }
-        umma_commit(tfull_bar(as));
+        umma_commit_elect(tfull_bar(as));
         if (++as == 2) {
           as = 0;
           aphase ^= 1u;

@@ -164,8 +164,12 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged and an elected lane issues (umma_bf16_elect): descriptors
+    // are a precomputed base plus a 16-byte-unit offset, all warp-uniform (tests/native/exp_mma_issue.cu).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      const uint64_t a_base = make_smem_desc_sw128(smem_base, 16, 1024);
+      const uint64_t b_base = make_smem_desc_sw128(smem_base + Cfg::kABytes, 16, 1024);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -175,21 +179,18 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t so = uint64_t(uint32_t(stage) * uint32_t(Cfg::kStageBytes >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_elect(d_tmem, a_base + so + uint64_t(kk * 2), b_base + so + uint64_t(kk * 2), idesc,
+                            (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_elect(empty_bar(stage));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(as));
+        umma_commit_elect(tfull_bar(as));
         if (++as == 2) {
           as = 0;
           aphase ^= 1u;

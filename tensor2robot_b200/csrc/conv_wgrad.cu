@@ -165,39 +165,38 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp converged, elected lane issues (see conv_igemm.cu)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      const uint64_t a_base = make_smem_desc_sw128(smem_base, Cfg::kTileBytes, 1024);
+      const uint64_t b_base = make_smem_desc_sw128(dy_base, Cfg::kTileBytes, 1024);
       int stage = 0, ds = 0;
       uint32_t phase = 0, dphase = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(dfull_bar(ds), dphase);
-        const uint32_t sb = dy_base + ds * Cfg::kDyBytes;
+        const uint64_t bs = b_base + uint64_t(uint32_t(ds) * uint32_t(Cfg::kDyBytes >> 4));
         for (int g = g0; g < g1; ++g) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kXBytes;
+          const uint64_t as_ = a_base + uint64_t(uint32_t(stage) * uint32_t(Cfg::kXBytes >> 4));
           const uint32_t d_tmem = tmem_base + (g - g0) * BLOCK_N;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 64 pixels = 4 x (K = 16)
-            const uint64_t adesc =
-                make_smem_desc_sw128(sa + kk * 2048, Cfg::kTileBytes, 1024);
-            const uint64_t bdesc =
-                make_smem_desc_sw128(sb + kk * 2048, Cfg::kTileBytes, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));
+          for (int kk = 0; kk < 4; ++kk)  // 64 pixels = 4 x (K = 16)
+            umma_bf16_elect(d_tmem, as_ + uint64_t(kk * 128), bs + uint64_t(kk * 128), idesc,
+                            (pt > pt0 || kk > 0) ? 1u : 0u);
+          umma_commit_elect(empty_bar(stage));
           if (++stage == Cfg::kXStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(dempty_bar(ds));
+        umma_commit_elect(dempty_bar(ds));
         if (++ds == Cfg::kDyStages) {
           ds = 0;
           dphase ^= 1u;
         }
       }
-      umma_commit(tfull_bar);
+      umma_commit_elect(tfull_bar);
     }
   } else if (warp >= 4) {
     const int quad = warp - 4;

@@ -118,36 +118,37 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_halo_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp converged, elected lane issues (see conv_igemm.cu)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
       const uint32_t sbo = uint32_t(p.HW) * 128u;
+      const uint64_t b_base = make_smem_desc_sw128(smem_base + p.halo_bytes, 8192, 1024, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sx = smem_base + stage * stage_bytes;
-        const uint32_t sb = sx + p.halo_bytes;
+        const uint64_t bs = b_base + uint64_t(uint32_t(stage) * (stage_bytes >> 4));
         for (int g = g0; g < g1; ++g) {
           const int t1 = 2 * g, t2 = min(2 * g + 1, p.n_taps - 1);
           const uint32_t a1 = (uint32_t(p.tap_dh[t1]) * p.HW + p.tap_dw[t1]) * 128u;
           const uint32_t a2 = (uint32_t(p.tap_dh[t2]) * p.HW + p.tap_dw[t2]) * 128u;
           const uint32_t lbo = a2 > a1 ? a2 - a1 : 128u;   // odd tap count: the spare M block is never stored
+          const uint64_t ad = make_smem_desc_sw128(sx + a1, lbo, sbo, 0);
           const uint32_t d_tmem = tmem_base + (g - g0) * BLOCK_N;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 64 pixels = 4 x (K = 16 = two 8-pixel tile rows)
-            const uint64_t adesc = make_smem_desc_sw128(sx + a1 + uint32_t(2 * kk) * sbo, lbo, sbo, 0);
-            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 2048, 8192, 1024, 0);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < 4; ++kk)  // 64 pixels = 4 x (K = 16 = two 8-pixel tile rows)
+            umma_bf16_elect(d_tmem, ad + uint64_t(uint32_t(2 * kk) * (sbo >> 4)), bs + uint64_t(kk * 128), idesc,
+                            (pt > pt0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(empty_bar(stage));
+        umma_commit_elect(empty_bar(stage));
         if (++stage == kWhStages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tfull_bar);
+      umma_commit_elect(tfull_bar);
     }
   } else if (warp >= 4) {
     const int quad = warp - 4;
