@@ -138,6 +138,11 @@ int32_t t2r_colsum_f32(const float* x, float* out, int64_t rows, int32_t C, void
 /* out[0] += scale * sum(x^2): the slim l2_regularizer loss term. */
 int32_t t2r_sumsq_f32(const float* x, float* out, int64_t n, float scale, void* stream);
 int32_t t2r_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+/* Inference-mode batch norm folded into the producing convolution (is_training=False graphs of
+ * slim.conv2d(normalizer_fn=slim.batch_norm) / tf.layers conv -> batch_normalization):
+ * w_bf16[co, k] = bf16(w[co, k] * scale[co]); the shift becomes the convolution's bias. */
+int32_t t2r_fold_bn_weights(const float* w_ohwi, const float* scale, void* w_bf16, int32_t Cout, int64_t K,
+                            void* stream);
 int32_t t2r_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 
 /* ---- batch norm (slim.batch_norm / tf.layers.batch_normalization, training + inference) - */

@@ -322,6 +322,33 @@ extern "C" int32_t t2r_cast_f32_to_bf16(const float* x, void* y, int64_t n, void
   return T2R_OK;
 }
 
+namespace t2r {
+// w' = bf16(w * scale[row]) for a [rows, K] fp32 matrix (K % 4 == 0): inference-mode batch norm folded
+// into the weights of the convolution that feeds it.
+__global__ void fold_scale_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                  __nv_bfloat16* __restrict__ out, long long n4, int K4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float s = scale[i / K4];
+    const float4 v = reinterpret_cast<const float4*>(w)[i];
+    uint2 o;
+    o.x = pack_bf16(v.x * s, v.y * s);
+    o.y = pack_bf16(v.z * s, v.w * s);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+}  // namespace t2r
+
+extern "C" int32_t t2r_fold_bn_weights(const float* w, const float* scale, void* w_bf16, int32_t Cout, int64_t K,
+                                       void* stream) {
+  T2R_CHECK_ARG(w && scale && w_bf16 && Cout > 0 && K > 0 && K % 4 == 0, "fold_bn_weights: bad args");
+  const long long n4 = (long long)Cout * K / 4;
+  t2r::fold_scale_kernel<<<t2r::grid_for(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, scale, static_cast<__nv_bfloat16*>(w_bf16), n4, int(K / 4));
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
 extern "C" int32_t t2r_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
   T2R_CHECK_ARG(x && y && n > 0, "bad cast args");
   cast_bf16_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(

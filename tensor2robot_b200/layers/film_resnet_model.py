@@ -57,13 +57,15 @@ def _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters
       preact, shortcut = batch_norm(inputs, training, namer, relu=True, passthrough=True)
     else:
       preact, shortcut = batch_norm(inputs, training, namer, relu=True), inputs
-    first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay)
+    first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay,
+                                 defer_for_bn=not training)
     return shortcut, first
   preact = batch_norm(inputs, training, namer, relu=True)
   fused = getattr(projection_shortcut, 'fused_args', None)
   if fused is None or not training:
     shortcut = projection_shortcut(preact)
-    first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay)
+    first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay,
+                                 defer_for_bn=not training)
     return shortcut, first
   proj_filters, proj_strides = fused
   shortcut, first = nn.conv2d_pair(preact, _conv_spec(proj_filters, 1, proj_strides, namer, weight_decay),
@@ -72,14 +74,14 @@ def _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters
 
 
 def conv2d_fixed_padding(inputs, filters, kernel_size, strides, namer, weight_decay=None, residual=None,
-                         needs_dgrad=True):
+                         needs_dgrad=True, defer_for_bn=False):
   """Strided convs use explicit (k-1)//2 padding + VALID, others SAME (film_resnet_model.py:89-105).
   The kernel variable is named 'kernel' like tf.layers.conv2d; weight_decay only marks the
   variable as regularised (the l2 gradient is applied by the fused optimizer kernel)."""
   padding = 'SAME' if strides == 1 else 'FIXED'
   return nn.conv2d(inputs, filters, kernel_size, strides, padding, use_bias=False, scope=namer('conv2d'),
                    regularize=weight_decay is not None, residual=residual, needs_dgrad=needs_dgrad,
-                   names=('kernel', 'bias'))
+                   names=('kernel', 'bias'), defer_for_bn=defer_for_bn)
 
 
 def _film_tensor(film_gamma_beta):
@@ -101,7 +103,7 @@ def _bottleneck_block_v2(inputs, filters, training, projection_shortcut, strides
   shortcut, inputs = _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters, 1, 1,
                                             weight_decay)
   inputs = batch_norm(inputs, training, namer, relu=True)
-  inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay)
+  inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay, defer_for_bn=not training)
   inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta))
   return conv2d_fixed_padding(inputs, 4 * filters, 1, 1, namer, weight_decay, residual=shortcut)
 

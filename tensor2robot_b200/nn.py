@@ -407,6 +407,8 @@ def conv_geometry(h, w, kh, kw, stride, padding):
 # pass (one full HBM read of the activation).  Any op in between creates a new tensor object
 # without the attribute, which falls back to t2r_bn_stats.
 FUSE_BN_STATS = os.environ.get('T2R_FUSE_BN_STATS', '1') != '0'
+# Inference graphs: fold batch norm (+ReLU) into the convolution that feeds it (DeferredConv).
+FOLD_INFERENCE_BN = os.environ.get('T2R_FOLD_INFERENCE_BN', '1') != '0'
 
 
 def _new_bn_stats(channels, device):
@@ -501,7 +503,9 @@ class _DualConvFn(torch.autograd.Function):
     st = _stream()
     dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
     wrote = False
-    for var, d, dy in zip(ctx.vars, ctx.descs, (dy1, dy2)):
+    # second convolution first: a strided 1x1 projection reaches only one output phase, so running it
+    # last (accumulate) touches that phase only instead of zero-filling the others first
+    for var, d, dy in reversed(list(zip(ctx.vars, ctx.descs, (dy1, dy2)))):
       if dy is None:
         continue
       dy = dy.contiguous()
@@ -596,10 +600,41 @@ class _StemConvFn(torch.autograd.Function):
     return None, None, None, None, None, None
 
 
+class DeferredConv(object):
+  """An inference-mode convolution whose launch is postponed until the batch norm that consumes it:
+  batch_norm() then folds its scale into the weights and its shift + ReLU into the epilogue, so the
+  pre-normalisation tensor is never written (conv2d(..., defer_for_bn=True))."""
+
+  def __init__(self, x, wv, geom, scope):
+    self.x, self.wv, self.geom, self.scope = x, wv, geom, scope
+    n = x.shape[0]
+    self.shape = (n, geom[1], geom[2], wv.shape[0])
+    self.device = x.device
+
+  def run(self, weights_bf16=None, bias=None, relu=False):
+    x, wv = self.x, self.wv
+    n, h, w, cin = x.shape
+    cout, kh, kw, _ = wv.shape
+    stride, ho, wo, pt, pl = self.geom
+    flags = (_lib.T2R_EPI_BIAS if bias is not None else 0) | (_lib.T2R_EPI_RELU if relu else 0)
+    d = _conv_desc(n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo, flags)
+    y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+    with _prof('fprop', d):
+      _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x), _p(weights_bf16 if weights_bf16 is not None else wv.bf16),
+                _p(bias), None, _p(y), _stream())
+    return y
+
+  def materialize(self):
+    return _trace('conv', self.scope, self.run())
+
+
 def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, scope='conv',
            initializer=None, regularize=True, residual=None, relu=False, needs_dgrad=True,
-           trainable=True, out_f32=False, names=('weights', 'biases')):
-  """slim.conv2d / tf.layers.conv2d without normaliser or activation (compose with batch_norm)."""
+           trainable=True, out_f32=False, names=('weights', 'biases'), defer_for_bn=False):
+  """slim.conv2d / tf.layers.conv2d without normaliser or activation (compose with batch_norm).
+  defer_for_bn=True (only honoured without autograd): returns a DeferredConv for batch_norm to fuse."""
+  if isinstance(x, DeferredConv):
+    x = x.materialize()
   _require_cuda(x, 'conv2d')
   vs = current_store()
   kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
@@ -628,6 +663,9 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   if small:
     return _trace('conv', scope, _StemConvFn.apply(x.contiguous(), vs.anchor, wv, bv,
                                                    (kh, kw, stride, ho, wo, pt, pl), vs))
+  if (defer_for_bn and FOLD_INFERENCE_BN and not torch.is_grad_enabled() and residual is None and bv is None and
+      not relu and not out_f32):
+    return DeferredConv(x.contiguous(), wv, (stride, ho, wo, pt, pl), scope)
   stats = None if (out_f32 or relu) else _new_bn_stats(filters, x.device)
   # a leaf input (e.g. the FiLM generator's embedding) would leave the node out of the autograd graph and
   # its weights without a gradient: the store's anchor scalar keeps it in
@@ -786,7 +824,11 @@ class _BatchNormFn(torch.autograd.Function):
 def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=0.997, eps=1e-5,
                film=None, trainable=True, passthrough=False):
   """slim.batch_norm / tf.layers.batch_normalization(fused=True) followed by an optional ReLU."""
-  _require_cuda(x, 'batch_norm')
+  deferred = x if isinstance(x, DeferredConv) else None
+  if deferred is not None and (training or film is not None or passthrough):
+    x, deferred = deferred.materialize(), None
+  if deferred is None:
+    _require_cuda(x, 'batch_norm')
   vs = current_store()
   c = x.shape[-1]
   if c > 4096:
@@ -803,6 +845,18 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
     for k in ('gamma', 'beta'):
       if bn[k] is not None and bn[k].grad is None:
         bn[k].grad = torch.zeros(bn[k].shape, dtype=F32, device=x.device)
+  if deferred is not None:
+    # y = relu(conv(u, W) * scale + shift) = relu(conv(u, W * scale) + shift)
+    st = _stream()
+    scale_t = torch.empty(c, dtype=F32, device=x.device)
+    shift_t = torch.empty(c, dtype=F32, device=x.device)
+    _lib.call('t2r_bn_infer_params', c, _p(bn['gamma'].data if bn['gamma'] is not None else None),
+              _p(bn['beta'].data), _p(bn['moving_mean'].data), _p(bn['moving_variance'].data), bn['eps'],
+              _p(scale_t), _p(shift_t), st)
+    wv = deferred.wv
+    folded = torch.empty(wv.shape, dtype=BF16, device=x.device)
+    _lib.call('t2r_fold_bn_weights', _p(wv.data), _p(scale_t), _p(folded), wv.shape[0], wv.numel // wv.shape[0], st)
+    return _trace('bn', scope, deferred.run(folded, shift_t, relu))
   fused = getattr(x, '_t2r_bn_stats', None) if (training and x.is_contiguous()) else None
   if passthrough:
     y, x_pass = _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs, True, fused)

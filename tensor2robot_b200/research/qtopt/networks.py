@@ -55,7 +55,8 @@ class Grasping44FlexibleGraspParams(GraspingModel):
   def _conv_bn_relu(self, net, k, scope, is_training, padding='SAME'):
     """slim.conv2d with normalizer_fn=slim.batch_norm, activation relu (no bias)."""
     init = nn.truncated_normal(0.01)
-    net = nn.conv2d(net, 64, k, 1, padding, use_bias=False, scope=scope, initializer=init)
+    net = nn.conv2d(net, 64, k, 1, padding, use_bias=False, scope=scope, initializer=init,
+                    defer_for_bn=not is_training)
     return nn.batch_norm(net, is_training, scope=scope + '/BatchNorm', scale=True, relu=True,
                          momentum=self._batch_norm_decay, eps=self._batch_norm_epsilon)
 

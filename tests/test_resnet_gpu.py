@@ -96,7 +96,9 @@ def test_resnet_critic_inference_matches_oracle(resnet_size):
   print('rel_l2(logits) vs bf16-storage oracle %.3e, vs fp32 oracle %.3e; max|dq| %.3e / %.3e' % (
       _rel_l2(le, res['bf16'][0]), _rel_l2(le, res['fp32'][0]), np.abs(q - res['bf16'][1]).max(),
       np.abs(q - res['fp32'][1]).max()))
-  assert _rel_l2(le, res['bf16'][0]) < 2e-2
+  # 53 bf16 layers compound to ~2e-2 on the logits of ResNet-50 (7e-3 for ResNet-18); with inference batch
+  # norm folded into the convolutions the engine rounds at different points than the bf16-storage oracle
+  assert _rel_l2(le, res['bf16'][0]) < (3e-2 if resnet_size == 50 else 1.5e-2)
   assert np.abs(q - res['bf16'][1]).max() < 1e-2
   assert np.abs(q - res['fp32'][1]).max() < 2e-2
 
