@@ -205,6 +205,10 @@ int32_t t2r_global_mean_bwd(const void* dy, void* dx, int32_t N, int32_t HW, int
 int32_t t2r_add_context_fwd(const void* x, const void* ctx, void* y, int32_t B, int32_t A,
                             int32_t HW, int32_t C, void* stream);
 /* dx[b,p,c] = sum_a dy[(b*A+a),p,c]; dctx[(b*A+a),c] = sum_p dy[(b*A+a),p,c]. */
+/* Inference fusion of the merge with the batch norm (+ReLU) that consumes it:
+ * y[(b*A+a),p,:] = relu?((x[b,p,:] + ctx[(b*A+a),:]) * scale + shift), scale / shift from t2r_bn_infer_params. */
+int32_t t2r_add_context_affine_fwd(const void* x, const void* ctx, const float* scale, const float* shift, void* y,
+                                   int32_t B, int32_t A, int32_t HW, int32_t C, int32_t relu, void* stream);
 int32_t t2r_add_context_bwd(const void* dy, void* dx, void* dctx, int32_t B, int32_t A,
                             int32_t HW, int32_t C, void* stream);
 /* y = a + b (bf16), used for gradient fan-in. */

@@ -162,6 +162,41 @@ __global__ void __launch_bounds__(256) add_context_fwd_kernel(const uint4* __res
   }
 }
 
+// Inference fusion of the merge with the batch norm (+ReLU) that follows it:
+// y[(b*A+a), p, :] = relu?((x[b, p, :] + ctx[(b*A+a), :]) * scale + shift)
+__global__ void __launch_bounds__(256) add_context_affine_kernel(const uint4* __restrict__ x,
+                                                                 const uint4* __restrict__ ctx,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 uint4* __restrict__ y, long long total8, int A,
+                                                                 int HW, int cg, int relu) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % cg);
+    long long r = i / cg;
+    const int p = int(r % HW);
+    const long long ba = r / HW;
+    const long long b = ba / A;
+    float fx[8], fc[8];
+    unpack8(x[(b * HW + p) * cg + g], fx);
+    unpack8(ctx[ba * cg + g], fc);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g + 1);
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g);
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // the unfused path stores x + ctx in bf16 before normalising: keep that rounding for parity
+      const float sum = __bfloat162float(__float2bfloat16_rn(fx[j] + fc[j]));
+      fx[j] = fmaf(sum, sc[j], sh[j]);
+      if (relu) fx[j] = fmaxf(fx[j], 0.f);
+    }
+    y[i] = pack8(fx);
+  }
+}
+
 // dx[b,p,:] = sum_a dy[(b*A+a),p,:]
 __global__ void __launch_bounds__(256) add_context_bwd_x_kernel(const uint4* __restrict__ dy,
                                                                 uint4* __restrict__ dx, long long total8,
@@ -394,6 +429,19 @@ extern "C" int32_t t2r_add_context_fwd(const void* x, const void* ctx, void* y, 
   add_context_fwd_kernel<<<grid_for(total8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<const uint4*>(ctx), static_cast<uint4*>(y), total8, A, HW,
       C / 8);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_add_context_affine_fwd(const void* x, const void* ctx, const float* scale, const float* shift,
+                                              void* y, int32_t B, int32_t A, int32_t HW, int32_t C, int32_t relu,
+                                              void* stream) {
+  T2R_CHECK_ARG(x && ctx && scale && shift && y && B > 0 && A > 0 && HW > 0 && C % 8 == 0,
+                "add_context_affine_fwd: bad args");
+  const long long total8 = (long long)B * A * HW * (C / 8);
+  add_context_affine_kernel<<<grid_for(total8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(ctx), scale, shift, static_cast<uint4*>(y), total8, A,
+      HW, C / 8, relu);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

@@ -633,7 +633,7 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
            trainable=True, out_f32=False, names=('weights', 'biases'), defer_for_bn=False):
   """slim.conv2d / tf.layers.conv2d without normaliser or activation (compose with batch_norm).
   defer_for_bn=True (only honoured without autograd): returns a DeferredConv for batch_norm to fuse."""
-  if isinstance(x, DeferredConv):
+  if isinstance(x, (DeferredConv, DeferredContext)):
     x = x.materialize()
   _require_cuda(x, 'conv2d')
   vs = current_store()
@@ -824,7 +824,7 @@ class _BatchNormFn(torch.autograd.Function):
 def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=0.997, eps=1e-5,
                film=None, trainable=True, passthrough=False):
   """slim.batch_norm / tf.layers.batch_normalization(fused=True) followed by an optional ReLU."""
-  deferred = x if isinstance(x, DeferredConv) else None
+  deferred = x if isinstance(x, (DeferredConv, DeferredContext)) else None
   if deferred is not None and (training or film is not None or passthrough):
     x, deferred = deferred.materialize(), None
   if deferred is None:
@@ -853,6 +853,8 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
     _lib.call('t2r_bn_infer_params', c, _p(bn['gamma'].data if bn['gamma'] is not None else None),
               _p(bn['beta'].data), _p(bn['moving_mean'].data), _p(bn['moving_variance'].data), bn['eps'],
               _p(scale_t), _p(shift_t), st)
+    if isinstance(deferred, DeferredContext):
+      return _trace('bn', scope, deferred.run(scale_t, shift_t, relu))
     wv = deferred.wv
     folded = torch.empty(wv.shape, dtype=BF16, device=x.device)
     _lib.call('t2r_fold_bn_weights', _p(wv.data), _p(scale_t), _p(folded), wv.shape[0], wv.numel // wv.shape[0], st)
@@ -975,12 +977,35 @@ class _AddContextFn(torch.autograd.Function):
     return dx, dctx, None
 
 
-def add_context(x, context, action_batch_size=1):
+class DeferredContext(object):
+  """Inference-mode merge whose consumer is a batch norm: batch_norm() runs ONE pass
+  relu((x + ctx) * scale + shift) instead of add, read, normalise, write (add_context(defer_for_bn=True))."""
+
+  def __init__(self, x, context, a):
+    self.x, self.context, self.a = x, context, a
+    self.shape = (context.shape[0],) + tuple(x.shape[1:])
+    self.device = x.device
+
+  def run(self, scale, shift, relu):
+    x, a = self.x, self.a
+    b, h, w, c = x.shape
+    y = torch.empty(self.shape, dtype=BF16, device=x.device)
+    _lib.call('t2r_add_context_affine_fwd', _p(x), _p(self.context), _p(scale), _p(shift), _p(y), b, a, h * w, c,
+              1 if relu else 0, _stream())
+    return y
+
+  def materialize(self):
+    return _trace('add_context', None, _AddContextFn.apply(self.x, self.context, self.a))
+
+
+def add_context(x, context, action_batch_size=1, defer_for_bn=False):
   """tile_batch(x, A) + context[:, None, None, :] without materialising the tile
   (research/qtopt/networks.py:513-522; research/dql_grasping_lib/tf_modules.py:74-93)."""
   _require_cuda(x, 'add_context')
   if context.shape[0] != x.shape[0] * action_batch_size:
     raise ValueError('context rows %d != batch %d * action_batch %d' % (context.shape[0], x.shape[0], action_batch_size))
+  if defer_for_bn and FOLD_INFERENCE_BN and not torch.is_grad_enabled():
+    return DeferredContext(x.contiguous(), context.contiguous(), action_batch_size)
   return _trace('add_context', None, _AddContextFn.apply(x.contiguous(), context.contiguous(), action_batch_size))
 
 

@@ -86,8 +86,9 @@ class ResNet50QCritic(networks.Grasping44E2EOpenCloseTerminateGripperStatusHeigh
         self.staged = (net, _clone_namer(namer))
       context = self._context(grasp_params.to(torch.float32).contiguous(), net.shape[-1], is_training,
                               end_points)
-      net = nn.add_context(net, context, a)
-      end_points['vsum'] = net
+      net = nn.add_context(net, context, a, defer_for_bn=not is_training)
+      if not isinstance(net, nn.DeferredContext):   # fused into the next batch norm in inference graphs
+        end_points['vsum'] = net
       films = self._resnet.film_params(None, None)
       with nn.variable_scope('resnet_model'):
         net = self._resnet.block_layers(net, is_training, namer, films, self._merge_after, None)
