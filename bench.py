@@ -293,9 +293,9 @@ def run_b200(args):
       'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops'],
       'peak_source': peaks['source'] + ' sustained cuBLAS bf16 (kernel timed inside a long step)',
       # ncu --set full, one launch of conv_igemm_kernel<256> (3x3 256->256 fprop at B=512): dram read + write
-      # bytes = 434 MB against 472 MB algorithmic (profiles/r01_ncu_summary.md, section 5)
-      'traffic': 434.2e6 if args.model == 'resnet50' else None,
-      'traffic_kernel': 'conv_igemm_kernel<256> 512x30x30x256->256 k3 (ncu, profiles/r01d_igemm256_3x3_256.ncu-rep)',
+      # bytes = 435 MB against 472 MB algorithmic (profiles/r01_ncu_summary.md, section 5)
+      'traffic': 434.9e6 if args.model == 'resnet50' else None,
+      'traffic_kernel': 'conv_igemm_kernel<256> 512x30x30x256->256 k3 (ncu, profiles/r01g_igemm256_3x3_256.ncu-rep)',
       'dominant': dominant, 'by_kind': kinds,
       'share_of_step': conv_ms / max(elapsed_ms, 1e-9),
   }
