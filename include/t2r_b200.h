@@ -312,6 +312,35 @@ int32_t t2r_sequence_example_parse_batch(const uint8_t* const* records, const ui
                                          int32_t B, const T2RFeaturePlan* plan, int32_t n_features,
                                          int32_t max_steps, int64_t* steps);
 
+/* ---- JPEG decode, split host / device (utils/tfdata.py:426-484 -> tf.image.decode_image) ---- *
+ * Baseline sequential Huffman JPEG (SOF0/SOF1, 8 bit, one interleaved scan, restart intervals; grey or
+ * YCbCr 4:4:4 / 4:2:2 / 4:2:0).  Host: headers + Huffman entropy decoding into quantised coefficient
+ * blocks (serial per image, threaded over the batch).  Device: dequantisation, libjpeg's ISLOW inverse
+ * DCT, fancy (triangle) chroma upsampling and the fixed-point YCbCr -> RGB tables: bit-exact with
+ * libjpeg(-turbo) defaults, i.e. with what TensorFlow decodes.  Anything else is rejected with
+ * T2R_ERR_PARSE (the caller may fall back to its host decoder). */
+typedef struct T2RJpegInfo {
+  uint32_t struct_size;
+  int32_t width, height, ncomp;      /* ncomp 1 (grey) or 3 (YCbCr)                                  */
+  int32_t comp_id[3], h[3], v[3], tq[3];
+  int32_t hmax, vmax, mcux, mcuy;    /* MCU grid: mcux x mcuy MCUs of (8*hmax) x (8*vmax) pixels      */
+  int32_t restart_interval;
+  int32_t reserved;
+  int64_t coef_offset[3];            /* component c: int16 [mcuy*v][mcux*h][64], natural order        */
+  int64_t coef_count;                /* int16 elements of one image                                   */
+  uint16_t qt[4][64];                /* quantisation tables, natural order                            */
+} T2RJpegInfo;
+int32_t t2r_jpeg_parse(const uint8_t* data, uint64_t len, T2RJpegInfo* info);
+/* coef: host (pinned) int16 [B][coef_stride]; infos[b] is filled for every image. */
+int32_t t2r_jpeg_entropy_decode_batch(const uint8_t* const* data, const uint64_t* lens, int32_t B,
+                                      T2RJpegInfo* infos, int16_t* coef, int64_t coef_stride);
+/* Device half.  All B images share the geometry of `geom` (width, height, sampling factors: the spec's
+ * static shape); qt: device uint16 [B][4][64] (per-image tables); coef: device int16 [B][coef_stride];
+ * planes: device uint8 workspace [B][coef_count] (IDCT output per component); out: uint8 [B,H,W,channels],
+ * channels 3 (RGB; grey replicated) or 1 (luma). */
+int32_t t2r_jpeg_idct_color(const int16_t* coef, const uint16_t* qt, const T2RJpegInfo* geom, uint8_t* planes,
+                            uint8_t* out, int32_t B, int64_t coef_stride, int32_t channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,15 @@ class DistortParams(C.Structure):
               ('crop_y', C.c_int32), ('crop_x', C.c_int32), ('reserved', C.c_int32)]
 
 
+class JpegInfo(C.Structure):
+  """T2RJpegInfo (include/t2r_b200.h)."""
+  _fields_ = [('struct_size', C.c_uint32), ('width', C.c_int32), ('height', C.c_int32), ('ncomp', C.c_int32),
+              ('comp_id', C.c_int32 * 3), ('h', C.c_int32 * 3), ('v', C.c_int32 * 3), ('tq', C.c_int32 * 3),
+              ('hmax', C.c_int32), ('vmax', C.c_int32), ('mcux', C.c_int32), ('mcuy', C.c_int32),
+              ('restart_interval', C.c_int32), ('reserved', C.c_int32), ('coef_offset', C.c_int64 * 3),
+              ('coef_count', C.c_int64), ('qt', (C.c_uint16 * 64) * 4)]
+
+
 class FeaturePlan(C.Structure):
   _fields_ = [('key', C.c_char_p), ('dtype', C.c_int32), ('count', C.c_int32),
               ('required', C.c_int32), ('dst', C.c_void_p), ('dst_len', C.c_void_p),
@@ -98,6 +107,9 @@ _PROTOS = {
     't2r_masked_crc32c': (C.c_uint32, [_P, _U64]),
     't2r_tfrecord_index': (_I64, [_P, _U64, _P, _P, _I64, _I32]),
     't2r_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32]),
+    't2r_jpeg_parse': (_I32, [_P, C.c_uint64, C.POINTER(JpegInfo)]),
+    't2r_jpeg_entropy_decode_batch': (_I32, [_P, _P, _I32, C.POINTER(JpegInfo), _P, _I64]),
+    't2r_jpeg_idct_color': (_I32, [_P, _P, C.POINTER(JpegInfo), _P, _P, _I32, _I64, _I32, _P]),
     't2r_sequence_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32, _I32, _P]),
 }
 

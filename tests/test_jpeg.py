@@ -78,3 +78,62 @@ def test_unsupported_and_corrupt_inputs_raise():
   prog = _encode(_picture(32, 32, 1), progressive=True)
   with pytest.raises(oracle_jpeg.JpegError):
     oracle_jpeg.decode(prog)
+
+
+# ---- the engine's split decoder ---------------------------------------------------------------------
+def _cases():
+  yield 'fixture', None
+  for h, w, sub, q in [(64, 64, 0, 90), (48, 80, 1, 75), (64, 96, 2, 85), (37, 29, 2, 60), (33, 50, 1, 95)]:
+    yield '%dx%d_s%d' % (h, w, sub), _encode(_picture(h, w, h + w), quality=q, subsampling=sub)
+  yield 'grey', _encode(_picture(40, 56, 3)[..., 0], quality=80)
+
+
+def _fixture_jpegs():
+  out = []
+  for rec in oracle_tfrecord.read_tfrecords(FIXTURE)[:3]:
+    for key, (kind, values) in oracle_tfrecord.parse_example(rec).items():
+      if kind == 'bytes' and values and values[0][:2] == b'\xff\xd8':
+        out.append(values[0])
+  return out
+
+
+def test_host_entropy_decoder_matches_oracle_coefficients():
+  """csrc/jpeg_host.cc (headers + Huffman, threaded over the batch) against the oracle's T.81 Annex F walk:
+  identical quantised coefficients, quantisation tables and geometry."""
+  from tensor2robot_b200.utils import jpeg
+  for name, data in _cases():
+    batch = _fixture_jpegs() if data is None else [data, data]
+    geom, coef, qt = jpeg.entropy_decode(batch, pinned=False)
+    for i, img in enumerate(batch):
+      info, coefs = oracle_jpeg.decode_coefficients(img)
+      assert (geom.width, geom.height, geom.ncomp) == (info['width'], info['height'], len(info['comps']))
+      for c, (comp, want) in enumerate(zip(info['comps'], coefs)):
+        n = want.size
+        got = coef[i, geom.coef_offset[c]:geom.coef_offset[c] + n].numpy().reshape(want.shape)
+        np.testing.assert_array_equal(got, want, err_msg='%s image %d component %d' % (name, i, c))
+        np.testing.assert_array_equal(qt[i].numpy().view(np.uint16)[geom.tq[c]], info['qt'][comp[3]])
+  with pytest.raises(jpeg.UnsupportedJpeg):
+    jpeg.entropy_decode([_encode(_picture(32, 32, 1), progressive=True)], pinned=False)
+  with pytest.raises(jpeg.UnsupportedJpeg):
+    jpeg.entropy_decode([_encode(_picture(32, 32, 1)), _encode(_picture(32, 40, 1))], pinned=False)
+
+
+@pytest.mark.gpu
+def test_split_decoder_matches_libjpeg_bit_exact():
+  """Host Huffman + device IDCT / upsampling / colour == libjpeg-turbo (PIL) == the oracle, bit for bit."""
+  import torch
+  from tensor2robot_b200.utils import jpeg
+  for name, data in _cases():
+    batch = _fixture_jpegs() if data is None else [data, data, data]
+    got = jpeg.decode_batch(batch, channels=3).cpu().numpy()
+    for i, img in enumerate(batch):
+      want = _pil(img, 'RGB')
+      np.testing.assert_array_equal(got[i], want, err_msg='%s image %d' % (name, i))
+      np.testing.assert_array_equal(got[i], oracle_jpeg.decode(img))
+  # luma-only output (tf.image.decode_image(channels=1) on a colour JPEG)
+  data = _encode(_picture(64, 96, 5), quality=85, subsampling=2)
+  np.testing.assert_array_equal(jpeg.decode_batch([data], channels=1).cpu().numpy()[0],
+                                oracle_jpeg.decode(data, channels=1))
+  # replay-frame size: 512 x 640, 4:2:0
+  big = _encode(_picture(512, 640, 9), quality=90, subsampling=2)
+  np.testing.assert_array_equal(jpeg.decode_batch([big] * 4).cpu().numpy()[3], _pil(big, 'RGB'))
