@@ -33,6 +33,9 @@ struct Huff {
   int32_t valptr[17];
   int32_t mincode[17];
   uint8_t symbols[256];
+  // AC tables only: for a 9-bit lookahead that holds a whole (code, magnitude bits) pair with a small
+  // value, (value << 8) | (run << 4) | total_bits; 0 otherwise (stb_image's "fast AC" idea)
+  int16_t fast_ac[512];
   bool present = false;
 };
 
@@ -61,6 +64,16 @@ bool build_huff(const uint8_t* counts, const uint8_t* symbols, int total, Huff* 
     code <<= 1;
   }
   h->maxcode[17] = 0x7fffffff;
+  for (int i = 0; i < 512; ++i) {
+    h->fast_ac[i] = 0;
+    const uint16_t f = h->fast[i];
+    if (!f) continue;
+    const int len = f >> 8, rs = f & 0xFF, run = rs >> 4, mag = rs & 15;
+    if (mag == 0 || len + mag > 9) continue;
+    int k = ((i << len) & 511) >> (9 - mag);          // the magnitude bits that follow the code
+    if (k < (1 << (mag - 1))) k += (-1 << mag) + 1;   // EXTEND
+    if (k >= -128 && k <= 127) h->fast_ac[i] = int16_t(k * 256 + run * 16 + len + mag);
+  }
   h->present = true;
   return true;
 }
@@ -183,6 +196,17 @@ struct BitReader {
   int n = 0;
   bool hit_marker = false;
   inline void fill() {
+    // fast path: four stream bytes at once when none of them is 0xFF (no stuffing, no marker)
+    if (n <= 32 && !hit_marker && end - p >= 4) {
+      const uint32_t v = (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3];
+      const uint32_t inv = ~v;
+      if (!((inv - 0x01010101u) & ~inv & 0x80808080u)) {   // no byte of v equals 0xFF
+        acc |= uint64_t(v) << (32 - n);
+        n += 32;
+        p += 4;
+        return;
+      }
+    }
     while (n <= 56) {
       uint32_t byte = 0;
       if (!hit_marker && p < end) {
@@ -255,8 +279,18 @@ int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t*
             if (t < 0 || t > 11) { t2r::set_error("jpeg: bad DC Huffman code"); return T2R_ERR_PARSE; }
             pred[c] += br.receive_extend(t);
             blk[0] = int16_t(pred[c]);
+            const Huff& hac = ps.ac[ps.ta[c]];
             for (int k = 1; k < 64;) {
-              const int rs = br.decode(ps.ac[ps.ta[c]]);
+              br.fill();
+              const int fa = hac.fast_ac[br.peek(9)];
+              if (fa) {                                   // code + magnitude bits in one lookup
+                k += (fa >> 4) & 15;
+                if (k > 63) { t2r::set_error("jpeg: AC coefficient index out of range"); return T2R_ERR_PARSE; }
+                br.skip(fa & 15);
+                blk[kZigzag[k++]] = int16_t(fa >> 8);
+                continue;
+              }
+              const int rs = br.decode(hac);
               if (rs < 0) { t2r::set_error("jpeg: bad AC Huffman code"); return T2R_ERR_PARSE; }
               const int r = rs >> 4, s = rs & 15;
               if (s == 0) {

@@ -145,6 +145,18 @@ def _decode_one(image_bytes, single_img_dims, np_dtype, name):
 
 _POOL = None
 
+# Where encoded images are decoded: 'host' (libjpeg-turbo / libpng through PIL on host threads, numpy out) or
+# 'device' (baseline JPEGs: Huffman on host threads, IDCT / upsampling / colour on the GPU, uint8 CUDA tensor
+# out, bit-identical; anything the split decoder rejects falls back to 'host').  utils/jpeg.py.
+IMAGE_DECODER = os.environ.get('T2R_IMAGE_DECODER', 'host')
+
+
+def set_image_decoder(kind):
+  global IMAGE_DECODER
+  if kind not in ('host', 'device'):
+    raise ValueError("image decoder must be 'host' or 'device'")
+  IMAGE_DECODER = kind
+
 
 def _pool():
   global _POOL
@@ -166,6 +178,20 @@ def _decode_images(tensor_spec, byte_rows):
     raise ValueError('Decoding an image requires tensorspec.data_type to be uint8 or uint16.')
   np_dtype = tensor_spec.dtype.as_numpy_dtype
   flat = [b for row in byte_rows for b in row]
+  per_row = len(byte_rows[0]) if byte_rows else 0
+  if IMAGE_DECODER == 'device' and np_dtype == np.uint8 and flat and all(b[:2] == b'\xff\xd8' for b in flat):
+    from tensor2robot_b200.utils import jpeg
+    try:
+      out = jpeg.decode_batch(flat, channels=dims[2])
+    except jpeg.UnsupportedJpeg:
+      out = None
+    if out is not None:
+      if tuple(out.shape[1:]) != dims:
+        raise ValueError('InvalidArgument: decoded image "%s" has shape %s, the spec requires %s' % (
+            tensor_spec.name, tuple(out.shape[1:]), dims))
+      if len(tensor_spec.shape) > 3 or tensor_spec.varlen_default_value is not None:
+        out = out.reshape((len(byte_rows), per_row) + dims)
+      return out
   if len(flat) >= 8:
     decoded = list(_pool().map(lambda b: _decode_one(b, dims, np_dtype, tensor_spec.name), flat))
   else:

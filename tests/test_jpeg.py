@@ -137,3 +137,23 @@ def test_split_decoder_matches_libjpeg_bit_exact():
   # replay-frame size: 512 x 640, 4:2:0
   big = _encode(_picture(512, 640, 9), quality=90, subsampling=2)
   np.testing.assert_array_equal(jpeg.decode_batch([big] * 4).cpu().numpy()[3], _pil(big, 'RGB'))
+
+
+@pytest.mark.gpu
+def test_parser_with_device_decoder_matches_host_decoder():
+  """create_parse_tf_example_fn on the reference fixture: T2R_IMAGE_DECODER=device returns the same pixels
+  (as a uint8 CUDA tensor) as the host (PIL) path."""
+  from tensor2robot_b200.utils import dtypes, tensorspec_utils as utils, tfdata
+  spec = utils.TensorSpecStruct(
+      state=utils.TensorSpecStruct(image=utils.ExtendedTensorSpec((64, 64, 3), dtypes.uint8, 'state/image',
+                                                                  data_format='jpeg')))
+  records = oracle_tfrecord.read_tfrecords(FIXTURE)[:6]
+  parse = tfdata.create_parse_tf_example_fn(spec)
+  host = parse(records).state.image
+  tfdata.set_image_decoder('device')
+  try:
+    dev = parse(records).state.image
+  finally:
+    tfdata.set_image_decoder('host')
+  assert hasattr(dev, 'is_cuda') and dev.is_cuda and tuple(dev.shape) == host.shape
+  np.testing.assert_array_equal(dev.cpu().numpy(), host)
