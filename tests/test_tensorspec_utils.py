@@ -285,3 +285,22 @@ def test_pickle_and_eq():
   assert pickle.loads(pickle.dumps(s)).to_dict() == s.to_dict()
   assert T1 == TSPEC((224, 224, 3), dtypes.float32, 'other')     # equality ignores the name (:261-263)
   assert dtypes.as_dtype(np.float32) == dtypes.float32 and dtypes.as_dtype(1) == dtypes.float32
+
+
+def test_stem_weight_layouts_round_trip():
+  """nn._stem_pack / _stem_unpack: [Cout,KH,KW,3] <-> the K layouts of t2r_stem_conv_* (include/t2r_b200.h):
+  one filter row per 64-wide chunk, or two rows x 8 pixels for stride-2 stems with KW <= 8."""
+  import numpy as np
+  from tensor2robot_b200 import nn
+  rng = np.random.RandomState(0)
+  for kh, kw, stride, k_expected in ((7, 7, 2, 256), (6, 6, 2, 192), (7, 7, 1, 448), (3, 9, 2, 192)):
+    w = rng.standard_normal((64, kh, kw, 3)).astype(np.float32)
+    packed = nn._stem_pack(w, stride)
+    assert packed.shape == (64, k_expected)
+    np.testing.assert_array_equal(nn._stem_unpack(packed, kh, kw, 3, stride), w)
+    assert np.count_nonzero(packed) == np.count_nonzero(w)     # padding slots are zero
+  # rows == 2 layout: slot = px * 8 + row * 4 + channel inside chunk kh // 2
+  w = np.zeros((1, 7, 7, 3), np.float32)
+  w[0, 3, 5, 2] = 1.0
+  packed = nn._stem_pack(w, 2)
+  assert packed[0, (3 // 2) * 64 + 5 * 8 + (3 % 2) * 4 + 2] == 1.0
