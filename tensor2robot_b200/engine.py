@@ -128,6 +128,47 @@ class CriticTrainStep(object):
     return end_points['predictions']
 
 
+class LaggedTarget(object):
+  """theta' of the Bellman target (SURVEY A-23): a lagged copy of the online critic's variables.
+
+  QT-Opt evaluates max_a Q_theta'(s', a) with lagged target networks; the reference's nearest hook is the
+  lagged checkpoint export of hooks/td3.py:37-132.  The copy lives in its own VariableStore (built by the
+  same model code, hence the same flat layout): a refresh is two device-to-device copies of the flat
+  buffers plus the bf16 recast.  `source='ema'` takes the MovingAverageOptimizer shadow instead of the raw
+  weights (optimizer_builder.BuildOpt's use_avg_model_params)."""
+
+  def __init__(self, step, update_every=100, source='online'):
+    if source not in ('online', 'ema'):
+      raise ValueError("source must be 'online' or 'ema'")
+    self.step, self.update_every, self.source = step, int(update_every), source
+    self.vs = nn.VariableStore(step.vs.device, seed=0)
+    self.last_update = None
+
+  def build(self, images_u8, actions):
+    """Creates the target variables with the same 2-sample pass as CriticTrainStep.build."""
+    step = self.step
+    if not self.vs.finalized:
+      with torch.no_grad(), nn.variable_store(self.vs):
+        x = step.preprocess(images_u8[:2], training=False)
+        step.critic.model((None, x), actions[:2], is_training=False)
+      self.vs.finalize()
+    self.update(force=True)
+
+  def update(self, force=False):
+    """Refreshes the copy when `update_every` optimizer steps have passed since the last refresh."""
+    gs = int(self.step.global_step)
+    if not force and self.last_update is not None and gs - self.last_update < self.update_every:
+      return False
+    ema = None
+    if self.source == 'ema':
+      ema = getattr(self.step.optimizer, '_ema', None)
+      if ema is None:
+        raise ValueError("source='ema' needs a MovingAverageOptimizer that has taken at least one step")
+    self.vs.copy_values_from(self.step.vs, ema)
+    self.last_update = gs
+    return True
+
+
 class CEMTargetComputer(object):
   """On-device cross-entropy-method maximisation of Q(s', a) and the Bellman target.
 

@@ -214,6 +214,20 @@ class VariableStore(object):
           v.dgrad = torch.empty(cin * kh * kw * cout, dtype=BF16, device=self.device)
         _lib.call('t2r_pack_weights', _p(v.data), None, _p(v.dgrad), cout, kh * kw, cin, st)
 
+  def copy_values_from(self, other, trainable_flat=None):
+    """Overwrites this (finalized, identically built) store's values with `other`'s: the trainable
+    parameters from `trainable_flat` (e.g. the optimizer's EMA shadow) or other.flat, the moving
+    statistics from other.state_flat; then refreshes the bf16 compute copies."""
+    if not (self._finalized and other._finalized) or list(self.vars) != list(other.vars):
+      raise ValueError('copy_values_from needs two finalized stores built by the same model')
+    src = other.flat if trainable_flat is None else trainable_flat
+    if src.numel() != self.flat.numel():
+      raise ValueError('flat buffer sizes differ')
+    self.flat.copy_(src)
+    if self.state_flat is not None and other.state_flat is not None:
+      self.state_flat.copy_(other.state_flat)
+    self.sync_compute_copies()
+
   def zero_grad(self):
     self.flat_grad.zero_()
 

@@ -175,3 +175,42 @@ def test_device_cem_and_bellman_target_invariants():
   mq = max_q.cpu().numpy()
   np.testing.assert_allclose(y, [0.9 * mq[0], 1 + 0.9 * mq[1], 1.0], rtol=1e-6)
   assert (y >= 0).all() and (y <= 1.9 + 1e-6).all()
+
+
+@pytest.mark.gpu
+def test_lagged_target_network_tracks_online_critic_with_a_lag():
+  """engine.LaggedTarget (SURVEY A-23: theta' of the Bellman target): equals the online critic right after a
+  refresh, stays frozen while the online critic trains, catches up at the next refresh; CEM evaluated on
+  the target store is unaffected by online updates in between."""
+  import torch
+  from tensor2robot_b200 import engine
+  from tensor2robot_b200.models import optimizers
+  from tensor2robot_b200.research.qtopt import networks
+  torch.manual_seed(0)
+  critic = networks.Grasping44E2EOpenCloseTerminateGripperStatusHeightToBottom()
+  step = engine.CriticTrainStep(critic, optimizers.MomentumOptimizer(learning_rate=0.05, momentum=0.9),
+                                input_hw=(512, 640), target_hw=(472, 472))
+  rng = np.random.RandomState(0)
+  images = torch.from_numpy(rng.randint(0, 256, (4, 512, 640, 3)).astype(np.uint8)).cuda()
+  actions = torch.from_numpy(rng.uniform(-1, 1, (4, 10)).astype(np.float32)).cuda()
+  reward = torch.from_numpy((rng.uniform(size=(4, 1)) < 0.5).astype(np.float32)).cuda()
+  step.build(images, actions)
+  target = engine.LaggedTarget(step, update_every=3)
+  target.build(images, actions)
+  cem = engine.CEMTargetComputer(critic, target.vs, action_size=10, cem_samples=16, cem_iters=2, num_elites=4, seed=1)
+  x = step.preprocess(images, training=False)
+  assert torch.equal(target.vs.flat, step.vs.flat) and torch.equal(target.vs.state_flat, step.vs.state_flat)
+  _, q0, _ = cem.maximize(x)
+  step.step(images, actions, reward)
+  step.step(images, actions, reward)
+  assert not target.update()                                   # only 2 optimizer steps since the refresh
+  assert not torch.equal(target.vs.flat, step.vs.flat)          # the online critic has moved on
+  cem.calls = 0
+  _, q1, _ = cem.maximize(x)
+  assert torch.equal(q0, q1)                                    # the target is frozen in between
+  step.step(images, actions, reward)
+  assert target.update()                                        # third step: refresh
+  assert torch.equal(target.vs.flat, step.vs.flat) and torch.equal(target.vs.state_flat, step.vs.state_flat)
+  cem.calls = 0
+  _, q2, _ = cem.maximize(x)
+  assert not torch.equal(q0, q2)
