@@ -238,6 +238,12 @@ int32_t t2r_crop_convert_distort(const uint8_t* src, void* dst, const T2RDistort
                                  uint64_t seed, uint64_t offset, void* stream);
 /* tf.image.resize_images bilinear, TF1 legacy sampling (align_corners=False, no half-pixel
  * centres: src = dst * in/out), preprocessors/distortion.py:56-107.  fp32 NHWC. */
+/* The same photometric distortions on an already converted float image [N,H,W,3] (BC-Z distorts AFTER the
+ * resize: preprocessors/distortion.py:56-107); params[n].crop_* must be 0.  In place (dst == src) is allowed
+ * when use_contrast is 0. */
+int32_t t2r_distort_f32(const float* src, float* dst, const T2RDistortParams* params, float* chan_mean,
+                        int32_t N, int32_t H, int32_t W, int32_t use_contrast, uint64_t seed, uint64_t offset,
+                        void* stream);
 int32_t t2r_resize_bilinear_legacy(const float* src, float* dst, int32_t N, int32_t H, int32_t W,
                                    int32_t C, int32_t h, int32_t w, void* stream);
 

@@ -75,19 +75,29 @@ __device__ __forceinline__ void pre_contrast(const T2RDistortParams& pr, float& 
   }
 }
 
-__global__ void __launch_bounds__(256) image_mean_kernel(const uint8_t* __restrict__ src,
+// Pixel loaders: uint8 frames are converted like tf.image.convert_image_dtype (x * 1/255); float frames
+// (already converted, e.g. after the BC-Z resize) are taken as they are.
+__device__ __forceinline__ void load_rgb(const uint8_t* px, float& r, float& g, float& b) {
+  r = float(px[0]) * (1.0f / 255.0f); g = float(px[1]) * (1.0f / 255.0f); b = float(px[2]) * (1.0f / 255.0f);
+}
+__device__ __forceinline__ void load_rgb(const float* px, float& r, float& g, float& b) {
+  r = px[0]; g = px[1]; b = px[2];
+}
+
+template <typename SrcT>
+__global__ void __launch_bounds__(256) image_mean_kernel(const SrcT* __restrict__ src,
                                                          const T2RDistortParams* __restrict__ params,
                                                          float* chan_mean, int H, int W, int h, int w) {
   const int n = blockIdx.y;
   const T2RDistortParams pr = params[n];
-  const uint8_t* img = src + (size_t)n * H * W * 3;
+  const SrcT* img = src + (size_t)n * H * W * 3;
   float acc[3] = {0.f, 0.f, 0.f};
   const int total = h * w;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int y = i / w, x = i - y * w;
-    const uint8_t* px = img + ((size_t)(y + pr.crop_y) * W + (x + pr.crop_x)) * 3;
-    float r = float(px[0]) * (1.0f / 255.0f), g = float(px[1]) * (1.0f / 255.0f),
-          b = float(px[2]) * (1.0f / 255.0f);
+    const SrcT* px = img + ((size_t)(y + pr.crop_y) * W + (x + pr.crop_x)) * 3;
+    float r, g, b;
+    load_rgb(px, r, g, b);
     pre_contrast(pr, r, g, b);
     acc[0] += r; acc[1] += g; acc[2] += b;
   }
@@ -106,22 +116,22 @@ __global__ void __launch_bounds__(256) image_mean_kernel(const uint8_t* __restri
   }
 }
 
-template <bool OUT_F32>
+template <typename SrcT, bool OUT_F32>
 __global__ void __launch_bounds__(256) crop_convert_distort_kernel(
-    const uint8_t* __restrict__ src, void* __restrict__ dst, const T2RDistortParams* __restrict__ params,
+    const SrcT* __restrict__ src, void* __restrict__ dst, const T2RDistortParams* __restrict__ params,
     const float* __restrict__ chan_mean, int H, int W, int h, int w, int use_contrast, uint64_t seed,
     uint64_t offset) {
   const int n = blockIdx.y;
   const T2RDistortParams pr = params[n];
-  const uint8_t* img = src + (size_t)n * H * W * 3;
+  const SrcT* img = src + (size_t)n * H * W * 3;
   const int total = h * w;
   float m[3] = {0.f, 0.f, 0.f};
   if (use_contrast) { m[0] = chan_mean[n * 3]; m[1] = chan_mean[n * 3 + 1]; m[2] = chan_mean[n * 3 + 2]; }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int y = i / w, x = i - y * w;
-    const uint8_t* px = img + ((size_t)(y + pr.crop_y) * W + (x + pr.crop_x)) * 3;
-    float r = float(px[0]) * (1.0f / 255.0f), g = float(px[1]) * (1.0f / 255.0f),
-          b = float(px[2]) * (1.0f / 255.0f);
+    const SrcT* px = img + ((size_t)(y + pr.crop_y) * W + (x + pr.crop_x)) * 3;
+    float r, g, b;
+    load_rgb(px, r, g, b);
     pre_contrast(pr, r, g, b);
     if (use_contrast && pr.contrast_scale != 1.f) {
       r = (r - m[0]) * pr.contrast_scale + m[0];
@@ -187,15 +197,33 @@ extern "C" int32_t t2r_crop_convert_distort(const uint8_t* src, void* dst, const
   const int bx = std::max(1, std::min((h * w + 255) / 256, std::max(1, 148 * 8 / N)));
   if (use_contrast) {
     T2R_CUDA_OK(cudaMemsetAsync(chan_mean, 0, sizeof(float) * 3 * N, st));
-    image_mean_kernel<<<dim3(bx, N), 256, 0, st>>>(src, params, chan_mean, H, W, h, w);
+    image_mean_kernel<uint8_t><<<dim3(bx, N), 256, 0, st>>>(src, params, chan_mean, H, W, h, w);
     T2R_LAUNCH_OK();
   }
   if (out_f32)
-    crop_convert_distort_kernel<true><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, h, w,
-                                                                   use_contrast, seed, offset);
+    crop_convert_distort_kernel<uint8_t, true><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, h, w,
+                                                                            use_contrast, seed, offset);
   else
-    crop_convert_distort_kernel<false><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, h, w,
-                                                                    use_contrast, seed, offset);
+    crop_convert_distort_kernel<uint8_t, false><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, h, w,
+                                                                             use_contrast, seed, offset);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_distort_f32(const float* src, float* dst, const T2RDistortParams* params, float* chan_mean,
+                                   int32_t N, int32_t H, int32_t W, int32_t use_contrast, uint64_t seed,
+                                   uint64_t offset, void* stream) {
+  T2R_CHECK_ARG(src && dst && params && N > 0 && H > 0 && W > 0, "distort_f32: bad args");
+  T2R_CHECK_ARG(!use_contrast || chan_mean, "distort_f32: contrast needs chan_mean workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int bx = std::max(1, std::min((H * W + 255) / 256, std::max(1, 148 * 8 / N)));
+  if (use_contrast) {
+    T2R_CUDA_OK(cudaMemsetAsync(chan_mean, 0, sizeof(float) * 3 * N, st));
+    image_mean_kernel<float><<<dim3(bx, N), 256, 0, st>>>(src, params, chan_mean, H, W, H, W);
+    T2R_LAUNCH_OK();
+  }
+  crop_convert_distort_kernel<float, true><<<dim3(bx, N), 256, 0, st>>>(src, dst, params, chan_mean, H, W, H, W,
+                                                                        use_contrast, seed, offset);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

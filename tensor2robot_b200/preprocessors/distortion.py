@@ -32,13 +32,10 @@ def preprocess_image(image, mode, is_sequence, input_size, target_size, crop_siz
   if tuple(crop) == tuple(target_size):
     out = image_transformations.convert_and_distort(cropped, params, torch.float32)
   else:
-    # the reference distorts AFTER the resize; distortions are pointwise except contrast (mean),
-    # so the kernel order is convert -> resize -> distort on the float image
+    # the reference distorts AFTER the resize (distortion.py:95-104): convert -> resize -> distort
     f = image_transformations.convert_and_distort(cropped, None, torch.float32)
     out = image_ops.resize_bilinear_legacy(f, tuple(target_size))
-    if params:
-      raise NotImplementedError('photometric distortion after resize runs on float images (BC-Z path): '
-                                'next-round item')
+    out = image_transformations.distort_float(out, params)   # also the final clip to [0, 1]
   if is_sequence:
     out = out.reshape(tuple(shape[:2]) + tuple(out.shape[1:]))
   return out

@@ -61,6 +61,26 @@ def crop_convert_distort(images_u8, out_hw, params, out_dtype=torch.bfloat16, se
   return out
 
 
+def distort_f32(images_f32, params, seed=0, offset=0):
+  """Photometric distortions on an already converted CUDA float32 image batch [N,H,W,3] in [0,1]
+  (the BC-Z order: distort after the resize, preprocessors/distortion.py:56-107)."""
+  if not images_f32.is_cuda or images_f32.dtype != torch.float32:
+    raise _lib.T2RError('distort_f32 needs a CUDA float32 tensor (no CPU path)')
+  n, h, w, c = images_f32.shape
+  if c != 3:
+    raise ValueError('photometric distortions are defined for 3-channel images, got %d channels' % c)
+  params = np.ascontiguousarray(params, dtype=DISTORT_DTYPE)
+  if params.shape != (n,) or params['crop_y'].any() or params['crop_x'].any():
+    raise ValueError('need one parameter record per image, without a crop')
+  dev_params = torch.from_numpy(params.view(np.uint8).reshape(n, -1)).to(images_f32.device, non_blocking=True)
+  use_contrast = bool((params['contrast_scale'] != 1.0).any())
+  out = torch.empty_like(images_f32)
+  chan_mean = torch.empty((n, 3), dtype=torch.float32, device=images_f32.device) if use_contrast else None
+  _lib.call('t2r_distort_f32', _p(images_f32.contiguous()), _p(out), _p(dev_params), _p(chan_mean), n, h, w,
+            1 if use_contrast else 0, int(seed), int(offset), _stream())
+  return out
+
+
 def resize_bilinear_legacy(images_f32, out_hw):
   """tf.image.resize_images(BILINEAR) with TF1 legacy sampling; CUDA float32 NHWC."""
   if not images_f32.is_cuda or images_f32.dtype != torch.float32:

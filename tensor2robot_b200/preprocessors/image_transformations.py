@@ -117,6 +117,18 @@ def convert_and_distort(image_u8, params=None, out_dtype=torch.bfloat16):
   return image_ops.crop_convert_distort(base, tuple(image_u8.shape[1:3]), rec, out_dtype, seed_value, 0)
 
 
+def distort_float(image_f32, params=None):
+  """The same distortions on an already converted float CUDA image [N,h,w,3] (t2r_distort_f32)."""
+  n = image_f32.shape[0]
+  rec = image_ops.identity_params(n)
+  if params:
+    for k in ('brightness_delta', 'saturation_scale', 'hue_delta', 'contrast_scale', 'noise_stddev'):
+      rec[k] = params.get(k, rec[k][0])
+  x = image_f32 if image_f32.dtype == torch.float32 else image_f32.float()
+  y = image_ops.distort_f32(x.contiguous(), rec, params.get('noise_seed', 0) if params else 0, 0)
+  return y if image_f32.dtype == torch.float32 else y.to(image_f32.dtype)
+
+
 def ApplyPhotometricImageDistortions(images, **kwargs):  # pylint: disable=invalid-name
   """images: list of float CUDA tensors [B,h,w,3] in [0,1] or of uint8 crops.  One parameter draw for
   the whole list; brightness, saturation, hue, contrast, noise, then clip (:176-264)."""
@@ -126,13 +138,7 @@ def ApplyPhotometricImageDistortions(images, **kwargs):  # pylint: disable=inval
     if image.dtype == torch.uint8:
       out.append(convert_and_distort(image, params))
     else:
-      # float input: quantisation-free path through the same kernel is not available; the float
-      # pipeline is uint8 -> kernel in this engine.  Plain clip when nothing is enabled.
-      if any(params[k] != v for k, v in (('brightness_delta', 0.0), ('saturation_scale', 1.0),
-                                         ('hue_delta', 0.0), ('contrast_scale', 1.0), ('noise_stddev', 0.0))):
-        raise NotImplementedError('photometric distortion of already-converted float images: pass the uint8 '
-                                  'crop so that conversion and distortion fuse into one kernel')
-      out.append(image.clamp(0.0, 1.0))
+      out.append(distort_float(image, params))
   return out
 
 

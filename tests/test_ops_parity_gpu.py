@@ -330,3 +330,32 @@ def test_spatial_softmax_matches_oracle(n, h, w, c):
   po = torch.cat([(s * xp).sum(1, keepdim=True), (s * yp).sum(1, keepdim=True)], 1).reshape(-1, 2 * c)
   (po * wgt).sum().backward()
   _check('spatial softmax dx', xg.grad.float().cpu(), xo.grad, BF16_TOL)
+
+
+@pytest.mark.gpu
+def test_bcz_preprocess_distorts_after_resize():
+  """preprocessors/distortion.py:56-107 (BC-Z): uint8 -> float, crop, TF1-legacy bilinear resize, THEN the
+  photometric distortions on the float image (t2r_distort_f32) and the clip."""
+  from oracle import image_ops as oracle
+  from tensor2robot_b200.preprocessors import distortion, image_ops, image_transformations
+  rng = np.random.RandomState(11)
+  frames = rng.randint(0, 256, (3, 96, 120, 3)).astype(np.uint8)
+  d = torch.from_numpy(frames).cuda()
+  # float-image distortion kernel against the oracle, every op chained
+  x = rng.uniform(0, 1, (3, 40, 50, 3)).astype(np.float32)
+  kwargs = {'brightness_delta': -0.05, 'saturation_scale': 1.2, 'hue_delta': 0.1, 'contrast_scale': 0.7}
+  p = image_ops.identity_params(3)
+  for k_, v_ in kwargs.items():
+    p[k_] = v_
+  got = image_ops.distort_f32(torch.from_numpy(x).cuda(), p).cpu().numpy()
+  assert np.abs(got - oracle.distort(x, **kwargs)).max() < 2e-5
+  # the whole BC-Z chain in eval mode (centre crop, no distortion) and in train mode with fixed draws
+  out = distortion.preprocess_image(d, 'eval', False, (96, 120), (30, 40), crop_size=(80, 100)).cpu().numpy()
+  ref = oracle.resize_bilinear_legacy(oracle.convert_image_dtype_f32(oracle.crop(frames, 8, 10, 80, 100)), 30, 40)
+  assert np.abs(out - np.clip(ref, 0, 1)).max() < 1e-6
+  image_transformations.seed(5)
+  out_t = distortion.preprocess_image(d, 'train', False, (96, 120), (30, 40), crop_size=(80, 100),
+                                      image_distortion_fn=dict(random_brightness=True, random_saturation=True,
+                                                               random_hue=True, random_contrast=True))
+  assert out_t.shape == (3, 30, 40, 3) and out_t.dtype == torch.float32
+  assert float(out_t.min()) >= 0.0 and float(out_t.max()) <= 1.0
