@@ -318,6 +318,17 @@ int32_t t2r_sequence_example_parse_batch(const uint8_t* const* records, const ui
                                          int32_t B, const T2RFeaturePlan* plan, int32_t n_features,
                                          int32_t max_steps, int64_t* steps);
 
+/* ---- metric learning (Grasp2Vec) ------------------------------------------------------------ */
+/* n-pairs loss with labels = range(B) (research/grasp2vec/losses.py:152-181 ->
+ * tf.contrib.losses.metric_learning.npairs_loss): loss = mean_i(logsumexp_j(a_i . p_j) - a_i . p_i)
+ * + 0.25 * reg_lambda * (mean_i |a_i|^2 + mean_i |p_i|^2); also writes d loss / d anchor, d positive.
+ * anchor, positive, d_*: fp32 [B, D]; sim_ws fp32 [B, B]; row_ws fp32 [B]; loss fp32 [1]. */
+int32_t t2r_npairs_loss(const float* anchor, const float* positive, int32_t B, int32_t D, float reg_lambda,
+                        float* sim_ws, float* row_ws, float* loss, float* d_anchor, float* d_positive,
+                        void* stream);
+/* y = max(x, 0) on bf16 (tf.nn.relu outside a fused epilogue; backward: t2r_relu_bwd_bf16). */
+int32_t t2r_relu_fwd_bf16(const void* x, void* y, int64_t n, void* stream);
+
 /* ---- JPEG decode, split host / device (utils/tfdata.py:426-484 -> tf.image.decode_image) ---- *
  * Baseline sequential Huffman JPEG (SOF0/SOF1, 8 bit, one interleaved scan, restart intervals; grey or
  * YCbCr 4:4:4 / 4:2:2 / 4:2:0).  Host: headers + Huffman entropy decoding into quantised coefficient

@@ -1023,6 +1023,62 @@ def add_context(x, context, action_batch_size=1, defer_for_bn=False):
   return _trace('add_context', None, _AddContextFn.apply(x.contiguous(), context.contiguous(), action_batch_size))
 
 
+class _ReluFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x):
+    y = torch.empty_like(x)
+    _lib.call('t2r_relu_fwd_bf16', _p(x), _p(y), x.numel(), _stream())
+    ctx.save_for_backward(y)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (y,) = ctx.saved_tensors
+    dy = dy.contiguous()
+    dx = torch.empty_like(dy)
+    _lib.call('t2r_relu_bwd_bf16', _p(dy), _p(y), _p(dx), dy.numel(), _stream())
+    return dx
+
+
+def relu(x):
+  """tf.nn.relu on a bf16 CUDA tensor (stand-alone; conv / batch-norm epilogues fuse their own)."""
+  _require_cuda(x, 'relu')
+  if x.dtype != BF16:
+    raise ValueError('relu expects bf16 activations')
+  return _ReluFn.apply(x.contiguous())
+
+
+class _NPairsLossFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, anchor, positive, reg_lambda):
+    b, d = anchor.shape
+    dev = anchor.device
+    sim = torch.empty((b, b), dtype=F32, device=dev)
+    rows = torch.empty(b, dtype=F32, device=dev)
+    loss = torch.empty(1, dtype=F32, device=dev)
+    da, dp = torch.empty_like(anchor), torch.empty_like(positive)
+    _lib.call('t2r_npairs_loss', _p(anchor), _p(positive), b, d, float(reg_lambda), _p(sim), _p(rows), _p(loss),
+              _p(da), _p(dp), _stream())
+    ctx.save_for_backward(da, dp)
+    return loss.reshape(())
+
+  @staticmethod
+  def backward(ctx, dloss):
+    da, dp = ctx.saved_tensors
+    return da * dloss, dp * dloss, None
+
+
+def npairs_loss(anchor, positive, reg_lambda=0.002):
+  """tf.contrib.losses.metric_learning.npairs_loss(labels=range(B), anchor, positive, reg_lambda) on fp32
+  [B, D] CUDA embeddings (research/grasp2vec/losses.py:176-178)."""
+  _require_cuda(anchor, 'npairs_loss')
+  if anchor.dtype != F32 or positive.dtype != F32 or anchor.shape != positive.shape or anchor.dim() != 2:
+    raise ValueError('npairs_loss expects two fp32 [B, D] tensors of the same shape')
+  return _NPairsLossFn.apply(anchor.contiguous(), positive.contiguous(), reg_lambda)
+
+
 class _CastFn(torch.autograd.Function):
 
   @staticmethod
