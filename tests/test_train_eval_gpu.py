@@ -87,6 +87,32 @@ def test_record_train_and_eval(tmp_path):
   assert out['eval']['steps'] == 2 and np.isfinite(out['eval']['loss'])
 
 
+def test_record_train_with_device_jpeg_decoder(tmp_path):
+  """The same TFRecord -> parse -> decode -> preprocess -> train path with the split JPEG decoder
+  (Huffman on host, IDCT / colour on the GPU): the parser hands CUDA uint8 frames to the preprocessor.  The
+  decoders are bit-identical (tests/test_jpeg.py); the first loss is only compared loosely because the TRAIN
+  record stream is non-deterministic by design (utils/tfdata.py:683-685) and BN statistics use atomics."""
+  from tensor2robot_b200.input_generators import default_input_generator as gens
+  from tensor2robot_b200.utils import tfdata, train_eval
+  data = str(tmp_path / 'replay.tfrecord')
+  _write_replay(data, 8)
+  losses = {}
+  from tensor2robot_b200.preprocessors import image_transformations
+  for kind in ('host', 'device'):
+    tfdata.set_image_decoder(kind)
+    image_transformations.seed(0)          # same random crop offsets in both runs
+    try:
+      out = train_eval.train_eval_model(
+          t2r_model=_model(), input_generator_train=gens.DefaultRecordInputGenerator(file_patterns=data, batch_size=4,
+                                                                                    seed=0),
+          max_train_steps=1, model_dir=str(tmp_path / ('run_' + kind)))
+    finally:
+      tfdata.set_image_decoder('host')
+    assert out['global_step'] == 1 and np.isfinite(out['loss'])
+    losses[kind] = out['loss']
+  assert abs(losses['host'] - losses['device']) < 0.05 * abs(losses['host']), losses
+
+
 def test_engine_requires_cuda_tensors():
   from tensor2robot_b200 import _lib, nn
   with pytest.raises(_lib.T2RError):
