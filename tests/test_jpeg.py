@@ -157,3 +157,28 @@ def test_parser_with_device_decoder_matches_host_decoder():
     tfdata.set_image_decoder('host')
   assert hasattr(dev, 'is_cuda') and dev.is_cuda and tuple(dev.shape) == host.shape
   np.testing.assert_array_equal(dev.cpu().numpy(), host)
+
+
+def test_host_entropy_decoder_property():
+  """Property test (hypothesis): for random small images, qualities and chroma subsamplings the C++ Huffman
+  decoder returns exactly the oracle's coefficients, and the oracle's pixels equal libjpeg-turbo's."""
+  import hypothesis
+  from hypothesis import strategies as st
+  from tensor2robot_b200.utils import jpeg
+
+  @hypothesis.settings(max_examples=25, deadline=None)
+  @hypothesis.given(st.integers(8, 40), st.integers(8, 40), st.integers(5, 100), st.sampled_from([0, 1, 2]),
+                    st.integers(0, 2**31 - 1))
+  def check(h, w, quality, subsampling, seed):
+    rng = np.random.RandomState(seed)
+    img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    img[: h // 2] = (img[: h // 2].astype(np.int32) // 4 + 96).astype(np.uint8)      # a smoother half
+    data = _encode(img, quality=quality, subsampling=subsampling)
+    geom, coef, _ = jpeg.entropy_decode([data], pinned=False)
+    info, coefs = oracle_jpeg.decode_coefficients(data)
+    for c, want in enumerate(coefs):
+      got = coef[0, geom.coef_offset[c]:geom.coef_offset[c] + want.size].numpy().reshape(want.shape)
+      np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(oracle_jpeg.decode(data), _pil(data, 'RGB'))
+
+  check()
