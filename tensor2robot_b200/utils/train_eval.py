@@ -48,6 +48,11 @@ def provide_input_generator_with_model_information(input_generator_or_generators
   return input_generator_or_generators
 
 
+def tfdata_image_decoder():
+  from tensor2robot_b200.utils import tfdata
+  return tfdata.IMAGE_DECODER
+
+
 class DeviceStager(object):
   """Pinned host staging + async H2D on a dedicated copy stream, double buffered."""
 
@@ -65,6 +70,9 @@ class DeviceStager(object):
     out = tensorspec_utils.TensorSpecStruct()
     with torch.cuda.stream(self.stream):
       for key, value in struct.items():
+        if isinstance(value, torch.Tensor) and value.is_cuda:
+          out[key] = value          # already on the device (e.g. frames from the split JPEG decoder)
+          continue
         t = value if isinstance(value, torch.Tensor) else torch.from_numpy(value)
         if t.dtype == torch.float64:
           t = t.float()
@@ -98,11 +106,74 @@ def save_checkpoint(t2r_model, model_dir, keep_checkpoint_max=5):
   return path
 
 
-def _batches(input_generator, t2r_model, mode, device):
-  """Host batches -> staged device batches -> preprocessed (features, labels)."""
+class Prefetcher(object):
+  """Runs a host-batch iterator on a background thread, `depth` batches ahead (tf.data's prefetch,
+  utils/tfdata.py:629-689).  Record reading, tf.Example parsing and image decoding spend their time in
+  C / C++ with the GIL released, so they overlap the main thread's kernel launches and the GPU step.
+  Exceptions of the producer are re-raised in the consumer; close() (or exhausting / deleting the
+  iterator) stops the thread."""
+  _END = object()
+
+  def __init__(self, iterable, depth=2):
+    import queue
+    import threading
+    self._queue = queue.Queue(maxsize=max(1, depth))
+    self._stop = threading.Event()
+    self._thread = threading.Thread(target=self._run, args=(iterable,), daemon=True)
+    self._thread.start()
+
+  def _run(self, iterable):
+    import queue
+    try:
+      for item in iterable:
+        while not self._stop.is_set():
+          try:
+            self._queue.put(item, timeout=0.1)
+            break
+          except queue.Full:
+            continue
+        if self._stop.is_set():
+          return
+      item = self._END
+    except BaseException as e:  # pylint: disable=broad-except
+      item = e
+    while not self._stop.is_set():
+      try:
+        self._queue.put(item, timeout=0.1)
+        return
+      except queue.Full:
+        continue
+
+  def __iter__(self):
+    return self
+
+  def __next__(self):
+    item = self._queue.get()
+    if item is self._END:
+      self._queue.put(item)       # stay exhausted
+      raise StopIteration
+    if isinstance(item, BaseException):
+      self._queue.put(item)
+      raise item
+    return item
+
+  def close(self):
+    self._stop.set()
+
+  def __del__(self):
+    self.close()
+
+
+def _batches(input_generator, t2r_model, mode, device, prefetch=2):
+  """Host batches (prefetched on a background thread) -> staged device batches -> preprocessed
+  (features, labels)."""
   stager = DeviceStager(device)
   preprocessor = t2r_model.preprocessor
-  for features, labels in input_generator.create_dataset(mode):
+  source = input_generator.create_dataset(mode)
+  if prefetch and tfdata_image_decoder() == 'host':
+    # the device JPEG decoder launches kernels on the consumer's CUDA stream: keep it on this thread
+    source = Prefetcher(source, prefetch)
+  for features, labels in source:
     flat = tensorspec_utils.flatten_spec_structure(features)
     n_feat = len(flat)
     merged = tensorspec_utils.TensorSpecStruct([('f/' + k, v) for k, v in flat.items()])

@@ -282,3 +282,43 @@ def test_example_parser_property_round_trip():
       assert back['s'][1] == [rows[records.index(rec)][2]] or back['s'][1] == []
 
   check()
+
+
+def test_prefetcher_order_errors_and_shutdown():
+  """train_eval.Prefetcher: same items in the same order, producer exceptions surface in the consumer,
+  an abandoned iterator stops its thread."""
+  import threading
+  import time
+  from tensor2robot_b200.utils import train_eval
+  assert list(train_eval.Prefetcher(iter(range(50)), depth=3)) == list(range(50))
+  assert list(train_eval.Prefetcher(iter([]), depth=1)) == []
+
+  def boom():
+    yield 1
+    yield 2
+    raise KeyError('bad record')
+
+  it = train_eval.Prefetcher(boom(), depth=2)
+  assert next(it) == 1 and next(it) == 2
+  with pytest.raises(KeyError):
+    next(it)
+  with pytest.raises(KeyError):      # stays failed
+    next(it)
+
+  produced = []
+
+  def endless():
+    i = 0
+    while True:
+      produced.append(i)
+      yield i
+      i += 1
+
+  it = train_eval.Prefetcher(endless(), depth=2)
+  assert next(it) == 0
+  before = threading.active_count()
+  it.close()
+  time.sleep(0.5)
+  n = len(produced)
+  time.sleep(0.3)
+  assert len(produced) == n and threading.active_count() <= before    # producer stopped
