@@ -184,7 +184,8 @@ def run_reference(args):
       'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'transitions/s', 'n_gpus': args.gpus,
       'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': workload_config(args, per_gpu_batch=args.cpu_batch),
+      # the same workload as the engine arm; the bounded CPU sample is described in cpu_baseline.sample
+      'config': workload_config(args, per_gpu_batch=args.batch),
       'cpu_baseline': {'value': rate, 'unit': 'transitions/s', 'cores': threads, 'kind': 'port', 'sample': sample},
       'e2e': {'value': rate, 'unit': 'transitions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
