@@ -326,6 +326,13 @@ int32_t t2r_sequence_example_parse_batch(const uint8_t* const* records, const ui
 int32_t t2r_npairs_loss(const float* anchor, const float* positive, int32_t B, int32_t D, float reg_lambda,
                         float* sim_ws, float* row_ws, float* loss, float* d_anchor, float* d_positive,
                         void* stream);
+/* Triplet loss with semi-hard negative mining (research/grasp2vec/losses.py:51-71 ->
+ * tf.contrib.losses.metric_learning.triplet_semihard_loss; the mining is restated in layers/tec.py:322-383):
+ * squared Euclidean pairwise distances, per (anchor, positive) the smallest negative distance beyond the
+ * positive one, else the largest negative distance; mean of max(margin + d_ap - d_an, 0) over the positive
+ * pairs.  emb fp32 [M, D], labels int32 [M]; ws: 3*M*M + M + 2 floats; writes loss [1] and d loss / d emb. */
+int32_t t2r_triplet_semihard_loss(const float* emb, const int32_t* labels, int32_t M, int32_t D, float margin,
+                                  float* ws, float* loss, float* d_emb, void* stream);
 /* y = max(x, 0) on bf16 (tf.nn.relu outside a fused epilogue; backward: t2r_relu_bwd_bf16). */
 int32_t t2r_relu_fwd_bf16(const void* x, void* y, int64_t n, void* stream);
 

@@ -26,3 +26,38 @@ def npairs_loss_both(pregrasp, goal, postgrasp, non_negativity_constraint=False)
   if non_negativity_constraint:
     pair_a = torch.relu(pair_a)
   return npairs_loss(pair_a, goal) + npairs_loss(goal, pair_a)
+
+
+def pairwise_distance_squared(e):
+  """tf.contrib metric_learning.pairwise_distance(squared=True): |a|^2 + |b|^2 - 2ab clamped at 0, zero diagonal."""
+  sq = (e ** 2).sum(1, keepdim=True)
+  d = torch.clamp(sq + sq.t() - 2.0 * e @ e.t(), min=0.0)
+  return d * (1.0 - torch.eye(e.shape[0], dtype=e.dtype))
+
+
+def triplet_semihard_loss(labels, embeddings, margin=1.0):
+  """The mining of layers/tec.py:322-383 (a reproduction of tf-slim's triplet_semihard_loss) with the squared
+  Euclidean distance tf-slim uses; written pair by pair, differentiable through torch."""
+  d = pairwise_distance_squared(embeddings)
+  m = d.shape[0]
+  total, num = 0.0, 0
+  for a in range(m):
+    neg = [n for n in range(m) if labels[n] != labels[a]]
+    for p in range(m):
+      if p == a or labels[p] != labels[a]:
+        continue
+      num += 1
+      if not neg:
+        continue
+      dn = d[a, neg]
+      outside = dn[dn > d[a, p]]
+      semi_hard = outside.min() if outside.numel() else dn.max()
+      total = total + torch.clamp(margin + d[a, p] - semi_hard, min=0.0)
+  return total / max(num, 1)
+
+
+def triplet_loss(pregrasp, goal, postgrasp):
+  pair_a = torch.nn.functional.normalize(pregrasp - postgrasp, dim=1, eps=1e-6)
+  pair_b = torch.nn.functional.normalize(goal, dim=1, eps=1e-6)
+  labels = list(range(pregrasp.shape[0])) * 2
+  return triplet_semihard_loss(labels, torch.cat([pair_a, pair_b], 0), margin=3.0)

@@ -76,6 +76,7 @@ _PROTOS = {
     't2r_cast_f32_to_bf16': (_I32, [_P, _P, _I64, _P]),
     't2r_add_context_affine_fwd': (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     't2r_npairs_loss': (_I32, [_P, _P, _I32, _I32, C.c_float, _P, _P, _P, _P, _P, _P]),
+    't2r_triplet_semihard_loss': (_I32, [_P, _P, _I32, _I32, C.c_float, _P, _P, _P, _P]),
     't2r_relu_fwd_bf16': (_I32, [_P, _P, _I64, _P]),
     't2r_fold_bn_weights': (_I32, [_P, _P, _P, _I32, _I64, _P]),
     't2r_cast_bf16_to_f32': (_I32, [_P, _P, _I64, _P]),

@@ -114,3 +114,146 @@ extern "C" int32_t t2r_relu_fwd_bf16(const void* x, void* y, int64_t n, void* st
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Triplet loss with semi-hard negative mining (Grasp2Vec TripletLoss, research/grasp2vec/losses.py:51-71 ->
+// tf.contrib.losses.metric_learning.triplet_semihard_loss, absent third-party code whose mining the
+// reference restates in layers/tec.py:322-383):
+//   D[i,j]   = max(|e_i|^2 + |e_j|^2 - 2 e_i.e_j, 0), D[i,i] = 0            (pairwise_distance, squared)
+//   for every anchor a and positive p (label[p] == label[a], p != a):
+//     outside = min{ D[a,n] : label[n] != label[a], D[a,n] > D[a,p] }          (if that set is not empty)
+//     inside  = max{ D[a,n] : label[n] != label[a] }
+//     loss   += max(margin + D[a,p] - (outside if it exists else inside), 0)
+//   loss /= number of (a, p) pairs
+// The backward pass is dD (the +-1/num_pos coefficients of the active pairs) pushed through D.
+// ---------------------------------------------------------------------------------------------
+namespace t2r {
+
+__global__ void pairwise_sqdist_kernel(const float* __restrict__ gram, float* __restrict__ dist, int M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= M) return;
+  const float d = gram[(long long)i * M + i] + gram[(long long)j * M + j] - 2.f * gram[(long long)i * M + j];
+  dist[(long long)i * M + j] = (i == j) ? 0.f : fmaxf(d, 0.f);
+}
+
+// One block per anchor.  coef[a, :] receives d loss / d D[a, :] (before the 1 / num_pos factor); stats[0]
+// accumulates the loss sum, stats[1] the number of positive pairs.
+__global__ void __launch_bounds__(256) triplet_semihard_kernel(const float* __restrict__ dist, const int* __restrict__ labels,
+                                                               float margin, int M, float* __restrict__ coef,
+                                                               float* __restrict__ stats) {
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  const int a = blockIdx.x;
+  const float* row = dist + (long long)a * M;
+  const int la = labels[a];
+  for (int j = threadIdx.x; j < M; j += 256) coef[(long long)a * M + j] = 0.f;
+  __syncthreads();
+  // inside: the largest negative distance (and where it is)
+  float best = -INFINITY;
+  int besti = -1;
+  for (int n = threadIdx.x; n < M; n += 256)
+    if (labels[n] != la && row[n] > best) { best = row[n]; besti = n; }
+  s_val[threadIdx.x] = best; s_idx[threadIdx.x] = besti;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float v = s_val[threadIdx.x + s];
+      const int vi = s_idx[threadIdx.x + s];
+      if (vi >= 0 && (s_idx[threadIdx.x] < 0 || v > s_val[threadIdx.x] ||
+                      (v == s_val[threadIdx.x] && vi < s_idx[threadIdx.x]))) {
+        s_val[threadIdx.x] = v; s_idx[threadIdx.x] = vi;
+      }
+    }
+    __syncthreads();
+  }
+  const float inside = s_val[0];
+  const int inside_i = s_idx[0];
+  __syncthreads();
+  for (int p = 0; p < M; ++p) {
+    if (p == a || labels[p] != la) continue;          // block-uniform
+    const float dap = row[p];
+    float o = INFINITY;
+    int oi = -1;
+    for (int n = threadIdx.x; n < M; n += 256)
+      if (labels[n] != la && row[n] > dap && row[n] < o) { o = row[n]; oi = n; }
+    s_val[threadIdx.x] = o; s_idx[threadIdx.x] = oi;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        const float v = s_val[threadIdx.x + s];
+        const int vi = s_idx[threadIdx.x + s];
+        if (vi >= 0 && (s_idx[threadIdx.x] < 0 || v < s_val[threadIdx.x] ||
+                        (v == s_val[threadIdx.x] && vi < s_idx[threadIdx.x]))) {
+          s_val[threadIdx.x] = v; s_idx[threadIdx.x] = vi;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const int ni = s_idx[0] >= 0 ? s_idx[0] : inside_i;
+      const float neg = s_idx[0] >= 0 ? s_val[0] : inside;
+      atomicAdd(stats + 1, 1.f);
+      if (ni >= 0) {
+        const float l = margin + dap - neg;
+        if (l > 0.f) {
+          atomicAdd(stats, l);
+          coef[(long long)a * M + p] += 1.f;
+          coef[(long long)a * M + ni] -= 1.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// S = (coef + coef^T) masked where the distance was clamped; also rowsum[i] = sum_j S[i, j]; in place into coef2.
+__global__ void triplet_sym_kernel(const float* __restrict__ coef, const float* __restrict__ dist, float* __restrict__ sym,
+                                   float* __restrict__ rowsum, int M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= M) return;
+  float v = coef[(long long)i * M + j] + coef[(long long)j * M + i];
+  if (i == j || !(dist[(long long)i * M + j] > 0.f)) v = 0.f;      // clamped / diagonal entries carry no gradient
+  sym[(long long)i * M + j] = v;
+  atomicAdd(rowsum + i, v);
+}
+
+// dE[i, :] = scale * (rowsum[i] * E[i, :] - (S @ E)[i, :]),  scale = 2 / num_pos; loss = stats[0] / stats[1]
+__global__ void triplet_finish_kernel(const float* __restrict__ emb, const float* __restrict__ rowsum,
+                                      const float* __restrict__ stats, float* __restrict__ d_emb, float* __restrict__ loss,
+                                      long long total, int D) {
+  const float np_ = fmaxf(stats[1], 1.f);
+  const float scale = 2.f / np_;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    d_emb[i] = scale * (rowsum[i / D] * emb[i] - d_emb[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) loss[0] = stats[0] / np_;
+}
+
+}  // namespace t2r
+
+extern "C" int32_t t2r_triplet_semihard_loss(const float* emb, const int32_t* labels, int32_t M, int32_t D, float margin,
+                                             float* ws /* 3*M*M + M + 2 floats */, float* loss, float* d_emb,
+                                             void* stream) {
+  T2R_CHECK_ARG(emb && labels && ws && loss && d_emb && M > 1 && D > 0, "triplet_semihard_loss: bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* gram = ws;                          // [M, M], reused for coef
+  float* dist = ws + (size_t)M * M;          // [M, M]
+  float* sym = ws + 2 * (size_t)M * M;       // [M, M]
+  float* rowsum = ws + 3 * (size_t)M * M;    // [M]
+  float* stats = rowsum + M;                 // [2]
+  if (int rc = t2r_sgemm(0, 1, M, M, D, 1.f, emb, D, emb, D, 0.f, gram, M, stream)) return rc;
+  const dim3 grid2((M + 127) / 128, M);
+  pairwise_sqdist_kernel<<<grid2, 128, 0, st>>>(gram, dist, M);
+  T2R_LAUNCH_OK();
+  T2R_CUDA_OK(cudaMemsetAsync(rowsum, 0, sizeof(float) * (size_t(M) + 2), st));
+  triplet_semihard_kernel<<<M, 256, 0, st>>>(dist, labels, margin, M, gram /* coef */, stats);
+  T2R_LAUNCH_OK();
+  triplet_sym_kernel<<<grid2, 128, 0, st>>>(gram, dist, sym, rowsum, M);
+  T2R_LAUNCH_OK();
+  // d_emb <- S @ E, then finished in place
+  if (int rc = t2r_sgemm(0, 0, M, D, M, 1.f, sym, M, emb, D, 0.f, d_emb, D, stream)) return rc;
+  const long long total = (long long)M * D;
+  triplet_finish_kernel<<<int(std::min<long long>((total + 255) / 256, 148LL * 8)), 256, 0, st>>>(emb, rowsum, stats,
+                                                                                                   d_emb, loss, total, D);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}

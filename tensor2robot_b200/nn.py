@@ -1087,6 +1087,35 @@ def npairs_loss(anchor, positive, reg_lambda=0.002):
   return _NPairsLossFn.apply(anchor.contiguous(), positive.contiguous(), reg_lambda)
 
 
+class _TripletSemihardFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, emb, labels, margin):
+    m, d = emb.shape
+    ws = torch.empty(3 * m * m + m + 2, dtype=F32, device=emb.device)
+    loss = torch.empty(1, dtype=F32, device=emb.device)
+    d_emb = torch.empty_like(emb)
+    _lib.call('t2r_triplet_semihard_loss', _p(emb), _p(labels), m, d, float(margin), _p(ws), _p(loss), _p(d_emb),
+              _stream())
+    ctx.save_for_backward(d_emb)
+    return loss.reshape(())
+
+  @staticmethod
+  def backward(ctx, dloss):
+    (d_emb,) = ctx.saved_tensors
+    return d_emb * dloss, None, None
+
+
+def triplet_semihard_loss(labels, embeddings, margin=1.0):
+  """tf.contrib.losses.metric_learning.triplet_semihard_loss on fp32 [M, D] CUDA embeddings with int labels
+  (research/grasp2vec/losses.py:69-71; mining restated in layers/tec.py:322-383)."""
+  _require_cuda(embeddings, 'triplet_semihard_loss')
+  if embeddings.dtype != F32 or embeddings.dim() != 2:
+    raise ValueError('triplet_semihard_loss expects fp32 [M, D] embeddings')
+  labels = labels.to(device=embeddings.device, dtype=torch.int32).contiguous()
+  return _TripletSemihardFn.apply(embeddings.contiguous(), labels, margin)
+
+
 class _CastFn(torch.autograd.Function):
 
   @staticmethod

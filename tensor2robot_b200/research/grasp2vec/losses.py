@@ -15,3 +15,15 @@ def NPairsLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding,  # pylin
   loss_1 = nn.npairs_loss(pair_a, pair_b)
   loss_2 = nn.npairs_loss(pair_b, pair_a)
   return loss_1 + loss_2
+
+
+def TripletLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding):  # pylint: disable=invalid-name
+  """Semi-hard mining triplet loss between l2-normalised (pre - post) and goal embeddings, labels
+  tile(range(B), 2), margin 3.0 (losses.py:51-71)."""
+  pre, post, goal = (nn.to_f32(t) for t in (pregrasp_embedding, postgrasp_embedding, goal_embedding))
+  pair_a = torch.nn.functional.normalize(pre - post, dim=1, eps=1e-6)    # tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))
+  pair_b = torch.nn.functional.normalize(goal, dim=1, eps=1e-6)
+  b = pre.shape[0]
+  labels = torch.arange(b, dtype=torch.int32).repeat(2)
+  pairs = torch.cat([pair_a, pair_b], dim=0)
+  return nn.triplet_semihard_loss(labels, pairs, margin=3.0)

@@ -71,3 +71,30 @@ def test_grasp2vec_model_train_step():
   assert np.isfinite(loss.item()) and 'embed_loss' in train_outputs
   g = vs.flat_grad
   assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+@pytest.mark.parametrize('m,d,nlabels,margin', [(16, 32, 8, 1.0), (64, 128, 32, 3.0), (48, 64, 5, 0.2)])
+def test_triplet_semihard_loss_matches_oracle(m, d, nlabels, margin):
+  from oracle import grasp2vec as oracle
+  from tensor2robot_b200 import nn
+  rng = np.random.RandomState(m + d)
+  e = torch.from_numpy(rng.standard_normal((m, d)).astype(np.float32) * 0.4)
+  labels = [int(v) for v in rng.randint(0, nlabels, m)]
+  eo = e.clone().double().requires_grad_(True)
+  lo = oracle.triplet_semihard_loss(labels, eo, margin)
+  lo.backward()
+  eg = e.cuda().requires_grad_(True)
+  l = nn.triplet_semihard_loss(torch.tensor(labels), eg, margin)
+  l.backward()
+  assert abs(l.item() - float(lo)) < 1e-4 * max(1.0, abs(float(lo))), (l.item(), float(lo))
+  np.testing.assert_allclose(eg.grad.cpu().numpy(), eo.grad.numpy(), rtol=2e-3, atol=2e-5)
+
+
+def test_grasp2vec_triplet_loss():
+  from oracle import grasp2vec as oracle
+  from tensor2robot_b200.research.grasp2vec import losses
+  rng = np.random.RandomState(2)
+  pre, goal, post = (torch.from_numpy(rng.uniform(size=(32, 512)).astype(np.float32)) for _ in range(3))
+  got = losses.TripletLoss(pre.cuda(), goal.cuda(), post.cuda())
+  want = oracle.triplet_loss(pre.double(), goal.double(), post.double())
+  assert abs(got.item() - float(want)) < 1e-4 * abs(float(want))
