@@ -39,6 +39,11 @@ def _p(t):
 
 
 def _require_cuda(t, what):
+  if not torch.is_tensor(t):
+    if hasattr(t, 'materialize'):
+      raise _lib.T2RError('%s received a deferred inference op (%s): only batch_norm / conv2d consume those; '
+                          'call .materialize() first' % (what, type(t).__name__))
+    raise _lib.T2RError('%s expects a CUDA tensor, got %s' % (what, type(t).__name__))
   if not t.is_cuda:
     raise _lib.T2RError('%s: tensor is on %s; the B200 engine has no CPU path' % (what, t.device))
 
