@@ -239,3 +239,44 @@ def test_film_resnet18_matches_oracle():
     assert np.isfinite(g).all() and np.abs(g).max() > 0
     print('%-16s rel_l2 %.3e' % (k, _rel_l2(g, go)))
     assert _rel_l2(g, go) < 0.3
+
+
+def test_bcz_resnet_film_network_trains():
+  """research/bcz/model.py:245-285 + layers/bcz_networks.py:107-145: FiLM-ResNet tower (ResNet-18 here) with one
+  MLP head per pose component, 3 waypoints (first from `action_trajectory`, the rest from
+  `auxiliary_trajectory` heads behind a stop_gradient); every trainable variable except the unused
+  classification head receives a gradient and the output shapes / variable scopes are the reference's."""
+  from tensor2robot_b200 import nn
+  from tensor2robot_b200.layers import resnet
+  from tensor2robot_b200.research.bcz import model as bcz
+  from tensor2robot_b200.utils import tensorspec_utils
+  b = 4
+  img = torch.from_numpy(_images(b, 96, 21)).cuda().to(torch.bfloat16)
+  emb = torch.from_numpy(np.random.RandomState(22).standard_normal((b, 64)).astype(np.float32)).cuda()
+  feats = tensorspec_utils.TensorSpecStruct(image=img)
+  comps = [('xyz', 3, True, 100.), ('quaternion', 4, False, 10.), ('target_close', 1, False, 1.)]
+
+  def run(mode):
+    return bcz.resnet_film_network(feats, mode, comps, num_waypoints=3, film_generator_fn=resnet.linear_film_generator,
+                                   condition_input=emb, resnet_size=18)
+
+  vs = nn.VariableStore('cuda', seed=1)
+  with torch.no_grad(), nn.variable_store(vs):
+    run('eval')
+  vs.finalize()
+  names = list(vs.export_tf().keys())
+  assert any(n.startswith('vision_model/action_trajectory/Stack/fully_connected_1/') for n in names)
+  assert any(n.startswith('vision_model/auxiliary_trajectory/') for n in names)
+  assert any(n.startswith('vision_model/film0/') for n in names)
+  with nn.variable_store(vs):
+    out, state = run('train')
+    assert sorted(out) == ['policy_image_features', 'quaternion', 'target_close', 'xyz_residual']
+    assert tuple(out['xyz_residual'].shape) == (b, 3, 3) and tuple(out['quaternion'].shape) == (b, 3, 4)
+    assert tuple(out['policy_image_features'].shape) == (b, 512) and tuple(state.shape) == (b, 256)
+    loss = sum((out[k] ** 2).sum() for k in ('xyz_residual', 'quaternion', 'target_close')) + (state ** 2).sum()
+    vs.zero_grad()
+    loss.backward()
+  torch.cuda.synchronize()
+  grads = vs.export_tf_grads()
+  dead = [k for k, g in grads.items() if not np.abs(g).max() > 0 and '/dense/' not in k]
+  assert np.isfinite(loss.item()) and not dead, dead[:5]
