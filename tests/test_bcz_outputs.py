@@ -1,0 +1,84 @@
+"""BC-Z pose assembly and losses (research/bcz/model.py:321-585) against an independent numpy restatement of the
+TF-1.x semantics they rely on: tf.losses.huber_loss / log_loss with SUM_BY_NONZERO_WEIGHTS, quaternion
+normalisation + Hamilton product ([x, y, z, w], tensorflow_graphics), residual composition, stop-token masking.
+CPU only: these are host-scale torch functions."""
+import numpy as np
+import torch
+
+from tensor2robot_b200.research.bcz import model as bcz
+from tensor2robot_b200.utils import tensorspec_utils as utils
+
+
+def _np_huber(label, pred, w):
+  e = np.abs(pred - label)
+  l = np.where(e <= 1.0, 0.5 * e * e, e - 0.5)
+  w = np.broadcast_to(np.asarray(w, np.float64), l.shape)
+  return (l * w).sum() / max((w != 0).sum(), 1)
+
+
+def _np_logloss(label, pred, w):
+  l = -label * np.log(pred + 1e-7) - (1 - label) * np.log(1 - pred + 1e-7)
+  w = np.broadcast_to(np.asarray(w, np.float64), l.shape)
+  return (l * w).sum() / max((w != 0).sum(), 1)
+
+
+def test_infer_and_training_outputs_match_restatement():
+  rng = np.random.RandomState(0)
+  b, wpts = 5, 3
+  comps = [('xyz', 3, True, 100.), ('quaternion', 4, True, 10.), ('target_close', 1, False, 1.)]
+  net = {'xyz_residual': rng.standard_normal((b, wpts, 3)), 'quaternion_residual': rng.standard_normal((b, wpts, 4)),
+         'target_close': rng.standard_normal((b, wpts, 1))}
+  cur_q = rng.standard_normal((b, 4)); cur_q /= np.linalg.norm(cur_q, axis=-1, keepdims=True)
+  present = {'xyz': rng.standard_normal((b, 3)), 'quaternion': cur_q}
+  features = utils.TensorSpecStruct()
+  features['present/xyz'] = torch.from_numpy(present['xyz'])
+  features['present/quaternion'] = torch.from_numpy(present['quaternion'])
+  out = bcz.infer_outputs(features, {k: torch.from_numpy(v) for k, v in net.items()}, comps, rescale_target_close=False)
+  # xyz: residual added to the present pose
+  np.testing.assert_allclose(out['action/xyz'].numpy(), net['xyz_residual'] + present['xyz'][:, None, :], rtol=1e-12)
+  # quaternion: normalise, then present * predicted (Hamilton product, xyzw)
+  qn = np.linalg.norm(net['quaternion_residual'], axis=-1, keepdims=True)
+  q = net['quaternion_residual'] / qn
+  a = np.broadcast_to(present['quaternion'][:, None, :], q.shape)
+  x1, y1, z1, w1 = [a[..., i] for i in range(4)]
+  x2, y2, z2, w2 = [q[..., i] for i in range(4)]
+  want_q = np.stack([x1 * w2 + y1 * z2 - z1 * y2 + w1 * x2, -x1 * z2 + y1 * w2 + z1 * x2 + w1 * y2,
+                     x1 * y2 - y1 * x2 + z1 * w2 + w1 * z2, -x1 * x2 - y1 * y2 - z1 * z2 + w1 * w2], -1)
+  np.testing.assert_allclose(out['action/quaternion'].numpy(), want_q, rtol=1e-10)
+  np.testing.assert_allclose(np.linalg.norm(out['action/quaternion'].numpy(), axis=-1), 1.0, rtol=1e-10)
+  np.testing.assert_allclose(out['quaternion_norm'].numpy(), qn, rtol=1e-12)
+  np.testing.assert_allclose(out['action/target_close'].numpy(), 1 / (1 + np.exp(-net['target_close'])), rtol=1e-10)
+  assert tuple(out['action_trajectory'].shape) == (b, wpts, 8)
+  np.testing.assert_allclose(bcz.xyz_action_trajectory(out).numpy(),
+                             np.concatenate([out['action/xyz'].numpy(), want_q], -1), rtol=1e-10)
+
+  # ---- losses on the UNMODIFIED head outputs (except the quaternion, overwritten by infer_outputs) ----
+  labels = utils.TensorSpecStruct()
+  lab = {'xyz_residual': rng.standard_normal((b, wpts, 3)), 'quaternion_residual': rng.standard_normal((b, wpts, 4)),
+         'target_close': (rng.uniform(size=(b, wpts, 1)) < 0.5).astype(np.float64),
+         'stop_token': (rng.uniform(size=(b, wpts, 1)) < 0.3).astype(np.float64)}
+  for k, v in lab.items():
+    labels['future/' + k] = torch.from_numpy(v)
+  netd = {k: torch.from_numpy(v) for k, v in net.items()}
+  netd['quaternion_norm'] = torch.from_numpy(qn)
+  loss, train = bcz.training_outputs(labels, netd, comps, quaternion_penalty=0.01, loss_name='huber')
+  mask = 1.0 - lab['stop_token']
+  want = {
+      'xyz_loss': _np_huber(lab['xyz_residual'], net['xyz_residual'], 100. * mask * np.ones_like(net['xyz_residual'])),
+      'quaternion_loss': _np_huber(lab['quaternion_residual'], net['quaternion_residual'],
+                                   10. * mask * np.ones_like(net['quaternion_residual'])),
+      'target_close_loss': _np_logloss(lab['target_close'], 1 / (1 + np.exp(-net['target_close'])), 1. * mask),
+      'quaternion_norm_loss': _np_huber(np.ones_like(qn), qn, 0.01 * mask),
+  }
+  for k, v in want.items():
+    np.testing.assert_allclose(float(train[k]), v, rtol=1e-9, err_msg=k)
+  np.testing.assert_allclose(float(loss), sum(want.values()), rtol=1e-9)
+  np.testing.assert_allclose(float(train['first_xyz_error']),
+                             _np_huber(lab['xyz_residual'][:, 0], net['xyz_residual'][:, 0], 100.), rtol=1e-9)
+  # all steps stopped -> every weight is zero -> the weighted losses vanish (SUM_BY_NONZERO_WEIGHTS of nothing)
+  labels['future/stop_token'] = torch.ones((b, wpts, 1), dtype=torch.float64)
+  loss0, _ = bcz.training_outputs(labels, netd, comps)
+  assert float(loss0) == 0.0
+  # piecewise scaling only kicks in above 1
+  f = bcz.piecewise_scaled_huber(lambda **kw: torch.tensor(kw['v']))
+  assert float(f(v=0.5)) == 0.5 and abs(float(f(v=3.0)) - (0.2 + 2.8 * 0.001)) < 1e-6
