@@ -127,6 +127,42 @@ int32_t t2r_spatial_softmax_fwd(const void* x, float* points, void* softmax, int
 int32_t t2r_spatial_softmax_bwd(const void* x, const float* points, const float* dpoints, void* dx, int32_t N,
                                 int32_t H, int32_t W, int32_t C, void* stream);
 
+/* ---- fp32 kernels of the small pose_env networks (layers/vision_layers.py:30-158, 277-350;
+ * research/pose_env/pose_env_models.py:118-181): 32-channel layers on 64x64 frames, below one tensor-core
+ * tile, hence CUDA-core kernels.  x NHWC fp32, w HWIO fp32 (the TF layout), padding given explicitly. */
+int32_t t2r_conv2d_direct_f32_fwd(const float* x, const float* w, const float* bias, float* y, int32_t N, int32_t H,
+                                  int32_t W, int32_t Cin, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                                  int32_t pad_top, int32_t pad_left, int32_t Ho, int32_t Wo, void* stream);
+int32_t t2r_conv2d_direct_f32_dgrad(const float* dy, const float* w, float* dx, int32_t N, int32_t H, int32_t W,
+                                    int32_t Cin, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_top,
+                                    int32_t pad_left, int32_t Ho, int32_t Wo, void* stream);
+/* dw is overwritten (Cout <= 256). */
+int32_t t2r_conv2d_direct_f32_wgrad(const float* x, const float* dy, float* dw, int32_t N, int32_t H, int32_t W,
+                                    int32_t Cin, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_top,
+                                    int32_t pad_left, int32_t Ho, int32_t Wo, void* stream);
+/* slim.layer_norm: moments over the D values of each of the N samples, per-channel gamma / beta (channel =
+ * index mod C), optional fused ReLU; mean / rstd [N] are saved for the backward pass, which overwrites
+ * dgamma / dbeta [C] (both may be NULL). */
+int32_t t2r_layer_norm_f32_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                               int32_t N, int32_t D, int32_t C, float eps, int32_t relu, void* stream);
+int32_t t2r_layer_norm_f32_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* mean,
+                               const float* rstd, float* dx, float* dgamma, float* dbeta, int32_t N, int32_t D,
+                               int32_t C, int32_t relu, void* stream);
+/* fp32 variant of t2r_spatial_softmax_* (any channel count). */
+int32_t t2r_spatial_softmax_f32_fwd(const float* x, float* points, float* softmax, int32_t N, int32_t H, int32_t W,
+                                    int32_t C, void* stream);
+int32_t t2r_spatial_softmax_f32_bwd(const float* x, const float* points, const float* dpoints, float* dx, int32_t N,
+                                    int32_t H, int32_t W, int32_t C, void* stream);
+/* pose_env critic action merge (pose_env_models.py:141-149): y[j] = x[j mod Nx] + ctx[j] broadcast over HW,
+ * x [Nx,HW,C], ctx [Nc,C], y [Nc,HW,C], Nc a multiple of Nx.  bwd: dx and / or dctx (either may be NULL). */
+int32_t t2r_tile_add_context_f32_fwd(const float* x, const float* ctx, float* y, int32_t Nx, int32_t Nc, int32_t HW,
+                                     int32_t C, void* stream);
+int32_t t2r_tile_add_context_f32_bwd(const float* dy, float* dx, float* dctx, int32_t Nx, int32_t Nc, int32_t HW,
+                                     int32_t C, void* stream);
+/* tf.nn.relu on fp32 (the default activation of the pose_env critic's fully connected layers). */
+int32_t t2r_relu_f32_fwd(const float* x, float* y, int64_t n, void* stream);
+int32_t t2r_relu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+
 /* ---- fp32 CUDA-core GEMM for the tiny action-context / logit layers -------------------- */
 /* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, op = transpose if flag set.
  * Replaces slim.fully_connected on grasp params and logits (networks.py:488-503,566-573). */

@@ -114,6 +114,17 @@ _PROTOS = {
     't2r_jpeg_parse': (_I32, [_P, C.c_uint64, C.POINTER(JpegInfo)]),
     't2r_jpeg_entropy_decode_batch': (_I32, [_P, _P, _I32, C.POINTER(JpegInfo), _P, _I64]),
     't2r_jpeg_idct_color': (_I32, [_P, _P, C.POINTER(JpegInfo), _P, _P, _I32, _I64, _I32, _P]),
+    't2r_conv2d_direct_f32_fwd': (_I32, [_P, _P, _P, _P] + [_I32] * 12 + [_P]),
+    't2r_conv2d_direct_f32_dgrad': (_I32, [_P, _P, _P] + [_I32] * 12 + [_P]),
+    't2r_conv2d_direct_f32_wgrad': (_I32, [_P, _P, _P] + [_I32] * 12 + [_P]),
+    't2r_layer_norm_f32_fwd': (_I32, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _I32, _P]),
+    't2r_layer_norm_f32_bwd': (_I32, [_P] * 9 + [_I32, _I32, _I32, _I32, _P]),
+    't2r_spatial_softmax_f32_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_spatial_softmax_f32_bwd': (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_tile_add_context_f32_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_tile_add_context_f32_bwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_relu_f32_fwd': (_I32, [_P, _P, _I64, _P]),
+    't2r_relu_f32_bwd': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_sequence_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32, _I32, _P]),
 }
 

@@ -35,13 +35,17 @@ def linear_film_generator(embedding, block_sizes, filter_sizes, enabled_block_la
       raise ValueError('Got {} bools for enabled_block_layers, expected {}'.format(
           len(enabled_block_layers), len(block_sizes)))
   film_gamma_betas = []
-  emb = nn.to_bf16(embedding)
+  tensor_core = embedding.shape[-1] % 64 == 0     # e.g. the 512-wide sentence embedding; one-hot task ids are not
+  emb = nn.to_bf16(embedding) if tensor_core else nn.to_f32(embedding)
   for i, num_blocks in enumerate(block_sizes):
     if enabled_block_layers and not enabled_block_layers[i]:
       film_gamma_betas.append([None] * num_blocks)
       continue
     num_filters = filter_sizes[i]
-    out = nn.dense(emb, num_blocks * num_filters * 2, scope='film{}'.format(i), use_bias=True)
+    if tensor_core:
+      out = nn.dense(emb, num_blocks * num_filters * 2, scope='film{}'.format(i), use_bias=True)
+    else:
+      out = nn.dense_f32(emb, num_blocks * num_filters * 2, scope='film{}'.format(i))
     film_gamma_betas.append(list(out.split(num_filters * 2, dim=-1)))
   return film_gamma_betas
 

@@ -4,6 +4,7 @@ import abc
 from tensor2robot_b200.models import abstract_model
 from tensor2robot_b200.models import model_interface
 from tensor2robot_b200.utils import tensorspec_utils
+from tensor2robot_b200.utils import tf_losses
 
 PREDICT = model_interface.PREDICT
 
@@ -11,7 +12,7 @@ PREDICT = model_interface.PREDICT
 class CriticModel(abstract_model.AbstractT2RModel):
   """Critic model with continuous actions trained using MC returns."""
 
-  def __init__(self, loss_function=None, action_batch_size=None, **kwargs):
+  def __init__(self, loss_function=tf_losses.mean_squared_error, action_batch_size=None, **kwargs):
     super(CriticModel, self).__init__(**kwargs)
     self._loss_function = loss_function
     self._action_batch_size = action_batch_size

@@ -925,6 +925,8 @@ def spatial_softmax(features, return_softmax=False):
   fp32 expected feature points [N, 2C] (interleaved x, y per channel, as the reference's reshape
   yields) and optionally the softmax heat map (no gradient flows through the map)."""
   _require_cuda(features, 'spatial_softmax')
+  if features.dtype == F32:      # the small pose_env tower (csrc/vision_small.cu)
+    return _SpatialSoftmaxF32Fn.apply(features.contiguous(), return_softmax)
   if features.shape[-1] % 8 != 0:
     raise ValueError('spatial_softmax needs a multiple of 8 channels')
   out = _SpatialSoftmaxFn.apply(features.contiguous(), return_softmax)
@@ -1041,7 +1043,7 @@ class _ReluFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, x):
     y = torch.empty_like(x)
-    _lib.call('t2r_relu_fwd_bf16', _p(x), _p(y), x.numel(), _stream())
+    _lib.call('t2r_relu_fwd_bf16' if x.dtype == BF16 else 't2r_relu_f32_fwd', _p(x), _p(y), x.numel(), _stream())
     ctx.save_for_backward(y)
     return y
 
@@ -1050,15 +1052,17 @@ class _ReluFn(torch.autograd.Function):
     (y,) = ctx.saved_tensors
     dy = dy.contiguous()
     dx = torch.empty_like(dy)
-    _lib.call('t2r_relu_bwd_bf16', _p(dy), _p(y), _p(dx), dy.numel(), _stream())
+    _lib.call('t2r_relu_bwd_bf16' if y.dtype == BF16 else 't2r_relu_f32_bwd', _p(dy), _p(y), _p(dx), dy.numel(), _stream())
     return dx
 
 
 def relu(x):
-  """tf.nn.relu on a bf16 CUDA tensor (stand-alone; conv / batch-norm epilogues fuse their own)."""
+  """tf.nn.relu on a bf16 or fp32 CUDA tensor (stand-alone; conv / norm epilogues fuse their own)."""
   _require_cuda(x, 'relu')
-  if x.dtype != BF16:
-    raise ValueError('relu expects bf16 activations')
+  if x.dtype not in (BF16, F32):
+    raise ValueError('relu expects bf16 or fp32 activations')
+  if x.numel() == 0:
+    return x
   return _ReluFn.apply(x.contiguous())
 
 
@@ -1195,7 +1199,7 @@ class _Fc32Fn(torch.autograd.Function):
 
 
 def dense_f32(x, units, scope='fc', bias_rows=1, initializer=None, regularize=True, trainable=True,
-              names=('weights', 'biases')):
+              names=('weights', 'biases'), bias_initializer=0.0):
   """fp32 slim.fully_connected for inner dimensions that are not multiples of 64.
 
   bias_rows > 1 models `tf.add_n` of several FC blocks that share the output (the reference's
@@ -1207,12 +1211,204 @@ def dense_f32(x, units, scope='fc', bias_rows=1, initializer=None, regularize=Tr
   with vs.scope(scope):
     wv = vs.get_variable(names[0], (k, units), initializer or glorot_uniform(k, units), trainable, regularize,
                          'fc32', None)
-    bv = vs.get_variable(names[1], (bias_rows, units), 0.0, trainable, False, 'fc32', None) if bias_rows else None
+    bv = vs.get_variable(names[1], (bias_rows, units), bias_initializer, trainable, False, 'fc32', None) if bias_rows else None
   if not vs.finalized:
     for v in (wv, bv):
       if v is not None and v.grad is None:
         v.grad = torch.zeros(v.shape, dtype=F32, device=x.device)
   return _trace('fc32', scope, _Fc32Fn.apply(x.contiguous(), vs.anchor, wv, bv))
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 layers of the small pose_env networks (csrc/vision_small.cu): 32-channel convolutions, slim
+# layer_norm, the tile + broadcast-add action merge and the bias-transform concat.
+# ---------------------------------------------------------------------------------------------
+def xavier_uniform(fan_in, fan_out):
+  """slim.xavier_initializer() (uniform): limit = sqrt(6 / (fan_in + fan_out))."""
+  return glorot_uniform(fan_in, fan_out)
+
+
+def _ensure_grad(vs, device, *variables):
+  if not vs.finalized:
+    for v in variables:
+      if v is not None and v.trainable and v.grad is None:
+        v.grad = torch.zeros(v.shape, dtype=F32, device=device)
+
+
+class _DirectConvFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, anchor, wv, bv, geom):
+    n, h, w, cin = x.shape
+    kh, kw, _, cout = wv.shape
+    stride, pt, pl, ho, wo = geom
+    y = torch.empty((n, ho, wo, cout), dtype=F32, device=x.device)
+    ctx.dims = (n, h, w, cin, cout, kh, kw, stride, pt, pl, ho, wo)
+    _lib.call('t2r_conv2d_direct_f32_fwd', _p(x), _p(wv.data), _p(bv.data if bv is not None else None), _p(y),
+              *ctx.dims, _stream())
+    ctx.wv, ctx.bv = wv, bv
+    ctx.save_for_backward(x)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (x,) = ctx.saved_tensors
+    wv, bv = ctx.wv, ctx.bv
+    dy = dy.contiguous()
+    st = _stream()
+    if wv.trainable:
+      _lib.call('t2r_conv2d_direct_f32_wgrad', _p(x), _p(dy), _p(wv.grad), *ctx.dims, st)
+    if bv is not None and bv.trainable:
+      _lib.call('t2r_colsum_f32', _p(dy), _p(bv.grad), dy.numel() // dy.shape[-1], dy.shape[-1], st)
+    dx = None
+    if ctx.needs_input_grad[0]:
+      dx = torch.empty_like(x)
+      _lib.call('t2r_conv2d_direct_f32_dgrad', _p(dy), _p(wv.data), _p(dx), *ctx.dims, st)
+    return dx, None, None, None, None
+
+
+def conv2d_f32(x, filters, kernel_size, stride=1, padding='VALID', use_bias=True, scope='conv', initializer=None,
+               bias_initializer=0.0, regularize=False, trainable=True):
+  """slim.conv2d in fp32 for layers below one tensor-core tile (3 / 32 channels): x fp32 NHWC, weights in the
+  TF HWIO layout under `<scope>/weights`, optional `<scope>/biases`."""
+  _require_cuda(x, 'conv2d_f32')
+  if x.dtype != F32:
+    raise ValueError('conv2d_f32 expects fp32 activations')
+  kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+  n, h, w, cin = x.shape
+  ho, wo, pt, pl = conv_geometry(h, w, kh, kw, stride, padding)
+  vs = current_store()
+  with vs.scope(scope):
+    wv = vs.get_variable('weights', (kh, kw, cin, filters), initializer or xavier_uniform(kh * kw * cin, kh * kw * filters),
+                         trainable, regularize, 'other', None)
+    bv = vs.get_variable('biases', (filters,), bias_initializer, trainable, False, 'other', None) if use_bias else None
+  _ensure_grad(vs, x.device, wv, bv)
+  return _trace('conv32', scope, _DirectConvFn.apply(x.contiguous(), vs.anchor, wv, bv, (stride, pt, pl, ho, wo)))
+
+
+class _LayerNormFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, anchor, gv, bv, eps, relu):
+    n, c = x.shape[0], x.shape[-1]
+    d = x.numel() // n
+    y = torch.empty_like(x)
+    mean = torch.empty(n, dtype=F32, device=x.device)
+    rstd = torch.empty(n, dtype=F32, device=x.device)
+    _lib.call('t2r_layer_norm_f32_fwd', _p(x), _p(gv.data), _p(bv.data), _p(y), _p(mean), _p(rstd), n, d, c, eps,
+              int(relu), _stream())
+    ctx.gv, ctx.bv, ctx.relu = gv, bv, relu
+    ctx.save_for_backward(x, mean, rstd)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, mean, rstd = ctx.saved_tensors
+    gv, bv = ctx.gv, ctx.bv
+    n, c = x.shape[0], x.shape[-1]
+    dx = torch.empty_like(x)
+    want = gv.trainable
+    _lib.call('t2r_layer_norm_f32_bwd', _p(x), _p(dy.contiguous()), _p(gv.data), _p(bv.data), _p(mean), _p(rstd), _p(dx),
+              _p(gv.grad if want else None), _p(bv.grad if want else None), n, x.numel() // n, c, int(ctx.relu), _stream())
+    return dx, None, None, None, None, None
+
+
+def layer_norm(x, scope='LayerNorm', relu=False, eps=1e-12, trainable=True):
+  """slim.layer_norm (center, scale; moments over every non-batch axis, parameters per channel) with an optional
+  fused ReLU.  x: fp32 [N, ..., C]."""
+  _require_cuda(x, 'layer_norm')
+  if x.dtype != F32:
+    raise ValueError('layer_norm expects fp32 activations')
+  c = x.shape[-1]
+  vs = current_store()
+  with vs.scope(scope):
+    bv = vs.get_variable('beta', (c,), 0.0, trainable, False, 'other', None)
+    gv = vs.get_variable('gamma', (c,), 1.0, trainable, False, 'other', None)
+  _ensure_grad(vs, x.device, gv, bv)
+  return _trace('layer_norm', scope, _LayerNormFn.apply(x.contiguous(), vs.anchor, gv, bv, eps, relu))
+
+
+class _SpatialSoftmaxF32Fn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, want_map):
+    n, h, w, c = x.shape
+    points = torch.empty((n, 2 * c), dtype=F32, device=x.device)
+    heat = torch.empty_like(x) if want_map else None
+    _lib.call('t2r_spatial_softmax_f32_fwd', _p(x), _p(points), _p(heat), n, h, w, c, _stream())
+    ctx.save_for_backward(x, points)
+    if want_map:
+      ctx.mark_non_differentiable(heat)
+      return points, heat
+    return points
+
+  @staticmethod
+  def backward(ctx, dpoints, _dheat=None):
+    x, points = ctx.saved_tensors
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    _lib.call('t2r_spatial_softmax_f32_bwd', _p(x), _p(points), _p(dpoints.contiguous().float()), _p(dx), n, h, w, c,
+              _stream())
+    return dx, None
+
+
+class _TileAddContextFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, context):
+    nx, h, w, c = x.shape
+    nc = context.shape[0]
+    y = torch.empty((nc, h, w, c), dtype=F32, device=x.device)
+    _lib.call('t2r_tile_add_context_f32_fwd', _p(x), _p(context), _p(y), nx, nc, h * w, c, _stream())
+    ctx.dims = (nx, nc, h, w, c)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    nx, nc, h, w, c = ctx.dims
+    dy = dy.contiguous()
+    dx = torch.empty((nx, h, w, c), dtype=F32, device=dy.device) if ctx.needs_input_grad[0] else None
+    dc = torch.empty((nc, c), dtype=F32, device=dy.device) if ctx.needs_input_grad[1] else None
+    _lib.call('t2r_tile_add_context_f32_bwd', _p(dy), _p(dx), _p(dc), nx, nc, h * w, c, _stream())
+    return dx, dc
+
+
+def tile_add_context(net, context):
+  """The pose_env critic's action merge (research/pose_env/pose_env_models.py:141-149): the image batch is tiled
+  (tf.tile: row j of the result is net[j mod B]) up to the context batch and context [Bc, C] is added at every
+  position.  fp32."""
+  _require_cuda(net, 'tile_add_context')
+  if net.dtype != F32 or context.dtype != F32:
+    raise ValueError('tile_add_context expects fp32 tensors')
+  if context.shape[0] % net.shape[0] != 0 or context.shape[1] != net.shape[-1]:
+    raise ValueError('context %s does not tile over net %s' % (tuple(context.shape), tuple(net.shape)))
+  return _TileAddContextFn.apply(net.contiguous(), context.contiguous())
+
+
+class _BiasTransformFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, anchor, bv):
+    ctx.bv, ctx.k = bv, x.shape[1]
+    return torch.cat([x, bv.data.reshape(1, -1).expand(x.shape[0], -1)], 1)
+
+  @staticmethod
+  def backward(ctx, dy):
+    bv, k = ctx.bv, ctx.k
+    if bv.trainable:
+      tail = dy[:, k:].contiguous()
+      _lib.call('t2r_colsum_f32', _p(tail), _p(bv.grad), tail.shape[0], tail.shape[1], _stream())
+    return dy[:, :k].contiguous(), None, None
+
+
+def bias_transform(x, size, scope='BiasAdd', initializer=0.01):
+  """vision_layers.py:325-329: concat([x, zeros[B, size] + biases], 1) with a learned bias vector."""
+  _require_cuda(x, 'bias_transform')
+  vs = current_store()
+  with vs.scope(scope):
+    bv = vs.get_variable('biases', (size,), initializer, True, False, 'other', None)
+  _ensure_grad(vs, x.device, bv)
+  return _BiasTransformFn.apply(x.contiguous(), vs.anchor, bv)
 
 
 # ---------------------------------------------------------------------------------------------

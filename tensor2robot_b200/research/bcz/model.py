@@ -1,6 +1,7 @@
-"""BC-Z image-to-action network (research/bcz/model.py:245-285): FiLM-conditioned ResNet tower + one MLP head
-per pose component.  The BCZModel class around it (specs, residual pose assembly, huber / log losses,
-research/bcz/model.py:321-950) is not built yet (coverage row A-18)."""
+"""BC-Z (research/bcz/model.py): FiLM-conditioned ResNet image-to-action network with one MLP head per pose
+component (:245-285), pose assembly (:321-460), weighted huber / log losses (:476-585), the BCZPreprocessor
+(:69-196) and the BCZModel T2R class (:641-950).  Not built: the spatial-softmax network variant, the
+stop-state head (`predict_stop`), mixup, eval metrics."""
 from tensor2robot_b200 import nn
 from tensor2robot_b200.layers import bcz_networks
 from tensor2robot_b200.layers import resnet
@@ -40,7 +41,9 @@ def resnet_film_network(features, mode, pose_components, num_waypoints, film_gen
 # ---------------------------------------------------------------------------------------------
 import torch  # pylint: disable=wrong-import-position
 
-MIN_GRIPPER_CLOSE = 0.0   # research/bcz/model.py:52-60 (rescaling target: [MIN_GRIPPER_CLOSE, 1])
+MIN_GRIPPER_CLOSE = 0.2                       # research/bcz/model.py:58-60
+GRIPPER_CLOSE_FRACTION_TO_OPEN_GRIPPER = 0.4
+NUM_DEBUG_TASKS = 21
 
 
 def quaternion_multiply(q1, q2):
@@ -55,29 +58,12 @@ def quaternion_multiply(q1, q2):
   return torch.stack([x, y, z, w], -1)
 
 
-def _weighted(loss, weights):
-  """tf.losses.compute_weighted_loss, Reduction.SUM_BY_NONZERO_WEIGHTS: sum(loss * w) / #{w != 0}."""
-  w = torch.as_tensor(weights, dtype=loss.dtype, device=loss.device)
-  w = torch.broadcast_to(w, loss.shape)
-  nonzero = (w != 0).sum().to(loss.dtype)
-  return (loss * w).sum() / torch.clamp(nonzero, min=1.0) if nonzero > 0 else (loss * w).sum()
+from tensor2robot_b200.utils import tf_losses  # pylint: disable=wrong-import-position
 
-
-def huber_loss(labels, predictions, weights=1.0, delta=1.0):
-  """tf.losses.huber_loss."""
-  err = (predictions - labels).abs()
-  quad = torch.clamp(err, max=delta)
-  return _weighted(0.5 * quad ** 2 + delta * (err - quad), weights)
-
-
-def mean_squared_error(labels, predictions, weights=1.0):
-  return _weighted((predictions - labels) ** 2, weights)
-
-
-def log_loss(labels, predictions, weights=1.0, epsilon=1e-7):
-  """tf.losses.log_loss."""
-  return _weighted(-labels * torch.log(predictions + epsilon) - (1 - labels) * torch.log(1 - predictions + epsilon),
-                   weights)
+_weighted = tf_losses.compute_weighted_loss
+huber_loss = tf_losses.huber_loss
+mean_squared_error = tf_losses.mean_squared_error
+log_loss = tf_losses.log_loss
 
 
 def piecewise_scaled_huber(loss_fn, threshold=0.2, slope=0.001):
@@ -181,3 +167,224 @@ def training_outputs(labels, network_output_dict, action_components, quaternion_
 def xyz_action_trajectory(outputs):
   rotation = outputs['action/quaternion'] if 'action/quaternion' in outputs else outputs['action/axis_angle']
   return torch.cat([outputs['action/xyz'], rotation], dim=-1)
+
+
+
+# ---------------------------------------------------------------------------------------------
+# Preprocessor and T2R model (research/bcz/model.py:63-196, 641-950)
+# ---------------------------------------------------------------------------------------------
+import enum  # pylint: disable=wrong-import-position
+
+import numpy as np  # pylint: disable=wrong-import-position
+
+from tensor2robot_b200.layers import resnet as resnet_layers  # pylint: disable=wrong-import-position
+from tensor2robot_b200.models import abstract_model  # pylint: disable=wrong-import-position
+from tensor2robot_b200.preprocessors import distortion  # pylint: disable=wrong-import-position
+from tensor2robot_b200.preprocessors import spec_transformation_preprocessor  # pylint: disable=wrong-import-position
+from tensor2robot_b200.research.bcz import pose_components_lib  # pylint: disable=wrong-import-position
+from tensor2robot_b200.utils import dtypes  # pylint: disable=wrong-import-position
+from tensor2robot_b200.utils import tensorspec_utils  # pylint: disable=wrong-import-position
+
+EVAL, PREDICT = 'eval', 'infer'
+TensorSpec = tensorspec_utils.ExtendedTensorSpec
+_RNG = np.random.RandomState(0)
+
+
+def _one_hot(ids, depth):
+  """tf.one_hot: ids outside [0, depth) give an all-zero row."""
+  return (ids.long()[:, None] == torch.arange(depth, device=ids.device)[None, :]).float()
+
+
+class ConditionMode(enum.Enum):
+  ONEHOT_TASKID = 1
+  LANGUAGE_EMBEDDING = 2
+
+
+class BCZPreprocessor(spec_transformation_preprocessor.SpecTransformationPreprocessor):
+  """Image conversion / crop / resize for single frames (model.py:69-196)."""
+
+  def __init__(self, image_size=(100, 100), crop_size=(512, 640), input_size=(512, 640), is_sequence=False,
+               mixup_alpha=0.0, cutout_size=0, mock_subtask=False, binarize_gripper=True, rescale_gripper=False,
+               image_distortion_fn=None, **kwargs):
+    if mixup_alpha > 0.0:
+      raise NotImplementedError('mixup regularisation is not built')
+    self._image_size = tuple(image_size)
+    self._crop_size = tuple(crop_size)
+    self._input_size = tuple(input_size)
+    self._is_sequence = is_sequence
+    self._cutout_size = cutout_size
+    self._mock_subtask = mock_subtask
+    self._binarize_gripper = binarize_gripper
+    self._rescale_gripper = rescale_gripper
+    self._image_distortion_fn = image_distortion_fn
+    super(BCZPreprocessor, self).__init__(**kwargs)
+
+  @property
+  def rescale_gripper(self):
+    return self._rescale_gripper
+
+  def get_in_feature_specification(self, mode):
+    flat = tensorspec_utils.flatten_spec_structure(self._model_feature_specification_fn(mode))
+    flat = tensorspec_utils.TensorSpecStruct(flat.items())
+    for key in ('original_image', 'original_depth_image'):   # produced by _preprocess_fn, never parsed
+      if mode != PREDICT and key in flat.keys():
+        del flat[key]
+    return self._transform_in_feature_specification(flat)
+
+  def _transform_in_feature_specification(self, flat_spec_structure):
+    self.update_spec(flat_spec_structure, 'image', shape=self._input_size + (3,), dtype=dtypes.uint8,
+                     data_format='jpeg')
+    return flat_spec_structure
+
+  def _preprocess_fn(self, features, labels, mode):
+    features.original_image = features.image
+    image = distortion.preprocess_image(features.image, mode, self._is_sequence, input_size=self._input_size,
+                                        target_size=self._image_size, crop_size=self._crop_size,
+                                        image_distortion_fn=self._image_distortion_fn)
+    features.image = nn.to_bf16(image)          # the tower computes in bf16
+    if self._cutout_size > 0 and mode == TRAIN:
+      raise NotImplementedError('Open-source BC-Z Model does not support cutout augmentation.')
+    key = 'target_close'
+    if labels is not None and key in labels.future.keys():
+      if self._binarize_gripper:
+        labels.future[key] = (labels.future[key] > GRIPPER_CLOSE_FRACTION_TO_OPEN_GRIPPER).to(labels.future[key].dtype)
+      if self._rescale_gripper:
+        labels.future[key] = torch.clamp((labels.future[key] - MIN_GRIPPER_CLOSE) / (1 - MIN_GRIPPER_CLOSE), min=0.)
+    if self._mock_subtask:
+      features.subtask_id = torch.zeros_like(features.subtask_id)
+    return features, labels
+
+
+class BCZModel(abstract_model.AbstractT2RModel):
+  """Single-image configurable regression model for BC-Z (model.py:641-950)."""
+
+  def __init__(self, state_components=None, action_components=None, predict_stop=False, image_size=(100, 100),
+               input_size=None, dataset_keys=None, num_waypoints=1, num_past=0, num_total_users=0,
+               network_fn=resnet_film_network, ignore_task_embedding=False, task_embedding_noise_std=0.1,
+               init_checkpoint=None, mask_stop_token=False, cond_modality=ConditionMode.ONEHOT_TASKID,
+               film_generator_fn=resnet_layers.linear_film_generator, resnet_size=50, **kwargs):
+    super(BCZModel, self).__init__(**kwargs)
+    if predict_stop:
+      raise NotImplementedError('the stop-state head (predict_stop) is not built')
+    self._image_size = tuple(image_size)
+    self._input_size = tuple(input_size) if input_size else None
+    self._dataset_keys = dataset_keys
+    self._num_waypoints = num_waypoints
+    self._num_past = num_past
+    self._network_fn = network_fn
+    self._ignore_task_embedding = ignore_task_embedding
+    self._task_embedding_noise_std = task_embedding_noise_std
+    self._action_components = action_components or pose_components_lib.DEFAULT_ACTION_COMPONENTS
+    self._state_components = state_components or []
+    self._init_checkpoint = init_checkpoint
+    self._mask_stop_token = mask_stop_token
+    self._num_total_users = num_total_users
+    self._cond_mode = cond_modality
+    self._film_generator_fn = film_generator_fn      # gin: resnet_film_network.film_generator_fn
+    self._resnet_size = resnet_size
+
+  @property
+  def default_preprocessor_cls(self):
+    return BCZPreprocessor
+
+  @property
+  def action_component_names(self):
+    return [p[0] for p in self._action_components]
+
+  @property
+  def is_joint_space(self):
+    return 'arm_joints' in self.action_component_names
+
+  @property
+  def is_xyz_space(self):
+    return 'xyz' in self.action_component_names
+
+  def pack_features(self, state, prev_episode_data, timestep):
+    del prev_episode_data, timestep
+    return state
+
+  def get_feature_specification(self, mode):
+    del mode
+    f32 = dtypes.float32
+    features = tensorspec_utils.TensorSpecStruct()
+    features.image = TensorSpec(shape=self._image_size + (3,), dtype=f32, name='present/image/encoded',
+                                data_format='jpeg', is_sequence=False)
+    present = tensorspec_utils.TensorSpecStruct()
+    for name, size, _ in self._state_components:
+      present[name] = TensorSpec(shape=(size,), dtype=f32, name='present/' + name, is_sequence=False)
+    for name, size, _, _ in self._action_components:
+      data_name = 'sensed_close' if name == 'target_close' else name   # target_close holds future information
+      present[name] = TensorSpec(shape=(size,), dtype=f32, name='present/' + data_name, is_sequence=False)
+    features.present = present
+    if self._cond_mode == ConditionMode.ONEHOT_TASKID:
+      features.subtask_id = TensorSpec(shape=(1,), dtype=dtypes.int64, name='subtask_id')
+    elif self._cond_mode == ConditionMode.LANGUAGE_EMBEDDING:
+      features.sentence_embedding = TensorSpec(shape=(512,), dtype=f32, name='sentence_embedding')
+    if self._num_total_users:
+      features.user_id = TensorSpec(shape=(1,), dtype=dtypes.int64, name='user_int')
+    features.camera_intrinsics = TensorSpec(shape=(3, 3), dtype=f32, name='present/camera_rgb/intrinsics',
+                                            is_optional=True)
+    features.camera_pose_base = TensorSpec(shape=(12,), dtype=f32, name='present/camera_pose_base', is_optional=True)
+    input_size = self._input_size if self._input_size else (512, 640)
+    features.original_image = TensorSpec(shape=input_size + (3,), dtype=dtypes.uint8, data_format='jpeg',
+                                         is_optional=True)
+    if self._num_past:
+      past = tensorspec_utils.TensorSpecStruct()
+      for name, size, residual in self._state_components:
+        past[name + '_residual' if residual else name] = TensorSpec(
+            shape=(self._num_past, size), dtype=f32, name='past/' + (name + '_residual' if residual else name),
+            is_sequence=False)
+      features.past = past
+    return features
+
+  def get_label_specification(self, mode):
+    del mode
+    future = tensorspec_utils.TensorSpecStruct()
+    for name, size, residual, _ in self._action_components:
+      key = name + '_residual' if residual else name
+      future[key] = TensorSpec(shape=(self._num_waypoints, size), dtype=dtypes.float32, name='future/' + key,
+                               is_sequence=False)
+    if self._mask_stop_token:
+      future.stop_token = TensorSpec(shape=(self._num_waypoints, 1), dtype=dtypes.float32, name='future/stop_token',
+                                     is_sequence=False)
+    return tensorspec_utils.TensorSpecStruct(future=future)
+
+  def augment_condition_input(self, condition_input, features, is_training):
+    if self._task_embedding_noise_std is not None and is_training:
+      noise = _RNG.standard_normal(tuple(condition_input.shape)).astype(np.float32) * self._task_embedding_noise_std
+      condition_input = condition_input + torch.from_numpy(noise).to(condition_input.device)
+    if self._ignore_task_embedding:
+      condition_input = None
+    extra = []
+    if self._state_components:
+      extra.append(torch.cat([features.present[t[0]].float() for t in self._state_components], dim=-1))
+    if self._num_total_users:
+      extra.append(_one_hot(features.user_id[:, 0], self._num_total_users))
+    if self._num_past:
+      prev = torch.cat([features.past[n + '_residual' if r else n].float() for n, _, r in self._state_components], -1)
+      extra.append(prev.reshape(prev.shape[0], -1))
+    for e in extra:
+      condition_input = e if condition_input is None else torch.cat([condition_input, e.to(condition_input.device)], -1)
+    return condition_input
+
+  def inference_network_fn(self, features, labels, mode, config=None, params=None):
+    del config, params
+    is_training = mode == TRAIN
+    if self._cond_mode == ConditionMode.ONEHOT_TASKID:
+      condition_input = _one_hot(features.subtask_id[:, 0], NUM_DEBUG_TASKS)
+    else:
+      condition_input = features.sentence_embedding.float()
+    condition_input = self.augment_condition_input(condition_input, features, is_training)
+    network_outputs_dict, _ = self._network_fn(
+        features, mode, self._action_components, self._num_waypoints, condition_input=condition_input,
+        film_generator_fn=self._film_generator_fn if condition_input is not None else None,
+        resnet_size=self._resnet_size)
+    outputs = infer_outputs(features, network_outputs_dict, self._action_components,
+                            self.preprocessor.rescale_gripper)
+    if not self._ignore_task_embedding:
+      outputs['condition_input'] = condition_input
+    return outputs
+
+  def model_train_fn(self, features, labels, inference_outputs, mode, config=None, params=None):
+    del features, mode, config, params
+    return training_outputs(labels, inference_outputs, self._action_components)

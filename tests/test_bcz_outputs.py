@@ -82,3 +82,30 @@ def test_infer_and_training_outputs_match_restatement():
   # piecewise scaling only kicks in above 1
   f = bcz.piecewise_scaled_huber(lambda **kw: torch.tensor(kw['v']))
   assert float(f(v=0.5)) == 0.5 and abs(float(f(v=3.0)) - (0.2 + 2.8 * 0.001)) < 1e-6
+
+
+def test_bcz_model_specs():
+  """research/bcz/model.py:690-790: feature / label specs and what the preprocessor asks the parser for."""
+  from tensor2robot_b200.research.bcz import model as bcz
+  from tensor2robot_b200.utils import dtypes
+  m = bcz.BCZModel(image_size=(100, 100), num_waypoints=10)
+  f = m.get_feature_specification('train')
+  assert f['image'].shape == (100, 100, 3) and f['image'].name == 'present/image/encoded'
+  assert f['present/target_close'].name == 'present/sensed_close'
+  assert f['subtask_id'].dtype == dtypes.int64 and 'sentence_embedding' not in f.keys()
+  l = m.get_label_specification('train')
+  assert sorted(l.keys()) == ['future/quaternion', 'future/target_close', 'future/xyz_residual']
+  assert l['future/xyz_residual'].shape == (10, 3) and l['future/xyz_residual'].name == 'future/xyz_residual'
+  pin = m.preprocessor.get_in_feature_specification('train')
+  assert pin['image'].shape == (512, 640, 3) and pin['image'].dtype == dtypes.uint8
+  assert 'original_image' not in pin.keys()
+  lang = bcz.BCZModel(cond_modality=bcz.ConditionMode.LANGUAGE_EMBEDDING)
+  assert lang.get_feature_specification('train')['sentence_embedding'].shape == (512,)
+  assert bcz.MIN_GRIPPER_CLOSE == 0.2 and bcz.NUM_DEBUG_TASKS == 21
+
+
+def test_tf_one_hot_semantics():
+  import torch
+  from tensor2robot_b200.research.bcz import model as bcz
+  oh = bcz._one_hot(torch.tensor([0, 20, 21, 254]), 21)
+  assert oh.shape == (4, 21) and oh.sum(1).tolist() == [1.0, 1.0, 0.0, 0.0]
