@@ -127,6 +127,16 @@ int32_t t2r_spatial_softmax_fwd(const void* x, float* points, void* softmax, int
 int32_t t2r_spatial_softmax_bwd(const void* x, const float* points, const float* dpoints, void* dx, int32_t N,
                                 int32_t H, int32_t W, int32_t C, void* stream);
 
+/* PCGrad gradient surgery (research/qtopt/pcgrad.py:123-154, per-variable implementation) on flat gradient buffers.
+ * grads: fp32 [T][stride], row t = the gradient of task loss t over the whole flat parameter buffer; variable v is
+ * the segment [seg_off[v], seg_off[v] + seg_len[v]) (device int64 [V]); use_pcgrad (device uint8 [V], may be NULL =
+ * all) marks the variables that pass the allow / deny lists, the others receive the plain sum of the task gradients.
+ * out[seg] = sum over tasks of the sequentially projected gradients, eps = 1e-5 in the reference.  Workspaces:
+ * gram fp32 [V][T][T], coef fp32 [V][T].  1 <= T <= 8.  Elements of `out` outside every segment are left untouched. */
+int32_t t2r_pcgrad_project(const float* grads, int32_t T, int64_t stride, const int64_t* seg_off,
+                           const int64_t* seg_len, const uint8_t* use_pcgrad, int32_t V, float eps, float* gram,
+                           float* coef, float* out, void* stream);
+
 /* ---- fp32 kernels of the small pose_env networks (layers/vision_layers.py:30-158, 277-350;
  * research/pose_env/pose_env_models.py:118-181): 32-channel layers on 64x64 frames, below one tensor-core
  * tile, hence CUDA-core kernels.  x NHWC fp32, w HWIO fp32 (the TF layout), padding given explicitly. */

@@ -24,6 +24,7 @@ from tensor2robot_b200.models import optimizers
 from tensor2robot_b200.utils import tensorspec_utils
 
 TRAIN, EVAL, PREDICT = model_interface.TRAIN, model_interface.EVAL, model_interface.PREDICT
+PCGRAD_LOSSES_COLLECTION = 'pcgrad_losses'   # key of the task-loss list in model_train_fn's train_outputs
 DEVICE_TYPE_CPU, DEVICE_TYPE_GPU, DEVICE_TYPE_TPU = 'cpu', 'gpu', 'tpu'
 
 ModelOutput = collections.namedtuple('ModelOutput', ['mode', 'loss', 'train_outputs', 'predictions', 'eval_metrics'])
@@ -206,8 +207,13 @@ class AbstractT2RModel(model_interface.ModelInterface):
     if not vs.finalized:
       self.build(features, labels)
     out = self.model_fn(features, labels, TRAIN, config, params)
-    vs.zero_grad()
-    out.loss.backward()
+    task_losses = (out.train_outputs or {}).get(PCGRAD_LOSSES_COLLECTION) if isinstance(out.train_outputs, dict) else None
+    if task_losses and hasattr(self.optimizer, 'compute_gradients'):
+      # research/qtopt/pcgrad.py:99-121 (use_collection_losses): one backward per task loss, projected gradients
+      self.optimizer.compute_gradients(list(task_losses), vs)
+    else:
+      vs.zero_grad()
+      out.loss.backward()
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     grad_scale = 1.0
     if world > 1:

@@ -88,7 +88,7 @@ def test_regression_network_matches_oracle(batch):
   loss_o = oracle.weighted_mse(torch.from_numpy(target.astype(np.float64)), pose_o, torch.from_numpy(reward.astype(np.float64)))
   loss_o.backward()
   assert tuple(out['state_features'].shape) == (batch, 64) and tuple(out['inference_output'].shape) == (batch, 2)
-  e_points = _rel(out['state_features'].cpu().numpy(), points_o.detach().numpy())
+  e_points = _rel(out['state_features'].detach().cpu().numpy(), points_o.detach().numpy())
   e_pose = _rel(out['inference_output'].detach().cpu().numpy(), pose_o.detach().numpy())
   e_loss = abs(float(loss) - float(loss_o)) / abs(float(loss_o))
   worst = _check_grads(vs.export_tf_grads(), ov)
