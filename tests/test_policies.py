@@ -1,0 +1,148 @@
+"""Serving side: policies on a mock predictor (CPU) and CheckpointPredictor + CEMPolicy / RegressionPolicy
+on the pose_env models (GPU; predictors/checkpoint_predictor_test.py:41-92)."""
+import numpy as np
+import pytest
+
+from tensor2robot_b200.policies import policies
+
+
+class _QuadraticPredictor(object):
+  """q(s, a) = -|a - target|^2 and a constant regression output."""
+
+  def __init__(self, target):
+    self.target = np.asarray(target, np.float64)
+    self.calls = []
+    self.global_step = 7
+
+  def predict(self, np_inputs):
+    if 'action' in np_inputs:
+      a = np.asarray(np_inputs['action'])
+      self.calls.append(a.shape)
+      return {'q_predicted': -np.sum((a - self.target) ** 2, axis=1)}
+    return {'inference_output': self.target[None]}
+
+  def init_randomly(self):
+    self.calls.append('init')
+
+  def restore(self):
+    self.calls.append('restore')
+
+  model_path = '/some/path'
+
+
+class _Model(object):
+
+  def pack_features(self, state, context, timestep, actions=None):
+    del context, timestep
+    out = {'state': np.expand_dims(state, 0)}
+    if actions is not None:
+      out['action'] = actions
+    return out
+
+
+def test_cem_policy_finds_the_argmax():
+  np.random.seed(0)
+  predictor = _QuadraticPredictor([0.4, -0.3])
+  policy = policies.CEMPolicy(_Model(), action_size=2, cem_iters=5, cem_samples=64, num_elites=10, predictor=predictor)
+  action = policy.SelectAction(np.zeros((4, 4, 3)), None, 0)
+  assert action.shape == (2,) and np.abs(action - [0.4, -0.3]).max() < 0.05
+  assert predictor.calls == [(64, 2)] * 5
+  best, debug = policy.get_cem_action(lambda s: -np.sum((s - 1.0) ** 2, axis=1))
+  assert set(debug) == {'q_predicted', 'final_params', 'best_idx'} and np.abs(best - 1.0).max() < 0.1
+  assert debug['final_params']['stddev'].shape == (2,)
+  assert policy.sample_action(np.zeros((4, 4, 3)), 0.5)[1] is None
+  policy.init_randomly()
+  policy.restore()
+  assert predictor.calls[-2:] == ['init', 'restore'] and policy.global_step == 7 and policy.model_path == '/some/path'
+
+
+def test_regression_policies():
+  np.random.seed(1)
+  predictor = _QuadraticPredictor([0.1, 0.2])
+  state = np.zeros((4, 4, 3))
+  np.testing.assert_allclose(policies.RegressionPolicy(_Model(), predictor=predictor).SelectAction(state, None, 0), [0.1, 0.2])
+  ou = policies.OUExploreRegressionPolicy(_Model(), action_size=2, predictor=predictor)
+  a1, a2 = ou.SelectAction(state, None, 0), ou.SelectAction(state, None, 1)
+  assert np.abs(a1 - [0.1, 0.2]).max() > 0 and np.abs(a2 - a1).max() > 0
+  ou.reset()
+  assert np.all(ou._x_t == 0)                                    # pylint: disable=protected-access
+  quiet = policies.OUExploreRegressionPolicy(_Model(), use_noise=False, predictor=predictor)
+  np.testing.assert_allclose(quiet.SelectAction(state, None, 0), [0.1, 0.2])
+  sched = policies.ScheduledExplorationRegressionPolicy(_Model(), stddev_0=0.7, slope=-0.1, predictor=predictor)
+  np.testing.assert_allclose(sched.SelectAction(state, None, 0), [0.1, 0.2])       # stddev = max(0.7 - 7 * 0.1, 0) = 0
+  assert policies.Policy.__abstractmethods__ == frozenset({'SelectAction'})
+  switch = policies.PerEpisodeSwitchPolicy(lambda: policies.RegressionPolicy(_Model(), predictor=_QuadraticPredictor([1., 1.])),
+                                           lambda: policies.RegressionPolicy(_Model(), predictor=predictor), explore_prob=0.5)
+  seen = set()
+  for _ in range(40):
+    switch.reset()
+    seen.add(tuple(switch.SelectAction(state, None, 0)))
+  assert seen == {(1.0, 1.0), (0.1, 0.2)} and switch.global_step == 7
+
+
+def test_predictor_contract_without_gpu():
+  from tensor2robot_b200.predictors import checkpoint_predictor
+  from tensor2robot_b200.research.pose_env import pose_env_models as pm
+  model = pm.PoseEnvRegressionModel()
+  with pytest.raises(ValueError):
+    checkpoint_predictor.CheckpointPredictor(t2r_model=model, use_gpu=False)
+  predictor = checkpoint_predictor.CheckpointPredictor(t2r_model=model)
+  with pytest.raises(ValueError):
+    predictor.restore()                        # no checkpoint_dir
+  with pytest.raises(ValueError):
+    predictor.predict({'does_not_matter': np.zeros(1)})
+  assert predictor.model_version == -1 and predictor.global_step == -1
+  assert list(predictor.get_feature_specification().keys()) == ['state']
+  missing = checkpoint_predictor.CheckpointPredictor(t2r_model=model, checkpoint_dir='/random/path/which/does/not/exist',
+                                                     timeout=1)
+  assert missing.restore() is False
+
+
+@pytest.mark.gpu
+def test_checkpoint_predictor_and_policies_on_pose_env(tmp_path):
+  from tensor2robot_b200.input_generators import default_input_generator as gens
+  from tensor2robot_b200.predictors import checkpoint_predictor
+  from tensor2robot_b200.research.pose_env import pose_env_models as pm
+  from tensor2robot_b200.utils import tensorspec_utils
+  from tensor2robot_b200.utils import train_eval
+  # regression: train 3 steps, restore into a fresh model, same predictions as the trained one
+  trained = pm.PoseEnvRegressionModel()
+  train_eval.train_eval_model(t2r_model=trained, input_generator_train=gens.DefaultRandomInputGenerator(batch_size=2),
+                              max_train_steps=3, model_dir=str(tmp_path))
+  model = pm.PoseEnvRegressionModel()
+  predictor = checkpoint_predictor.CheckpointPredictor(t2r_model=model, checkpoint_dir=str(tmp_path))
+  assert predictor.global_step == -1 and predictor.restore() and predictor.global_step == 3
+  assert predictor.model_path.endswith('model.ckpt-3.pt') and predictor.restore()        # unchanged checkpoint
+  spec = model.preprocessor.get_in_feature_specification('infer')
+  tensorspec_utils.assert_equal(predictor.get_feature_specification(), spec)
+  features = tensorspec_utils.make_random_numpy(spec, batch_size=2)
+  predictions = predictor.predict(features)
+  assert sorted(predictions) == ['inference_output'] and predictions['inference_output'].shape == (2, 2)
+  reference = checkpoint_predictor.CheckpointPredictor(t2r_model=trained, checkpoint_dir=str(tmp_path))
+  reference.init_randomly()                    # already built and trained: keeps its weights
+  np.testing.assert_allclose(reference.predict(features)['inference_output'], predictions['inference_output'], atol=1e-6)
+  obs = features['state'][0]
+  action = policies.RegressionPolicy(model, predictor=predictor).SelectAction(obs, None, 0)
+  np.testing.assert_allclose(action, predictions['inference_output'][0], atol=1e-6)
+  predictor.close()
+  with pytest.raises(ValueError):
+    predictor.predict(features)
+
+  # critic: CEM over Q(image, pose) with randomly initialised weights, 64 samples per iteration through the kernels
+  critic = pm.PoseEnvContinuousMCModel()
+  q_predictor = checkpoint_predictor.CheckpointPredictor(t2r_model=critic)
+  q_predictor.init_randomly()
+  seen = []
+
+  def pack_fn(t2r_model, state, context, timestep, samples):
+    del t2r_model, context, timestep
+    seen.append(samples.shape)
+    return {'state/image': np.expand_dims(state, 0), 'action/pose': samples.astype(np.float32)}
+
+  policy = policies.CEMPolicy(critic, action_size=2, cem_iters=3, cem_samples=64, num_elites=10, pack_fn=pack_fn,
+                              predictor=q_predictor)
+  np.random.seed(0)
+  best = policy.SelectAction(obs, None, 0)
+  assert best.shape == (2,) and np.isfinite(best).all() and seen == [(64, 2)] * 3
+  q = q_predictor.predict(pack_fn(None, obs, None, 0, np.stack([best, best + 0.5])))['q_predicted']
+  assert q.shape == (2,) and np.isfinite(q).all()
