@@ -127,7 +127,10 @@ def test_kernel_random_gradients(tasks):
   want = oracle.compute_gradients(host, list(shapes), denylist=['skip/*'])
   got = vs.export_tf_grads()
   for n in shapes:
-    err = np.linalg.norm(got[n] - want[n]) / np.linalg.norm(want[n])
+    # relative to the task gradients that went in: a 1-element variable with conflicting tasks projects to
+    # ~eps * g (a difference of O(1) terms), which fp32 - here as in TF - resolves to a few percent only
+    scale = max(np.linalg.norm(want[n]), 1e-2 * sum(np.linalg.norm(h[n]) for h in host))
+    err = np.linalg.norm(got[n] - want[n]) / scale
     assert err < 2e-5, (n, err)
   covered = torch.zeros(vs.flat.numel(), dtype=torch.bool)
   for v in vs.trainable_variables():
