@@ -292,6 +292,14 @@ int32_t t2r_distort_f32(const float* src, float* dst, const T2RDistortParams* pa
                         void* stream);
 int32_t t2r_resize_bilinear_legacy(const float* src, float* dst, int32_t N, int32_t H, int32_t W,
                                    int32_t C, int32_t h, int32_t w, void* stream);
+/* ApplyPhotometricImageDistortionsCheap (preprocessors/image_transformations.py:365-384): dst = src ** g_c per
+ * channel (n elements, channel = index mod C, C <= 4). */
+int32_t t2r_channel_gamma_f32(const float* src, float* dst, int64_t n, int32_t C, float g0, float g1, float g2, float g3,
+                              void* stream);
+/* ApplyDepthImageDistortions (image_transformations.py:403-459) for one tensor of the list:
+ * dst = clip(alpha * src + N(0, noise_stddev), min_depth, max_depth); Philox stream (seed, offset). */
+int32_t t2r_depth_distort_f32(const float* src, float* dst, int64_t n, float alpha, float noise_stddev, float min_depth,
+                              float max_depth, uint64_t seed, uint64_t offset, void* stream);
 
 /* ---- losses ---------------------------------------------------------------------------- */
 /* q = sigmoid(logit); loss = mean(-(y log(q+eps) + (1-y) log(1-q+eps))), eps = 1e-7

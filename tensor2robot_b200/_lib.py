@@ -99,6 +99,8 @@ _PROTOS = {
     't2r_relu_bwd_bf16': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_crop_convert_distort': (_I32, [_P, _P, _P, _P] + [_I32] * 7 + [_U64, _U64, _P]),
     't2r_distort_f32': (_I32, [_P, _P, _P, _P] + [_I32] * 4 + [_U64, _U64, _P]),
+    't2r_channel_gamma_f32': (_I32, [_P, _P, _I64, _I32, _F, _F, _F, _F, _P]),
+    't2r_depth_distort_f32': (_I32, [_P, _P, _I64, _F, _F, _F, _F, _U64, _U64, _P]),
     't2r_resize_bilinear_legacy': (_I32, [_P, _P] + [_I32] * 6 + [_P]),
     't2r_sigmoid_logloss': (_I32, [_P, _P, _P, _P, _P, _I64, _P]),
     't2r_sigmoid_f32': (_I32, [_P, _P, _I64, _P]),

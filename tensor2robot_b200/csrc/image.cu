@@ -182,6 +182,36 @@ __global__ void __launch_bounds__(256) resize_bilinear_legacy_kernel(const float
   }
 }
 
+// ApplyPhotometricImageDistortionsCheap (image_transformations.py:365-384): per-channel gamma, c ** g_c.
+__global__ void __launch_bounds__(256) channel_gamma_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            long long n, int C, float g0, float g1, float g2, float g3) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const int c = int(i % C);
+    const float g = c == 0 ? g0 : (c == 1 ? g1 : (c == 2 ? g2 : g3));
+    dst[i] = powf(src[i], g);
+  }
+}
+
+// ApplyDepthImageDistortions (image_transformations.py:403-459) for one tensor of the list:
+// clip(alpha * x + N(0, sigma), lo, hi); alpha = 1, sigma = 0 is the "noise not applied" branch.
+__global__ void __launch_bounds__(256) depth_distort_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            long long n, float alpha, float sigma, float lo, float hi,
+                                                            uint64_t seed, uint64_t offset) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < (n + 3) / 4; i += gridDim.x * 256LL) {
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sigma != 0.f) {
+      const Philox4 rnd = philox4x32_10(seed, (uint64_t)i, offset);
+      box_muller(rnd.v[0], rnd.v[1], &z[0], &z[1]);
+      box_muller(rnd.v[2], rnd.v[3], &z[2], &z[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i * 4 + k;
+      if (j < n) dst[j] = fminf(fmaxf(fmaf(alpha, src[j], sigma * z[k]), lo), hi);
+    }
+  }
+}
+
 }  // namespace t2r
 
 using namespace t2r;
@@ -234,6 +264,25 @@ extern "C" int32_t t2r_resize_bilinear_legacy(const float* src, float* dst, int3
   const long long total = (long long)N * h * w * C;
   const int grid = int(std::min<long long>((total + 255) / 256, 148LL * 16));
   resize_bilinear_legacy_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, N, H, W, C, h, w);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_channel_gamma_f32(const float* src, float* dst, int64_t n, int32_t C, float g0, float g1, float g2,
+                                         float g3, void* stream) {
+  T2R_CHECK_ARG(src && dst && n > 0 && C >= 1 && C <= 4 && n % C == 0, "channel_gamma_f32: bad args (1..4 channels)");
+  const int grid = int(std::min<long long>((n + 255) / 256, 148LL * 16));
+  channel_gamma_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, C, g0, g1, g2, g3);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_depth_distort_f32(const float* src, float* dst, int64_t n, float alpha, float noise_stddev, float min_depth,
+                                         float max_depth, uint64_t seed, uint64_t offset, void* stream) {
+  T2R_CHECK_ARG(src && dst && n > 0 && min_depth <= max_depth && noise_stddev >= 0.f, "depth_distort_f32: bad args");
+  const int grid = int(std::min<long long>(((n + 3) / 4 + 255) / 256, 148LL * 16));
+  depth_distort_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, alpha, noise_stddev, min_depth,
+                                                                            max_depth, seed, offset);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

@@ -90,3 +90,28 @@ def resize_bilinear_legacy(images_f32, out_hw):
   out = torch.empty((n, h, w, c), dtype=torch.float32, device=images_f32.device)
   _lib.call('t2r_resize_bilinear_legacy', _p(images_f32.contiguous()), _p(out), n, hh, ww, c, h, w, _stream())
   return out
+
+
+def channel_gamma(images_f32, gammas):
+  """dst = src ** gamma_c per channel (t2r_channel_gamma_f32): fp32 CUDA [..., C], C <= 4."""
+  if not images_f32.is_cuda or images_f32.dtype != torch.float32:
+    raise _lib.T2RError('channel_gamma needs a CUDA float32 tensor (no CPU path)')
+  c = images_f32.shape[-1]
+  if len(gammas) != c or c > 4:
+    raise ValueError('need one gamma per channel (at most 4 channels)')
+  g = [float(v) for v in gammas] + [1.0] * (4 - c)
+  x = images_f32.contiguous()
+  out = torch.empty_like(x)
+  _lib.call('t2r_channel_gamma_f32', _p(x), _p(out), x.numel(), c, g[0], g[1], g[2], g[3], _stream())
+  return out
+
+
+def depth_distort(depth_f32, alpha, noise_stddev, min_depth, max_depth, seed=0, offset=0):
+  """clip(alpha * x + N(0, noise_stddev), min_depth, max_depth) on a CUDA float32 tensor (t2r_depth_distort_f32)."""
+  if not depth_f32.is_cuda or depth_f32.dtype != torch.float32:
+    raise _lib.T2RError('depth_distort needs a CUDA float32 tensor (no CPU path)')
+  x = depth_f32.contiguous()
+  out = torch.empty_like(x)
+  _lib.call('t2r_depth_distort_f32', _p(x), _p(out), x.numel(), float(alpha), float(noise_stddev), float(min_depth),
+            float(max_depth), int(seed), int(offset), _stream())
+  return out

@@ -149,3 +149,62 @@ def ApplyRandomFlips(images):  # pylint: disable=invalid-name
   if _RNG.uniform() < 0.5:
     images = images.flip(-3)
   return images
+
+
+def draw_photometric_params_parallel(batch, **kwargs):
+  """One independent parameter draw per image (ApplyPhotometricImageDistortionsParallel: tf.map_fn over the batch,
+  image_transformations.py:316-362).  Returns (DISTORT_DTYPE records [batch], noise seed)."""
+  rec = image_ops.identity_params(batch)
+  seed_value = 0
+  for i in range(batch):
+    p = draw_photometric_params(**kwargs)
+    for k in ('brightness_delta', 'saturation_scale', 'hue_delta', 'contrast_scale', 'noise_stddev'):
+      rec[k][i] = p[k]
+    seed_value = seed_value or p['noise_seed']      # one Philox key per call; the counter separates the images
+  return rec, seed_value
+
+
+def ApplyPhotometricImageDistortionsParallel(images, custom_distortion_fn=None, **kwargs):  # pylint: disable=invalid-name
+  """images: ONE CUDA tensor [B,h,w,3] (uint8 or float in [0,1]); every image gets its own random brightness /
+  saturation / hue / contrast / noise draw, then the clip - still a single kernel launch, the per-image values are
+  rows of the parameter table (:268-362)."""
+  if custom_distortion_fn is not None:
+    raise NotImplementedError('custom_distortion_fn would run arbitrary per-image code between kernel stages')
+  rec, seed_value = draw_photometric_params_parallel(images.shape[0], **kwargs)
+  if images.dtype == torch.uint8:
+    return image_ops.crop_convert_distort(images.contiguous(), tuple(images.shape[1:3]), rec, torch.float32, seed_value, 0)
+  x = images if images.dtype == torch.float32 else images.float()
+  y = image_ops.distort_f32(x.contiguous(), rec, seed_value, 0)
+  return y if images.dtype == torch.float32 else y.to(images.dtype)
+
+
+def ApplyPhotometricImageDistortionsCheap(images):  # pylint: disable=invalid-name
+  """Per-channel random gamma correction, gamma ~ U[0.5, 1.5) drawn once per channel for the whole batch
+  (:365-384).  images: float CUDA tensor [B,h,w,3] in (0, 1)."""
+  gammas = [float(_RNG.uniform(0.5, 1.5)) for _ in range(images.shape[-1])]
+  x = images if images.dtype == torch.float32 else images.float()
+  y = image_ops.channel_gamma(x, gammas)
+  return y if images.dtype == torch.float32 else y.to(images.dtype)
+
+
+def ApplyDepthImageDistortions(depth_images, random_noise_level=0.05, random_noise_apply_probability=0.5,  # pylint: disable=invalid-name
+                               scaling_noise=True, gamma_shape=1000.0, gamma_scale_inverse=1000.0,
+                               min_depth_allowed=0.25, max_depth_allowed=2.5):
+  """depth_images: list of float CUDA tensors [B,h,w,1].  Per list entry: with probability
+  `random_noise_apply_probability` the tensor becomes alpha * depth + N(0, random_noise_level), alpha ~
+  Gamma(gamma_shape, rate gamma_scale_inverse); every tensor is clipped to the allowed depth range (:403-459).
+  (The reference leaves alpha undefined when scaling_noise is False; alpha = 1 here.)"""
+  assert depth_images[0].shape[-1] == 1
+  out = []
+  for image in depth_images:
+    alpha, sigma, seed_value = 1.0, 0.0, 0
+    if random_noise_level:
+      seed_value = int(_RNG.randint(0, 2**31 - 1))
+      drawn_alpha = float(_RNG.gamma(gamma_shape, 1.0 / gamma_scale_inverse)) if scaling_noise else 1.0
+      # tf.cond(uniform > p, image, alpha * image + noise): the distortion is applied when the draw is <= p
+      if not _RNG.uniform() > random_noise_apply_probability:
+        alpha, sigma = drawn_alpha, float(random_noise_level)
+    x = image if image.dtype == torch.float32 else image.float()
+    y = image_ops.depth_distort(x, alpha, sigma, min_depth_allowed, max_depth_allowed, seed_value, 0)
+    out.append(y if image.dtype == torch.float32 else y.to(image.dtype))
+  return out

@@ -27,3 +27,56 @@ def TripletLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding):  # pyl
   labels = torch.arange(b, dtype=torch.int32).repeat(2)
   pairs = torch.cat([pair_a, pair_b], dim=0)
   return nn.triplet_semihard_loss(labels, pairs, margin=3.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Alternative / auxiliary embedding losses (losses.py:29-53, 80-157, 222-238).  [B, D] embedding-sized tails:
+# plain torch on whatever device the embeddings live on.  Not built: NPairsLossMultilabel (sparse-label slim loss)
+# and TYloss (feature-map sized; no shipped config selects them).
+# ---------------------------------------------------------------------------------------------
+def _masked_mean(values, mask):
+  """tf.dynamic_partition(values, mask, 2)[1] averaged; zeros(1) when the mask is empty (the tf.cond else-branch)."""
+  mask = mask.reshape(-1).to(torch.int32)
+  if int(mask.sum()) <= 0:
+    return torch.zeros(1, dtype=torch.float32, device=values.device)
+  return values[mask == 1].mean().float()
+
+
+def L2ArithmeticLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding, mask):  # pylint: disable=invalid-name
+  """mean over the masked rows of ||pre - goal - post||^2 (losses.py:29-53)."""
+  pre, post, goal = (nn.to_f32(t) for t in (pregrasp_embedding, postgrasp_embedding, goal_embedding))
+  return _masked_mean(((pre - goal - post) ** 2).sum(1), mask)
+
+
+def CosineArithmeticLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding, mask):  # pylint: disable=invalid-name
+  """mean over the masked rows of the cosine distance 1 - <l2n(pre - post), l2n(goal)> (losses.py:80-107)."""
+  pre, post, goal = (nn.to_f32(t) for t in (pregrasp_embedding, postgrasp_embedding, goal_embedding))
+  pair_a = torch.nn.functional.normalize(pre - post, dim=1, eps=1e-6)
+  pair_b = torch.nn.functional.normalize(goal, dim=1, eps=1e-6)
+  return _masked_mean(1.0 - (pair_a * pair_b).sum(1), mask)
+
+
+def KeypointAccuracy(keypoints, labels):  # pylint: disable=invalid-name
+  """Quadrant accuracy and sigmoid cross-entropy of spatial-softmax keypoints (Shapes dataset, losses.py:110-135)."""
+  keypoints = nn.to_f32(keypoints).reshape(-1, 2)
+  centers = torch.tensor([[0.5, -0.5], [-0.5, -0.5], [0.5, 0.5], [-0.5, 0.5]], dtype=torch.float32,
+                         device=keypoints.device)
+  logits = keypoints @ centers.t()
+  labels = labels.reshape(-1).long()
+  correct = (labels == torch.softmax(logits, 1).argmax(1)).float()
+  onehot = torch.nn.functional.one_hot(labels, 4).float()
+  loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, onehot)
+  return correct.mean(), loss
+
+
+def SendToZeroLoss(tensor, mask):  # pylint: disable=invalid-name
+  """mean over the masked rows of ||tensor||_2 (losses.py:138-157)."""
+  return _masked_mean(torch.linalg.norm(nn.to_f32(tensor), dim=1), mask)
+
+
+def MatchNormsLoss(anchor_tensors, paired_tensors):  # pylint: disable=invalid-name
+  """tf.nn.l2_loss of the row-norm differences (sum d^2 / 2); gradients reach only the paired tensors
+  (losses.py:222-238)."""
+  anchor_norms = torch.linalg.norm(nn.to_f32(anchor_tensors), dim=1).detach()
+  paired_norms = torch.linalg.norm(nn.to_f32(paired_tensors), dim=1)
+  return ((anchor_norms - paired_norms) ** 2).sum() / 2

@@ -359,3 +359,56 @@ def test_bcz_preprocess_distorts_after_resize():
                                                                random_hue=True, random_contrast=True))
   assert out_t.shape == (3, 30, 40, 3) and out_t.dtype == torch.float32
   assert float(out_t.min()) >= 0.0 and float(out_t.max()) <= 1.0
+
+
+def test_parallel_cheap_and_depth_distortions():
+  """preprocessors/image_transformations.py:268-459: per-image parameter draws (Parallel), per-channel gamma (Cheap)
+  and the depth-image distortions, against the oracle / numpy with the same drawn parameters."""
+  from oracle import image_ops as oracle
+  from tensor2robot_b200.preprocessors import image_ops
+  from tensor2robot_b200.preprocessors import image_transformations as it
+  rng = np.random.RandomState(5)
+  x = rng.uniform(0.02, 0.98, (4, 24, 20, 3)).astype(np.float32)
+  xg = torch.from_numpy(x).cuda()
+  kwargs = dict(random_brightness=True, random_saturation=True, random_hue=True, random_contrast=True)
+  it.seed(3)
+  got = it.ApplyPhotometricImageDistortionsParallel(xg, **kwargs).cpu().numpy()
+  it.seed(3)
+  rec, _ = it.draw_photometric_params_parallel(4, **kwargs)
+  assert len({float(v) for v in rec['brightness_delta']}) == 4               # one draw per image
+  for i in range(4):
+    want = oracle.distort(x[i:i + 1], brightness_delta=float(rec['brightness_delta'][i]),
+                          saturation_scale=float(rec['saturation_scale'][i]), hue_delta=float(rec['hue_delta'][i]),
+                          contrast_scale=float(rec['contrast_scale'][i]))
+    assert np.abs(got[i:i + 1] - want).max() < 2e-5
+  u8 = torch.from_numpy(rng.randint(0, 256, (4, 24, 20, 3)).astype(np.uint8)).cuda()
+  it.seed(3)
+  got_u8 = it.ApplyPhotometricImageDistortionsParallel(u8, **kwargs).cpu().numpy()
+  want_u8 = np.concatenate([oracle.distort(u8[i:i + 1].cpu().numpy().astype(np.float32) / np.float32(255.0),
+                                           brightness_delta=float(rec['brightness_delta'][i]),
+                                           saturation_scale=float(rec['saturation_scale'][i]), hue_delta=float(rec['hue_delta'][i]),
+                                           contrast_scale=float(rec['contrast_scale'][i])) for i in range(4)])
+  assert np.abs(got_u8 - want_u8).max() < 2e-5
+  with pytest.raises(NotImplementedError):
+    it.ApplyPhotometricImageDistortionsParallel(xg, custom_distortion_fn=lambda im: im)
+
+  it.seed(11)
+  cheap = it.ApplyPhotometricImageDistortionsCheap(xg).cpu().numpy()
+  it.seed(11)
+  gammas = [it._RNG.uniform(0.5, 1.5) for _ in range(3)]                    # pylint: disable=protected-access
+  assert np.abs(cheap - np.power(x.astype(np.float64), np.array(gammas))).max() < 2e-6
+
+  depth = rng.uniform(0.1, 3.0, (2, 16, 12, 1)).astype(np.float32)
+  dg = torch.from_numpy(depth).cuda()
+  exact = image_ops.depth_distort(dg, 1.01, 0.0, 0.25, 2.5).cpu().numpy()
+  np.testing.assert_allclose(exact, np.clip(np.float32(1.01) * depth, 0.25, 2.5), rtol=1e-6)
+  big = torch.full((1, 256, 256, 1), 1.0, device='cuda')
+  noisy = image_ops.depth_distort(big, 1.0, 0.05, 0.25, 2.5, seed=4).cpu().numpy().ravel()
+  assert abs(noisy.mean() - 1.0) < 1e-3 and abs(noisy.std() - 0.05) < 1e-3
+  assert not np.array_equal(noisy, image_ops.depth_distort(big, 1.0, 0.05, 0.25, 2.5, seed=5).cpu().numpy().ravel())
+  it.seed(2)
+  outs = it.ApplyDepthImageDistortions([dg] * 6, random_noise_level=0.05)
+  changed = [not np.array_equal(o.cpu().numpy(), np.clip(depth, 0.25, 2.5)) for o in outs]
+  assert any(changed) and not all(changed)                                   # the coin is drawn per list entry
+  for o in outs:
+    assert float(o.min()) >= 0.25 and float(o.max()) <= 2.5
