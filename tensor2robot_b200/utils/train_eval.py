@@ -96,8 +96,10 @@ def latest_checkpoint(model_dir):
 
 
 def save_checkpoint(t2r_model, model_dir, keep_checkpoint_max=5):
-  os.makedirs(model_dir, exist_ok=True)
   path = os.path.join(model_dir, 'model.ckpt-%d.pt' % t2r_model.global_step)
+  if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+    return path          # replicas hold identical parameters: the chief writes (the Estimator's chief-only saver)
+  os.makedirs(model_dir, exist_ok=True)
   torch.save(t2r_model.state_dict(), path)
   existing = sorted(glob.glob(os.path.join(model_dir, 'model.ckpt-*.pt')),
                     key=lambda p: int(re.search(r'-(\d+)\.pt$', p).group(1)))
