@@ -14,6 +14,7 @@ Session.run of the reference's train_op.
 """
 import abc
 import collections
+import logging
 
 import torch
 import torch.distributed as dist
@@ -28,6 +29,43 @@ PCGRAD_LOSSES_COLLECTION = 'pcgrad_losses'   # key of the task-loss list in mode
 DEVICE_TYPE_CPU, DEVICE_TYPE_GPU, DEVICE_TYPE_TPU = 'cpu', 'gpu', 'tpu'
 
 ModelOutput = collections.namedtuple('ModelOutput', ['mode', 'loss', 'train_outputs', 'predictions', 'eval_metrics'])
+
+
+class _RestorableVariable(object):
+  """What filter_restorables_fn sees: `.name` / `.op.name` = the reference variable name, `.shape`."""
+
+  def __init__(self, name, shape):
+    self.name = name
+    self.shape = tuple(shape)
+    self.op = self
+
+
+def default_init_from_checkpoint_fn(checkpoint, allow_partial_restore=False, filter_restorables_fn=None):
+  """init_from_checkpoint_fn that initialises a model from a TensorFlow (tensor-bundle) checkpoint by variable name
+  (abstract_model.py:87-126).  Returns the callable the model invokes once its variables exist.
+
+  allow_partial_restore: tolerate model variables that are missing in the checkpoint (otherwise ValueError).
+  filter_restorables_fn: optional predicate on a variable (`.name`, `.op.name`, `.shape`) choosing what to restore."""
+  from tensor2robot_b200.utils import tf_checkpoint
+
+  def init_fn(t2r_model):
+    logging.info('Initializing model weights from %s', checkpoint)
+    reader = tf_checkpoint.load_checkpoint(checkpoint)
+    vs = t2r_model.variable_store
+    arrays = {}
+    for name, value in vs.export_tf().items():
+      if filter_restorables_fn is not None and not filter_restorables_fn(_RestorableVariable(name, value.shape)):
+        continue
+      if reader.has_tensor(name):
+        logging.info('Loading variable %s from checkpoint', name)
+        arrays[name] = reader.get_tensor(name)
+      elif allow_partial_restore:
+        logging.warning('Variable %s is not in the checkpoint, skipping.', name)
+      else:
+        raise ValueError('Attempting to restore variable {} which is not in the checkpoint.'.format(name))
+    vs.import_tf(arrays, strict=False)
+
+  return init_fn
 
 
 class AbstractT2RModel(model_interface.ModelInterface):

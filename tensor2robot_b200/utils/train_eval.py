@@ -16,6 +16,8 @@ import logging
 import os
 import re
 
+import numpy as np
+
 import torch
 
 from tensor2robot_b200.models import model_interface
@@ -106,6 +108,23 @@ def save_checkpoint(t2r_model, model_dir, keep_checkpoint_max=5):
   for old in existing[:-keep_checkpoint_max]:
     os.remove(old)
   return path
+
+
+def save_tf_checkpoint(t2r_model, model_dir):
+  """Writes the model variables (reference names, TF layouts) + global_step as a TensorFlow tensor-bundle checkpoint
+  `model_dir/model.ckpt-<step>.{index,data-00000-of-00001}` with the `checkpoint` state file tf.train.latest_checkpoint
+  reads: weights trained here load into the reference (tf.train.load_checkpoint / init_from_checkpoint) by name."""
+  from tensor2robot_b200.utils import tf_checkpoint
+  name = 'model.ckpt-%d' % t2r_model.global_step
+  prefix = os.path.join(model_dir, name)
+  if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+    return prefix
+  tensors = dict(t2r_model.variable_store.export_tf())
+  tensors['global_step'] = np.asarray(t2r_model.global_step, np.int64)
+  tf_checkpoint.write_checkpoint(prefix, tensors)
+  with open(os.path.join(model_dir, 'checkpoint'), 'w') as f:
+    f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (name, name))
+  return prefix
 
 
 class Prefetcher(object):
