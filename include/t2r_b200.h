@@ -172,6 +172,14 @@ int32_t t2r_tile_add_context_f32_bwd(const float* dy, float* dx, float* dctx, in
 /* tf.nn.relu on fp32 (the default activation of the pose_env critic's fully connected layers). */
 int32_t t2r_relu_f32_fwd(const float* x, float* y, int64_t n, void* stream);
 int32_t t2r_relu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* MockT2RModel layers (utils/mocks.py:160-176): tf.nn.elu and tf.layers.batch_normalization(training=False) on fp32
+ * [rows, C]: y = (x - mean) * rsqrt(var + eps) * gamma + beta; bwd overwrites dgamma / dbeta [C] (may both be NULL). */
+int32_t t2r_elu_f32_fwd(const float* x, float* y, int64_t n, void* stream);
+int32_t t2r_elu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+int32_t t2r_bn_infer_f32_fwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* var,
+                             float* y, int64_t rows, int32_t C, float eps, void* stream);
+int32_t t2r_bn_infer_f32_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* var,
+                             float* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C, float eps, void* stream);
 
 /* ---- fp32 CUDA-core GEMM for the tiny action-context / logit layers -------------------- */
 /* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, op = transpose if flag set.

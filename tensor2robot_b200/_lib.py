@@ -126,6 +126,10 @@ _PROTOS = {
     't2r_tile_add_context_f32_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_tile_add_context_f32_bwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_pcgrad_project': (_I32, [_P, _I32, _I64, _P, _P, _P, _I32, _F, _P, _P, _P, _P]),
+    't2r_elu_f32_fwd': (_I32, [_P, _P, _I64, _P]),
+    't2r_elu_f32_bwd': (_I32, [_P, _P, _P, _I64, _P]),
+    't2r_bn_infer_f32_fwd': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P]),
+    't2r_bn_infer_f32_bwd': (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P]),
     't2r_relu_f32_fwd': (_I32, [_P, _P, _I64, _P]),
     't2r_relu_f32_bwd': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_sequence_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32, _I32, _P]),

@@ -291,6 +291,61 @@ __global__ void __launch_bounds__(256) relu_f32_bwd_kernel(const float* __restri
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
 
+// tf.nn.elu (the MockT2RModel activation, utils/mocks.py:166-170): x > 0 ? x : exp(x) - 1.
+__global__ void __launch_bounds__(256) elu_f32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) y[i] = x[i] > 0.f ? x[i] : expm1f(x[i]);
+}
+
+// d elu = x > 0 ? 1 : elu(x) + 1, from the saved output.
+__global__ void __launch_bounds__(256) elu_f32_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                          float* __restrict__ dx, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL)
+    dx[i] = y[i] > 0.f ? dy[i] : dy[i] * (y[i] + 1.f);
+}
+
+// tf.layers.batch_normalization(training=False) on [rows, C] fp32: y = (x - mean) * rsqrt(var + eps) * gamma + beta.
+__global__ void __launch_bounds__(256) bn_infer_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ mean,
+                                                               const float* __restrict__ var, float* __restrict__ y,
+                                                               long long n, int C, float eps) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const int c = int(i % C);
+    y[i] = (x[i] - mean[c]) * rsqrtf(var[c] + eps) * gamma[c] + beta[c];
+  }
+}
+
+// dx = dy * gamma * rstd; dgamma[c] = sum dy * (x - mean) * rstd; dbeta[c] = sum dy.  One block per 32 channels,
+// threads (32 channels x 8 row lanes); rows reduced through shared memory.
+__global__ void __launch_bounds__(256) bn_infer_f32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                               const float* __restrict__ var, float* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               long long rows, int C, float eps) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
+  float ag = 0.f, ab = 0.f;
+  if (c < C) {
+    const float rstd = rsqrtf(var[c] + eps), m = mean[c], g = gamma[c];
+    for (long long r = part; r < rows; r += 8) {
+      const float d = dy[r * C + c], xh = (x[r * C + c] - m) * rstd;
+      dx[r * C + c] = d * g * rstd;
+      ag = fmaf(d, xh, ag);
+      ab += d;
+    }
+  }
+  sg[part][lane] = ag;
+  sb[part][lane] = ab;
+  __syncthreads();
+  if (part == 0 && c < C && dgamma != nullptr) {
+    for (int p = 1; p < 8; ++p) {
+      ag += sg[p][lane];
+      ab += sb[p][lane];
+    }
+    dgamma[c] = ag;
+    dbeta[c] = ab;
+  }
+}
+
 static int grid_for(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = 148LL * 16;
@@ -420,6 +475,39 @@ extern "C" int32_t t2r_relu_f32_fwd(const float* x, float* y, int64_t n, void* s
 extern "C" int32_t t2r_relu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
   T2R_CHECK_ARG(dy && y && dx && n > 0, "relu_f32_bwd: bad args");
   relu_f32_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, dx, n);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_elu_f32_fwd(const float* x, float* y, int64_t n, void* stream) {
+  T2R_CHECK_ARG(x && y && n > 0, "elu_f32_fwd: bad args");
+  elu_f32_fwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_elu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  T2R_CHECK_ARG(dy && y && dx && n > 0, "elu_f32_bwd: bad args");
+  elu_f32_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, dx, n);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_bn_infer_f32_fwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* var,
+                                        float* y, int64_t rows, int32_t C, float eps, void* stream) {
+  T2R_CHECK_ARG(x && gamma && beta && mean && var && y && rows > 0 && C > 0, "bn_infer_f32_fwd: bad args");
+  bn_infer_f32_fwd_kernel<<<grid_for(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, mean, var, y,
+                                                                                           rows * C, C, eps);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_bn_infer_f32_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* var,
+                                        float* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C, float eps, void* stream) {
+  T2R_CHECK_ARG(x && dy && gamma && mean && var && dx && rows > 0 && C > 0 && ((dgamma == nullptr) == (dbeta == nullptr)),
+                "bn_infer_f32_bwd: bad args");
+  bn_infer_f32_bwd_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, gamma, mean, var, dx, dgamma, dbeta,
+                                                                                      rows, C, eps);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

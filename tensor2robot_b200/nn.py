@@ -1411,6 +1411,74 @@ def bias_transform(x, size, scope='BiasAdd', initializer=0.01):
   return _BiasTransformFn.apply(x.contiguous(), vs.anchor, bv)
 
 
+
+class _EluFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x):
+    y = torch.empty_like(x)
+    _lib.call('t2r_elu_f32_fwd', _p(x), _p(y), x.numel(), _stream())
+    ctx.save_for_backward(y)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (y,) = ctx.saved_tensors
+    dy = dy.contiguous()
+    dx = torch.empty_like(dy)
+    _lib.call('t2r_elu_f32_bwd', _p(dy), _p(y), _p(dx), dy.numel(), _stream())
+    return dx
+
+
+def elu(x):
+  """tf.nn.elu on an fp32 CUDA tensor."""
+  _require_cuda(x, 'elu')
+  if x.dtype != F32:
+    raise ValueError('elu expects fp32 activations')
+  return _EluFn.apply(x.contiguous())
+
+
+class _BnInferF32Fn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, anchor, gv, bv, mv, vv, eps):
+    c = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.call('t2r_bn_infer_f32_fwd', _p(x), _p(gv.data), _p(bv.data), _p(mv.data), _p(vv.data), _p(y), x.numel() // c, c,
+              eps, _stream())
+    ctx.vars, ctx.eps = (gv, bv, mv, vv), eps
+    ctx.save_for_backward(x)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (x,) = ctx.saved_tensors
+    gv, bv, mv, vv = ctx.vars
+    c = x.shape[-1]
+    dx = torch.empty_like(x)
+    want = gv.trainable
+    _lib.call('t2r_bn_infer_f32_bwd', _p(x), _p(dy.contiguous()), _p(gv.data), _p(mv.data), _p(vv.data), _p(dx),
+              _p(gv.grad if want else None), _p(bv.grad if want else None), x.numel() // c, c, ctx.eps, _stream())
+    return dx, None, None, None, None, None, None
+
+
+def batch_normalization_f32(x, scope, eps=1e-3, trainable=True):
+  """tf.layers.batch_normalization(x, name=scope) with its default training=False on an fp32 [..., C] tensor: the moving
+  statistics (zeros / ones unless a checkpoint says otherwise) normalise, gamma / beta train (utils/mocks.py:171-172)."""
+  _require_cuda(x, 'batch_normalization_f32')
+  if x.dtype != F32:
+    raise ValueError('batch_normalization_f32 expects fp32 activations')
+  c = x.shape[-1]
+  vs = current_store()
+  with vs.scope(scope):
+    gv = vs.get_variable('gamma', (c,), 1.0, trainable, False, 'other', None)
+    bv = vs.get_variable('beta', (c,), 0.0, trainable, False, 'other', None)
+    mv = vs.get_variable('moving_mean', (c,), 0.0, False, False, 'other', None)
+    vv = vs.get_variable('moving_variance', (c,), 1.0, False, False, 'other', None)
+  _ensure_grad(vs, x.device, gv, bv)
+  return _BnInferF32Fn.apply(x.contiguous(), vs.anchor, gv, bv, mv, vv, eps)
+
+
 # ---------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------
