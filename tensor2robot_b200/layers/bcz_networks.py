@@ -5,8 +5,7 @@ from tensor2robot_b200 import nn
 
 
 def _relu32(x):
-  # tiny fp32 [B, 100] activations of the heads: left to torch autograd (host-scale work)
-  return torch.relu(x)
+  return nn.relu(x)
 
 
 def MultiHeadMLP(net, action_sizes, num_waypoints, fc_layers, is_training,  # pylint: disable=invalid-name

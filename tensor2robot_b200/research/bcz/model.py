@@ -1,7 +1,7 @@
 """BC-Z (research/bcz/model.py): FiLM-conditioned ResNet image-to-action network with one MLP head per pose
 component (:245-285), pose assembly (:321-460), weighted huber / log losses (:476-585), the BCZPreprocessor
-(:69-196) and the BCZModel T2R class (:641-950).  Not built: the spatial-softmax network variant, the
-stop-state head (`predict_stop`), mixup, eval metrics."""
+(:69-196) and the BCZModel T2R class (:641-950).  Not built: the spatial-softmax network variant, mixup,
+eval metrics."""
 from tensor2robot_b200 import nn
 from tensor2robot_b200.layers import bcz_networks
 from tensor2robot_b200.layers import resnet
@@ -73,6 +73,32 @@ def piecewise_scaled_huber(loss_fn, threshold=0.2, slope=0.001):
   return clipped_loss_fn
 
 
+def predict_stop_network(state_embedding, fc_layers=(100, 100), num_waypoints=1, scope_name='predict_stop'):
+  """Small MLP predicting (continue, fail / help, success) logits [B, num_waypoints * 3] from the state embedding
+  (model.py:286-317): slim.stack of fully_connected + layer_norm + ReLU, a 3-way head, and - behind a stop_gradient -
+  the heads of the remaining waypoints."""
+  with nn.variable_scope(scope_name):
+    net = nn.to_f32(state_embedding)
+    for i, units in enumerate(fc_layers):
+      scope = 'Stack/fully_connected_%d' % (i + 1)
+      net = nn.dense_f32(net, units, scope=scope, bias_rows=0)        # slim drops the bias under a normaliser
+      net = nn.layer_norm(net, scope=scope + '/LayerNorm', relu=True)
+    logits = nn.dense_f32(net, 3, scope='fully_connected')
+    if num_waypoints > 1:
+      rest_logits = nn.dense_f32(net.detach(), (num_waypoints - 1) * 3, scope='fully_connected_1')
+      logits = torch.cat([logits, rest_logits], dim=-1)
+  return logits
+
+
+def compute_stop_state_loss(stop_state_labels, stop_state_predictions, class_weights):
+  """tf.losses.softmax_cross_entropy of the one-hot stop-state labels, each example weighted by its class weight
+  (model.py:462-473; `class_weights` is gin.REQUIRED in the reference)."""
+  weights = (stop_state_labels * torch.as_tensor(class_weights, dtype=stop_state_labels.dtype,
+                                                 device=stop_state_labels.device)).sum(-1)
+  ce = -(stop_state_labels * torch.log_softmax(stop_state_predictions.float(), dim=-1)).sum(-1)
+  return tf_losses.compute_weighted_loss(ce, weights)
+
+
 def infer_outputs(features, network_output_dict, action_components, rescale_target_close):
   """Network head outputs -> absolute pose components (model.py:321-460): residual components are added to
   the present pose, quaternions are normalised (and composed with the present one when residual), gripper /
@@ -123,7 +149,7 @@ def infer_outputs(features, network_output_dict, action_components, rescale_targ
 
 
 def training_outputs(labels, network_output_dict, action_components, quaternion_penalty=0.01, loss_name='huber',
-                     regularization_loss=None):
+                     regularization_loss=None, stop_state_class_weights=None):
   """Per-component regression / log losses with the component weights, masked after the stop token, plus the
   QuaterNet norm penalty (model.py:476-585).  Returns (loss, train_outputs)."""
   if loss_name == 'mse':
@@ -157,6 +183,12 @@ def training_outputs(labels, network_output_dict, action_components, quaternion_
     predicted = network_output_dict['quaternion_norm']
     train_outputs['quaternion_norm_loss'] = reg_loss_fn(labels=torch.ones_like(predicted), predictions=predicted,
                                                         weights=quaternion_penalty * stop_mask_value)
+  if 'stop_state' in network_output_dict:          # stop state prediction loss (model.py:566-573)
+    if stop_state_class_weights is None:
+      raise ValueError('compute_stop_state_loss.class_weights is required (gin.REQUIRED in the reference)')
+    stop_labels = _one_hot(labels.future.stop_state.reshape(-1), 3)       # tf.one_hot: out-of-range -> zero row
+    train_outputs['stop_state_loss'] = compute_stop_state_loss(stop_labels, network_output_dict['stop_state'],
+                                                               stop_state_class_weights)
   if regularization_loss is not None:
     train_outputs['total_regularization_loss'] = regularization_loss
   loss = sum(train_outputs.values())
@@ -262,10 +294,11 @@ class BCZModel(abstract_model.AbstractT2RModel):
                input_size=None, dataset_keys=None, num_waypoints=1, num_past=0, num_total_users=0,
                network_fn=resnet_film_network, ignore_task_embedding=False, task_embedding_noise_std=0.1,
                init_checkpoint=None, mask_stop_token=False, cond_modality=ConditionMode.ONEHOT_TASKID,
-               film_generator_fn=resnet_layers.linear_film_generator, resnet_size=50, **kwargs):
+               film_generator_fn=resnet_layers.linear_film_generator, resnet_size=50, stop_state_class_weights=None,
+               **kwargs):
     super(BCZModel, self).__init__(**kwargs)
-    if predict_stop:
-      raise NotImplementedError('the stop-state head (predict_stop) is not built')
+    self._predict_stop = predict_stop
+    self._stop_state_class_weights = stop_state_class_weights
     self._image_size = tuple(image_size)
     self._input_size = tuple(input_size) if input_size else None
     self._dataset_keys = dataset_keys
@@ -344,6 +377,8 @@ class BCZModel(abstract_model.AbstractT2RModel):
       key = name + '_residual' if residual else name
       future[key] = TensorSpec(shape=(self._num_waypoints, size), dtype=dtypes.float32, name='future/' + key,
                                is_sequence=False)
+    if self._predict_stop:
+      future['stop_state'] = TensorSpec(shape=(), dtype=dtypes.int64, name='present/stop_state')
     if self._mask_stop_token:
       future.stop_token = TensorSpec(shape=(self._num_waypoints, 1), dtype=dtypes.float32, name='future/stop_token',
                                      is_sequence=False)
@@ -375,16 +410,19 @@ class BCZModel(abstract_model.AbstractT2RModel):
     else:
       condition_input = features.sentence_embedding.float()
     condition_input = self.augment_condition_input(condition_input, features, is_training)
-    network_outputs_dict, _ = self._network_fn(
+    network_outputs_dict, state_embedding = self._network_fn(
         features, mode, self._action_components, self._num_waypoints, condition_input=condition_input,
         film_generator_fn=self._film_generator_fn if condition_input is not None else None,
         resnet_size=self._resnet_size)
     outputs = infer_outputs(features, network_outputs_dict, self._action_components,
                             self.preprocessor.rescale_gripper)
+    if self._predict_stop:
+      outputs['stop_state'] = predict_stop_network(state_embedding)
     if not self._ignore_task_embedding:
       outputs['condition_input'] = condition_input
     return outputs
 
   def model_train_fn(self, features, labels, inference_outputs, mode, config=None, params=None):
     del features, mode, config, params
-    return training_outputs(labels, inference_outputs, self._action_components)
+    return training_outputs(labels, inference_outputs, self._action_components,
+                            stop_state_class_weights=self._stop_state_class_weights)

@@ -109,3 +109,28 @@ def test_tf_one_hot_semantics():
   from tensor2robot_b200.research.bcz import model as bcz
   oh = bcz._one_hot(torch.tensor([0, 20, 21, 254]), 21)
   assert oh.shape == (4, 21) and oh.sum(1).tolist() == [1.0, 1.0, 0.0, 0.0]
+
+
+def test_stop_state_loss_and_spec():
+  """model.py:462-473, 566-573: softmax cross-entropy of the one-hot stop state, weighted per class."""
+  import torch
+  from tensor2robot_b200.research.bcz import model as bcz
+  rng = np.random.RandomState(3)
+  logits = rng.standard_normal((5, 3)).astype(np.float32)
+  state = np.array([0, 2, 1, 1, 7])                       # 7 is out of range: tf.one_hot row of zeros, weight 0
+  class_weights = [1.0, 0.5, 3.0]
+  onehot = np.zeros((5, 3), np.float32)
+  for i, s_ in enumerate(state):
+    if s_ < 3:
+      onehot[i, s_] = 1
+  logp = logits - np.log(np.exp(logits).sum(1, keepdims=True))
+  ce = -(onehot * logp).sum(1)
+  w = (onehot * np.array(class_weights, np.float32)).sum(1)
+  want = (ce * w).sum() / (w != 0).sum()
+  got = bcz.compute_stop_state_loss(torch.from_numpy(onehot), torch.from_numpy(logits), class_weights)
+  np.testing.assert_allclose(float(got), want, rtol=1e-6)
+  np.testing.assert_array_equal(bcz._one_hot(torch.from_numpy(state), 3).numpy(), onehot)
+  m = bcz.BCZModel(predict_stop=True, stop_state_class_weights=class_weights)
+  spec = m.get_label_specification('train')['future/stop_state']
+  assert spec.shape == () and spec.name == 'present/stop_state'
+  assert 'future/stop_state' not in bcz.BCZModel().get_label_specification('train').keys()
