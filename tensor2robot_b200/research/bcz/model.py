@@ -1,12 +1,35 @@
 """BC-Z (research/bcz/model.py): FiLM-conditioned ResNet image-to-action network with one MLP head per pose
 component (:245-285), pose assembly (:321-460), weighted huber / log losses (:476-585), the BCZPreprocessor
-(:69-196) and the BCZModel T2R class (:641-950).  Not built: the spatial-softmax network variant, mixup,
-eval metrics."""
+(:69-196) and the BCZModel T2R class (:641-950).  Not built: mixup, eval metrics."""
 from tensor2robot_b200 import nn
 from tensor2robot_b200.layers import bcz_networks
 from tensor2robot_b200.layers import resnet
 
 TRAIN = 'train'
+
+
+def spatial_softmax_network(features, is_training, pose_components, num_waypoints, condition_input=None):
+  """Spatial-softmax image-to-action network (model.py:196-242): the vision_layers tower, the task embedding
+  concatenated to the feature points, one pose MLP emitting every component of every waypoint.  Returns
+  ({component: fp32 [B, num_waypoints, size]}, feature_points)."""
+  from tensor2robot_b200.layers import vision_layers
+  image = features.image if hasattr(features, 'image') else features['image']
+  with nn.variable_scope('vision_model'):
+    feature_points, _ = vision_layers.BuildImagesToFeaturesModel(nn.to_f32(image), is_training=is_training)
+    if condition_input is not None:
+      feature_points = torch.cat([feature_points, condition_input.to(feature_points.dtype)], -1)
+    action_sizes = [t[1] for t in pose_components]
+    estimated_pose, _ = vision_layers.BuildImageFeaturesToPoseModel(
+        feature_points, aux_input=None, aux_output_dim=0, num_outputs=sum(action_sizes) * num_waypoints)
+  network_output_dict = {}
+  i = 0
+  for name, size, is_residual, _ in pose_components:
+    if is_residual:
+      name += '_residual'
+    n = size * num_waypoints
+    network_output_dict[name] = estimated_pose[..., i:i + n].reshape(-1, num_waypoints, size)
+    i += n
+  return network_output_dict, feature_points
 
 
 def resnet_film_network(features, mode, pose_components, num_waypoints, film_generator_fn=None,
@@ -206,6 +229,7 @@ def xyz_action_trajectory(outputs):
 # Preprocessor and T2R model (research/bcz/model.py:63-196, 641-950)
 # ---------------------------------------------------------------------------------------------
 import enum  # pylint: disable=wrong-import-position
+import inspect  # pylint: disable=wrong-import-position
 
 import numpy as np  # pylint: disable=wrong-import-position
 
@@ -410,10 +434,15 @@ class BCZModel(abstract_model.AbstractT2RModel):
     else:
       condition_input = features.sentence_embedding.float()
     condition_input = self.augment_condition_input(condition_input, features, is_training)
+    # what gin binds in the reference (resnet_film_network.film_generator_fn / resnet_size) are constructor arguments
+    accepted = inspect.signature(self._network_fn).parameters
+    extra = {}
+    if 'film_generator_fn' in accepted:
+      extra['film_generator_fn'] = self._film_generator_fn if condition_input is not None else None
+    if 'resnet_size' in accepted:
+      extra['resnet_size'] = self._resnet_size
     network_outputs_dict, state_embedding = self._network_fn(
-        features, mode, self._action_components, self._num_waypoints, condition_input=condition_input,
-        film_generator_fn=self._film_generator_fn if condition_input is not None else None,
-        resnet_size=self._resnet_size)
+        features, mode, self._action_components, self._num_waypoints, condition_input=condition_input, **extra)
     outputs = infer_outputs(features, network_outputs_dict, self._action_components,
                             self.preprocessor.rescale_gripper)
     if self._predict_stop:

@@ -86,7 +86,7 @@ def test_triplet_semihard_loss_matches_oracle(m, d, nlabels, margin):
   eg = e.cuda().requires_grad_(True)
   l = nn.triplet_semihard_loss(torch.tensor(labels), eg, margin)
   l.backward()
-  assert abs(l.item() - float(lo)) < 1e-4 * max(1.0, abs(float(lo))), (l.item(), float(lo))
+  assert abs(l.detach().item() - float(lo)) < 1e-4 * max(1.0, abs(float(lo))), (l.detach().item(), float(lo))
   np.testing.assert_allclose(eg.grad.cpu().numpy(), eo.grad.numpy(), rtol=2e-3, atol=2e-5)
 
 
