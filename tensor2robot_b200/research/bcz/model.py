@@ -81,6 +81,7 @@ def quaternion_multiply(q1, q2):
   return torch.stack([x, y, z, w], -1)
 
 
+from tensor2robot_b200.hooks import golden_values_hook_builder  # pylint: disable=wrong-import-position
 from tensor2robot_b200.utils import tf_losses  # pylint: disable=wrong-import-position
 
 _weighted = tf_losses.compute_weighted_loss
@@ -216,6 +217,8 @@ def training_outputs(labels, network_output_dict, action_components, quaternion_
     train_outputs['total_regularization_loss'] = regularization_loss
   loss = sum(train_outputs.values())
   train_outputs.update(nonloss_outputs)
+  for name, tensor in train_outputs.items():          # each of the losses joins the golden collection (:581-583)
+    golden_values_hook_builder.add_golden_tensor(tensor, name)
   return loss, train_outputs
 
 

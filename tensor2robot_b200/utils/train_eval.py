@@ -215,11 +215,19 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
                      chief_train_hook_builders=None, eval_hook_builders=None, device=None, log_every_n_steps=100):
   """Trains (and evaluates) a T2R model.  Returns {'global_step', 'loss', 'eval'}.
 
-  Hooks / exporters of the Estimator world have no analogue here and must be None."""
+  train_hook_builders / chief_train_hook_builders: tensor2robot_b200.hooks.HookBuilder objects (begin / before_step /
+  after_step / end hooks).  Exporters and eval hooks of the Estimator world have no analogue here and must be None."""
   del eval_throttle_secs, use_continuous_eval
-  if any(x is not None for x in (create_exporters_fn, export_generator, train_hook_builders,
-                                 chief_train_hook_builders, eval_hook_builders)):
-    raise NotImplementedError('Estimator hooks / SavedModel exporters are outside the B200 engine (SURVEY 2)')
+  if any(x is not None for x in (create_exporters_fn, export_generator, eval_hook_builders)):
+    raise NotImplementedError('SavedModel exporters / eval hooks are outside the B200 engine (SURVEY 2)')
+  hooks = []
+  is_chief = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+      torch.distributed.get_rank() == 0
+  for builder in list(train_hook_builders or []) + (list(chief_train_hook_builders or []) if is_chief else []):
+    if not hasattr(builder, 'create_hooks'):
+      raise NotImplementedError('train hooks must come from a tensor2robot_b200.hooks.HookBuilder; TF SessionRunHooks '
+                                'have no analogue here')
+    hooks.extend(builder.create_hooks(t2r_model, model_dir))
   if t2r_model is None:
     raise ValueError('t2r_model is required')
   device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -229,6 +237,7 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
   if input_generator_train is not None:
     provide_input_generator_with_model_information(input_generator_train, t2r_model, ModeKeys.TRAIN)
     resumed = False
+    started = False
     last_loss = None
     for features, labels in _batches(input_generator_train, t2r_model, ModeKeys.TRAIN, device):
       if not resumed:
@@ -241,14 +250,25 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
         resumed = True
       if t2r_model.global_step >= max_train_steps:
         break
+      if not started:
+        for hook in hooks:
+          hook.begin()
+        started = True
+      for hook in hooks:
+        hook.before_step(t2r_model.global_step)
       last_loss = t2r_model.train_step(features, labels)
       step = t2r_model.global_step
+      for hook in hooks:
+        hook.after_step(step, last_loss)
       if step % log_every_n_steps == 0:
         logging.info('step %d loss %.5f', step, float(last_loss))
       if step % run_config.get('save_checkpoints_steps', 1000) == 0:
         save_checkpoint(t2r_model, model_dir, run_config.get('keep_checkpoint_max', 5))
     if resumed:
       save_checkpoint(t2r_model, model_dir, run_config.get('keep_checkpoint_max', 5))
+    if started:
+      for hook in hooks:
+        hook.end()
     result['global_step'] = t2r_model.global_step
     result['loss'] = float(last_loss) if last_loss is not None else None
   if input_generator_eval is not None:
