@@ -42,8 +42,20 @@ def _worker(rank, world, port, out_dir):
   scale = engine.reduce_gradients(flat_grad)
   params = torch.full((4,), float(rank + 1))
   dist.broadcast(params, src=0)
+  # the chief alone writes checkpoints / runs chief hooks (replicas hold identical parameters)
+  from tensor2robot_b200.utils import train_eval
+
+  class _Model(object):
+    global_step = 7
+
+    def state_dict(self):
+      return {'variables': {}, 'global_step': 7, 'rank': rank}
+
+  path = train_eval.save_checkpoint(_Model(), os.path.join(out_dir, 'ckpt'))
+  dist.barrier()
+  wrote = torch.load(path, weights_only=False)['rank'] if os.path.exists(path) else None
   np.save(os.path.join(out_dir, 'rank%d.npy' % rank), {'poses': poses, 'grad': flat_grad.numpy(), 'scale': scale,
-                                                       'params': params.numpy()}, allow_pickle=True)
+                                                       'params': params.numpy(), 'ckpt_rank': wrote}, allow_pickle=True)
   dist.barrier()
   dist.destroy_process_group()
 
@@ -61,6 +73,7 @@ def test_two_rank_sharding_and_gradient_reduction(tmp_path):
     np.testing.assert_allclose(r['grad'], total.sum(0), rtol=1e-5)      # identical sum on every rank
     np.testing.assert_allclose(r['grad'] * r['scale'], total.sum(0) / 2, rtol=1e-5)
     np.testing.assert_array_equal(r['params'], np.full(4, 1.0, np.float32))   # rank 0's initial values
+    assert r['ckpt_rank'] == 0                                          # one checkpoint file, written by rank 0
 
 
 def test_single_process_is_identity():
