@@ -751,6 +751,18 @@ def make_random_tensors(spec_structure, batch_size=2):
   return _map_structure(lambda a: torch.from_numpy(a), make_random_numpy(spec_structure, batch_size, None))
 
 
+def map_feed_dict_unsafe(feature_placeholders_spec, np_inputs_spec):
+  """Deprecated (:1012-1045): {placeholder key: numpy} without checking dtypes / shapes / unused inputs; numpy inputs
+  that the spec does not know are dropped with a warning."""
+  logging.warning('map_feed_dict_unsafe is deprecated. Please update to map_feed_dict.')
+  flat_spec = flatten_spec_structure(feature_placeholders_spec)
+  flat_np_inputs = flatten_spec_structure(np_inputs_spec)
+  for key in flat_np_inputs.keys():
+    if key not in flat_spec:
+      logging.warning('np_inputs has an input: %s, not found in the tensorspec.', key)
+  return {key: flat_np_inputs[key] for key in flat_spec.keys()}      # a missing input fails on lookup, as in the reference
+
+
 def map_feed_dict(spec_placeholders, spec_numpy, feed_dict=None, ignore_batch=False):
   """{placeholder key: numpy} after validating the arrays against the specs (:923-965)."""
   if not is_flat_spec_or_tensors_structure(spec_placeholders):

@@ -22,10 +22,12 @@ import ctypes as C
 import glob
 import io
 import itertools
+import logging
 import mmap
 import os
 
 import numpy as np
+from PIL import Image
 
 from tensor2robot_b200 import _lib
 from tensor2robot_b200.models import model_interface
@@ -505,3 +507,106 @@ def get_input_fn(feature_spec, label_spec, file_patterns, mode, batch_size, prep
                                  is_training=(mode == ModeKeys.TRAIN), preprocess_fn=preprocess_fn, mode=mode,
                                  **kwargs)
   return input_fn
+
+
+# ---------------------------------------------------------------------------------------------
+# Remaining helpers of the reference module (utils/tfdata.py:143-238, 546-626), as host-side iterators.
+# ---------------------------------------------------------------------------------------------
+def get_dataset_metadata(file_patterns):
+  """(data_format, num_shards, approximate num_examples_per_shard) for shuffling parameters (:143-171): the first
+  shard is indexed; like the reference the count starts at one ("at least one example per shard")."""
+  data_format, files = get_data_format_and_filenames(file_patterns)
+  logging.info('Estimating dataset size from %s...', files[0])
+  return data_format, len(files), 1 + len(TFRecordFile(files[0]))
+
+
+def parallel_read(file_patterns, num_shards=None, num_readers=None, num_epochs=None, seed=None):
+  """Serialized tf.Example protos of the files (:174-210): shards shuffled per epoch and read `num_readers` at a time,
+  one record from each in turn (the interleave that breaks intra-shard correlation); repeats `num_epochs` times,
+  forever if None."""
+  _, filenames = get_data_format_and_filenames(file_patterns)
+  if num_shards is None:
+    num_shards = len(filenames)
+  if num_readers is None:
+    num_readers = num_shards
+  rng = np.random.RandomState(seed)
+  opened = {}
+  epoch = 0
+  while num_epochs is None or epoch < num_epochs:
+    epoch += 1
+    order = list(rng.permutation(len(filenames)))
+    active = []
+    while order or active:
+      while order and len(active) < max(1, num_readers):
+        name = filenames[order.pop(0)]
+        if name not in opened:
+          opened[name] = TFRecordFile(name)
+        active.append(iter(opened[name]))
+      for reader in list(active):
+        try:
+          yield next(reader)
+        except StopIteration:
+          active.remove(reader)
+
+
+def serialized_to_parsed(dataset, feature_tspec, label_tspec, num_parallel_calls=2):
+  """Maps the spec-generated parser over an iterable of serialized batches - lists of protos, or {dataset_key: list}
+  dicts (:213-238).  num_parallel_calls is accepted for signature parity; the C++ parser is already batched."""
+  del num_parallel_calls
+  parse_tf_example_fn = create_parse_tf_example_fn(feature_tspec=feature_tspec, label_tspec=label_tspec)
+  for serialized in dataset:
+    yield parse_tf_example_fn(serialized)
+
+
+def _jpeg_specs(spec):
+  return [(key, value) for key, value in tensorspec_utils.flatten_spec_structure(spec).items()
+          if getattr(value, 'data_format', None) == 'jpeg'] if spec is not None else []
+
+
+def create_compress_fn(feature_spec, label_spec, quality=90):
+  """compress_fn(features, labels=None): every tensor whose spec has data_format 'jpeg' becomes an object array of
+  JPEG strings, one per batch element (:546-585; the infeed compression of the TPU path).  Host numpy in, host out."""
+
+  def compress(tensor):
+    tensor = np.asarray(tensor)
+    if tensor.dtype != np.uint8:       # tf.image.convert_image_dtype(float -> uint8): scale, round half up, saturate
+      tensor = np.clip(np.floor(tensor.astype(np.float32) * 255.0 + 0.5), 0, 255).astype(np.uint8)
+    out = np.empty(tensor.shape[0], dtype=object)
+    for i, img in enumerate(tensor):
+      buf = io.BytesIO()
+      Image.fromarray(img[..., 0] if img.shape[-1] == 1 else img).save(buf, format='JPEG', quality=quality)
+      out[i] = buf.getvalue()
+    return out
+
+  def compress_fn(features, labels=None):
+    for key, _ in _jpeg_specs(feature_spec):
+      features[key] = compress(features[key])
+    if labels is not None:
+      for key, _ in _jpeg_specs(label_spec):
+        labels[key] = compress(labels[key])
+    return features, labels
+
+  return compress_fn
+
+
+def create_decompress_fn(feature_spec, label_spec):
+  """The inverse of create_compress_fn (:588-626): JPEG strings -> [batch] + spec.shape arrays in the spec's dtype
+  (floats in [0, 1])."""
+
+  def decompress(strings, spec):
+    shape = tuple(spec.shape)
+    images = np.stack([np.asarray(Image.open(io.BytesIO(s))).reshape(shape) for s in strings])
+    np_dtype = spec.dtype.as_numpy_dtype
+    if np.issubdtype(np_dtype, np.floating):
+      return (images.astype(np.float32) / np.float32(255.0)).astype(np_dtype)
+    return images.astype(np_dtype)
+
+  def decompress_fn(features, labels=None):
+    for key, value in _jpeg_specs(feature_spec):
+      features[key] = decompress(features[key], value)
+    if labels is not None:
+      for key, value in _jpeg_specs(label_spec):
+        labels[key] = decompress(labels[key], value)
+    return features, labels
+
+  return decompress_fn

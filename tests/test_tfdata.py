@@ -322,3 +322,55 @@ def test_prefetcher_order_errors_and_shutdown():
   n = len(produced)
   time.sleep(0.3)
   assert len(produced) == n and threading.active_count() <= before    # producer stopped
+
+
+def test_dataset_metadata_parallel_read_and_parsed_stream(tmp_path):
+  """utils/tfdata.py:143-238: shard statistics, interleaved shard reading, parsing an iterable of serialized batches."""
+  from oracle import tfrecord
+  records = tfrecord.read_tfrecords(FIXTURE)
+  for shard in range(3):
+    tfrecord.write_tfrecords(str(tmp_path / ('data-%d.tfrecord' % shard)), records[shard::3])
+  pattern = str(tmp_path / 'data-*.tfrecord')
+  assert tfdata.get_dataset_metadata(pattern) == ('tfrecord', 3, 1 + 34)
+  one_epoch = list(tfdata.parallel_read(pattern, num_epochs=1, seed=0))
+  assert sorted(one_epoch) == sorted(records)
+  shard_of = {r: i % 3 for i, r in enumerate(records)}
+  assert len({shard_of[r] for r in one_epoch[:3]}) == 3                  # one record from every shard in turn
+  sequential = list(tfdata.parallel_read(pattern, num_readers=1, num_epochs=1, seed=0))
+  assert len({shard_of[r] for r in sequential[:30]}) == 1                # a single reader drains shard after shard
+  two_epochs = list(tfdata.parallel_read(pattern, num_epochs=2, seed=1))
+  assert len(two_epochs) == 200
+  forever = tfdata.parallel_read(pattern)
+  assert len([next(forever) for _ in range(350)]) == 350
+  feature_spec, label_spec = _pose_env_specs()
+  batches = [records[:4], records[4:10]]
+  parsed = list(tfdata.serialized_to_parsed(batches, feature_spec, label_spec))
+  assert parsed[0][0].action.pose.shape == (4, 2) and parsed[1][1].reward.shape == (6, 1)
+  np.testing.assert_array_equal(parsed[1][0].action.pose, GOLDEN['pose'][4:10])
+
+
+def test_compress_decompress_fns():
+  """utils/tfdata.py:546-626: only the tensors with data_format 'jpeg' are touched."""
+  spec = utils.TensorSpecStruct(image=TSPEC((32, 48, 3), dtypes.float32, 'image', data_format='jpeg'),
+                                depth=TSPEC((32, 48, 1), dtypes.uint8, 'depth', data_format='jpeg'),
+                                pose=TSPEC((2,), dtypes.float32, 'pose'))
+  rng = np.random.RandomState(0)
+  smooth = np.linspace(0, 1, 32 * 48 * 3, dtype=np.float32).reshape(1, 32, 48, 3).repeat(2, 0)
+  features = {'image': smooth.copy(), 'depth': (smooth[..., :1] * 255).astype(np.uint8), 'pose': rng.uniform(size=(2, 2))}
+  compress = tfdata.create_compress_fn(spec, None, quality=95)
+  packed, labels = compress(dict(features))
+  assert labels is None and packed['image'].dtype == object and packed['image'][0][:2] == b'\xff\xd8'
+  np.testing.assert_array_equal(packed['pose'], features['pose'])
+  restored, _ = tfdata.create_decompress_fn(spec, None)(dict(packed))
+  assert restored['image'].shape == (2, 32, 48, 3) and restored['image'].dtype == np.float32
+  assert restored['depth'].shape == (2, 32, 48, 1) and restored['depth'].dtype == np.uint8
+  assert np.abs(restored['image'] - features['image']).max() < 0.05
+  assert np.abs(restored['depth'].astype(np.int32) - features['depth'].astype(np.int32)).max() < 10
+
+
+def test_map_feed_dict_unsafe():
+  spec = utils.TensorSpecStruct(a=TSPEC((2,), dtypes.float32, 'a'), b=TSPEC((1,), dtypes.float32, 'b'))
+  out = utils.map_feed_dict_unsafe(spec, {'a': np.zeros((3, 2)), 'b': np.zeros((3, 1)), 'extra': np.ones(1)})
+  assert list(out) == ['a', 'b']                     # unknown inputs are dropped (with a warning)
+  with pytest.raises((KeyError, AttributeError)):      # a missing input fails on lookup, as in the reference
+    utils.map_feed_dict_unsafe(spec, {'a': np.zeros((3, 2))})
