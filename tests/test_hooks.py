@@ -68,3 +68,91 @@ def test_golden_values_from_a_training_run(tmp_path):
   assert len(values) == 2 and 'xyz_loss' in values[0] and 'quaternion_norm_loss' in values[0]
   total = sum(float(v) for k, v in values[1].items() if k.endswith('_loss'))
   assert np.isfinite(total) and abs(total - out['loss']) < 1e-4 * max(1.0, abs(total))
+
+
+def _fake_export_fn(export_dir, global_step):
+  path = os.path.join(export_dir, '%010d' % global_step)
+  os.makedirs(path, exist_ok=True)
+  with open(os.path.join(path, 'weights'), 'w') as f:
+    f.write(str(global_step))
+  return path
+
+
+def test_lagged_listener_stays_one_export_behind(tmp_path):
+  """hooks/checkpoint_hooks.py:91-201 (the reference's checkpoint_hooks_test scenario): current vs lagged directory
+  contents, version garbage collection, and resuming from directories left by an earlier run."""
+  from tensor2robot_b200.hooks import checkpoint_hooks
+  export_dir, lagged_dir = str(tmp_path / 'export'), str(tmp_path / 'lagged')
+  listener = checkpoint_hooks.LaggedCheckpointListener(_fake_export_fn, export_dir, lagged_dir, num_versions=2)
+  names = lambda d: sorted(os.listdir(d))
+  listener.after_save(None, 10)
+  assert names(export_dir) == ['0000000010'] and names(lagged_dir) == ['0000000010']     # nothing older yet
+  listener.after_save(None, 20)
+  assert names(export_dir) == ['0000000010', '0000000020'] and names(lagged_dir) == ['0000000010']
+  listener.after_save(None, 30)
+  assert names(export_dir) == ['0000000020', '0000000030']                                # num_versions = 2
+  assert names(lagged_dir) == ['0000000010', '0000000020']
+  listener.after_save(None, 40)
+  assert names(export_dir) == ['0000000030', '0000000040'] and names(lagged_dir) == ['0000000020', '0000000030']
+  assert open(os.path.join(lagged_dir, '0000000030', 'weights')).read() == '30'
+  # a new listener over the same directories resumes one behind
+  resumed = checkpoint_hooks.LaggedCheckpointListener(_fake_export_fn, export_dir, lagged_dir, num_versions=2)
+  resumed.after_save(None, 50)
+  assert names(export_dir) == ['0000000040', '0000000050'] and names(lagged_dir) == ['0000000030', '0000000040']
+  # a lagged directory that fell behind is repaired at construction
+  import shutil
+  shutil.rmtree(lagged_dir)
+  checkpoint_hooks.LaggedCheckpointListener(_fake_export_fn, export_dir, lagged_dir, num_versions=2)
+  assert names(lagged_dir) == ['0000000040']
+  plain = checkpoint_hooks.CheckpointExportListener(_fake_export_fn, str(tmp_path / 'plain'))
+  for step in (1, 2, 3):
+    plain.after_save(None, step)
+  assert len(names(str(tmp_path / 'plain'))) == 3                                          # no GC without num_versions
+
+
+def test_td3_hook_builder_triggers_every_save_steps(tmp_path):
+  from tensor2robot_b200.hooks import td3
+  assert td3.TD3Hooks(export_dir=None, lagged_export_dir=None).create_hooks(None, None) == []
+  builder = td3.TD3Hooks(export_dir=str(tmp_path / 'e'), lagged_export_dir=str(tmp_path / 'l'), save_steps=5,
+                         num_versions=3, export_fn=_fake_export_fn)
+  (hook,) = builder.create_hooks(None, str(tmp_path))
+  hook.begin()
+  for step in range(1, 18):
+    hook.before_step(step - 1)
+    hook.after_step(step, 0.0)
+  hook.end()
+  assert sorted(os.listdir(str(tmp_path / 'e'))) == ['0000000005', '0000000010', '0000000015']
+  assert sorted(os.listdir(str(tmp_path / 'l'))) == ['0000000005', '0000000010']
+
+
+def test_export_model_layout(tmp_path):
+  """An export directory: TF-bundle checkpoint (+ `checkpoint` state file) and assets.extra/t2r_assets.pbtxt."""
+  from tensor2robot_b200.hooks import td3
+  from tensor2robot_b200.utils import dtypes
+  from tensor2robot_b200.utils import tensorspec_utils as tu
+  from tensor2robot_b200.utils import tf_checkpoint
+
+  class _Store(object):
+
+    def export_tf(self):
+      return {'q_func/fc/weights': np.arange(6, dtype=np.float32).reshape(2, 3), 'q_func/fc/biases': np.zeros(3, np.float32)}
+
+  class _Model(object):
+    global_step = 12
+    variable_store = _Store()
+
+    def get_feature_specification_for_packing(self, mode):
+      return tu.TensorSpecStruct(x=tu.ExtendedTensorSpec(shape=(3,), dtype=dtypes.float32, name='measured_position'))
+
+    def get_label_specification_for_packing(self, mode):
+      return tu.TensorSpecStruct(y=tu.ExtendedTensorSpec(shape=(1,), dtype=dtypes.float32, name='valid_position'))
+
+  path = td3.export_model(_Model(), str(tmp_path / 'export'), 12)
+  assert os.path.basename(path) == '0000000012'
+  reader = tf_checkpoint.load_checkpoint(path)
+  assert int(reader.get_tensor('global_step')) == 12
+  np.testing.assert_array_equal(reader.get_tensor('q_func/fc/weights'), np.arange(6, dtype=np.float32).reshape(2, 3))
+  assets = tu.load_t2r_assets_to_file(os.path.join(path, 'assets.extra', 't2r_assets.pbtxt'))
+  assert assets.global_step == 12
+  spec = tu.TensorSpecStruct.from_proto(assets.feature_spec)
+  assert spec.x.shape == (3,) and spec.x.name == 'measured_position'

@@ -146,3 +146,68 @@ def test_checkpoint_predictor_and_policies_on_pose_env(tmp_path):
   assert best.shape == (2,) and np.isfinite(best).all() and seen == [(64, 2)] * 3
   q = q_predictor.predict(pack_fn(None, obs, None, 0, np.stack([best, best + 0.5])))['q_predicted']
   assert q.shape == (2,) and np.isfinite(q).all()
+
+
+def test_exported_model_predictor_version_selection(tmp_path):
+  """Newest complete numbered export wins; exports in flight (temp dirs, missing assets) are ignored; the specs and the
+  global step come from t2r_assets.pbtxt (predictors/exported_savedmodel_predictor.py:52-260)."""
+  import os
+  from tensor2robot_b200.hooks import td3
+  from tensor2robot_b200.predictors import exported_model_predictor as emp
+  from tensor2robot_b200.research.pose_env import pose_env_models as pm
+  from tensor2robot_b200.utils import dtypes
+  from tensor2robot_b200.utils import tensorspec_utils as tu
+
+  class _Store(object):
+
+    def export_tf(self):
+      return {'w': np.ones((2, 2), np.float32)}
+
+  class _Model(object):
+    variable_store = _Store()
+
+    def __init__(self, step):
+      self.global_step = step
+
+    def get_feature_specification_for_packing(self, mode):
+      return tu.TensorSpecStruct(state=tu.ExtendedTensorSpec(shape=(64, 64, 3), dtype=dtypes.uint8, name='state/image'))
+
+    def get_label_specification_for_packing(self, mode):
+      return tu.TensorSpecStruct(target_pose=tu.ExtendedTensorSpec(shape=(2,), dtype=dtypes.float32, name='target_pose'))
+
+  export_dir = str(tmp_path / 'export')
+  assert emp.valid_export_versions(export_dir) == []
+  for step in (5, 20, 100):
+    td3.export_model(_Model(step), export_dir, step)
+  os.makedirs(os.path.join(export_dir, 'temp-0000000200'))
+  os.makedirs(os.path.join(export_dir, '0000000300'))                     # started, nothing written yet
+  versions = emp.valid_export_versions(export_dir)
+  assert [os.path.basename(v) for v in versions] == ['0000000005', '0000000020', '0000000100']
+
+  loaded = []
+  predictor = emp.ExportedModelPredictor(export_dir, pm.PoseEnvRegressionModel(), timeout=1)
+  assert predictor.global_step == -1 and predictor.model_version == -1
+  with pytest.raises(ValueError):
+    predictor.get_feature_specification()
+  real_load = predictor._load_version                                       # pylint: disable=protected-access
+
+  def spy(path):                    # the weight upload needs a GPU; the assets / bookkeeping part runs here
+    loaded.append(os.path.basename(path))
+    predictor._ensure_built = lambda: (_ for _ in ()).throw(RuntimeError('stop before the device'))   # pylint: disable=protected-access
+    try:
+      real_load(path)
+    except RuntimeError:
+      pass
+
+  predictor._load_version = spy                                             # pylint: disable=protected-access
+  assert predictor.restore() and loaded == ['0000000100']
+  assert predictor.global_step == 100 and predictor.model_version == 100 and predictor.model_path.endswith('0000000100')
+  assert predictor.get_feature_specification().state.shape == (64, 64, 3)
+  assert predictor.get_label_specification().target_pose.name == 'target_pose'
+  assert predictor.restore() and loaded == ['0000000100']                  # unchanged: not reloaded
+  td3.export_model(_Model(400), export_dir, 400)
+  assert predictor.restore() and loaded == ['0000000100', '0000000400'] and predictor.global_step == 400
+  empty = emp.ExportedModelPredictor(str(tmp_path / 'nothing'), pm.PoseEnvRegressionModel(), timeout=1)
+  assert empty.restore() is False
+  pinned = emp.ExportedModelPredictor(os.path.join(export_dir, '0000000020'), pm.PoseEnvRegressionModel(), timeout=1)
+  assert pinned._newest_version().endswith('0000000020')                    # pylint: disable=protected-access
