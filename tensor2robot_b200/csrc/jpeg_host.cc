@@ -42,9 +42,13 @@ struct Huff {
 struct Parsed {
   T2RJpegInfo info;
   Huff dc[4], ac[4];
-  int td[3], ta[3];
-  uint64_t scan_offset;
+  int td[3] = {-1, -1, -1}, ta[3] = {-1, -1, -1};
+  uint64_t scan_offset = 0;
 };
+
+// Frames beyond this are refused before anything is allocated for them (a corrupted SOF can claim 65535 x 65535).
+constexpr int kMaxSide = 16384;
+constexpr int64_t kMaxPixels = int64_t(1) << 26;
 
 bool build_huff(const uint8_t* counts, const uint8_t* symbols, int total, Huff* h) {
   memset(h->fast, 0, sizeof(h->fast));
@@ -54,6 +58,7 @@ bool build_huff(const uint8_t* counts, const uint8_t* symbols, int total, Huff* 
     h->valptr[len] = k;
     h->mincode[len] = code;
     for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+      if (code >= (1 << len)) return false;          // over-subscribed table: would index past the lookahead
       if (len <= 9) {
         const int shift = 9 - len;
         for (int f = 0; f < (1 << shift); ++f) h->fast[(code << shift) | f] = uint16_t((len << 8) | symbols[k]);
@@ -71,7 +76,7 @@ bool build_huff(const uint8_t* counts, const uint8_t* symbols, int total, Huff* 
     const int len = f >> 8, rs = f & 0xFF, run = rs >> 4, mag = rs & 15;
     if (mag == 0 || len + mag > 9) continue;
     int k = ((i << len) & 511) >> (9 - mag);          // the magnitude bits that follow the code
-    if (k < (1 << (mag - 1))) k += (-1 << mag) + 1;   // EXTEND
+    if (k < (1 << (mag - 1))) k += 1 - (1 << mag);    // EXTEND
     if (k >= -128 && k <= 127) h->fast_ac[i] = int16_t(k * 256 + run * 16 + len + mag);
   }
   h->present = true;
@@ -155,6 +160,11 @@ int parse_headers(const uint8_t* b, uint64_t len, Parsed* out) {
         for (int c = 0; c < out->info.ncomp; ++c)
           if (out->info.comp_id[c] == cid) { out->td[c] = t >> 4; out->ta[c] = t & 15; }
       }
+      for (int c = 0; c < out->info.ncomp; ++c)
+        if (out->td[c] < 0 || out->td[c] > 3 || out->ta[c] < 0 || out->ta[c] > 3) {
+          t2r::set_error("jpeg: scan header does not name a valid Huffman table for every frame component");
+          return T2R_ERR_PARSE;
+        }
       out->scan_offset = p + n;
       break;
     }
@@ -162,6 +172,10 @@ int parse_headers(const uint8_t* b, uint64_t len, Parsed* out) {
   }
   T2RJpegInfo& in = out->info;
   if (in.width <= 0 || in.height <= 0) { t2r::set_error("jpeg: empty image"); return T2R_ERR_PARSE; }
+  if (in.width > kMaxSide || in.height > kMaxSide || int64_t(in.width) * in.height > kMaxPixels) {
+    t2r::set_error("jpeg: %d x %d frame exceeds the supported size", in.width, in.height);
+    return T2R_ERR_PARSE;
+  }
   int hmax = 1, vmax = 1;
   for (int c = 0; c < in.ncomp; ++c) {
     if (in.h[c] < 1 || in.h[c] > 2 || in.v[c] < 1 || in.v[c] > 2) {

@@ -171,29 +171,44 @@ def _signed(v):
   return v - (1 << 64) if v >= (1 << 63) else v
 
 
+def _expect(wire, wanted, what):
+  if wire != wanted:
+    raise CheckpointError('%s has protobuf wire type %d, expected %d' % (what, wire, wanted))
+
+
 def _parse_entry(buf):
   dtype, shape, shard_id, offset, size, crc = 0, [], 0, 0, 0, 0
   for field, wire, value in _fields(buf):
     if field == 1:
+      _expect(wire, 0, 'BundleEntryProto.dtype')
       dtype = value
     elif field == 2:                      # TensorShapeProto{repeated Dim dim = 2 {int64 size = 1}}
-      for f2, _, dim in _fields(value):
+      _expect(wire, 2, 'BundleEntryProto.shape')
+      for f2, w2, dim in _fields(value):
         if f2 == 2:
+          _expect(w2, 2, 'TensorShapeProto.dim')
           dim_size = 0
-          for f3, _, v3 in _fields(dim):
+          for f3, w3, v3 in _fields(dim):
             if f3 == 1:
+              _expect(w3, 0, 'TensorShapeProto.Dim.size')
               dim_size = _signed(v3)
           shape.append(dim_size)
     elif field == 3:
+      _expect(wire, 0, 'BundleEntryProto.shard_id')
       shard_id = value
     elif field == 4:
+      _expect(wire, 0, 'BundleEntryProto.offset')
       offset = value
     elif field == 5:
+      _expect(wire, 0, 'BundleEntryProto.size')
       size = value
-    elif field == 6 and wire == 5:
+    elif field == 6:
+      _expect(wire, 5, 'BundleEntryProto.crc32c')
       (crc,) = struct.unpack('<I', value)
     elif field == 7:
       raise CheckpointError('partitioned (sliced) variables are not supported')
+  if any(d < 0 for d in shape):
+    raise CheckpointError('negative tensor dimension')
   return BundleEntry(dtype, tuple(shape), shard_id, offset, size, crc)
 
 
@@ -203,31 +218,43 @@ class CheckpointReader(object):
   def __init__(self, prefix, verify=True):
     self._prefix = prefix
     self._verify = verify
+    self._entries = collections.OrderedDict()
+    self.num_shards = 1
+    self._shards = {}
     with open(prefix + '.index', 'rb') as f:
       data = f.read()
+    try:
+      self._parse_index(data)
+    except CheckpointError:
+      raise
+    except (IndexError, struct.error, UnicodeDecodeError, OverflowError, ValueError, TypeError) as e:
+      raise CheckpointError('%s.index is corrupt: %s' % (prefix, e))
+
+  def _parse_index(self, data):
+    prefix, verify = self._prefix, self._verify
     if len(data) < _FOOTER_LEN or struct.unpack_from('<Q', data, len(data) - 8)[0] != _TABLE_MAGIC:
       raise CheckpointError('%s.index is not a TensorFlow tensor-bundle index (bad table magic)' % prefix)
     footer = data[-_FOOTER_LEN:]
     _, _, pos = _block_handle(footer)               # meta-index block: unused by bundles
     index_offset, index_size, _ = _block_handle(footer, pos)
-    self._entries = collections.OrderedDict()
-    self.num_shards = 1
     for _, handle in _iter_block(_read_block(data, index_offset, index_size, verify)):
       offset, size, _ = _block_handle(handle)
       for key, value in _iter_block(_read_block(data, offset, size, verify)):
         if key == b'':
-          for field, _, v in _fields(value):          # BundleHeaderProto{num_shards = 1, endianness = 2}
+          for field, _w, v in _fields(value):         # BundleHeaderProto{num_shards = 1, endianness = 2}
             if field == 1:
+              _expect(_w, 0, 'BundleHeaderProto.num_shards')
               self.num_shards = v
             elif field == 2 and v != 0:
               raise CheckpointError('big-endian bundles are not supported')
         else:
           self._entries[key.decode('utf-8')] = _parse_entry(value)
-    self._shards = {}
 
   def _shard(self, shard_id):
     if shard_id not in self._shards:
       path = '%s.data-%05d-of-%05d' % (self._prefix, shard_id, self.num_shards)
+      if not os.path.exists(path):
+        raise CheckpointError('data shard %s is missing' % path)
       self._shards[shard_id] = np.memmap(path, dtype=np.uint8, mode='r') if os.path.getsize(path) else np.zeros(0, np.uint8)
     return self._shards[shard_id]
 

@@ -149,3 +149,38 @@ def test_model_round_trip_through_a_tf_checkpoint(tmp_path):
   np.testing.assert_array_equal(values['a_func/state_features/conv2/weights'], reader.get_tensor('a_func/state_features/conv2/weights'))
   np.testing.assert_array_equal(values['a_func/pose_fc0/LayerNorm/gamma'], np.ones(100, np.float32))    # filtered out
   del torch
+
+
+def test_mutated_indexes_only_raise_checkpoint_errors(tmp_path):
+  """Fuzz: byte flips, truncations and insertions in the index (TensorFlow's snappy blocks and this module's
+  uncompressed ones), with checksum verification off so that the mutations reach the decoders."""
+  reader = tc.load_checkpoint(PREFIX)
+  tc.write_checkpoint(str(tmp_path / 'w'), {n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()})
+  seeds = [open(PREFIX + '.index', 'rb').read(), open(str(tmp_path / 'w.index'), 'rb').read()]
+  shutil.copy(PREFIX + '.data-00000-of-00001', str(tmp_path / 'f.data-00000-of-00001'))
+  rng = np.random.RandomState(0)
+  parsed = rejected = 0
+  for it in range(1500):
+    b = bytearray(seeds[it % 2])
+    mode = rng.randint(3)
+    if mode == 0:
+      for _ in range(rng.randint(1, 5)):
+        b[rng.randint(len(b))] = rng.randint(256)
+    elif mode == 1:
+      b = b[:rng.randint(1, len(b))]
+    else:
+      i = rng.randint(len(b))
+      b[i:i] = bytes(rng.randint(0, 256, rng.randint(1, 9)).astype(np.uint8))
+    with open(str(tmp_path / 'f.index'), 'wb') as f:
+      f.write(bytes(b))
+    try:
+      mutated = tc.CheckpointReader(str(tmp_path / 'f'), verify=False)
+      for name in list(mutated.get_variable_to_shape_map())[:30]:
+        try:
+          mutated.get_tensor(name)
+        except (tc.CheckpointError, KeyError):
+          pass
+      parsed += 1
+    except tc.CheckpointError:
+      rejected += 1
+  assert parsed > 50 and rejected > 50
