@@ -104,7 +104,22 @@ static long fuzz_records(const std::vector<uint8_t>& file, bool sequence) {
   plan[2].key = "ids"; plan[2].dtype = T2R_DT_INT64; plan[2].count = 3; plan[2].required = 0; plan[2].dst = ids.data();
   plan[3].key = "state/image"; plan[3].dtype = T2R_DT_BYTES; plan[3].count = 1; plan[3].required = 0;
   plan[3].dst = img.data(); plan[3].dst_len = img_len.data();
-  if (!sequence) return t2r_example_parse_batch(recs.data(), lens.data(), B, plan, 4) == 0;
+  if (!sequence) {
+    long ok = t2r_example_parse_batch(recs.data(), lens.data(), B, plan, 4) == 0;
+    // variable-length features (count < 0: at most |count| values per row, padded) and a required key
+    std::vector<float> vpose(static_cast<size_t>(B) * 3, 0.f);
+    std::vector<int64_t> vids(static_cast<size_t>(B) * 2, 0);
+    std::vector<uint64_t> vpose_n(static_cast<size_t>(B), 0), vids_n(static_cast<size_t>(B), 0);
+    T2RFeaturePlan vplan[3];
+    memset(vplan, 0, sizeof(vplan));
+    vplan[0].key = "pose"; vplan[0].dtype = T2R_DT_FLOAT; vplan[0].count = -3; vplan[0].dst = vpose.data();
+    vplan[0].dst_len = vpose_n.data(); vplan[0].pad_float = -1.f;
+    vplan[1].key = "ids"; vplan[1].dtype = T2R_DT_INT64; vplan[1].count = -2; vplan[1].dst = vids.data();
+    vplan[1].dst_len = vids_n.data(); vplan[1].pad_int64 = -7;
+    vplan[2].key = "reward"; vplan[2].dtype = T2R_DT_FLOAT; vplan[2].count = 1; vplan[2].required = 1; vplan[2].dst = reward.data();
+    ok += t2r_example_parse_batch(recs.data(), lens.data(), B, vplan, 3) == 0;
+    return ok;
+  }
   const int T = 5;
   std::vector<float> spose(static_cast<size_t>(B) * T * 2, 0.f);
   std::vector<int64_t> seq_len(static_cast<size_t>(B), 0);
