@@ -5,7 +5,6 @@ directly: Example{features = 1}, Features{map<string, Feature> feature = 1}, Fea
 int64_list = 3}, the lists hold `repeated value = 1` (floats and int64s packed).  Map entries are written in insertion
 order (protobuf defines no canonical map order; the runtime that wrote the reference's fixture varies it per record) -
 re-inserting the parsed features in each record's wire order reproduces that fixture byte for byte (tests/test_writer.py)."""
-import struct
 
 import numpy as np
 
