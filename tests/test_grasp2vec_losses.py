@@ -46,3 +46,39 @@ def test_match_norms_and_keypoints():
   want_ce = (np.maximum(logits, 0) - logits * onehot + np.log1p(np.exp(-np.abs(logits)))).mean()
   np.testing.assert_allclose(float(acc), 0.8, rtol=1e-6)      # the last keypoint lies in quadrant 2, labelled 0
   np.testing.assert_allclose(float(ce), want_ce, rtol=1e-6)
+
+
+# the reference's own cases (research/grasp2vec/losses_test.py:46-148)
+import pytest  # noqa: E402
+
+_RNG = np.random.RandomState(7)
+_FAKE = {k: _RNG.random_sample((32, 8)).astype(np.float32) for k in ('pre', 'post', 'goal')}
+
+
+def _cos(x, y):
+  return 1 - (x * y).sum(1) / (np.linalg.norm(x, axis=1) * np.linalg.norm(y, axis=1))
+
+
+@pytest.mark.parametrize('mask_kind', ['zeros', 'ones', 'mixed'])
+def test_reference_arithmetic_loss_cases(mask_kind):
+  mask = {'zeros': np.zeros(32), 'ones': np.ones(32), 'mixed': np.eye(1, 32)[0]}[mask_kind]
+  t = torch.from_numpy
+  cosine = float(losses.CosineArithmeticLoss(t(_FAKE['pre']), t(_FAKE['goal']), t(_FAKE['post']), t(mask)))
+  l2 = float(losses.L2ArithmeticLoss(t(_FAKE['pre']), t(_FAKE['goal']), t(_FAKE['post']), t(mask)))
+  if mask_kind == 'zeros':
+    assert cosine == 0 and l2 == 0
+    return
+  rows = slice(None) if mask_kind == 'ones' else slice(0, 1)
+  want_cos = _cos(_FAKE['pre'][rows] - _FAKE['post'][rows], _FAKE['goal'][rows]).mean()
+  want_l2 = (np.linalg.norm(_FAKE['pre'][rows] - (_FAKE['post'][rows] + _FAKE['goal'][rows]), axis=1) ** 2).mean()
+  assert abs(cosine - want_cos) < 1e-3 and abs(l2 - want_l2) < 1e-3           # assertAlmostEqual(places=3)
+
+
+@pytest.mark.parametrize('keypoints,labels,expected_accuracy', [
+    ([[-0.5, -0.5], [-0.5, 0.5], [0.5, -0.5], [0.5, 0.5]], [1, 3, 0, 2], 1.0),          # CorrectKeypoints
+    ([[-0.5, -0.5], [-0.5, 0.5], [0.5, -0.5], [0.5, 0.5]], [2, 0, 3, 1], 0.0),          # IncorrectKeypoints
+    ([[-0.6, -0.4], [-0.4, 0.1], [0.3, -0.6], [0.7, 0.9]], [1, 0, 0, 1], 0.5),          # HalfcorrectKeypoints
+])
+def test_reference_keypoint_accuracy_cases(keypoints, labels, expected_accuracy):
+  acc, _ = losses.KeypointAccuracy(torch.tensor(keypoints, dtype=torch.float32), torch.tensor(labels))
+  assert float(acc) == expected_accuracy

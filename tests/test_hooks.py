@@ -156,3 +156,91 @@ def test_export_model_layout(tmp_path):
   assert assets.global_step == 12
   spec = tu.TensorSpecStruct.from_proto(assets.feature_spec)
   assert spec.x.shape == (3,) and spec.x.name == 'measured_position'
+
+
+# ---- the scenarios of the reference's hooks/checkpoint_hooks_test.py:58-178, one by one ---------------------
+class _Exporter(object):
+  """_MakeSavedModel: export_dir/<id>/savedModel.txt + variables/variables.txt; ids count up per export."""
+
+  def __init__(self, start=0):
+    self.export_id = start
+
+  @staticmethod
+  def make(export_dir, checkpoint_id):
+    path = os.path.join(export_dir, str(checkpoint_id))
+    os.makedirs(os.path.join(path, 'variables'))
+    for name in ('savedModel.txt', os.path.join('variables', 'variables.txt')):
+      with open(os.path.join(path, name), 'w') as f:
+        f.write('abc')
+    return path
+
+  def __call__(self, export_dir, global_step):
+    del global_step
+    self.export_id += 1
+    return self.make(export_dir, self.export_id)
+
+
+def _exists(base, checkpoint_id):
+  return os.path.exists(os.path.join(base, str(checkpoint_id)))
+
+
+def test_reference_checkpoint_export_listener_cases(tmp_path):
+  from tensor2robot_b200.hooks import checkpoint_hooks
+  export_dir = str(tmp_path / 'a')
+  listener = checkpoint_hooks.CheckpointExportListener(_Exporter(), export_dir)              # testCheckpointExportListener
+  listener.after_save(None, 10)
+  assert _exists(export_dir, 1)
+  export_dir = str(tmp_path / 'b')
+  listener = checkpoint_hooks.CheckpointExportListener(_Exporter(), export_dir, num_versions=3)   # ...GC
+  for step in range(5):
+    listener.after_save(None, step)
+  assert _exists(export_dir, 5) and not _exists(export_dir, 2)
+  export_dir = str(tmp_path / 'c')                                                          # ...GCRestore
+  os.makedirs(export_dir)
+  for step in range(6):
+    _Exporter.make(export_dir, step)
+  checkpoint_hooks.CheckpointExportListener(_Exporter(), export_dir, num_versions=3)       # the initializer GCs
+  assert _exists(export_dir, 5) and not _exists(export_dir, 2)
+
+
+def _lagged(tmp_path, name, exporter):
+  from tensor2robot_b200.hooks import checkpoint_hooks
+  export_dir, lagged_dir = str(tmp_path / name / 'export'), str(tmp_path / name / 'lagged_export')
+  os.makedirs(export_dir, exist_ok=True)
+  os.makedirs(lagged_dir, exist_ok=True)
+  make = lambda: checkpoint_hooks.LaggedCheckpointListener(export_fn=exporter, export_dir=export_dir,
+                                                           lagged_export_dir=lagged_dir, num_versions=3)
+  return export_dir, lagged_dir, make
+
+
+def test_reference_lagged_listener_cases(tmp_path):
+  exporter = _Exporter()                                                                    # testEmptyDir
+  export_dir, lagged_dir, make = _lagged(tmp_path, 'empty', exporter)
+  listener = make()
+  listener.after_save(None, 10)
+  assert _exists(lagged_dir, 1) and _exists(export_dir, 1)
+  listener.after_save(None, 11)
+  assert _exists(export_dir, 2) and not _exists(lagged_dir, 2)          # the lagged policy has not updated
+  listener.after_save(None, 12)
+  assert _exists(export_dir, 3) and _exists(lagged_dir, 2)              # now it has
+
+  exporter = _Exporter()                                                                    # testInitOneSavedModel
+  export_dir, lagged_dir, make = _lagged(tmp_path, 'one', exporter)
+  _Exporter.make(export_dir, 1)
+  make()
+  assert _exists(export_dir, 1) and _exists(lagged_dir, 1)              # the constructor copies the SavedModel over
+
+  exporter = _Exporter(start=1)                                                             # testInitSavedModelUptoDate
+  export_dir, lagged_dir, make = _lagged(tmp_path, 'uptodate', exporter)
+  _Exporter.make(export_dir, 1)
+  _Exporter.make(lagged_dir, 1)
+  make().after_save(None, 11)
+  assert _exists(export_dir, 2) and not _exists(lagged_dir, 2)
+
+  exporter = _Exporter(start=2)                                                             # ...FromLaggedPosition
+  export_dir, lagged_dir, make = _lagged(tmp_path, 'lagged', exporter)
+  _Exporter.make(export_dir, 1)
+  _Exporter.make(export_dir, 2)
+  _Exporter.make(lagged_dir, 1)
+  make().after_save(None, 11)
+  assert _exists(export_dir, 3) and _exists(lagged_dir, 2)
