@@ -55,20 +55,48 @@ def CenterCropImages(images, input_shape, target_shape):  # pylint: disable=inva
 
 
 def CustomCropImages(images, input_shape, target_shape, target_locations):  # pylint: disable=invalid-name
-  """Crops around given (y, x) centres, clamped so the window stays inside the image
-  (image_transformations.py:104-172)."""
-  _check_shapes(images, input_shape, target_shape)
+  """Crops around given centres, moved so the window stays inside the image (image_transformations.py:104-172).
+  target_locations: one entry per image tensor, either a [batch, 2] array of (y, x) centres - one window per batch
+  element, gathered into a new tensor - or a single (y, x) pair shared by the batch (a view, no copy).
+  Note: the reference clamps y / x as documented but hands them to tf.image.extract_glimpse in (x, y) order; the two
+  only coincide for equal coordinates (its tests use [10, 10]).  The documented (y, x) meaning is implemented here."""
+  if len(input_shape) != 3:
+    raise ValueError('The input shape has to be of the form (height, width, channels) but has len {}'.format(
+        len(input_shape)))
+  if len(target_shape) != 2:
+    raise ValueError('The target shape has to be of the form (height, width) but has len {}'.format(
+        len(target_shape)))
   if len(target_locations) != len(images):
-    raise ValueError('There should be one target location per image. Found {} for {} images'.format(
-        len(target_locations), len(images)))
+    raise ValueError('There should be one target location per image. Found {} images for {} locations'.format(
+        len(images), len(target_locations)))
+  if input_shape[0] == target_shape[0] and input_shape[1] == target_shape[1]:
+    return list(images)
+  if input_shape[0] < target_shape[0] or input_shape[1] < target_shape[1]:
+    raise ValueError('The target shape {} is larger than the input image size {}'.format(target_shape, input_shape[:2]))
+  _check_shapes(images, input_shape, target_shape)
+  th, tw = target_shape
+
+  def window(loc):
+    y = int(np.clip(loc[0], th // 2, input_shape[0] - th // 2))
+    x = int(np.clip(loc[1], tw // 2, input_shape[1] - tw // 2))
+    return y - th // 2, x - tw // 2
+
   out = []
   for img, loc in zip(images, target_locations):
-    if len(loc) != 2:
-      raise ValueError('Target locations have to be of the form (y, x): {}'.format(loc))
-    y = int(np.clip(loc[0], target_shape[0] // 2, input_shape[0] - target_shape[0] // 2))
-    x = int(np.clip(loc[1], target_shape[1] // 2, input_shape[1] - target_shape[1] // 2))
-    oy, ox = y - target_shape[0] // 2, x - target_shape[1] // 2
-    out.append(img[..., oy:oy + target_shape[0], ox:ox + target_shape[1], :])
+    loc = np.asarray(loc.cpu() if torch.is_tensor(loc) else loc)
+    if loc.ndim == 1:
+      if loc.shape[0] != 2:
+        raise ValueError('Target locations have to be of the form (y, x): {}'.format(loc))
+      oy, ox = window(loc)
+      out.append(img[..., oy:oy + th, ox:ox + tw, :])
+      continue
+    if loc.ndim != 2 or loc.shape[1] != 2 or loc.shape[0] != img.shape[0]:
+      raise ValueError('Target locations have to be of shape [batch, 2], got {}'.format(loc.shape))
+    crops = []
+    for b in range(img.shape[0]):
+      oy, ox = window(loc[b])
+      crops.append(img[b, ..., oy:oy + th, ox:ox + tw, :])
+    out.append(torch.stack(crops, 0))
   return out
 
 
