@@ -374,3 +374,50 @@ def test_map_feed_dict_unsafe():
   assert list(out) == ['a', 'b']                     # unknown inputs are dropped (with a warning)
   with pytest.raises((KeyError, AttributeError)):      # a missing input fails on lookup, as in the reference
     utils.map_feed_dict_unsafe(spec, {'a': np.zeros((3, 2))})
+
+
+@pytest.mark.parametrize('batch_size', [1, 2])
+def test_varlen_images_feature_spec(tmp_path, batch_size):
+  """utils/tfdata_test.py:262-345: a variable number of PNG images per record, padded to the spec with black frames;
+  an image of the wrong size is an error."""
+  from tensor2robot_b200.utils import image as image_lib
+  h, w, padded = 48, 64, 3
+  rng = np.random.RandomState(0)
+  image_np = rng.uniform(size=(h, w), high=255).astype(np.int32)
+  png = image_lib.numpy_to_image_string(image_np, 'png')
+  path = str(tmp_path / 'test.tfrecord')
+  oracle.write_tfrecords(path, [oracle.make_example({'varlen_images': [png]}),
+                                oracle.make_example({'varlen_images': [png, png]})])
+  feature_spec = utils.TensorSpecStruct()
+  feature_spec.varlen_images = TSPEC(shape=(padded, h, w, 1), dtype=dtypes.uint8, name='varlen_images', data_format='png',
+                                     varlen_default_value=0)
+  batches = [list(tfdata.parallel_read(path, num_epochs=1, num_readers=1))[:batch_size]]
+  (features,) = list(tfdata.serialized_to_parsed(batches, feature_spec, None))
+  black = np.zeros((h, w))
+  want = np.stack([np.stack([image_np, black, black]), np.stack([image_np, image_np, black])])[:batch_size, ..., None]
+  assert features.varlen_images.shape == (batch_size, padded, h, w, 1)
+  np.testing.assert_array_equal(features.varlen_images, want)
+  # an image whose size differs from the spec
+  big = image_lib.numpy_to_image_string(np.ones((2 * h, 2 * w)) * 255, 'png')
+  bad_path = str(tmp_path / 'bad.tfrecord')
+  oracle.write_tfrecords(bad_path, [oracle.make_example({'varlen_images': [big]}),
+                                    oracle.make_example({'varlen_images': [png, big]})])
+  bad = [list(tfdata.parallel_read(bad_path, num_epochs=1, num_readers=1))[:batch_size]]
+  with pytest.raises(ValueError):
+    list(tfdata.serialized_to_parsed(bad, feature_spec, None))
+
+
+def test_compress_decompress_on_the_fixture():
+  """utils/tfdata_test.py:100-141: parse, compress (quality 100), decompress: the frames agree to one decimal."""
+  feature_spec = utils.TensorSpecStruct(state=TSPEC((64, 64, 3), dtypes.uint8, 'state/image', data_format='jpeg'),
+                                        action=TSPEC((2,), dtypes.bfloat16, 'pose'))
+  label_spec = utils.TensorSpecStruct(reward=TSPEC((), dtypes.float32, 'reward'))
+  records = list(tfdata.parallel_read(FIXTURE, num_epochs=1))[:5]
+  (features, labels), = list(tfdata.serialized_to_parsed([records], feature_spec, label_spec))
+  assert features.state.shape == (5, 64, 64, 3)
+  original = np.array(features.state)
+  flat_f, flat_l = utils.flatten_spec_structure(features), utils.flatten_spec_structure(labels)
+  packed, _ = tfdata.create_compress_fn(feature_spec, label_spec, quality=100)(dict(flat_f.items()), dict(flat_l.items()))
+  restored, _ = tfdata.create_decompress_fn(feature_spec, label_spec)(packed, dict(flat_l.items()))
+  assert restored['state'].shape == (5, 64, 64, 3)
+  np.testing.assert_almost_equal(original.astype(np.float32) / 255, restored['state'].astype(np.float32) / 255, decimal=1)
