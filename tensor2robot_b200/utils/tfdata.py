@@ -25,6 +25,7 @@ import itertools
 import logging
 import mmap
 import os
+import struct
 
 import numpy as np
 from PIL import Image
@@ -127,16 +128,19 @@ def read_records(filename, verify_crc=True):
 def _decode_one(image_bytes, single_img_dims, np_dtype, name):
   if not image_bytes:
     return np.zeros(single_img_dims, np_dtype)          # '' -> zeros (utils/tfdata.py:465-473)
-  from PIL import Image
-  with Image.open(io.BytesIO(image_bytes)) as im:
-    channels = single_img_dims[2]
-    if np_dtype == np.uint16:
-      arr = np.asarray(im)
-      if arr.dtype != np.uint16:
-        arr = arr.astype(np.uint16)
-    else:
-      im = im.convert('L' if channels == 1 else 'RGB')
-      arr = np.asarray(im, dtype=np.uint8)
+  try:
+    with Image.open(io.BytesIO(image_bytes)) as im:
+      channels = single_img_dims[2]
+      if np_dtype == np.uint16:
+        arr = np.asarray(im)
+        if arr.dtype != np.uint16:
+          arr = arr.astype(np.uint16)
+      else:
+        im = im.convert('L' if channels == 1 else 'RGB')
+        arr = np.asarray(im, dtype=np.uint8)
+  except (OSError, SyntaxError, EOFError, struct.error, Image.DecompressionBombError) as e:
+    # tf.image.decode_image reports corrupt data as InvalidArgument; PIL raises a family of exception types
+    raise ValueError('InvalidArgument: image "%s" cannot be decoded: %s' % (name, e))
   if arr.ndim == 2:
     arr = arr[:, :, None]
   if tuple(arr.shape) != tuple(single_img_dims):

@@ -88,3 +88,38 @@ def test_sanitizer_harness():
   out = subprocess.run([os.path.join(ROOT, 'scripts', 'host_fuzz.sh'), '6000'], capture_output=True, text=True, timeout=600)
   assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
   assert 'no memory error' in out.stdout
+
+
+def test_mutated_records_only_raise_value_errors():
+  """The python parse layer (C++ wire parser + image decoding) turns every malformed record - truncated protos, corrupt
+  JPEG payloads, wrong counts - into a ValueError, the analogue of TF's InvalidArgumentError."""
+  from oracle import tfrecord
+  from tensor2robot_b200.utils import dtypes
+  from tensor2robot_b200.utils import tensorspec_utils as utils
+  from tensor2robot_b200.utils import tfdata
+  tspec = utils.ExtendedTensorSpec
+  feature_spec = utils.TensorSpecStruct(
+      state=utils.TensorSpecStruct(image=tspec((64, 64, 3), dtypes.uint8, 'state/image', data_format='jpeg')),
+      action=utils.TensorSpecStruct(pose=tspec((2,), dtypes.float32, 'pose')))
+  label_spec = utils.TensorSpecStruct(reward=tspec((1,), dtypes.float32, 'reward'))
+  parse = tfdata.create_parse_tf_example_fn(feature_spec, label_spec)
+  records = tfrecord.read_tfrecords(os.path.join(ROOT, 'tests', 'golden', 'pose_env_test_data.tfrecord'))[:8]
+  rng = np.random.RandomState(0)
+  parsed = rejected = 0
+  for it in range(800):
+    b = bytearray(records[it % 8])
+    mode = rng.randint(3)
+    if mode == 0:
+      for _ in range(rng.randint(1, 6)):
+        b[rng.randint(len(b))] = rng.randint(256)
+    elif mode == 1:
+      b = b[:rng.randint(1, len(b))]
+    else:
+      i = rng.randint(len(b))
+      b[i:i] = bytes(rng.randint(0, 256, rng.randint(1, 9)).astype(np.uint8))
+    try:
+      parse([bytes(b), records[0]])
+      parsed += 1
+    except ValueError:
+      rejected += 1
+  assert parsed > 50 and rejected > 50
