@@ -420,6 +420,11 @@ int32_t t2r_jpeg_parse(const uint8_t* data, uint64_t len, T2RJpegInfo* info);
 /* coef: host (pinned) int16 [B][coef_stride]; infos[b] is filled for every image. */
 int32_t t2r_jpeg_entropy_decode_batch(const uint8_t* const* data, const uint64_t* lens, int32_t B,
                                       T2RJpegInfo* infos, int16_t* coef, int64_t coef_stride);
+/* Complete decode on host threads into out uint8 [B,H,W,channels] (channels 3: RGB, grey replicated; 1: luma): the
+ * 'host' image decoder of the record parser for baseline JPEGs, same integer arithmetic as the device half, i.e.
+ * bit-identical with libjpeg(-turbo).  Every stream must be H x W; unsupported streams give T2R_ERR_PARSE. */
+int32_t t2r_jpeg_decode_host_batch(const uint8_t* const* data, const uint64_t* lens, int32_t B, int32_t H, int32_t W,
+                                   int32_t channels, uint8_t* out);
 /* Device half.  All B images share the geometry of `geom` (width, height, sampling factors: the spec's
  * static shape); qt: device uint16 [B][4][64] (per-image tables); coef: device int16 [B][coef_stride];
  * planes: device uint8 workspace [B][coef_count] (IDCT output per component); out: uint8 [B,H,W,channels],

@@ -28,7 +28,7 @@ tfrecord.write_tfrecords(os.path.join(out, 'examples2.tfrecord'), extra)
 seqs = [tfrecord.make_sequence_example({'reward': [1.0]}, {'pose': [[0.1 * t, 0.2 * t] for t in range(n)]}) for n in (1, 3, 5)]
 tfrecord.write_tfrecords(os.path.join(out, 'seq.tfrecord'), seqs)
 PY
-g++ -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fno-sanitize-recover=all -std=c++17 -pthread \
+g++ -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fno-sanitize-recover=all -fwrapv -std=c++17 -pthread \
     tests/native/fuzz/host_fuzz.cc tensor2robot_b200/csrc/jpeg_host.cc tensor2robot_b200/csrc/host_io.cc -o "$SEEDS/host_fuzz"
 "$SEEDS/host_fuzz" "$SEEDS" "$ITER"
 rm -rf "$SEEDS"

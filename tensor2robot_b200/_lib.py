@@ -115,6 +115,7 @@ _PROTOS = {
     't2r_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32]),
     't2r_jpeg_parse': (_I32, [_P, C.c_uint64, C.POINTER(JpegInfo)]),
     't2r_jpeg_entropy_decode_batch': (_I32, [_P, _P, _I32, C.POINTER(JpegInfo), _P, _I64]),
+    't2r_jpeg_decode_host_batch': (_I32, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_jpeg_idct_color': (_I32, [_P, _P, C.POINTER(JpegInfo), _P, _P, _I32, _I64, _I32, _P]),
     't2r_conv2d_direct_f32_fwd': (_I32, [_P, _P, _P, _P] + [_I32] * 12 + [_P]),
     't2r_conv2d_direct_f32_dgrad': (_I32, [_P, _P, _P] + [_I32] * 12 + [_P]),

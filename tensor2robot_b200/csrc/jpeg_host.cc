@@ -8,8 +8,13 @@
 // (one image per task); everything that is data parallel moves to the GPU and only int16 coefficients
 // (already ~the size of the decoded image, but written once into pinned memory) cross PCIe.
 #include <stdint.h>
+#include <unistd.h>
 #include <string.h>
 
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -209,6 +214,7 @@ struct BitReader {
   uint64_t acc = 0;
   int n = 0;
   bool hit_marker = false;
+  bool exhausted = false;     // the input ended inside the scan (no marker): TF / libjpeg's JERR_INPUT_EOF
   inline void fill() {
     // fast path: four stream bytes at once when none of them is 0xFF (no stuffing, no marker)
     if (n <= 32 && !hit_marker && end - p >= 4) {
@@ -223,9 +229,11 @@ struct BitReader {
     }
     while (n <= 56) {
       uint32_t byte = 0;
+      if (!hit_marker && p >= end) exhausted = true;
       if (!hit_marker && p < end) {
         byte = *p++;
         if (byte == 0xFF) {
+          if (p >= end) exhausted = true;
           const uint8_t nx = p < end ? *p : 0;
           if (nx == 0) ++p;
           else { --p; byte = 0; hit_marker = true; }   // marker inside the scan: feed zeros, do not consume
@@ -320,6 +328,246 @@ int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t*
           }
       }
     }
+  if (br.exhausted) {      // what tf.image.decode_image reports for a truncated file (try_recover_truncated = False)
+    t2r::set_error("jpeg: premature end of data inside the entropy-coded segment");
+    return T2R_ERR_PARSE;
+  }
+  return T2R_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Complete host decode (the 'host' image decoder of the record parser): the same integer arithmetic as the device half
+// in jpeg.cu - jidctint.c ISLOW, jdsample.c fancy upsampling, jdcolor.c tables - so host, device and libjpeg-turbo
+// outputs are bit-identical.  PIL's JPEG plugin keeps the GIL while decoding, so its thread pool does not scale;
+// these run on plain C++ threads.
+// ---------------------------------------------------------------------------------------------
+constexpr int CONST_BITS = 13, PASS1_BITS = 2;
+constexpr int F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270;
+constexpr int F_0_899976223 = 7373, F_1_175875602 = 9633, F_1_501321110 = 12299, F_1_847759065 = 15137;
+constexpr int F_1_961570560 = 16069, F_2_053119869 = 16819, F_2_562915447 = 20995, F_3_072711026 = 25172;
+
+inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// One 1-D pass of jpeg_idct_islow.  Products are formed in 32-bit like libjpeg's INT32 (values stay below 2^31 for
+// 8-bit data); intermediate wrap-around cannot occur for coefficients a conforming stream can hold.
+inline void idct8(const int* d, int stride, int* o, int ostride, int shift) {
+  int z2 = d[2 * stride], z3 = d[6 * stride];
+  int z1 = (z2 + z3) * F_0_541196100;
+  const int t2e = z1 + z3 * (-F_1_847759065);
+  const int t3e = z1 + z2 * F_0_765366865;
+  const int t0e = int(uint32_t(d[0] + d[4 * stride]) << CONST_BITS);
+  const int t1e = int(uint32_t(d[0] - d[4 * stride]) << CONST_BITS);
+  const int tmp10 = t0e + t3e, tmp13 = t0e - t3e, tmp11 = t1e + t2e, tmp12 = t1e - t2e;
+  int tmp0 = d[7 * stride], tmp1 = d[5 * stride], tmp2 = d[3 * stride], tmp3 = d[1 * stride];
+  z1 = tmp0 + tmp3;
+  z2 = tmp1 + tmp2;
+  z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * F_1_175875602;
+  tmp0 *= F_0_298631336;
+  tmp1 *= F_2_053119869;
+  tmp2 *= F_3_072711026;
+  tmp3 *= F_1_501321110;
+  z1 *= -F_0_899976223;
+  z2 *= -F_2_562915447;
+  z3 = z3 * (-F_1_961570560) + z5;
+  z4 = z4 * (-F_0_390180644) + z5;
+  tmp0 += z1 + z3;
+  tmp1 += z2 + z4;
+  tmp2 += z2 + z3;
+  tmp3 += z1 + z4;
+  o[0 * ostride] = descale(tmp10 + tmp3, shift); o[7 * ostride] = descale(tmp10 - tmp3, shift);
+  o[1 * ostride] = descale(tmp11 + tmp2, shift); o[6 * ostride] = descale(tmp11 - tmp2, shift);
+  o[2 * ostride] = descale(tmp12 + tmp1, shift); o[5 * ostride] = descale(tmp12 - tmp1, shift);
+  o[3 * ostride] = descale(tmp13 + tmp0, shift); o[4 * ostride] = descale(tmp13 - tmp0, shift);
+}
+
+inline uint8_t clamp255(int v) { return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+void idct_block(const int16_t* c, const uint16_t* q, uint8_t* dst, int pw) {
+  int in[64], ws[64], o[8];
+  for (int i = 0; i < 64; ++i) in[i] = int(c[i]) * int(q[i]);
+  for (int col = 0; col < 8; ++col) idct8(in + col, 8, ws + col, 8, CONST_BITS - PASS1_BITS);      // columns
+  for (int r = 0; r < 8; ++r) {
+    idct8(ws + r * 8, 1, o, 1, CONST_BITS + PASS1_BITS + 3);                                       // rows
+    for (int k = 0; k < 8; ++k) dst[size_t(r) * pw + k] = clamp255(o[k] + 128);
+  }
+}
+
+inline int chroma_at(const uint8_t* pl, int pw, int cw, int ch, int hs, int vs, int y, int x) {
+  if (hs == 1) return pl[size_t(y) * pw + x];
+  const int cx = x >> 1;
+  if (vs == 1) {                                            // h2v1_fancy_upsample
+    const int v0 = pl[size_t(y) * pw + cx];
+    if (x & 1) return cx == cw - 1 ? v0 : (3 * v0 + pl[size_t(y) * pw + cx + 1] + 2) >> 2;
+    return cx == 0 ? v0 : (3 * v0 + pl[size_t(y) * pw + cx - 1] + 1) >> 2;
+  }
+  const int cy = y >> 1;                                    // h2v2_fancy_upsample
+  const int oy = (y & 1) ? (cy + 1 < ch ? cy + 1 : ch - 1) : (cy > 0 ? cy - 1 : 0);
+  const uint8_t* r0 = pl + size_t(cy) * pw;
+  const uint8_t* r1 = pl + size_t(oy) * pw;
+  const int col = 3 * r0[cx] + r1[cx];
+  if (x & 1) return cx == cw - 1 ? (4 * col + 7) >> 4 : (3 * col + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+  return cx == 0 ? (4 * col + 8) >> 4 : (3 * col + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+// A persistent worker pool: threads are created once (per process) and reused by every batch call, so a call does not
+// pay thread creation and its workers are already spread over the cores.  run(n, fn) executes fn(0..n-1), the caller
+// participating; nested or concurrent calls serialise on the pool mutex.  After a fork() the child rebuilds the pool.
+class WorkerPool {
+ public:
+  static WorkerPool& instance() {
+    static WorkerPool* pool = new WorkerPool();     // intentionally leaked: workers may outlive static destructors
+    return *pool;
+  }
+
+  void run(int n, const std::function<void(int)>& fn) {
+    if (n <= 1) {
+      for (int i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    std::lock_guard<std::mutex> call_lock(call_mutex_);
+    ensure_threads(n - 1);
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      fn_ = &fn;
+      total_ = n;
+      next_ = 0;
+      pending_ = n;
+      ++generation_;
+    }
+    wake_.notify_all();
+    work_until_empty();
+    std::unique_lock<std::mutex> lock(mutex_);
+    done_.wait(lock, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void ensure_threads(int wanted) {
+    const pid_t pid = getpid();
+    if (pid != owner_) {              // first use, or a forked child: the parent's threads do not exist here
+      threads_ = 0;
+      owner_ = pid;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    const int cap = int(hw ? (hw > 16 ? 16 : hw) : 1) - 1;
+    wanted = wanted < cap ? wanted : cap;
+    while (threads_ < wanted) {
+      std::thread(&WorkerPool::worker_loop, this).detach();
+      ++threads_;
+    }
+  }
+
+  void work_until_empty() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* fn;
+      {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (fn_ == nullptr || next_ >= total_) return;
+        i = next_++;
+        fn = fn_;
+      }
+      (*fn)(i);
+      std::lock_guard<std::mutex> lock(mutex_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+
+  void worker_loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lock(mutex_);
+        wake_.wait(lock, [&] { return generation_ != seen; });
+        seen = generation_;
+      }
+      work_until_empty();
+    }
+  }
+
+  std::mutex call_mutex_, mutex_;
+  std::condition_variable wake_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int total_ = 0, next_ = 0, pending_ = 0, threads_ = 0;
+  unsigned long generation_ = 0;
+  pid_t owner_ = 0;
+};
+
+struct Scratch {
+  std::vector<int16_t> coef;
+  std::vector<uint8_t> planes;
+};
+// The free list (like the pool) lives on the heap for the life of the process: reused buffers keep their pages.
+std::mutex g_scratch_mutex;
+std::vector<Scratch*>* g_scratch_free = new std::vector<Scratch*>();
+
+Scratch* acquire_scratch() {
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  if (g_scratch_free->empty()) return new Scratch();
+  Scratch* s = g_scratch_free->back();
+  g_scratch_free->pop_back();
+  return s;
+}
+
+void release_scratch(Scratch* s) {
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  if (g_scratch_free->size() < 64) g_scratch_free->push_back(s);
+  else delete s;
+}
+
+int decode_one_host(const uint8_t* data, uint64_t len, int H, int W, int channels, uint8_t* out, std::vector<int16_t>* coef,
+                    std::vector<uint8_t>* planes) {
+  Parsed ps;
+  int rc = parse_headers(data, len, &ps);
+  if (rc != T2R_OK) return rc;
+  const T2RJpegInfo& in = ps.info;
+  if (in.width != W || in.height != H) {
+    t2r::set_error("jpeg: stream is %d x %d, the caller expects %d x %d", in.width, in.height, W, H);
+    return T2R_ERR_INVALID_ARG;
+  }
+  coef->resize(size_t(in.coef_count));
+  planes->resize(size_t(in.coef_count));
+  rc = entropy_decode(data, len, ps, coef->data());
+  if (rc != T2R_OK) return rc;
+  const int ncomp_needed = channels == 1 ? 1 : in.ncomp;
+  int bw[3] = {0, 0, 0};
+  for (int c = 0; c < in.ncomp; ++c) bw[c] = in.mcux * in.h[c];
+  for (int c = 0; c < ncomp_needed; ++c) {
+    const int bh = in.mcuy * in.v[c], pw = bw[c] * 8;
+    const int16_t* cc = coef->data() + in.coef_offset[c];
+    uint8_t* pl = planes->data() + in.coef_offset[c];
+    for (int by = 0; by < bh; ++by)
+      for (int bx = 0; bx < bw[c]; ++bx)
+        idct_block(cc + (size_t(by) * bw[c] + bx) * 64, in.qt[in.tq[c]], pl + size_t(by) * 8 * pw + bx * 8, pw);
+  }
+  const uint8_t* yp = planes->data() + in.coef_offset[0];
+  const int ypw = bw[0] * 8;
+  if (in.ncomp == 1 || channels == 1) {
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const uint8_t v = yp[size_t(y) * ypw + x];
+        uint8_t* o = out + (size_t(y) * W + x) * channels;
+        for (int k = 0; k < channels; ++k) o[k] = v;
+      }
+    return T2R_OK;
+  }
+  const int hs = in.hmax / in.h[1], vs = in.vmax / in.v[1];
+  const int cw = (W * in.h[1] + in.hmax - 1) / in.hmax, ch = (H * in.v[1] + in.vmax - 1) / in.vmax;
+  const uint8_t* cbp = planes->data() + in.coef_offset[1];
+  const uint8_t* crp = planes->data() + in.coef_offset[2];
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const int yy = yp[size_t(y) * ypw + x];
+      const int cb = chroma_at(cbp, bw[1] * 8, cw, ch, hs, vs, y, x) - 128;
+      const int cr = chroma_at(crp, bw[2] * 8, cw, ch, hs, vs, y, x) - 128;
+      uint8_t* o = out + (size_t(y) * W + x) * 3;
+      o[0] = clamp255(yy + ((91881 * cr + 32768) >> 16));                       // jdcolor.c tables, SCALEBITS = 16
+      o[1] = clamp255(yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+      o[2] = clamp255(yy + ((116130 * cb + 32768) >> 16));
+    }
   return T2R_OK;
 }
 
@@ -336,36 +584,49 @@ extern "C" int32_t t2r_jpeg_parse(const uint8_t* data, uint64_t len, T2RJpegInfo
 extern "C" int32_t t2r_jpeg_entropy_decode_batch(const uint8_t* const* data, const uint64_t* lens, int32_t B,
                                                  T2RJpegInfo* infos, int16_t* coef, int64_t coef_stride) {
   if (!data || !lens || !infos || !coef || B <= 0) { t2r::set_error("jpeg_entropy_decode_batch: bad args"); return T2R_ERR_INVALID_ARG; }
-  unsigned hw = std::thread::hardware_concurrency();
-  const int nthreads = B >= 8 ? int(hw ? (hw > 16 ? 16 : hw) : 1) : 1;
   std::vector<int> rcs(size_t(B), T2R_OK);
-  std::vector<std::string> msgs(static_cast<size_t>(nthreads));
-  auto work = [&](int t) {
-    for (int b = t; b < B; b += nthreads) {
-      Parsed ps;
-      int rc = parse_headers(data[b], lens[b], &ps);
-      if (rc == T2R_OK && ps.info.coef_count > coef_stride) {
-        t2r::set_error("jpeg: image %d needs %lld coefficients, stride is %lld", b, (long long)ps.info.coef_count,
-                       (long long)coef_stride);
-        rc = T2R_ERR_INVALID_ARG;
-      }
-      if (rc == T2R_OK) rc = entropy_decode(data[b], lens[b], ps, coef + int64_t(b) * coef_stride);
-      if (rc != T2R_OK) { msgs[size_t(t)] = t2r_last_error(); }
-      infos[b] = ps.info;
-      rcs[size_t(b)] = rc;
+  std::vector<std::string> msgs(static_cast<size_t>(B));
+  WorkerPool::instance().run(B, [&](int b) {
+    Parsed ps;
+    int rc = parse_headers(data[b], lens[b], &ps);
+    if (rc == T2R_OK && ps.info.coef_count > coef_stride) {
+      t2r::set_error("jpeg: image %d needs %lld coefficients, stride is %lld", b, (long long)ps.info.coef_count,
+                     (long long)coef_stride);
+      rc = T2R_ERR_INVALID_ARG;
     }
-  };
-  if (nthreads == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
-    for (auto& x : th) x.join();
-  }
+    if (rc == T2R_OK) rc = entropy_decode(data[b], lens[b], ps, coef + int64_t(b) * coef_stride);
+    if (rc != T2R_OK) msgs[size_t(b)] = t2r_last_error();
+    infos[b] = ps.info;
+    rcs[size_t(b)] = rc;
+  });
   for (int b = 0; b < B; ++b)
     if (rcs[size_t(b)] != T2R_OK) {
-      for (auto& m : msgs)
-        if (!m.empty()) { t2r::set_error("%s", m.c_str()); break; }
+      t2r::set_error("%s", msgs[size_t(b)].c_str());
+      return rcs[size_t(b)];
+    }
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_jpeg_decode_host_batch(const uint8_t* const* data, const uint64_t* lens, int32_t B, int32_t H, int32_t W,
+                                              int32_t channels, uint8_t* out) {
+  if (!data || !lens || !out || B <= 0 || H <= 0 || W <= 0 || (channels != 1 && channels != 3)) {
+    t2r::set_error("jpeg_decode_host_batch: bad args");
+    return T2R_ERR_INVALID_ARG;
+  }
+  std::vector<int> rcs(size_t(B), T2R_OK);
+  std::vector<std::string> msgs(static_cast<size_t>(B));
+  const size_t frame = size_t(H) * W * channels;
+  WorkerPool::instance().run(B, [&](int b) {
+    Scratch* scratch = acquire_scratch();      // coefficient / plane buffers persist across calls (no page faults)
+    const int rc = decode_one_host(data[b], lens[b], H, W, channels, out + size_t(b) * frame, &scratch->coef,
+                                   &scratch->planes);
+    if (rc != T2R_OK) msgs[size_t(b)] = t2r_last_error();
+    rcs[size_t(b)] = rc;
+    release_scratch(scratch);
+  });
+  for (int b = 0; b < B; ++b)
+    if (rcs[size_t(b)] != T2R_OK) {
+      t2r::set_error("%s", msgs[size_t(b)].c_str());
       return rcs[size_t(b)];
     }
   return T2R_OK;

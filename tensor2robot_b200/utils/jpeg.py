@@ -80,3 +80,25 @@ def decode_batch(images, channels=3, device='cuda'):
   _lib.call('t2r_jpeg_idct_color', C.c_void_p(coef_d.data_ptr()), C.c_void_p(qt_d.data_ptr()), C.byref(geom),
             C.c_void_p(planes.data_ptr()), C.c_void_p(out.data_ptr()), b, int(geom.coef_count), channels, stream)
   return out
+
+
+def decode_batch_host(images, height, width, channels=3):
+  """list of baseline JPEG byte strings, all height x width -> numpy uint8 [B, height, width, channels], decoded
+  completely on host threads (t2r_jpeg_decode_host_batch): the same integer arithmetic as the device half, bit-identical
+  with libjpeg-turbo.  Raises UnsupportedJpeg for streams outside the supported subset or of another size."""
+  b = len(images)
+  if b == 0:
+    raise ValueError('empty batch')
+  out = np.empty((b, height, width, channels), np.uint8)
+  ptrs = (C.c_void_p * b)()
+  lens = (C.c_uint64 * b)()
+  keep = []
+  for i, img in enumerate(images):
+    buf = (C.c_char * len(img)).from_buffer_copy(img)
+    keep.append(buf)
+    ptrs[i], lens[i] = C.addressof(buf), len(img)
+  rc = _lib.lib().t2r_jpeg_decode_host_batch(ptrs, lens, b, height, width, channels, out.ctypes.data)
+  del keep
+  if rc != 0:
+    raise UnsupportedJpeg(_lib.last_error())
+  return out

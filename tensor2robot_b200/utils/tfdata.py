@@ -198,6 +198,19 @@ def _decode_images(tensor_spec, byte_rows):
       if len(tensor_spec.shape) > 3 or tensor_spec.varlen_default_value is not None:
         out = out.reshape((len(byte_rows), per_row) + dims)
       return out
+  if np_dtype == np.uint8 and flat and all(b[:2] == b'\xff\xd8' for b in flat):
+    # baseline JPEGs: the C++ host decoder (csrc/jpeg_host.cc; bit-identical with libjpeg-turbo, real threads - PIL's
+    # JPEG plugin decodes under the GIL).  Anything it refuses (progressive, CMYK, another size) goes through PIL below,
+    # which decodes it or reports the InvalidArgument.
+    from tensor2robot_b200.utils import jpeg
+    try:
+      out = jpeg.decode_batch_host(flat, dims[0], dims[1], dims[2])
+    except jpeg.UnsupportedJpeg:
+      out = None
+    if out is not None:
+      if len(tensor_spec.shape) > 3 or tensor_spec.varlen_default_value is not None:
+        out = out.reshape((len(byte_rows), per_row) + dims)
+      return out
   if len(flat) >= 8:
     decoded = list(_pool().map(lambda b: _decode_one(b, dims, np_dtype, tensor_spec.name), flat))
   else:

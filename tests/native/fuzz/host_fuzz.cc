@@ -3,7 +3,7 @@
 // Mutates valid seed inputs (byte flips, truncation, insertion, marker injection) and calls the C-ABI; the only
 // acceptable outcomes are T2R_OK or an error status - any out-of-bounds access aborts under ASan.
 //
-//   g++ -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -std=c++17 -pthread \
+//   g++ -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fwrapv -std=c++17 -pthread \
 //       tests/native/fuzz/host_fuzz.cc tensor2robot_b200/csrc/jpeg_host.cc tensor2robot_b200/csrc/host_io.cc \
 //       -o /tmp/host_fuzz && /tmp/host_fuzz <seed dir> <iterations>
 // (scripts/host_fuzz.sh writes the seed files and runs it.)
@@ -78,7 +78,16 @@ static long fuzz_jpeg(const std::vector<uint8_t>& in) {
   const uint8_t* ptr = in.data();
   const uint64_t len = in.size();
   T2RJpegInfo out;
-  return t2r_jpeg_entropy_decode_batch(&ptr, &len, 1, &out, coef.data(), info.coef_count) == 0;
+  long ok = t2r_jpeg_entropy_decode_batch(&ptr, &len, 1, &out, coef.data(), info.coef_count) == 0;
+  // the complete host decoder, three copies at once so that the worker pool runs too
+  if (int64_t(info.width) * info.height <= (1 << 20)) {
+    const uint8_t* ptrs[3] = {ptr, ptr, ptr};
+    const uint64_t lens[3] = {len, len, len};
+    std::vector<uint8_t> rgb(size_t(3) * info.width * info.height * 3);
+    ok += t2r_jpeg_decode_host_batch(ptrs, lens, 3, info.height, info.width, 3, rgb.data()) == 0;
+    ok += t2r_jpeg_decode_host_batch(ptrs, lens, 2, info.height, info.width, 1, rgb.data()) == 0;
+  }
+  return ok;
 }
 
 static long fuzz_records(const std::vector<uint8_t>& file, bool sequence) {

@@ -7,6 +7,7 @@ import os
 
 import numpy as np
 import pytest
+from hypothesis import given, settings, strategies as st
 from PIL import Image
 
 from oracle import jpeg as oracle_jpeg
@@ -182,3 +183,67 @@ def test_host_entropy_decoder_property():
     np.testing.assert_array_equal(oracle_jpeg.decode(data), _pil(data, 'RGB'))
 
   check()
+
+
+# ---- the complete host decoder (t2r_jpeg_decode_host_batch): the 'host' image decoder of the record parser ----------
+def test_host_decoder_matches_libjpeg_bit_exact():
+  """Huffman + ISLOW IDCT + fancy upsampling + colour on C++ host threads == libjpeg-turbo (PIL), bit for bit, for every
+  sampling layout, odd sizes, restart intervals, grey streams, luma-only output, and the whole reference fixture."""
+  from tensor2robot_b200.utils import jpeg
+  fixture = []
+  for rec in oracle_tfrecord.read_tfrecords(FIXTURE):
+    fixture.append(oracle_tfrecord.parse_example(rec)['state/image'][1][0])
+  got = jpeg.decode_batch_host(fixture, 64, 64, 3)
+  want = np.stack([np.asarray(Image.open(io.BytesIO(b)).convert('RGB')) for b in fixture])
+  np.testing.assert_array_equal(got, want)
+  for name, data in _cases():
+    if data is None:
+      continue
+    ref = np.asarray(Image.open(io.BytesIO(data)))
+    h, w = ref.shape[:2]
+    rgb = ref if ref.ndim == 3 else np.repeat(ref[..., None], 3, -1)
+    np.testing.assert_array_equal(jpeg.decode_batch_host([data] * 9, h, w, 3), np.stack([rgb] * 9), err_msg=name)
+    if ref.ndim == 2:
+      np.testing.assert_array_equal(jpeg.decode_batch_host([data], h, w, 1)[0, ..., 0], ref)
+  restart = _encode(_picture(50, 70, 9), quality=70, subsampling=2, restart_marker_blocks=3)
+  np.testing.assert_array_equal(jpeg.decode_batch_host([restart], 50, 70)[0], np.asarray(Image.open(io.BytesIO(restart))))
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(8, 70), st.integers(8, 70), st.sampled_from([0, 1, 2]), st.integers(20, 100), st.integers(0, 2**31 - 1))
+def test_host_decoder_property(h, w, subsampling, quality, seed):
+  from tensor2robot_b200.utils import jpeg
+  rng = np.random.RandomState(seed)
+  img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+  data = _encode(img, quality=quality, subsampling=subsampling)
+  np.testing.assert_array_equal(jpeg.decode_batch_host([data], h, w)[0], np.asarray(Image.open(io.BytesIO(data))))
+
+
+def test_host_decoder_rejections_and_parser_fallback():
+  from tensor2robot_b200.utils import dtypes
+  from tensor2robot_b200.utils import jpeg
+  from tensor2robot_b200.utils import tensorspec_utils as utils
+  from tensor2robot_b200.utils import tfdata
+  data = _encode(_picture(48, 64, 1), quality=80, subsampling=2)
+  with pytest.raises(jpeg.UnsupportedJpeg, match='expects'):
+    jpeg.decode_batch_host([data], 64, 48)                       # another size
+  with pytest.raises(jpeg.UnsupportedJpeg, match='premature end'):
+    jpeg.decode_batch_host([data[:len(data) // 2]], 48, 64)      # truncated: tf.image.decode_image refuses it too
+  with pytest.raises(jpeg.UnsupportedJpeg, match='premature end'):
+    jpeg.decode_batch_host([data[:-2]], 48, 64)                  # EOI missing
+  buf = io.BytesIO()
+  Image.fromarray(_picture(48, 64, 1)).save(buf, format='JPEG', quality=80, progressive=True)
+  progressive = buf.getvalue()
+  with pytest.raises(jpeg.UnsupportedJpeg, match='baseline'):
+    jpeg.decode_batch_host([progressive], 48, 64)
+  # the record parser sends what the C++ decoder refuses through PIL: same pixels as PIL's own decode
+  spec = utils.TensorSpecStruct(image=utils.ExtendedTensorSpec((48, 64, 3), dtypes.uint8, 'image', data_format='jpeg'))
+  records = [oracle_tfrecord.make_example({'image': progressive}), oracle_tfrecord.make_example({'image': progressive})]
+  parsed = tfdata.create_parse_tf_example_fn(spec)(records)
+  np.testing.assert_array_equal(np.asarray(parsed.image)[1], np.asarray(Image.open(io.BytesIO(progressive))))
+  mixed = [oracle_tfrecord.make_example({'image': data}), oracle_tfrecord.make_example({'image': progressive})]
+  parsed = tfdata.create_parse_tf_example_fn(spec)(mixed)
+  np.testing.assert_array_equal(np.asarray(parsed.image)[0], np.asarray(Image.open(io.BytesIO(data))))
+  bad = [oracle_tfrecord.make_example({'image': data[:300]})]
+  with pytest.raises(ValueError):
+    tfdata.create_parse_tf_example_fn(spec)(bad)
