@@ -331,6 +331,10 @@ def decode(data, channels=3):
     pl = pl[:, :cw]
     if (hs, vs) == (1, 1):
       up = pl
+    elif cw <= 2:
+      # jdsample.c jinit_upsampler: the fancy (triangle) filters are only selected when downsampled_width > 2;
+      # narrower components are upsampled by replication (h2v1_upsample / h2v2_upsample)
+      up = np.repeat(np.repeat(pl[:ch] if vs == 2 else pl, hs, 1), vs, 0)
     elif (hs, vs) == (2, 1):
       up = _h2v1_fancy(pl)
     elif (hs, vs) == (2, 2):

@@ -74,10 +74,15 @@ def main():
                                     vertical_rotation=spec.vertical_rotation, grasp_success=spec.grasp_success)
   t, raw = best(lambda: tfdata.create_parse_tf_example_fn(raw_spec)(records))
   print('tf.Example wire parse (no image decode): %.2f ms  (%.0f records/s)' % (t * 1e3, n / t))
-  t, _ = best(lambda: tfdata.create_parse_tf_example_fn(spec)(records), reps=2)
-  print('parse + host JPEG decode (PIL / libjpeg-turbo threads): %.1f ms  (%.0f frames/s)' % (t * 1e3, n / t))
+  t, _ = best(lambda: tfdata.create_parse_tf_example_fn(spec)(records), reps=8)
+  print('parse + host JPEG decode (C++ decoder, worker pool): %.1f ms  (%.0f frames/s)' % (t * 1e3, n / t))
+  def pil():
+    return [np.asarray(Image.open(io.BytesIO(b)).convert('RGB')) for b in jpegs[:16]]
   jpegs = [bytes(b) for b in raw.image]
-  t, _ = best(lambda: jpeg.entropy_decode(jpegs, pinned=False), reps=3)
+  t, _ = best(pil, reps=2)
+  print('PIL (libjpeg-turbo, decodes under the GIL: threads do not help): %.2f ms / frame  (%.0f frames/s)' % (
+      t / 16 * 1e3, 16 / t))
+  t, _ = best(lambda: jpeg.entropy_decode(jpegs, pinned=False), reps=8)
   print('split decoder, host half (Huffman threads): %.1f ms  (%.0f frames/s); the IDCT / colour half runs on the GPU' % (
       t * 1e3, n / t))
   print('host threads available: %d' % len(os.sched_getaffinity(0)))

@@ -388,10 +388,87 @@ inline uint8_t clamp255(int v) { return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v))
 void idct_block(const int16_t* c, const uint16_t* q, uint8_t* dst, int pw) {
   int in[64], ws[64], o[8];
   for (int i = 0; i < 64; ++i) in[i] = int(c[i]) * int(q[i]);
-  for (int col = 0; col < 8; ++col) idct8(in + col, 8, ws + col, 8, CONST_BITS - PASS1_BITS);      // columns
-  for (int r = 0; r < 8; ++r) {
-    idct8(ws + r * 8, 1, o, 1, CONST_BITS + PASS1_BITS + 3);                                       // rows
-    for (int k = 0; k < 8; ++k) dst[size_t(r) * pw + k] = clamp255(o[k] + 128);
+  for (int col = 0; col < 8; ++col) {                                                              // columns
+    const int* d = in + col;
+    if ((d[8] | d[16] | d[24] | d[32] | d[40] | d[48] | d[56]) == 0) {
+      // jidctint.c's shortcut for a column without AC terms; the full butterfly gives exactly d[0] << PASS1_BITS too
+      const int dc = int(uint32_t(d[0]) << PASS1_BITS);
+      for (int r = 0; r < 8; ++r) ws[r * 8 + col] = dc;
+      continue;
+    }
+    idct8(d, 8, ws + col, 8, CONST_BITS - PASS1_BITS);
+  }
+  for (int r = 0; r < 8; ++r) {                                                                    // rows
+    const int* w = ws + r * 8;
+    uint8_t* out = dst + size_t(r) * pw;
+    if ((w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
+      const uint8_t v = clamp255(descale(w[0], PASS1_BITS + 3) + 128);     // identical to the butterfly on zeros
+      for (int k = 0; k < 8; ++k) out[k] = v;
+      continue;
+    }
+    idct8(w, 1, o, 1, CONST_BITS + PASS1_BITS + 3);
+    for (int k = 0; k < 8; ++k) out[k] = clamp255(o[k] + 128);
+  }
+}
+
+// jdcolor.c build_ycc_rgb_table (SCALEBITS = 16): per-sample terms of the YCbCr -> RGB conversion.
+struct YccTables {
+  int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
+  YccTables() {
+    for (int i = 0; i < 256; ++i) {
+      const int x = i - 128;
+      cr_r[i] = (91881 * x + 32768) >> 16;
+      cb_b[i] = (116130 * x + 32768) >> 16;
+      cr_g[i] = -46802 * x;
+      cb_g[i] = -22554 * x + 32768;
+    }
+  }
+};
+const YccTables kYcc;
+
+// One full-resolution row of a chroma plane (jdsample.c: h2v2 / h2v1 fancy upsampling, or a copy for 4:4:4).
+void upsample_row(const uint8_t* pl, int pw, int cw, int ch, int hs, int vs, int y, int W, int* col, uint8_t* row) {
+  if (hs == 1) {
+    memcpy(row, pl + size_t(y) * pw, size_t(W));
+    return;
+  }
+  if (cw <= 2) {     // jinit_upsampler picks the fancy filters only for downsampled_width > 2: replication otherwise
+    const uint8_t* r0 = pl + size_t(vs == 2 ? y >> 1 : y) * pw;
+    for (int x = 0; x < W; ++x) row[x] = r0[x >> 1];
+    return;
+  }
+  if (vs == 1) {                                            // h2v1: 3/4 nearer + 1/4 further sample
+    const uint8_t* r0 = pl + size_t(y) * pw;
+    for (int cx = 0; cx < cw; ++cx) col[cx] = r0[cx];
+    const int last = (W - 1) >> 1;                          // chroma column of the last pixel
+    for (int cx = 1; cx < last; ++cx) {                     // interior: no edge cases, vectorisable
+      row[2 * cx] = uint8_t((3 * col[cx] + col[cx - 1] + 1) >> 2);
+      row[2 * cx + 1] = uint8_t((3 * col[cx] + col[cx + 1] + 2) >> 2);
+    }
+    for (int x = 0; x < W; ++x) {                           // the first and last chroma columns
+      const int cx = x >> 1;
+      if (cx > 0 && cx < last) { x = 2 * last - 1; continue; }
+      const int v0 = col[cx];
+      if (x & 1) row[x] = uint8_t(cx == cw - 1 ? v0 : (3 * v0 + col[cx + 1] + 2) >> 2);
+      else row[x] = uint8_t(cx == 0 ? v0 : (3 * v0 + col[cx - 1] + 1) >> 2);
+    }
+    return;
+  }
+  const int cy = y >> 1;                                    // h2v2: vertical 3:1 first, then horizontal 3:1
+  const int oy = (y & 1) ? (cy + 1 < ch ? cy + 1 : ch - 1) : (cy > 0 ? cy - 1 : 0);
+  const uint8_t* r0 = pl + size_t(cy) * pw;
+  const uint8_t* r1 = pl + size_t(oy) * pw;
+  for (int cx = 0; cx < cw; ++cx) col[cx] = 3 * r0[cx] + r1[cx];
+  const int last = (W - 1) >> 1;
+  for (int cx = 1; cx < last; ++cx) {                       // interior: no edge cases, vectorisable
+    row[2 * cx] = uint8_t((3 * col[cx] + col[cx - 1] + 8) >> 4);
+    row[2 * cx + 1] = uint8_t((3 * col[cx] + col[cx + 1] + 7) >> 4);
+  }
+  for (int x = 0; x < W; ++x) {                             // the first and last chroma columns
+    const int cx = x >> 1;
+    if (cx > 0 && cx < last) { x = 2 * last - 1; continue; }
+    if (x & 1) row[x] = uint8_t(cx == cw - 1 ? (4 * col[cx] + 7) >> 4 : (3 * col[cx] + col[cx + 1] + 7) >> 4);
+    else row[x] = uint8_t(cx == 0 ? (4 * col[cx] + 8) >> 4 : (3 * col[cx] + col[cx - 1] + 8) >> 4);
   }
 }
 
@@ -558,16 +635,20 @@ int decode_one_host(const uint8_t* data, uint64_t len, int H, int W, int channel
   const int cw = (W * in.h[1] + in.hmax - 1) / in.hmax, ch = (H * in.v[1] + in.vmax - 1) / in.vmax;
   const uint8_t* cbp = planes->data() + in.coef_offset[1];
   const uint8_t* crp = planes->data() + in.coef_offset[2];
-  for (int y = 0; y < H; ++y)
-    for (int x = 0; x < W; ++x) {
-      const int yy = yp[size_t(y) * ypw + x];
-      const int cb = chroma_at(cbp, bw[1] * 8, cw, ch, hs, vs, y, x) - 128;
-      const int cr = chroma_at(crp, bw[2] * 8, cw, ch, hs, vs, y, x) - 128;
-      uint8_t* o = out + (size_t(y) * W + x) * 3;
-      o[0] = clamp255(yy + ((91881 * cr + 32768) >> 16));                       // jdcolor.c tables, SCALEBITS = 16
-      o[1] = clamp255(yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
-      o[2] = clamp255(yy + ((116130 * cb + 32768) >> 16));
+  std::vector<int> col(size_t(cw) + 1);
+  std::vector<uint8_t> cbrow(static_cast<size_t>(W)), crrow(static_cast<size_t>(W));
+  for (int y = 0; y < H; ++y) {
+    upsample_row(cbp, bw[1] * 8, cw, ch, hs, vs, y, W, col.data(), cbrow.data());
+    upsample_row(crp, bw[2] * 8, cw, ch, hs, vs, y, W, col.data(), crrow.data());
+    const uint8_t* yrow = yp + size_t(y) * ypw;
+    uint8_t* o = out + size_t(y) * W * 3;
+    for (int x = 0; x < W; ++x, o += 3) {
+      const int yy = yrow[x], cb = cbrow[x], cr = crrow[x];
+      o[0] = clamp255(yy + kYcc.cr_r[cr]);
+      o[1] = clamp255(yy + ((kYcc.cb_g[cb] + kYcc.cr_g[cr]) >> 16));
+      o[2] = clamp255(yy + kYcc.cb_b[cb]);
     }
+  }
   return T2R_OK;
 }
 

@@ -68,6 +68,10 @@ def entropy_decode(images, pinned=True):
 def decode_batch(images, channels=3, device='cuda'):
   """list of JPEG byte strings (same geometry) -> uint8 CUDA tensor [B, H, W, channels]."""
   geom, coef, qt = entropy_decode(images)
+  if geom.ncomp == 3 and geom.hmax == 2 and geom.width <= 4:
+    # libjpeg switches from the fancy to the replicating upsampler when the chroma planes are <= 2 samples wide; the
+    # device kernels implement the fancy filters only, the host decoder covers this corner
+    raise UnsupportedJpeg('chroma planes of a %d pixel wide frame are upsampled by replication' % geom.width)
   dev = torch.device(device)
   if dev.type != 'cuda':
     raise _lib.T2RError('jpeg.decode_batch: the device half has no CPU path (device=%s)' % device)

@@ -247,3 +247,24 @@ def test_host_decoder_rejections_and_parser_fallback():
   bad = [oracle_tfrecord.make_example({'image': data[:300]})]
   with pytest.raises(ValueError):
     tfdata.create_parse_tf_example_fn(spec)(bad)
+
+
+def test_host_decoder_every_small_size():
+  """All frame sizes 1..12 (+ a few around the MCU sizes) x 4:4:4 / 4:2:2 / 4:2:0: edge columns, odd sizes and libjpeg's
+  switch to the replicating upsampler for chroma planes <= 2 samples wide (jdsample.c jinit_upsampler) - host decoder
+  and oracle against libjpeg-turbo; the device decoder hands the narrow-plane corner to the host decoder."""
+  from tensor2robot_b200.utils import jpeg
+  rng = np.random.RandomState(0)
+  sizes = list(range(1, 13)) + [15, 16, 17, 31, 32, 33]
+  for h in sizes:
+    for w in sizes:
+      img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+      for subsampling in (0, 1, 2):
+        data = _encode(img, quality=75, subsampling=subsampling)
+        want = np.asarray(Image.open(io.BytesIO(data)).convert('RGB'))
+        np.testing.assert_array_equal(jpeg.decode_batch_host([data], h, w)[0], want, err_msg=str((h, w, subsampling)))
+        if w <= 5 and h in (1, 2, 9):
+          np.testing.assert_array_equal(oracle_jpeg.decode(data), want, err_msg='oracle ' + str((h, w, subsampling)))
+  narrow = _encode(rng.randint(0, 256, (16, 4, 3)).astype(np.uint8), quality=75, subsampling=2)
+  with pytest.raises(jpeg.UnsupportedJpeg, match='replication'):
+    jpeg.decode_batch([narrow])
