@@ -91,8 +91,10 @@ class TFRecordFile(object):
     self.filename = filename
     size = os.path.getsize(filename)
     self._file = open(filename, 'rb')
-    self._map = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ) if size else b''
-    self._buf = (C.c_char * size).from_buffer_copy(self._map) if size else (C.c_char * 0)()
+    # a private copy-on-write mapping: nothing is read until a record is touched, nothing is ever written back, and
+    # (unlike a read-only mapping) ctypes can take its address without copying the shard
+    self._map = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_COPY) if size else None
+    self._buf = (C.c_char * size).from_buffer(self._map) if size else (C.c_char * 0)()
     self._base = C.addressof(self._buf)
     n = _lib.lib().t2r_tfrecord_index(self._base, size, None, None, 0, 1 if verify_crc else 0)
     if n < 0:
