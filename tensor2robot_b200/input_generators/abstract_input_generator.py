@@ -1,6 +1,7 @@
 """AbstractInputGenerator (input_generators/abstract_input_generator.py:34-160 of the reference)."""
 import abc
 import functools
+import inspect
 
 from tensor2robot_b200.models import model_interface
 from tensor2robot_b200.utils import tensorspec_utils
@@ -47,8 +48,12 @@ class AbstractInputGenerator(abc.ABC):
     self._label_spec, self._out_label_spec = label_spec, out_label_spec
 
   def set_preprocess_fn(self, preprocess_fn):
-    if isinstance(preprocess_fn, functools.partial) and 'mode' not in preprocess_fn.keywords:
-      raise ValueError('The preprocess_fn mode has to be set if a partial function has been passed.')
+    if isinstance(preprocess_fn, functools.partial):
+      if 'mode' not in preprocess_fn.keywords:
+        raise ValueError('The preprocess_fn mode has to be set if a partial function has been passed.')
+    elif 'mode' in inspect.getfullargspec(preprocess_fn).args:
+      raise ValueError('The passed preprocess_fn has an open argument `mode` which should be patched by a closure or '
+                       'with functools.partial.')
     self._preprocess_fn = preprocess_fn
 
   def _assert_specs_initialized(self):

@@ -86,3 +86,21 @@ def test_constant_dataset():
   features, labels = _check_input_generator(default_input_generator.DefaultConstantInputGenerator(constant_value=1,
                                                                                                   batch_size=2))
   assert (np.asarray(features.action) == 1).all() and (np.asarray(labels.reward) == 1).all()
+
+
+def test_abstract_input_generator():
+  """input_generators/abstract_input_generator_test.py:31-49."""
+  import functools
+  from tensor2robot_b200.input_generators import abstract_input_generator
+  from tensor2robot_b200.preprocessors import noop_preprocessor
+  from tensor2robot_b200.utils import mocks
+  with pytest.raises(TypeError):
+    abstract_input_generator.AbstractInputGenerator()              # pylint: disable=abstract-class-instantiated
+  generator = mocks.MockInputGenerator(batch_size=32)
+  preprocessor = noop_preprocessor.NoOpPreprocessor()
+  with pytest.raises(ValueError):
+    generator.set_preprocess_fn(preprocessor.preprocess)           # `mode` is still open
+  with pytest.raises(ValueError):
+    generator.set_preprocess_fn(functools.partial(preprocessor.preprocess, labels=None))   # a partial without `mode`
+  generator.set_preprocess_fn(functools.partial(preprocessor.preprocess, mode='train'))
+  generator.set_preprocess_fn(lambda features, labels: (features, labels))
