@@ -268,3 +268,17 @@ def test_host_decoder_every_small_size():
   narrow = _encode(rng.randint(0, 256, (16, 4, 3)).astype(np.uint8), quality=75, subsampling=2)
   with pytest.raises(jpeg.UnsupportedJpeg, match='replication'):
     jpeg.decode_batch([narrow])
+
+
+def test_luma_only_output_is_the_y_plane():
+  """tf.image.decode_image(channels=1) asks libjpeg for JCS_GRAYSCALE, i.e. the Y plane - not an RGB -> L conversion.
+  PIL reaches the same libjpeg mode through draft('L')."""
+  from tensor2robot_b200.utils import jpeg
+  data = _encode(_picture(40, 56, 5), quality=85, subsampling=2)
+  got = jpeg.decode_batch_host([data], 40, 56, channels=1)[0, ..., 0]
+  im = Image.open(io.BytesIO(data))
+  im.draft('L', im.size)
+  np.testing.assert_array_equal(got, np.asarray(im))
+  np.testing.assert_array_equal(got, oracle_jpeg.decode(data, channels=1)[..., 0])
+  converted = np.asarray(Image.open(io.BytesIO(data)).convert('L'))
+  assert np.abs(got.astype(np.int32) - converted.astype(np.int32)).max() <= 2      # close to, but not, the RGB -> L formula

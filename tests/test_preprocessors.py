@@ -79,3 +79,10 @@ def test_noop_preprocessor_preprocess_fn():
     _preprocess(broken, mock_features_required, mock_labels, flatten=False)
   with pytest.raises(ValueError):
     _preprocess(broken, mock_features_required, mock_labels, flatten=True)
+
+
+def test_abstract_preprocessor_is_abstract():
+  """preprocessors/abstract_preprocessor_test.py."""
+  from tensor2robot_b200.preprocessors import abstract_preprocessor
+  with pytest.raises(TypeError):
+    abstract_preprocessor.AbstractPreprocessor()        # pylint: disable=abstract-class-instantiated
