@@ -281,4 +281,5 @@ def test_luma_only_output_is_the_y_plane():
   np.testing.assert_array_equal(got, np.asarray(im))
   np.testing.assert_array_equal(got, oracle_jpeg.decode(data, channels=1)[..., 0])
   converted = np.asarray(Image.open(io.BytesIO(data)).convert('L'))
-  assert np.abs(got.astype(np.int32) - converted.astype(np.int32)).max() <= 2      # close to, but not, the RGB -> L formula
+  diff = np.abs(got.astype(np.int32) - converted.astype(np.int32))
+  assert 0 < diff.max() <= 8                          # close to, but not, PIL's RGB -> L formula (clipped RGB)
