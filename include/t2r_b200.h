@@ -82,6 +82,30 @@ int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const void* w_dgr
  * zeroes dw once per step.  Requires Cin % 64 == 0, Cout % 64 == 0. */
 int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const void* dy, float* dw,
                          void* stream);
+/* ---- batch-norm operand fusion of the training step ----------------------------------------
+ * In the reference every convolution of a ResNet block reads z = relu(batch_norm(x)) (pre-activation blocks,
+ * layers/film_resnet_model.py:283-340 with batch_norm :50-57), and TensorFlow materialises z.  On B200 the
+ * normalise-and-rectify pass is pure HBM traffic (4 B per element forward, 4 B for the reduction of the backward),
+ * so the kernels below take the RAW tensor x plus the per-channel affine scale[c] = gamma*invstd, shift[c] =
+ * beta - mean*scale (t2r_bn_finalize) and never write z:
+ *   fprop_bnrelu : y = conv1x1(relu(scale*x + shift), w) (+residual); the A tile is rewritten in shared memory.
+ *   wgrad_bnrelu : dw += dy^T * relu(scale*x + shift), same rewrite of the X tiles.
+ *   dgrad_bnrelu : g = conv_transpose(dy, w) * [scale*x + shift > 0] (any geometry), and the epilogue accumulates
+ *                  red[c] += sum g, red[Cin + c] += sum g*x (fp64 [2*Cin], caller zeroes): exactly what
+ *                  t2r_bn_backward's reduction pass computes, so t2r_bn_backward_presummed can follow directly.
+ *                  accumulate != 0: g += ... and the reduction then covers the COMPLETE sum (call it last, and
+ *                  use plain t2r_conv2d_dgrad for the earlier contributions).  Launches the epilogue cannot fuse
+ *                  (halo kernel, accumulation) run the stand-alone reduction pass instead: same results.
+ * Values are bit-identical to t2r_bn_apply + t2r_conv2d_* on the materialised z (same fmaf, same bf16 rounding).
+ * fprop / wgrad require KH = KW = 1 and no padding (zero padding must stay zero after the affine map). */
+int32_t t2r_conv2d_fprop_bnrelu(const T2RConvDesc* d, const void* x_raw, const float* bn_scale,
+                                const float* bn_shift, const void* w_ohwi, const void* residual, void* y,
+                                double* stats, void* stream);
+int32_t t2r_conv2d_wgrad_bnrelu(const T2RConvDesc* d, const void* x_raw, const float* bn_scale,
+                                const float* bn_shift, const void* dy, float* dw, void* stream);
+int32_t t2r_conv2d_dgrad_bnrelu(const T2RConvDesc* d, const void* dy, const void* w_dgrad, const void* x_raw,
+                                const float* bn_scale, const float* bn_shift, void* g, int32_t accumulate,
+                                double* red, void* stream);
 /* fp32 master OHWI -> bf16 OHWI (w_fprop) and bf16 [Cin][taps][Cout] (w_dgrad; may be NULL). */
 int32_t t2r_pack_weights(const float* w, void* w_fprop, void* w_dgrad, int32_t Cout,
                          int32_t taps, int32_t Cin, void* stream);
@@ -231,6 +255,14 @@ int32_t t2r_bn_backward(const void* dy, const void* x, const void* dres, void* d
                         int32_t C, const float* gamma, const float* mean, const float* invstd,
                         const float* scale, const float* shift, int32_t relu, double* red,
                         float* dgamma, float* dbeta, void* stream);
+/* Second half of t2r_bn_backward for callers that already hold red[c] = sum dz, red[C + c] = sum dz*x with
+ * dz = dy*[scale*x + shift > 0] (t2r_conv2d_dgrad_bnrelu): dgamma / dbeta from red, then
+ * dx = scale*dz - (scale*dgamma*invstd/rows)*(x - mean) - scale*dbeta/rows (+ dres).  The mask is re-applied
+ * (idempotent), so dy may hold either the masked or the unmasked gradient. */
+int32_t t2r_bn_backward_presummed(const void* dy, const void* x, const void* dres, void* dx, int64_t rows,
+                                  int32_t C, const float* mean, const float* invstd, const float* scale,
+                                  const float* shift, int32_t relu, const double* red, float* dgamma,
+                                  float* dbeta, void* stream);
 
 /* Backward of y = relu?((1 + film_gamma[n,c]) * bn(x) + film_beta[n,c]) (FiLM-conditioned batch norm,
  * layers/film_resnet_model.py:108-115): film fp32 [N][2C] (gamma part then beta part), dfilm same shape

@@ -61,6 +61,9 @@ _PROTOS = {
     't2r_conv2d_fprop_stats': (_I32, [_CD, _P, _P, _P, _P, _P, _P, _P]),
     't2r_conv2d_dgrad': (_I32, [_CD, _P, _P, _P, _I32, _P]),
     't2r_conv2d_wgrad': (_I32, [_CD, _P, _P, _P, _P]),
+    't2r_conv2d_fprop_bnrelu': (_I32, [_CD, _P, _P, _P, _P, _P, _P, _P, _P]),
+    't2r_conv2d_wgrad_bnrelu': (_I32, [_CD, _P, _P, _P, _P, _P, _P]),
+    't2r_conv2d_dgrad_bnrelu': (_I32, [_CD, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
     't2r_pack_weights': (_I32, [_P, _P, _P, _I32, _I32, _I32, _P]),
     't2r_im2col_small_cin': (_I32, [_CD, _P, _P, _I32, _P]),
     't2r_pad_nhwc3_c4': (_I32, [_P, _P] + [_I32] * 7 + [_P]),
@@ -86,6 +89,7 @@ _PROTOS = {
     't2r_bn_infer_params': (_I32, [_I32, _P, _P, _P, _P, _F, _P, _P, _P]),
     't2r_bn_apply': (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P]),
     't2r_bn_backward': (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    't2r_bn_backward_presummed': (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     't2r_spatial_softmax_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_spatial_softmax_bwd': (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_bn_film_backward': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),

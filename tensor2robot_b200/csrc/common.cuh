@@ -255,5 +255,52 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// v[j] = value at (row = lane, column j) of a 32 x 32 tile held one row per lane.  Returns, in lane l, the
+// sum of column l over the 32 rows: a butterfly that halves the number of live values per step
+// (16 + 8 + 4 + 2 + 1 = 31 shuffles), all register indices static.  Destroys v.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int n = 16; n >= 1; n >>= 1) {
+    const bool up = (lane & n) != 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const float send = up ? v[j] : v[j + n];
+      const float keep = up ? v[j + n] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+    }
+  }
+  return v[0];
+}
+
+// In-place z = relu(sc * x + sh) on 16-byte pieces of a bf16 tile that TMA wrote with SWIZZLE_128B (row r of 64
+// channels at r * 128 B, logical 16-byte chunk c of the row at ((c ^ (r & 7)) * 16)): the batch-norm apply of the
+// operand-fused convolutions.  `piece` is the shared address of the caller's first piece, `n` pieces `step` bytes
+// apart (the caller picks rows that share r & 7, so the chunk position is the same for all of them); sc / sh are the
+// 8 channels of the caller's logical chunk.  Arithmetic and rounding are those of bn_apply_rows_kernel (norm.cu).
+__device__ __forceinline__ void bnrelu_pieces_inplace(uint32_t piece, int n, uint32_t step, const float (&sc)[8],
+                                                      const float (&sh)[8]) {
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    uint4 q;
+    const uint32_t a = piece + uint32_t(i) * step;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
+    const float f0 = fmaxf(fmaf(bf16_lo(q.x), sc[0], sh[0]), 0.f), f1 = fmaxf(fmaf(bf16_hi(q.x), sc[1], sh[1]), 0.f);
+    const float f2 = fmaxf(fmaf(bf16_lo(q.y), sc[2], sh[2]), 0.f), f3 = fmaxf(fmaf(bf16_hi(q.y), sc[3], sh[3]), 0.f);
+    const float f4 = fmaxf(fmaf(bf16_lo(q.z), sc[4], sh[4]), 0.f), f5 = fmaxf(fmaf(bf16_hi(q.z), sc[5], sh[5]), 0.f);
+    const float f6 = fmaxf(fmaf(bf16_lo(q.w), sc[6], sh[6]), 0.f), f7 = fmaxf(fmaf(bf16_hi(q.w), sc[7], sh[7]), 0.f);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(f0, f1)), "r"(pack_bf16(f2, f3)),
+                 "r"(pack_bf16(f4, f5)), "r"(pack_bf16(f6, f7))
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA stores, tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 }  // namespace t2r
 #endif  // __CUDACC__

@@ -22,6 +22,17 @@ int make_phase_maps(CUtensorMap* maps, const void* x, int N, int H, int W, int C
 
 constexpr int kMaxStatChannels = 2048;
 
+// Internal flag bits above the public T2R_EPI_* ones: batch-norm fusions of the training step.
+//   kEpiBnBwd  (data gradients): the epilogue turns the gradient w.r.t. z = relu(bn_scale * x + bn_shift) into
+//              g = dz * [z > 0] (x = bn_x, the tensor the batch norm normalised, same shape / strides as the
+//              output) and accumulates stats[c] += sum g, stats[Cout + c] += sum g * x: the reduction pass of
+//              the batch-norm backward (bn_bwd_reduce_kernel, norm.cu) without its two HBM reads.
+//   kProBnRelu (1x1 fprop): the activation tensor map points at the RAW tensor x and four extra warps rewrite
+//              every landed A tile in shared memory as relu(bn_scale * x + bn_shift) before the MMA reads it: the
+//              batch-norm apply pass (bn_apply_rows_kernel) without writing / re-reading z.
+constexpr int kEpiBnBwd = 1 << 8;
+constexpr int kProBnRelu = 1 << 9;
+
 struct IgemmParams {
   CUtensorMap tmap_a[4];
   CUtensorMap tmap_b;
@@ -40,6 +51,9 @@ struct IgemmParams {
   const float* bias;
   int flags;
   double* stats;  // optional fp64 [2*Cout]: per-channel sum / sum of squares of the bf16 output (fused bn_stats)
+  const void* bn_x;        // kEpiBnBwd: the normalised tensor, addressed like `out`
+  const float* bn_scale;   // kEpiBnBwd: [Cout] of the output view; kProBnRelu: [Cin]
+  const float* bn_shift;
 };
 
 // The tap-table kernel with a TMA epilogue (conv_igemm_tma.cu): residual tile in by TMA, output tile
@@ -71,6 +85,9 @@ struct HaloRequest {
   const float* bias;
   int flags;
   double* stats;       // optional fused bn_stats output, fp64 [2*Cout]
+  const void* bn_x;    // kEpiBnBwd operands (see IgemmParams)
+  const float* bn_scale;
+  const float* bn_shift;
 };
 bool conv_halo_eligible(int stride, int n_taps, int k_channels, int n_channels);
 int conv_halo_launch(const HaloRequest& r, cudaStream_t stream);
@@ -78,6 +95,11 @@ int conv_halo_launch(const HaloRequest& r, cudaStream_t stream);
 // Weight gradient of stride-1 KxK convolutions with 64 input channels through the halo kernel
 // (conv_wgrad_halo.cu).
 bool conv_wgrad_halo_eligible(int stride, int n_taps, int Cin, int Cout);
+// Reduction pass of the batch-norm backward (norm.cu): red[c] += sum dz, red[C + c] += sum dz * x with
+// dz = dy * [scale * x + shift > 0] when relu; red is fp64 [2C], caller-zeroed.
+int bn_bwd_reduce_launch(const void* dy, const void* x, long long rows, int C, const float* mean, const float* invstd,
+                         const float* scale, const float* shift, int relu, double* red, cudaStream_t stream);
+
 int conv_wgrad_halo_launch(const void* x, const void* dy, float* dw, int N, int H, int W, int Ho, int Wo, int Cout,
                            const ConvTap* taps, int n_taps, cudaStream_t stream);
 

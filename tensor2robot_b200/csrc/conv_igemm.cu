@@ -41,8 +41,10 @@ struct IgemmCfg {
       kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStoreStageBytes + kStatBytes;
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
+// kPro: four extra warps (12..15) apply relu(bn_scale * x + bn_shift) to every landed A tile in place
+// (kProBnRelu, conv_common.cuh); the MMA warp then waits on the `ready` barriers instead of `full`.
+template <int BLOCK_N, bool kPro>
+__global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 5 + s); };
   const uint32_t store_stage_base = bar_base + 256u;
   float* stat_acc = reinterpret_cast<float*>(smem_raw + (store_stage_base + Cfg::kStoreStageBytes - smem_u32(smem_raw)));
   volatile uint32_t* tmem_ptr_gen =
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      if (kPro) mbar_init(ready_bar(s), 4);  // one arrival per transformer warp
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(kPro ? ready_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint64_t so = uint64_t(uint32_t(stage) * uint32_t(Cfg::kStageBytes >> 4));
 #pragma unroll
@@ -162,6 +166,32 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         }
       }
     }
+  } else if (kPro && warp >= 12) {
+    // ===================== operand transform: 4 warps =====================
+    // Thread t owns the logical 16-byte chunk (t & 7) = 8 channels of rows (t >> 3) + 16 i of the 128-row A tile:
+    // a quarter warp covers one full 128-byte row (no bank conflicts) and all of a thread's rows share r & 7.
+    const int t = threadIdx.x - 384;
+    const uint32_t j = uint32_t(t) & 7u, r0 = uint32_t(t) >> 3;
+    const uint32_t piece0 = r0 * 128u + ((j ^ (r0 & 7u)) << 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tp = 0; tp < p.n_taps; ++tp)
+        for (int c = 0; c < p.chunks_per_tap; ++c) {
+          float sc[8], sh[8];
+          load8(p.bn_scale + c * 64 + j * 8, sc);
+          load8(p.bn_shift + c * 64 + j * 8, sh);
+          mbar_wait(full_bar(stage), phase);
+          bnrelu_pieces_inplace(smem_base + stage * Cfg::kStageBytes + piece0, 8, 2048u, sc, sh);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(stage));
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps =====================
     // Warp w may read TMEM lanes 32*(w%4)..+31 (one output pixel per thread); the two warpgroups
@@ -178,6 +208,9 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
     const int tw = row - th * p.TW;
     const bool out_f32 = (p.flags & T2R_EPI_OUT_F32) != 0;
     const bool has_res = (p.flags & T2R_EPI_RESIDUAL) != 0;
+    const bool bnbwd = (p.flags & kEpiBnBwd) != 0;   // never together with a residual
+    const bool has_aux = has_res || bnbwd;
+    const __nv_bfloat16* aux = static_cast<const __nv_bfloat16*>(bnbwd ? p.bn_x : p.residual);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -202,9 +235,9 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         rvalid[i] = (roh < p.Ho) && (row_w < p.Wo);
         roff[i] = img * p.os_n + roh * p.os_h + row_w * p.os_w;
       }
-      uint4 rnext[4];
-      if (has_res && valid && ch0 < p.Cout) {
-        const uint4* r = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch0);
+      uint4 rnext[4] = {};
+      if (has_aux && valid && ch0 < p.Cout) {
+        const uint4* r = reinterpret_cast<const uint4*>(aux + pix_off + ch0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rnext[j] = r[j];
       }
@@ -216,8 +249,8 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         uint4 rcur[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-        if (c + 1 < kChunks && has_res && valid && ch + 32 < p.Cout) {
-          const uint4* r = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix_off + ch + 32);
+        if (c + 1 < kChunks && has_aux && valid && ch + 32 < p.Cout) {
+          const uint4* r = reinterpret_cast<const uint4*>(aux + pix_off + ch + 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rnext[j] = r[j];
         }
@@ -248,6 +281,37 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           if (p.flags & T2R_EPI_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (bnbwd) {
+            // g = dz * [scale * x + shift > 0], rounded to bf16 like the stored value; column sums of g * x
+            // (those of g itself come out of the staged tile below, as for the fused bn_stats)
+            float xv[32];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = rcur[j];
+              xv[8 * j + 0] = bf16_lo(q.x); xv[8 * j + 1] = bf16_hi(q.x);
+              xv[8 * j + 2] = bf16_lo(q.y); xv[8 * j + 3] = bf16_hi(q.y);
+              xv[8 * j + 4] = bf16_lo(q.z); xv[8 * j + 5] = bf16_hi(q.z);
+              xv[8 * j + 6] = bf16_lo(q.w); xv[8 * j + 7] = bf16_hi(q.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.bn_scale + ch + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.bn_shift + ch + j));
+              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+              for (int i = 0; i < 4; i += 2) {
+                const float g0 = (valid && fmaf(xv[j + i], scv[i], shv[i]) > 0.f) ? f[j + i] : 0.f;
+                const float g1 = (valid && fmaf(xv[j + i + 1], scv[i + 1], shv[i + 1]) > 0.f) ? f[j + i + 1] : 0.f;
+                const uint32_t pk = pack_bf16(g0, g1);
+                f[j + i] = bf16_lo(pk);
+                f[j + i + 1] = bf16_hi(pk);
+                xv[j + i] *= f[j + i];
+                xv[j + i + 1] *= f[j + i + 1];
+              }
+            }
+            const float sgx = warp_transpose_sum32(xv, lane);
+            atomicAdd(stat_acc + p.Cout + ch + lane, sgx);
           }
           if (out_f32) {
             float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix_off + ch);
@@ -285,7 +349,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
                 s2 = fmaf(v, v, s2);
               }
               atomicAdd(stat_acc + ch + lane, s1);
-              atomicAdd(stat_acc + p.Cout + ch + lane, s2);
+              if (!bnbwd) atomicAdd(stat_acc + p.Cout + ch + lane, s2);
             }
             const uint32_t jj = uint32_t(lane) & 3u;
 #pragma unroll
@@ -388,20 +452,24 @@ int make_phase_maps(CUtensorMap* maps, const void* x, int N, int H, int W, int C
 
 static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int BLOCK_N>
-static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
+template <int BLOCK_N, bool kPro>
+static int launch_igemm_v(const IgemmParams& p, cudaStream_t stream) {
   using Cfg = IgemmCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>,
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, kPro>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = std::min(p.total_tiles, num_sms());
-  conv_igemm_kernel<BLOCK_N><<<grid, 384, Cfg::kSmemBytes, stream>>>(p);
+  conv_igemm_kernel<BLOCK_N, kPro><<<grid, kPro ? 512 : 384, Cfg::kSmemBytes, stream>>>(p);
   T2R_LAUNCH_OK();
   return T2R_OK;
+}
+template <int BLOCK_N>
+static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
+  return (p.flags & kProBnRelu) ? launch_igemm_v<BLOCK_N, true>(p, stream) : launch_igemm_v<BLOCK_N, false>(p, stream);
 }
 
 // Tile width and epilogue flavour.  bf16 outputs with N <= 128 use the TMA epilogue
@@ -462,9 +530,31 @@ extern "C" int32_t t2r_conv2d_fprop(const T2RConvDesc* d, const void* x, const v
   return t2r_conv2d_fprop_stats(d, x, w, bias, residual, y, nullptr, stream);
 }
 
+static int32_t fprop_impl(const T2RConvDesc* d, const void* x, const float* bn_scale, const float* bn_shift,
+                          const void* w, const float* bias, const void* residual, void* y, double* stats,
+                          void* stream);
+
 extern "C" int32_t t2r_conv2d_fprop_stats(const T2RConvDesc* d, const void* x, const void* w,
                                           const float* bias, const void* residual, void* y,
                                           double* stats, void* stream) {
+  return fprop_impl(d, x, nullptr, nullptr, w, bias, residual, y, stats, stream);
+}
+
+extern "C" int32_t t2r_conv2d_fprop_bnrelu(const T2RConvDesc* d, const void* x_raw, const float* bn_scale,
+                                           const float* bn_shift, const void* w, const void* residual, void* y,
+                                           double* stats, void* stream) {
+  T2R_CHECK_ARG(d != nullptr && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc size");
+  T2R_CHECK_ARG(bn_scale && bn_shift, "conv2d_fprop_bnrelu: null scale / shift");
+  T2R_CHECK_ARG(d->KH == 1 && d->KW == 1 && d->pad_top == 0 && d->pad_left == 0,
+                "conv2d_fprop_bnrelu: only 1x1 convolutions without padding fuse the batch-norm apply "
+                "(zero padding would have to stay zero after the affine map)");
+  T2R_CHECK_ARG(!(d->flags & (T2R_EPI_OUT_F32 | T2R_EPI_BIAS)), "conv2d_fprop_bnrelu: bf16 output without bias only");
+  return fprop_impl(d, x_raw, bn_scale, bn_shift, w, nullptr, residual, y, stats, stream);
+}
+
+static int32_t fprop_impl(const T2RConvDesc* d, const void* x, const float* bn_scale, const float* bn_shift,
+                          const void* w, const float* bias, const void* residual, void* y, double* stats,
+                          void* stream) {
   if (int rc = check_desc(d)) return rc;
   T2R_CHECK_ARG(x && w && y, "null pointer");
   T2R_CHECK_ARG(stats == nullptr || (!(d->flags & T2R_EPI_OUT_F32) && d->Cout <= kMaxStatChannels),
@@ -517,13 +607,39 @@ extern "C" int32_t t2r_conv2d_fprop_stats(const T2RConvDesc* d, const void* x, c
   p.os_h = (long long)d->Wo * d->Cout;
   p.os_n = (long long)d->Ho * d->Wo * d->Cout;
   p.out = y; p.residual = residual; p.bias = bias; p.flags = d->flags; p.stats = stats;
+  if (bn_scale != nullptr) {
+    p.flags |= kProBnRelu;
+    p.bn_scale = bn_scale;
+    p.bn_shift = bn_shift;
+  }
   return dispatch_igemm(p, block_n, tma, static_cast<cudaStream_t>(stream));
 }
 
+static int32_t dgrad_impl(const T2RConvDesc* d, const void* dy, const void* w_dgrad, void* dx, int32_t accumulate,
+                          const void* bn_x, const float* bn_scale, const float* bn_shift, double* red, void* stream);
+
 extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const void* w_dgrad,
                                     void* dx, int32_t accumulate, void* stream) {
+  return dgrad_impl(d, dy, w_dgrad, dx, accumulate, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int32_t t2r_conv2d_dgrad_bnrelu(const T2RConvDesc* d, const void* dy, const void* w_dgrad,
+                                           const void* x_raw, const float* bn_scale, const float* bn_shift, void* g,
+                                           int32_t accumulate, double* red, void* stream) {
+  T2R_CHECK_ARG(x_raw && bn_scale && bn_shift && red, "conv2d_dgrad_bnrelu: null pointer");
+  return dgrad_impl(d, dy, w_dgrad, g, accumulate, x_raw, bn_scale, bn_shift, red, stream);
+}
+
+static int32_t dgrad_impl(const T2RConvDesc* d, const void* dy, const void* w_dgrad, void* dx, int32_t accumulate,
+                          const void* bn_x, const float* bn_scale, const float* bn_shift, double* red, void* stream) {
   if (int rc = check_desc(d)) return rc;
   T2R_CHECK_ARG(dy && w_dgrad && dx, "null pointer");
+  // Batch-norm backward fusion: the epilogues mask and reduce while they write (kEpiBnBwd) unless the launch
+  // accumulates into dx (the mask would have to cover the sum) or runs on the halo kernel; those cases run the
+  // plain data gradient followed by the stand-alone reduction pass over (dx, x).
+  static const bool no_bnbwd = std::getenv("T2R_DISABLE_BNBWD_EPI") != nullptr;
+  const bool want_bn = bn_x != nullptr;
+  bool fuse_bn = want_bn && !no_bnbwd && !accumulate && d->Cin <= kMaxStatChannels;
   const int s = d->stride;
   const int taps_total = d->KH * d->KW;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -551,8 +667,10 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
       p.n_taps = t;
       bool tma = false;
       const int block_n = pick_block_n(d->Cin, (long long)t * d->Cout, 0, &tma);
-      char* out = static_cast<char*>(dx) + (size_t(ph) * d->W + pw) * d->Cin * 2;
+      const size_t view_off = (size_t(ph) * d->W + pw) * d->Cin * 2;
+      char* out = static_cast<char*>(dx) + view_off;
       if (conv_halo_eligible(s, t, d->Cout, d->Cin)) {
+        fuse_bn = false;
         HaloRequest r;
         memset(&r, 0, sizeof(r));
         r.x = dy; r.N = d->N; r.H = d->Ho; r.W = d->Wo; r.C = d->Cout;
@@ -583,6 +701,13 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
       p.out = out;
       p.residual = accumulate ? out : nullptr;
       p.flags = accumulate ? T2R_EPI_RESIDUAL : 0;
+      if (fuse_bn) {
+        p.flags |= kEpiBnBwd;
+        p.bn_x = static_cast<const char*>(bn_x) + view_off;
+        p.bn_scale = bn_scale;
+        p.bn_shift = bn_shift;
+        p.stats = red;
+      }
       if (t == 0) {
         // No tap reaches this phase (e.g. 1x1 stride-2): the gradient there is zero.
         if (!accumulate) {
@@ -596,6 +721,9 @@ extern "C" int32_t t2r_conv2d_dgrad(const T2RConvDesc* d, const void* dy, const 
       }
       if (int rc = dispatch_igemm(p, block_n, tma, st)) return rc;
     }
+  if (want_bn && !fuse_bn)
+    return bn_bwd_reduce_launch(dx, bn_x, (long long)d->N * d->H * d->W, d->Cin, nullptr, nullptr, bn_scale, bn_shift,
+                                1, red, st);
   return T2R_OK;
 }
 

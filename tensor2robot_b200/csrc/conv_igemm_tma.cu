@@ -46,8 +46,9 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_constant__ IgemmTmaParams pp) {
+// kPro: see conv_igemm.cu (warps 12..15 rewrite each landed A tile as relu(bn_scale * x + bn_shift)).
+template <int BLOCK_N, bool kPro>
+__global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(const __grid_constant__ IgemmTmaParams pp) {
   using Cfg = IgemmTmaCfg<BLOCK_N>;
   const IgemmParams& p = pp.g;
   extern __shared__ uint8_t smem_raw[];
@@ -62,13 +63,15 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
   auto cfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 4 + s); };
   auto cempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 6 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::kStages + 8);
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 9 + s); };
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
   float* stat_acc = reinterpret_cast<float*>(smem_raw + (stat_base - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool has_res = (p.flags & T2R_EPI_RESIDUAL) != 0;
+  const bool bnbwd = (p.flags & kEpiBnBwd) != 0;  // the "residual" tile is then the normalised tensor x
+  const bool has_res = (p.flags & T2R_EPI_RESIDUAL) != 0 || bnbwd;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmap_a[i]);
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      if (kPro) mbar_init(ready_bar(s), 4);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(kPro ? ready_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint64_t so = uint64_t(uint32_t(stage) * uint32_t(Cfg::kStageBytes >> 4));
 #pragma unroll
@@ -196,6 +200,30 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
           aphase ^= 1u;
         }
       }
+    }
+  } else if (kPro && warp >= 12) {
+    // ===================== operand transform: 4 warps (see conv_igemm.cu) =====================
+    const int t = threadIdx.x - 384;
+    const uint32_t j = uint32_t(t) & 7u, r0 = uint32_t(t) >> 3;
+    const uint32_t piece0 = r0 * 128u + ((j ^ (r0 & 7u)) << 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tp = 0; tp < p.n_taps; ++tp)
+        for (int c = 0; c < p.chunks_per_tap; ++c) {
+          float sc[8], sh[8];
+          load8(p.bn_scale + c * 64 + j * 8, sc);
+          load8(p.bn_shift + c * 64 + j * 8, sh);
+          mbar_wait(full_bar(stage), phase);
+          bnrelu_pieces_inplace(smem_base + stage * Cfg::kStageBytes + piece0, 8, 2048u, sc, sh);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(stage));
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps =====================
@@ -248,7 +276,41 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
           }
         }
         const uint32_t chunk0 = uint32_t(colc) >> 3;          // first 16-byte chunk of these 32 columns
-        if (has_res) {
+        if (bnbwd) {
+          // g = dz * [scale * x + shift > 0] (x = the tile warp 3 loaded), rounded to bf16 like the stored value;
+          // column sums of g * x by shuffles, those of g from the staged tile below (as the fused bn_stats)
+          float xv[32];
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(crow + (((chunk0 + j) ^ rsw) << 4))
+                         : "memory");
+            xv[8 * j + 0] = bf16_lo(q.x); xv[8 * j + 1] = bf16_hi(q.x);
+            xv[8 * j + 2] = bf16_lo(q.y); xv[8 * j + 3] = bf16_hi(q.y);
+            xv[8 * j + 4] = bf16_lo(q.z); xv[8 * j + 5] = bf16_hi(q.z);
+            xv[8 * j + 6] = bf16_lo(q.w); xv[8 * j + 7] = bf16_hi(q.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.bn_scale + ch + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.bn_shift + ch + j));
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+              const float g0 = (valid && fmaf(xv[j + i], scv[i], shv[i]) > 0.f) ? f[j + i] : 0.f;
+              const float g1 = (valid && fmaf(xv[j + i + 1], scv[i + 1], shv[i + 1]) > 0.f) ? f[j + i + 1] : 0.f;
+              const uint32_t pk = pack_bf16(g0, g1);
+              f[j + i] = bf16_lo(pk);
+              f[j + i + 1] = bf16_hi(pk);
+              xv[j + i] *= f[j + i];
+              xv[j + i + 1] *= f[j + i + 1];
+            }
+          }
+          const float sgx = warp_transpose_sum32(xv, lane);
+          atomicAdd(stat_acc + p.Cout + ch + lane, sgx);
+        } else if (has_res) {
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) {
             uint4 q;
@@ -290,7 +352,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
             s2 = fmaf(x, x, s2);
           }
           atomicAdd(stat_acc + ch + lane, s1);
-          atomicAdd(stat_acc + p.Cout + ch + lane, s2);
+          if (!bnbwd) atomicAdd(stat_acc + p.Cout + ch + lane, s2);
         }
       }
       // accumulator stage is free for the MMA of tile i+2
@@ -336,19 +398,23 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_tma_kernel(const __grid_con
   }
 }
 
-template <int BLOCK_N>
-static int launch(const IgemmTmaParams& pp, cudaStream_t stream) {
+template <int BLOCK_N, bool kPro>
+static int launch_v(const IgemmTmaParams& pp, cudaStream_t stream) {
   using Cfg = IgemmTmaCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_tma_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_tma_kernel<BLOCK_N, kPro>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = std::min(pp.g.total_tiles, num_sms());
-  conv_igemm_tma_kernel<BLOCK_N><<<grid, 384, Cfg::kSmemBytes, stream>>>(pp);
+  conv_igemm_tma_kernel<BLOCK_N, kPro><<<grid, kPro ? 512 : 384, Cfg::kSmemBytes, stream>>>(pp);
   T2R_LAUNCH_OK();
   return T2R_OK;
+}
+template <int BLOCK_N>
+static int launch(const IgemmTmaParams& pp, cudaStream_t stream) {
+  return (pp.g.flags & kProBnRelu) ? launch_v<BLOCK_N, true>(pp, stream) : launch_v<BLOCK_N, false>(pp, stream);
 }
 
 int conv_igemm_tma_launch(const IgemmParams& p, int block_n, cudaStream_t stream) {
@@ -361,7 +427,8 @@ int conv_igemm_tma_launch(const IgemmParams& p, int block_n, cudaStream_t stream
   uint64_t strides[3] = {uint64_t(p.os_w) * 2, uint64_t(p.os_h) * 2, uint64_t(p.os_n) * 2};
   uint32_t box[4] = {64, uint32_t(p.TW), uint32_t(p.TH), 1};
   if (encode_tmap_bf16(&pp.tmap_c, p.out, 4, dims, strides, box) != 0) return T2R_ERR_CUDA;
-  if (encode_tmap_bf16(&pp.tmap_r, p.residual ? p.residual : p.out, 4, dims, strides, box) != 0) return T2R_ERR_CUDA;
+  const void* aux = (p.flags & kEpiBnBwd) ? p.bn_x : p.residual;
+  if (encode_tmap_bf16(&pp.tmap_r, aux ? aux : p.out, 4, dims, strides, box) != 0) return T2R_ERR_CUDA;
   return block_n == 128 ? launch<128>(pp, stream) : launch<64>(pp, stream);
 }
 

@@ -44,6 +44,10 @@ struct WgradParams {
   int Ktot;            // taps * Cin
   int Cout;
   float* dw;
+  // kPro: x is the RAW tensor a batch norm normalised; the (otherwise idle) epilogue warps rewrite every landed
+  // X tile as relu(bn_scale * x + bn_shift) before the MMA reads it (see kProBnRelu, conv_common.cuh)
+  const float* bn_scale;
+  const float* bn_shift;
 };
 
 template <int BLOCK_N>
@@ -55,10 +59,10 @@ struct WgradCfg {
   static constexpr int kXStages = BLOCK_N == 64 ? 10 : (BLOCK_N == 128 ? 8 : 6);
   static constexpr int kDyStages = 3;
   static constexpr int kMaxGroups = 512 / BLOCK_N;
-  static constexpr int kSmemBytes = kXStages * kXBytes + kDyStages * kDyBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kXStages * kXBytes + kDyStages * kDyBytes + 1024 + 512;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kPro>
 __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -71,6 +75,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
   auto dempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kXStages + Cfg::kDyStages + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::kXStages + 2 * Cfg::kDyStages);
   const uint32_t tmem_ptr_addr = tfull_bar + 8u;
+  auto ready_bar = [&](int s) { return tfull_bar + 16u + 8u * s; };
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
@@ -85,6 +90,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     for (int s = 0; s < Cfg::kXStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      if (kPro) mbar_init(ready_bar(s), 4);
     }
     for (int s = 0; s < Cfg::kDyStages; ++s) {
       mbar_init(dfull_bar(s), 1);
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
         mbar_wait(dfull_bar(ds), dphase);
         const uint64_t bs = b_base + uint64_t(uint32_t(ds) * uint32_t(Cfg::kDyBytes >> 4));
         for (int g = g0; g < g1; ++g) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(kPro ? ready_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint64_t as_ = a_base + uint64_t(uint32_t(stage) * uint32_t(Cfg::kXBytes >> 4));
           const uint32_t d_tmem = tmem_base + (g - g0) * BLOCK_N;
@@ -201,6 +207,34 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
   } else if (warp >= 4) {
     const int quad = warp - 4;
     const int row = quad * 32 + lane;
+    if (kPro) {
+      // operand transform: thread t works on tile h = t / 64 of the stage (64 rows x 128 B), logical chunk t & 7 of
+      // rows ((t & 63) >> 3) + 8 i: a quarter warp covers one full row, a thread's rows share r & 7
+      const int t = threadIdx.x - 128;
+      const int h = t >> 6;
+      const uint32_t j = uint32_t(t) & 7u, r0 = (uint32_t(t) & 63u) >> 3;
+      const uint32_t piece0 = uint32_t(h) * Cfg::kTileBytes + r0 * 128u + ((j ^ r0) << 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt0; pt < pt1; ++pt)
+        for (int g = g0; g < g1; ++g) {
+          int slot = 2 * g + h;
+          if (slot >= p.n_slots) slot = p.n_slots - 1;
+          const int c = slot % p.chunks_per_tap;
+          float sc[8], sh[8];
+          load8(p.bn_scale + c * 64 + j * 8, sc);
+          load8(p.bn_shift + c * 64 + j * 8, sh);
+          mbar_wait(full_bar(stage), phase);
+          bnrelu_pieces_inplace(smem_base + stage * Cfg::kXBytes + piece0, 8, 1024u, sc, sh);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(stage));
+          if (++stage == Cfg::kXStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+    }
     if (pt1 > pt0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
@@ -238,7 +272,10 @@ static int launch_wgrad(WgradParams& p, cudaStream_t stream) {
   using Cfg = WgradCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    T2R_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N>,
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
     configured = true;
@@ -254,7 +291,10 @@ static int launch_wgrad(WgradParams& p, cudaStream_t stream) {
   ks = std::max(1, std::min(ks, std::max(1, p.total_ptiles / 4)));
   p.ksplits = ks;
   const int grid = base_items * ks;
-  conv_wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  if (p.bn_scale != nullptr)
+    conv_wgrad_kernel<BLOCK_N, true><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  else
+    conv_wgrad_kernel<BLOCK_N, false><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
@@ -263,8 +303,25 @@ static int launch_wgrad(WgradParams& p, cudaStream_t stream) {
 
 using namespace t2r;
 
+static int32_t wgrad_impl(const T2RConvDesc* d, const void* x, const float* bn_scale, const float* bn_shift,
+                          const void* dy, float* dw, void* stream);
+
 extern "C" int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const void* dy,
                                     float* dw, void* stream) {
+  return wgrad_impl(d, x, nullptr, nullptr, dy, dw, stream);
+}
+
+extern "C" int32_t t2r_conv2d_wgrad_bnrelu(const T2RConvDesc* d, const void* x_raw, const float* bn_scale,
+                                           const float* bn_shift, const void* dy, float* dw, void* stream) {
+  T2R_CHECK_ARG(d != nullptr && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc size");
+  T2R_CHECK_ARG(bn_scale && bn_shift, "conv2d_wgrad_bnrelu: null scale / shift");
+  T2R_CHECK_ARG(d->KH == 1 && d->KW == 1 && d->pad_top == 0 && d->pad_left == 0,
+                "conv2d_wgrad_bnrelu: only 1x1 convolutions without padding fuse the batch-norm apply");
+  return wgrad_impl(d, x_raw, bn_scale, bn_shift, dy, dw, stream);
+}
+
+static int32_t wgrad_impl(const T2RConvDesc* d, const void* x, const float* bn_scale, const float* bn_shift,
+                          const void* dy, float* dw, void* stream) {
   T2R_CHECK_ARG(d != nullptr && d->struct_size == sizeof(T2RConvDesc), "bad T2RConvDesc size");
   T2R_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
   T2R_CHECK_ARG(d->KH * d->KW <= kMaxTaps, "filter too large");
@@ -302,6 +359,8 @@ extern "C" int32_t t2r_conv2d_wgrad(const T2RConvDesc* d, const void* x, const v
   p.Ktot = t * d->Cin;
   p.Cout = d->Cout;
   p.dw = dw;
+  p.bn_scale = bn_scale;
+  p.bn_shift = bn_shift;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d->Cout % 256 == 0) return launch_wgrad<256>(p, st);
   if (d->Cout % 128 == 0) return launch_wgrad<128>(p, st);

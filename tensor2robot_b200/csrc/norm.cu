@@ -8,7 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace t2r {
 
@@ -310,6 +310,16 @@ __global__ void __launch_bounds__(256, 6) bn_apply_rows_kernel(const uint4* __re
   }
 }
 
+int bn_bwd_reduce_launch(const void* dy, const void* x, long long rows, int C, const float* mean, const float* invstd,
+                         const float* scale, const float* shift, int relu, double* red, cudaStream_t stream) {
+  const RowPartition pr = partition(rows, C, 4);   // <= 64 registers/thread: 4 CTAs per SM
+  bn_bwd_reduce_kernel<<<dim3(pr.row_blocks, pr.col_blocks), 256, 0, stream>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), rows, C, pr.cgb, pr.lanes_r,
+      pr.rows_per_block, mean, invstd, scale, shift, relu, red);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
 static inline int grid_for(long long n) {
   return int(std::min<long long>(std::max<long long>((n + 255) / 256, 1), 148LL * 16));
 }
@@ -486,11 +496,19 @@ extern "C" int32_t t2r_bn_backward(const void* dy, const void* x, const void* dr
   T2R_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_backward: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   T2R_CUDA_OK(cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st));
-  const RowPartition pr = partition(rows, C, 4);   // <= 64 registers/thread: 4 CTAs per SM
-  bn_bwd_reduce_kernel<<<dim3(pr.row_blocks, pr.col_blocks), 256, 0, st>>>(
-      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), rows, C, pr.cgb, pr.lanes_r,
-      pr.rows_per_block, mean, invstd, scale, shift, relu, red);
-  T2R_LAUNCH_OK();
+  if (int rc = bn_bwd_reduce_launch(dy, x, rows, C, mean, invstd, scale, shift, relu, red, st)) return rc;
+  return t2r_bn_backward_presummed(dy, x, dres, dx, rows, C, mean, invstd, scale, shift, relu, red, dgamma, dbeta,
+                                   stream);
+}
+
+extern "C" int32_t t2r_bn_backward_presummed(const void* dy, const void* x, const void* dres, void* dx,
+                                             int64_t rows, int32_t C, const float* mean, const float* invstd,
+                                             const float* scale, const float* shift, int32_t relu,
+                                             const double* red, float* dgamma, float* dbeta, void* stream) {
+  T2R_CHECK_ARG(dy && x && dx && mean && invstd && scale && shift && red && dgamma && dbeta,
+                "bn_backward_presummed: null pointer");
+  T2R_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "bn_backward_presummed: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const RowPartition p = partition(rows, C, 4);    // 64 registers/thread: 4 CTAs per SM
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, C, mean, invstd, dgamma, dbeta);
   T2R_LAUNCH_OK();

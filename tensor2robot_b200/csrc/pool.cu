@@ -95,6 +95,127 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restric
   }
 }
 
+
+// 3x3 / stride-2 pooling (the ResNet stem pool, film_resnet_model.py:567-575; 3.65 GB of activations at
+// batch 512), specialised so that every byte moves through L2 once.
+//
+// forward: a thread produces TWO horizontally adjacent outputs from one 3 x 5 patch (15 loads instead of 18, all
+// issued before the first compare).  The (kh, kw) scan order and the strict `>` keep the generic kernel's
+// first-maximum tie rule.
+__global__ void __launch_bounds__(256) maxpool_fwd_k3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                               uint2* __restrict__ argmax, int H, int W, int cg, int pt,
+                                                               int pl, int Ho, int Wo) {
+  const int n = blockIdx.x / Ho, oh = blockIdx.x - n * Ho;
+  const uint4* xn = x + (long long)n * H * W * cg;
+  const long long orow = ((long long)n * Ho + oh) * Wo * cg;
+  const int pairs = (Wo + 1) >> 1;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // bf16 -inf
+  for (int t = threadIdx.x; t < pairs * cg; t += blockDim.x) {
+    const int op = t / cg, g = t - op * cg;
+    const int ow = 2 * op;
+    uint4 q[3][5];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 + kh - pt;
+#pragma unroll
+      for (int kc = 0; kc < 5; ++kc) {
+        const int iw = ow * 2 + kc - pl;
+        q[kh][kc] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? xn[(ih * W + iw) * cg + g] : ninf;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      if (ow + o >= Wo) break;
+      float best[8];
+      unsigned idx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; idx[j] = 0; }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float f[8];
+          unpack8(q[kh][2 * o + kw], f);
+          const unsigned code = unsigned(kh * 3 + kw);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (f[j] > best[j]) { best[j] = f[j]; idx[j] = code; }
+        }
+      const long long oi = orow + (long long)(ow + o) * cg + g;
+      y[oi] = pack8(best);
+      if (argmax) {
+        uint2 a;
+        a.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+        a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+        argmax[oi] = a;
+      }
+    }
+  }
+}
+
+// backward: in padded coordinates u = ih + pad_top the rows (2a, 2a+1) belong to window a (kh = 0 / 1) and row 2a
+// also to window a - 1 (kh = 2); the same for columns.  A thread therefore owns the 2 x 2 input quad (a, b) and
+// reads its (at most) four candidate windows ONCE - 96 B for 64 B written instead of 216 B in the gather form.
+// Windows are visited in the generic kernel's order (oh, then ow, ascending): sums are bit-identical.
+__global__ void __launch_bounds__(256) maxpool_bwd_k3s2_kernel(const uint4* __restrict__ dy,
+                                                               const uint2* __restrict__ argmax,
+                                                               uint4* __restrict__ dx, int H, int W, int cg, int pt, int pl,
+                                                               int Ho, int Wo, int Hq, int Wq) {
+  const int n = blockIdx.x / Hq, a = blockIdx.x - n * Hq;
+  const long long obase = (long long)n * Ho * Wo * cg;
+  const long long ibase = (long long)n * H * W * cg;
+  for (int t = threadIdx.x; t < Wq * cg; t += blockDim.x) {
+    const int b = t / cg, g = t - b * cg;
+    float acc[2][2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][c][j] = 0.f;
+#pragma unroll
+    for (int da = -1; da <= 0; ++da) {
+      const int oh = a + da;
+      if (oh < 0 || oh >= Ho) continue;
+#pragma unroll
+      for (int db = -1; db <= 0; ++db) {
+        const int ow = b + db;
+        if (ow < 0 || ow >= Wo) continue;
+        const long long o = obase + (long long)(oh * Wo + ow) * cg + g;
+        const uint2 am = argmax[o];
+        float f[8];
+        unpack8(dy[o], f);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (da < 0 && r == 1) continue;           // row 2a+1 is not in window a-1
+          const int kh = da < 0 ? 2 : r;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (db < 0 && c == 1) continue;
+            const unsigned code = unsigned(kh * 3 + (db < 0 ? 2 : c));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const unsigned sel = ((j < 4 ? am.x : am.y) >> (8 * (j & 3))) & 0xFFu;
+              if (sel == code) acc[r][c][j] += f[j];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int ih = 2 * a + r - pt;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int iw = 2 * b + c - pl;
+        if (iw < 0 || iw >= W) continue;
+        dx[ibase + (long long)(ih * W + iw) * cg + g] = pack8(acc[r][c]);
+      }
+    }
+  }
+}
+
 // x [N, HW, C] -> y [N, C]: one block per (image, 32 column groups), 8 row lanes.
 __global__ void __launch_bounds__(256) global_mean_fwd_kernel(const uint4* __restrict__ x,
                                                               uint4* __restrict__ y, int HW, int cg) {
@@ -382,6 +503,13 @@ extern "C" int32_t t2r_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int3
                                    int32_t pad_left, int32_t Ho, int32_t Wo, void* stream) {
   T2R_CHECK_ARG(x && y && C % 8 == 0 && k >= 1 && k * k <= 255 && stride >= 1, "maxpool_fwd: bad args");
   T2R_CHECK_ARG((long long)N * Ho < (1LL << 31) && (long long)H * W * (C / 8) < (1LL << 31), "maxpool_fwd: too large");
+  if (k == 3 && stride == 2) {
+    maxpool_fwd_k3s2_kernel<<<N * Ho, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), reinterpret_cast<uint2*>(argmax), H, W, C / 8, pad_top,
+        pad_left, Ho, Wo);
+    T2R_LAUNCH_OK();
+    return T2R_OK;
+  }
   maxpool_fwd_kernel<<<N * Ho, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), reinterpret_cast<uint2*>(argmax), N, H, W,
       C / 8, k, stride, pad_top, pad_left, Ho, Wo);
@@ -395,6 +523,15 @@ extern "C" int32_t t2r_maxpool_bwd(const void* dy, const uint8_t* argmax, void* 
                                    void* stream) {
   T2R_CHECK_ARG(dy && argmax && dx && C % 8 == 0, "maxpool_bwd: bad args");
   T2R_CHECK_ARG((long long)N * H < (1LL << 31) && (long long)Ho * Wo * (C / 8) < (1LL << 31), "maxpool_bwd: too large");
+  if (k == 3 && stride == 2) {
+    const int Hq = (H + pad_top + 1) / 2, Wq = (W + pad_left + 1) / 2;   // quads of the padded image
+    T2R_CHECK_ARG((long long)N * Hq < (1LL << 31), "maxpool_bwd: too large");
+    maxpool_bwd_k3s2_kernel<<<N * Hq, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(argmax), static_cast<uint4*>(dx), H, W, C / 8,
+        pad_top, pad_left, Ho, Wo, Hq, Wq);
+    T2R_LAUNCH_OK();
+    return T2R_OK;
+  }
   maxpool_bwd_kernel<<<N * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(argmax), static_cast<uint4*>(dx), N,
       H, W, C / 8, k, stride, pad_top, pad_left, Ho, Wo);

@@ -238,3 +238,20 @@ class CEMTargetComputer(object):
               C.c_void_p(done.contiguous().data_ptr()), C.c_void_p(max_q.data_ptr()), float(gamma),
               C.c_void_p(target.data_ptr()), max_q.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     return target
+
+
+def device_cem_selector(train_step, computer):
+  """Robot-side use of the Bellman-target machinery: returns state -> (action [D] numpy, q float) for
+  `policies.CEMPolicy(device_maximizer=...)`.  `state` is one uint8 camera frame [H, W, 3]; it is centre-cropped /
+  converted by the train step's PREDICT preprocessing, the state tower runs once and CEM runs on the device
+  (`CEMTargetComputer.maximize` at batch 1) - one H2D copy of the frame and one D2H copy of the action per call,
+  instead of one predictor round trip per CEM iteration (policies/policies.py:164-182 in the reference)."""
+  device = train_step.vs.device
+
+  def select(state):
+    frame = torch.from_numpy(np.ascontiguousarray(state)[None]).to(device, non_blocking=True)
+    x = train_step.preprocess(frame, training=False)
+    action, q, _ = computer.maximize(x)
+    return action[0].float().cpu().numpy(), float(q[0])
+
+  return select

@@ -1,106 +1,95 @@
-"""Export listeners (hooks/checkpoint_hooks.py:28-201): after a checkpoint, export the model into `export_dir`; the
-lagged listener additionally keeps `lagged_export_dir` exactly one export behind - the TD3 / QT-Opt target network that
-remote actors and Bellman updaters load.  An export here is a directory
-`<export_dir>/<global_step>/` holding a TensorFlow-bundle checkpoint + `assets.extra/t2r_assets.pbtxt`
-(`export_fn` decides); the in-process, on-device equivalent is `engine.LaggedTarget`."""
-import collections
+"""Export listeners of the training loop (behaviour of the reference's hooks/checkpoint_hooks.py:28-201,
+pinned by the scenarios of its checkpoint_hooks_test.py, which tests/test_hooks.py replays).
+
+Two contracts:
+
+* `CheckpointExportListener.after_save(session, global_step)` calls `export_fn(export_dir, global_step)`, which writes
+  one version directory and returns its path; with `num_versions` only that many newest versions are kept.
+* `LaggedCheckpointListener` additionally maintains `lagged_export_dir` so that its newest version is always the
+  export that was current BEFORE the latest one (the very first export is mirrored immediately, so the directory is
+  never empty): the lagged / target network that TD3 and QT-Opt actors and Bellman updaters poll.  The in-process,
+  on-device equivalent is `engine.LaggedTarget`.
+
+Both are written as operations on a `_VersionDir` (an ordered set of version directories with a retention limit);
+the lagged listener is one idempotent rule - "make `name` the newest lagged version" - applied at construction (which
+is what repairs or resumes from directories left by an earlier run) and after every export."""
 import logging
 import os
+import re
 import shutil
 
 
-class _DirectoryVersionGC(object):
-  """Observes a stream of incoming directories and removes the oldest ones."""
+def _natural_key(name):
+  return [int(tok) if tok.isdigit() else tok for tok in re.split(r'(\d+)', name)]
 
-  def __init__(self, num_versions):
-    self._queue = collections.deque()
-    self._num_versions = num_versions
 
-  def observe(self, directory):
-    self._queue.append(directory)
-    self._remove_if_necessary()
+class _VersionDir(object):
+  """Version directories under `root`, oldest first: what was on disk at construction (sorted), then every `add`."""
 
-  def observe_multiple(self, directory_list):
-    self._queue.extend(directory_list)
-    self._remove_if_necessary()
+  def __init__(self, root, keep=None):
+    self.root = str(root)
+    self.keep = keep
+    os.makedirs(self.root, exist_ok=True)
+    self.versions = sorted(os.listdir(self.root), key=_natural_key)
+    self._prune()
 
-  def _remove_if_necessary(self):
-    while len(self._queue) > self._num_versions:
-      shutil.rmtree(self._queue.popleft(), ignore_errors=True)
+  def path(self, name):
+    return os.path.join(self.root, name)
+
+  @property
+  def newest(self):
+    return self.versions[-1] if self.versions else None
+
+  def add(self, name):
+    if name in self.versions:
+      self.versions.remove(name)
+    self.versions.append(name)
+    self._prune()
+
+  def _prune(self):
+    while self.keep and len(self.versions) > self.keep:
+      shutil.rmtree(self.path(self.versions.pop(0)), ignore_errors=True)
 
 
 class CheckpointExportListener(object):
-  """Exports the model after a checkpoint was created."""
+  """Exports the model after a checkpoint was written; keeps the `num_versions` newest exports (None: all)."""
 
   def __init__(self, export_fn, export_dir, num_versions=None):
-    """export_fn(export_dir, global_step) -> exported path; num_versions: exports to keep (None: all)."""
     self._export_fn = export_fn
-    self._export_dir = str(export_dir)
-    os.makedirs(self._export_dir, exist_ok=True)
-    self._gc = None
-    if num_versions:
-      self._gc = _DirectoryVersionGC(num_versions)
-      self._gc.observe_multiple([os.path.join(self._export_dir, f) for f in sorted(os.listdir(self._export_dir))])
+    self._exports = _VersionDir(export_dir, num_versions)
+
+  def _export(self, global_step):
+    path = str(self._export_fn(self._exports.root, global_step))
+    logging.info('exported the model of global step %d to %s', global_step, path)
+    return path, os.path.basename(os.path.normpath(path))
 
   def after_save(self, session, global_step):
     del session
-    logging.info('Exporting model at global_step %d', global_step)
-    exported_path = str(self._export_fn(self._export_dir, global_step))
-    logging.info('Saved model to %s', exported_path)
-    if self._gc:
-      self._gc.observe(exported_path)
-    return exported_path
+    path, name = self._export(global_step)
+    self._exports.add(name)
+    return path
 
 
 class LaggedCheckpointListener(CheckpointExportListener):
-  """Also exports the **second newest** model to a separate directory (the lagged / target network)."""
+  """Keeps `lagged_export_dir` one export behind `export_dir`."""
 
   def __init__(self, export_fn, export_dir, lagged_export_dir, num_versions):
-    CheckpointExportListener.__init__(self, export_fn, export_dir, num_versions)
-    self._lagged_export_dir = str(lagged_export_dir)
-    self._current_model_dir = None
-    self._lagged_model_dir = None
-    self._lagged_gc = _DirectoryVersionGC(num_versions) if self._gc else None
-    os.makedirs(self._lagged_export_dir, exist_ok=True)
-    export_dir_contents = sorted(os.listdir(self._export_dir))
-    lagged_export_dir_contents = sorted(os.listdir(self._lagged_export_dir))
-    if self._lagged_gc:
-      self._lagged_gc.observe_multiple([os.path.join(self._lagged_export_dir, f) for f in lagged_export_dir_contents])
-    # resume: re-establish "lagged is one export behind current" from what is on disk (:137-160)
-    if len(export_dir_contents) == 1:
-      self._current_model_dir = os.path.join(self._export_dir, export_dir_contents[0])
-      if export_dir_contents == lagged_export_dir_contents:
-        self._lagged_model_dir = os.path.join(self._lagged_export_dir, lagged_export_dir_contents[0])
-      else:
-        self._lagged_model_dir = self._copy_savedmodel(self._current_model_dir, self._lagged_export_dir)
-    elif len(export_dir_contents) > 1:
-      second_last_exported_model = export_dir_contents[-2]
-      self._current_model_dir = os.path.join(self._export_dir, export_dir_contents[-1])
-      if not lagged_export_dir_contents or second_last_exported_model != lagged_export_dir_contents[-1]:
-        self._lagged_model_dir = self._copy_savedmodel(os.path.join(self._export_dir, second_last_exported_model),
-                                                       self._lagged_export_dir)
-      else:
-        self._lagged_model_dir = os.path.join(self._lagged_export_dir, lagged_export_dir_contents[-1])
+    super(LaggedCheckpointListener, self).__init__(export_fn, export_dir, num_versions)
+    self._lagged = _VersionDir(lagged_export_dir, num_versions)
+    on_disk = self._exports.versions
+    if on_disk:   # the version before the newest, or the only one
+      self._make_newest_lagged(on_disk[-2] if len(on_disk) > 1 else on_disk[-1])
 
-  def _copy_savedmodel(self, source_dir, destination):
-    dest_base_dir = os.path.join(str(destination), os.path.basename(str(source_dir)))
-    shutil.copytree(str(source_dir), dest_base_dir, dirs_exist_ok=True)
-    return dest_base_dir
-
-  def _copy_lagged_model(self, source_dir, destination):
-    destination_path = self._copy_savedmodel(source_dir, destination)
-    if self._lagged_gc:
-      self._lagged_gc.observe(destination_path)
-    return destination_path
+  def _make_newest_lagged(self, name):
+    if self._lagged.newest == name:
+      return
+    shutil.copytree(self._exports.path(name), self._lagged.path(name), dirs_exist_ok=True)
+    self._lagged.add(name)
 
   def after_save(self, session, global_step):
-    """Exports to the current directory; the lagged directory receives the export that was current until now."""
-    export_dir = CheckpointExportListener.after_save(self, session, global_step)
-    if not self._current_model_dir:
-      self._lagged_model_dir = self._copy_lagged_model(export_dir, self._lagged_export_dir)
-    elif os.path.basename(self._current_model_dir) == os.path.basename(self._lagged_model_dir):
-      pass
-    else:
-      self._lagged_model_dir = self._copy_lagged_model(self._current_model_dir, self._lagged_export_dir)
-    self._current_model_dir = export_dir
-    return export_dir
+    del session
+    previous = self._exports.newest
+    path, name = self._export(global_step)
+    self._make_newest_lagged(previous if previous is not None else name)   # before retention can retire `previous`
+    self._exports.add(name)
+    return path

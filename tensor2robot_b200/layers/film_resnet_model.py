@@ -31,12 +31,14 @@ class _Namer(object):
     return base if n == 0 else '%s_%d' % (base, n)
 
 
-def batch_norm(inputs, training, namer, relu=False, film=None, passthrough=False):
+def batch_norm(inputs, training, namer, relu=False, film=None, passthrough=False, defer=False):
   """tf.layers.batch_normalization(momentum=.997, eps=1e-5, fused=True) [+FiLM] [+ReLU].
   passthrough=True additionally returns `inputs` routed through the same autograd node (used for
-  the identity shortcut, whose gradient the BN backward kernel then adds for free)."""
+  the identity shortcut, whose gradient the BN backward kernel then adds for free).
+  defer=True: may return an nn.DeferredBN that the consuming convolution fuses with (training only)."""
   return nn.batch_norm(inputs, training, scope=namer('batch_normalization'), scale=True, relu=relu,
-                       momentum=_BATCH_NORM_DECAY, eps=_BATCH_NORM_EPSILON, film=film, passthrough=passthrough)
+                       momentum=_BATCH_NORM_DECAY, eps=_BATCH_NORM_EPSILON, film=film, passthrough=passthrough,
+                       defer=defer)
 
 
 def _conv_spec(filters, kernel_size, strides, namer, weight_decay):
@@ -54,15 +56,21 @@ def _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters
   one autograd node whose second data gradient accumulates into the first (nn.conv2d_pair)."""
   if projection_shortcut is None:
     if training and torch.is_grad_enabled():
-      preact, shortcut = batch_norm(inputs, training, namer, relu=True, passthrough=True)
+      out = batch_norm(inputs, training, namer, relu=True, passthrough=True, defer=True)
+      if isinstance(out, nn.DeferredBN):   # BN + ReLU + conv as one node; the shortcut comes out of it
+        first = conv2d_fixed_padding(out, filters, kernel_size, strides, namer, weight_decay)
+        return out.shortcut, first
+      preact, shortcut = out
     else:
       preact, shortcut = batch_norm(inputs, training, namer, relu=True), inputs
     first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay,
                                  defer_for_bn=not training)
     return shortcut, first
-  preact = batch_norm(inputs, training, namer, relu=True)
+  preact = batch_norm(inputs, training, namer, relu=True, defer=True)
   fused = getattr(projection_shortcut, 'fused_args', None)
   if fused is None or not training:
+    if isinstance(preact, nn.DeferredBN):
+      preact = preact.materialize()
     shortcut = projection_shortcut(preact)
     first = conv2d_fixed_padding(preact, filters, kernel_size, strides, namer, weight_decay,
                                  defer_for_bn=not training)
@@ -93,7 +101,7 @@ def _building_block_v2(inputs, filters, training, projection_shortcut, strides, 
   """BN-ReLU-conv3x3-BN-[FiLM]-ReLU-conv3x3 + shortcut (film_resnet_model.py:166-223)."""
   shortcut, inputs = _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters, 3, strides,
                                             weight_decay)
-  inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta))
+  inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta), defer=True)
   return conv2d_fixed_padding(inputs, filters, 3, 1, namer, weight_decay, residual=shortcut)
 
 
@@ -102,9 +110,9 @@ def _bottleneck_block_v2(inputs, filters, training, projection_shortcut, strides
   """BN-ReLU-1x1-BN-ReLU-3x3(stride)-BN-[FiLM]-ReLU-1x1(4x) + shortcut (film_resnet_model.py:283-340)."""
   shortcut, inputs = _preact_and_first_conv(inputs, training, namer, projection_shortcut, filters, 1, 1,
                                             weight_decay)
-  inputs = batch_norm(inputs, training, namer, relu=True)
+  inputs = batch_norm(inputs, training, namer, relu=True, defer=True)
   inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay, defer_for_bn=not training)
-  inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta))
+  inputs = batch_norm(inputs, training, namer, relu=True, film=_film_tensor(film_gamma_beta), defer=True)
   return conv2d_fixed_padding(inputs, 4 * filters, 1, 1, namer, weight_decay, residual=shortcut)
 
 

@@ -430,6 +430,28 @@ FUSE_BN_STATS = os.environ.get('T2R_FUSE_BN_STATS', '1') != '0'
 FOLD_INFERENCE_BN = os.environ.get('T2R_FOLD_INFERENCE_BN', '1') != '0'
 
 
+# Training graphs: batch norm + ReLU and the convolution(s) that consume it run as ONE autograd node
+# (_BnReluConvFn): the data gradient's epilogue masks and reduces for the batch-norm backward
+# (t2r_conv2d_dgrad_bnrelu), and 1x1 consumers that are bound by HBM traffic read the RAW tensor and apply
+# the normalisation to their operand tiles in shared memory (t2r_conv2d_{fprop,wgrad}_bnrelu), so the
+# normalised activation is never written.  T2R_FUSE_BN_NODE=0 restores the separate nodes;
+# T2R_FUSE_BN_OPERAND = 0 | auto | all selects which 1x1 consumers fuse the apply pass.
+FUSE_BN_NODE = os.environ.get('T2R_FUSE_BN_NODE', '1') != '0'
+FUSE_BN_OPERAND = os.environ.get('T2R_FUSE_BN_OPERAND', 'auto')
+# flop / byte above which a 1x1 convolution is bound by the tensor pipe rather than by HBM (measured
+# sustained 1.4 PFLOP/s over 6.6 TB/s = 215): there the shared-memory rewrite would cost MMA time
+_BN_OPERAND_MAX_INTENSITY = float(os.environ.get('T2R_BN_OPERAND_MAX_INTENSITY', '180'))
+
+
+def _bn_operand_fusable(cin, cout, kh, kw, pt, pl, has_res):
+  if FUSE_BN_OPERAND == '0' or kh != 1 or kw != 1 or pt or pl:
+    return False
+  if FUSE_BN_OPERAND == 'all':
+    return True
+  intensity = 2.0 * cin * cout / (2.0 * (cin + cout * (2 if has_res else 1)))
+  return intensity <= _BN_OPERAND_MAX_INTENSITY
+
+
 def _new_bn_stats(channels, device):
   if not (FUSE_BN_STATS and torch.is_grad_enabled()) or channels > 2048:
     return None
@@ -543,7 +565,9 @@ class _DualConvFn(torch.autograd.Function):
 def conv2d_pair(x, spec1, spec2):
   """spec = dict(filters, kernel_size, stride, padding, scope, names, regularize).  Returns (y1, y2);
   variables are created in the order (spec1, spec2)."""
-  _require_cuda(x, 'conv2d_pair')
+  deferred_bn = x if isinstance(x, DeferredBN) else None
+  if deferred_bn is None:
+    _require_cuda(x, 'conv2d_pair')
   vs = current_store()
   n, h, w, cin = x.shape
   out = []
@@ -559,6 +583,9 @@ def conv2d_pair(x, spec1, spec2):
     if not vs.finalized:
       _ensure_bf16(wv)
     out.append((wv, (stride, ho, wo, pt, pl)))
+  if deferred_bn is not None:
+    y1, y2 = deferred_bn.run_convs(out)
+    return _trace('conv', spec1['scope'], y1), _trace('conv', spec2['scope'], y2)
   stats2 = _new_bn_stats(out[1][0].shape[0], x.device)
   y1, y2 = _DualConvFn.apply(x, out[0][0], out[0][1], out[1][0], out[1][1], stats2)
   if stats2 is not None:
@@ -655,6 +682,160 @@ class DeferredConv(object):
     return _trace('conv', self.scope, self.run())
 
 
+
+class _BnReluConvFn(torch.autograd.Function):
+  """z = relu(batch_norm(x)) consumed by one or two bias-free bf16 convolutions, as one autograd node.
+
+  forward : statistics (from the producer's epilogue when available) -> scale / shift; then either the
+            operand-fused 1x1 kernels on the raw x, or t2r_bn_apply + the plain kernels on z.
+  backward: weight gradients; data gradients whose LAST launch masks with [z > 0] and reduces
+            sum g / sum g*x in its epilogue (t2r_conv2d_dgrad_bnrelu); t2r_bn_backward_presummed.
+  Outputs : (y_1[, y_2][, x]) - the trailing x (passthrough) routes an identity shortcut's gradient into
+            this node, where the batch-norm apply kernel adds it for free.
+  Reference semantics: layers/film_resnet_model.py:50-57 (batch_norm), :283-340 (the block wiring)."""
+
+  @staticmethod
+  def forward(ctx, x, residual, bn, vs, convs, fused_stats, passthrough, operand_fused):
+    n, h, w, c = x.shape
+    rows = n * h * w
+    st = _stream()
+    mean = torch.empty(c, dtype=F32, device=x.device)
+    invstd = torch.empty(c, dtype=F32, device=x.device)
+    scale = torch.empty(c, dtype=F32, device=x.device)
+    shift = torch.empty(c, dtype=F32, device=x.device)
+    if fused_stats is not None:
+      stats = fused_stats
+    else:
+      stats = vs.scratch('bn_stats', 2 * 4096, torch.float64)
+      _lib.call('t2r_bn_stats', _p(x), rows, c, _p(stats), st)
+    _lib.call('t2r_bn_finalize', _p(stats), rows, c, _p(bn['gamma'].data if bn['gamma'] is not None else None),
+              _p(bn['beta'].data), bn['eps'], bn['momentum'], _p(bn['moving_mean'].data),
+              _p(bn['moving_variance'].data), _p(mean), _p(invstd), _p(scale), _p(shift), st)
+    z = None
+    if not operand_fused:
+      z = torch.empty_like(x)
+      _lib.call('t2r_bn_apply', _p(x), _p(z), rows, c, _p(scale), _p(shift), None, h * w, 1, st)
+    outs, descs = [], []
+    for var, (stride, ho, wo, pt, pl), ostats in convs:
+      cout, kh, kw, _ = var.shape
+      flags = _lib.T2R_EPI_RESIDUAL if residual is not None else 0
+      d = _conv_desc(n, h, w, c, cout, kh, kw, stride, pt, pl, ho, wo, flags)
+      y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+      with _prof('fprop', d):
+        if operand_fused:
+          _lib.call('t2r_conv2d_fprop_bnrelu', C.byref(d), _p(x), _p(scale), _p(shift), _p(var.bf16), _p(residual),
+                    _p(y), _p(ostats), st)
+        else:
+          _lib.call('t2r_conv2d_fprop_stats', C.byref(d), _p(z), _p(var.bf16), None, _p(residual), _p(y), _p(ostats), st)
+      outs.append(y)
+      descs.append(d)
+    ctx.bn, ctx.vs, ctx.descs, ctx.vars = bn, vs, descs, [cv[0] for cv in convs]
+    ctx.operand_fused, ctx.passthrough, ctx.has_res = operand_fused, passthrough, residual is not None
+    ctx.save_for_backward(x, mean, invstd, scale, shift, z)
+    if passthrough:
+      outs.append(x.view_as(x))
+    return tuple(outs)
+
+  @staticmethod
+  def backward(ctx, *grads):
+    x, mean, invstd, scale, shift, z = ctx.saved_tensors
+    bn, vs = ctx.bn, ctx.vs
+    n, h, w, c = x.shape
+    rows = n * h * w
+    st = _stream()
+    dpass = grads[len(ctx.vars)] if ctx.passthrough else None
+    if dpass is not None:
+      dpass = dpass.contiguous()
+    dys = [g.contiguous() if g is not None else None for g in grads[:len(ctx.vars)]]
+    for var, d, dy in zip(ctx.vars, ctx.descs, dys):
+      if dy is None or not var.trainable:
+        continue
+      with _prof('wgrad', d):
+        if ctx.operand_fused:
+          _lib.call('t2r_conv2d_wgrad_bnrelu', C.byref(d), _p(x), _p(scale), _p(shift), _p(dy), _p(var.grad), st)
+        else:
+          _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(z), _p(dy), _p(var.grad), st)
+    dx = None
+    if ctx.needs_input_grad[0]:
+      # the convolution that covers every input pixel first; a strided projection (conv 0 of a pair) then
+      # accumulates into its phase only.  The last launch masks and reduces.
+      live = [(var, d, dy) for var, d, dy in reversed(list(zip(ctx.vars, ctx.descs, dys))) if dy is not None]
+      g = torch.empty_like(x)
+      red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
+      if not live:
+        g.zero_()
+      for i, (var, d, dy) in enumerate(live):
+        if var.dgrad is None:
+          raise _lib.T2RError('conv %s needs a data gradient but was built with needs_dgrad=False' % var.name)
+        with _prof('dgrad', d):
+          if i == len(live) - 1:
+            _lib.call('t2r_conv2d_dgrad_bnrelu', C.byref(d), _p(dy), _p(var.dgrad), _p(x), _p(scale), _p(shift), _p(g),
+                      1 if i else 0, _p(red), st)
+          else:
+            _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(g), 1 if i else 0, st)
+      gamma = bn['gamma']
+      dgamma = gamma.grad if (gamma is not None and gamma.trainable) else vs.scratch('bn_dgamma', 4096, F32)
+      dbeta = bn['beta'].grad if bn['beta'].trainable else vs.scratch('bn_dbeta', 4096, F32)
+      dx = torch.empty_like(x)
+      _lib.call('t2r_bn_backward_presummed', _p(g), _p(x), _p(dpass), _p(dx), rows, c, _p(mean), _p(invstd), _p(scale),
+                _p(shift), 1, _p(red), _p(dgamma), _p(dbeta), st)
+    dres = dys[0] if (ctx.has_res and ctx.needs_input_grad[1]) else None
+    return dx, dres, None, None, None, None, None, None
+
+
+class DeferredBN(object):
+  """A training-mode batch norm + ReLU whose launch waits for its consumer: conv2d / conv2d_pair turn the pair
+  into one _BnReluConvFn node; anything else calls materialize() (the stand-alone _BatchNormFn).
+  `shortcut` (passthrough=True) is the input routed through the node, available once the node has run."""
+
+  def __init__(self, x, bn, vs, scope, fused_stats, passthrough):
+    self.x, self.bn, self.vs, self.scope = x, bn, vs, scope
+    self.fused_stats, self.passthrough = fused_stats, passthrough
+    self.shape, self.device = x.shape, x.device
+    self.shortcut = None
+    self._z = None
+    self._consumed = False
+
+  def _consume(self):
+    if self._consumed:
+      raise _lib.T2RError('a deferred batch norm (%s) can feed only one consumer; call .materialize() to share it'
+                          % self.scope)
+    self._consumed = True
+
+  def materialize(self):
+    if self._z is None:
+      self._consume()
+      if self.passthrough:
+        z, self.shortcut = _BatchNormFn.apply(self.x, None, self.bn, True, True, self.vs, True, self.fused_stats)
+      else:
+        z = _BatchNormFn.apply(self.x, None, self.bn, True, True, self.vs, False, self.fused_stats)
+      self._z = _trace('bn', self.scope, z)
+    return self._z
+
+  def run_convs(self, convs, residual=None):
+    """convs: [(weight variable, (stride, ho, wo, pt, pl))] -> list of outputs (with fused bn_stats attached)."""
+    self._consume()
+    c = self.x.shape[-1]
+    fused = all(_bn_operand_fusable(c, var.shape[0], var.shape[1], var.shape[2], geom[3], geom[4], residual is not None)
+                for var, geom in convs)
+    packed = []
+    for var, geom in convs:
+      packed.append((var, geom, _new_bn_stats(var.shape[0], self.device)))
+    outs = _BnReluConvFn.apply(self.x, residual, self.bn, self.vs, tuple(packed), self.fused_stats, self.passthrough,
+                               fused)
+    if self.passthrough:
+      self.shortcut = outs[-1]
+    ys = list(outs[:len(convs)])
+    for y, (_, _, ostats) in zip(ys, packed):
+      if ostats is not None:
+        y._t2r_bn_stats = ostats
+    return ys
+
+
+def _node_fusable_conv(x, wv, bv, relu, out_f32):
+  return bv is None and not relu and not out_f32 and wv.trainable and len(wv.shape) == 4 and x.shape[-1] % 64 == 0
+
+
 def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, scope='conv',
            initializer=None, regularize=True, residual=None, relu=False, needs_dgrad=True,
            trainable=True, out_f32=False, names=('weights', 'biases'), defer_for_bn=False):
@@ -662,7 +843,9 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
   defer_for_bn=True (only honoured without autograd): returns a DeferredConv for batch_norm to fuse."""
   if isinstance(x, (DeferredConv, DeferredContext)):
     x = x.materialize()
-  _require_cuda(x, 'conv2d')
+  deferred_bn = x if isinstance(x, DeferredBN) else None
+  if deferred_bn is None:
+    _require_cuda(x, 'conv2d')
   vs = current_store()
   kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
   n, h, w, cin = x.shape
@@ -687,6 +870,11 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
     bv = vs.get_variable(names[1], (filters,), 0.0, trainable, False) if use_bias else None
   if not vs.finalized:
     _ensure_bf16(wv)
+  if deferred_bn is not None:
+    if not small and _node_fusable_conv(deferred_bn, wv, bv, relu, out_f32):
+      (y,) = deferred_bn.run_convs([(wv, (stride, ho, wo, pt, pl))], residual)
+      return _trace('conv', scope, y)
+    x = deferred_bn.materialize()
   if small:
     return _trace('conv', scope, _StemConvFn.apply(x.contiguous(), vs.anchor, wv, bv,
                                                    (kh, kw, stride, ho, wo, pt, pl), vs))
@@ -849,8 +1037,10 @@ class _BatchNormFn(torch.autograd.Function):
 
 
 def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=0.997, eps=1e-5,
-               film=None, trainable=True, passthrough=False):
-  """slim.batch_norm / tf.layers.batch_normalization(fused=True) followed by an optional ReLU."""
+               film=None, trainable=True, passthrough=False, defer=False):
+  """slim.batch_norm / tf.layers.batch_normalization(fused=True) followed by an optional ReLU.
+  defer=True (honoured in training graphs with relu, without FiLM): returns a DeferredBN for the consuming
+  convolution to fuse with; every other consumer must call .materialize()."""
   deferred = x if isinstance(x, (DeferredConv, DeferredContext)) else None
   if deferred is not None and (training or film is not None or passthrough):
     x, deferred = deferred.materialize(), None
@@ -887,6 +1077,9 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
     _lib.call('t2r_fold_bn_weights', _p(wv.data), _p(scale_t), _p(folded), wv.shape[0], wv.numel // wv.shape[0], st)
     return _trace('bn', scope, deferred.run(folded, shift_t, relu))
   fused = getattr(x, '_t2r_bn_stats', None) if (training and x.is_contiguous()) else None
+  if (defer and FUSE_BN_NODE and training and relu and film is None and torch.is_grad_enabled() and TRACE is None and
+      x.dtype == BF16 and x.dim() == 4 and x.requires_grad):
+    return DeferredBN(x.contiguous(), bn, vs, scope, fused, passthrough)
   if passthrough:
     y, x_pass = _BatchNormFn.apply(x.contiguous(), film, bn, training, relu, vs, True, fused)
     return _trace('bn', scope, y), x_pass

@@ -1,202 +1,114 @@
-"""Policies: action selection on top of a predictor (policies/policies.py:30-364).  Host-side numpy logic; the
-Q-function / regression evaluations go through predictor.predict (the CUDA kernels at batch 1 x samples)."""
-import abc
+"""Robot-side action selection on top of a predictor (contract of the reference's
+policies/policies.py:30-184: `SelectAction(state, context, timestep)`, `reset`, `restore`, `init_randomly`,
+`global_step`, `model_path`, `sample_action`).
 
+Two policies are on the path this repository accelerates:
+
+* `CEMPolicy` - arg-max of a Q critic over continuous actions by the cross-entropy method.  Host mode drives
+  `predictor.predict` once per CEM iteration with `cem_samples` candidate actions (one kernel pass of
+  [1 x samples] through the critic).  Device mode (`device_maximizer=`, see `engine.device_cem_selector`) hands the
+  whole search to `engine.CEMTargetComputer`: the state tower runs once, its features stay staged in HBM and
+  sampling / Q evaluation / elite refit are kernels - the same code that computes Bellman targets, at batch 1.
+* `RegressionPolicy` - the action is the regression model's `inference_output`.
+
+CEM semantics (pinned by goldens generated from the reference's utils/cross_entropy.py, tests/golden): mean 0 /
+stddev 1 start, ascending stable ordering with the last `num_elites` refitting mean and np.std(ddof=1), and the
+answer is the best of the LAST iteration's samples."""
 import numpy as np
 
 from tensor2robot_b200.utils import cross_entropy
 
 
-class Policy(abc.ABC):
-  """Base Policy class."""
+class Policy(object):
+  """Holds the predictor and forwards the bookkeeping calls to it; subclasses implement SelectAction."""
 
   def __init__(self, predictor=None):
     self._predictor = predictor
 
-  @abc.abstractmethod
   def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
-    """Selects an action given the current state; must not modify state or context."""
+    raise NotImplementedError('%s does not implement SelectAction' % type(self).__name__)
 
   def reset(self):
-    """Reset the policy."""
+    """Start of an episode: stateless policies have nothing to do."""
+
+  def _forward(self, method):
+    if self._predictor is not None:
+      getattr(self._predictor, method)()
 
   def init_randomly(self):
-    if self._predictor is not None:
-      self._predictor.init_randomly()
+    self._forward('init_randomly')
 
   def restore(self):
-    if self._predictor is not None:
-      self._predictor.restore()
+    self._forward('restore')
 
   @property
   def model_path(self):
-    if self._predictor is not None:
-      return self._predictor.model_path
-    return 'No model path defined.'
+    return 'No model path defined.' if self._predictor is None else self._predictor.model_path
 
   @property
   def global_step(self):
-    if self._predictor is not None:
-      return self._predictor.global_step
-    return 0
+    return 0 if self._predictor is None else self._predictor.global_step
 
   def sample_action(self, obs, explore_prob):
-    """dql_grasping run_env compatibility: (action, debug); explore_prob is ignored."""
+    """dql_grasping's run_env protocol: (action, debug); exploration is the caller's business here."""
     del explore_prob
     return self.SelectAction(obs, None, None), None
 
 
 class CEMPolicy(Policy):
-  """CEM policy for continuous-action critic models."""
+  """Cross-entropy-method arg-max over a critic's continuous action space."""
 
-  def __init__(self, t2r_model, action_size=2, cem_iters=3, cem_samples=64, num_elites=10, pack_fn=None, **parent_kwargs):
+  def __init__(self, t2r_model, action_size=2, cem_iters=3, cem_samples=64, num_elites=10, pack_fn=None,
+               device_maximizer=None, **parent_kwargs):
+    """pack_fn(t2r_model, state, context, timestep, samples) -> numpy feature struct for predictor.predict
+    (default: t2r_model.pack_features).  device_maximizer(state) -> (action [D], q) replaces the host loop."""
     super(CEMPolicy, self).__init__(**parent_kwargs)
-    self._cem_iters = cem_iters
-    self._cem_samples = cem_samples
-    self._action_size = action_size
-    self._num_elites = num_elites
-    self.sample_fn = self._default_sample_fn
-    self.pack_fn = pack_fn if pack_fn is not None else self._default_pack_fn
     self._t2r_model = t2r_model
+    self._population = (int(cem_samples), int(action_size))
+    self._cem_iters, self._num_elites = int(cem_iters), int(num_elites)
+    self._device_maximizer = device_maximizer
+    self.sample_fn = self._gaussian_population
+    self.pack_fn = pack_fn if pack_fn is not None else (
+        lambda model, state, context, timestep, samples: model.pack_features(state, context, timestep, samples))
 
-  def _default_sample_fn(self, mean, stddev):
-    return mean + stddev * np.random.standard_normal((self._cem_samples, self._action_size))
+  def _gaussian_population(self, mean, stddev):
+    return mean + stddev * np.random.standard_normal(self._population)
+
+  @staticmethod
+  def _refit(params, elites):
+    del params
+    elites = np.asarray(elites)
+    return dict(mean=elites.mean(axis=0), stddev=elites.std(axis=0, ddof=1))
 
   def get_cem_action(self, objective_fn):
-    """CEM approximate argmax of objective_fn: (best sample, debug dict)."""
-
-    def update_fn(params, elite_samples):
-      del params
-      return {'mean': np.mean(elite_samples, axis=0), 'stddev': np.std(elite_samples, axis=0, ddof=1)}
-
-    initial_params = {'mean': np.zeros(self._action_size), 'stddev': np.ones(self._action_size)}
-    samples, values, final_params = cross_entropy.CrossEntropyMethod(
-        self.sample_fn, objective_fn, update_fn, initial_params, num_elites=self._num_elites,
-        num_iterations=self._cem_iters)
-    idx = np.argmax(values)
-    debug = {'q_predicted': values[idx], 'final_params': final_params, 'best_idx': idx}
-    return samples[idx], debug
-
-  def _default_pack_fn(self, t2r_model, state, context, timestep, samples):
-    return t2r_model.pack_features(state, context, timestep, samples)
+    """objective_fn(samples [S, D]) -> values [S].  Returns (arg-max sample of the last iteration, debug dict with
+    'q_predicted', 'final_params' {'mean', 'stddev'} and 'best_idx')."""
+    dims = self._population[1]
+    samples, values, params = cross_entropy.CrossEntropyMethod(
+        self.sample_fn, objective_fn, self._refit, dict(mean=np.zeros(dims), stddev=np.ones(dims)),
+        num_elites=self._num_elites, num_iterations=self._cem_iters)
+    best = int(np.argmax(values))
+    return samples[best], dict(q_predicted=values[best], final_params=params, best_idx=best)
 
   def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
+    if self._device_maximizer is not None:
+      action, _ = self._device_maximizer(state)
+      return np.asarray(action)
 
-    def objective_fn(samples):
-      np_inputs = self.pack_fn(self._t2r_model, state, context, timestep, samples)
-      return self._predictor.predict(np_inputs)['q_predicted']
+    def q_values(samples):
+      features = self.pack_fn(self._t2r_model, state, context, timestep, samples)
+      return self._predictor.predict(features)['q_predicted']
 
-    action, _ = self.get_cem_action(objective_fn)
-    return action
-
-
-class LSTMCEMPolicy(CEMPolicy):
-  """Like CEMPolicy, but caches the hidden state of the critic."""
-
-  def __init__(self, hidden_state_size, **kwargs):
-    self._hidden_state_size = hidden_state_size
-    super(LSTMCEMPolicy, self).__init__(**kwargs)
-
-  def reset(self):
-    self._hidden_state = np.zeros((self._hidden_state_size,), dtype=np.float32)
-
-  def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
-
-    def objective_fn(samples):
-      np_inputs = self.pack_fn(self._t2r_model, state, self._hidden_state, timestep, samples)
-      predictions = self._predictor.predict(np_inputs)
-      self._hidden_state_batch = predictions['lstm_hidden_state']   # all hidden states of this CEM iteration
-      return predictions['q_predicted']
-
-    action, debug = self.get_cem_action(objective_fn)
-    self._hidden_state = self._hidden_state_batch[debug['best_idx']]
-    return action
+    return self.get_cem_action(q_values)[0]
 
 
 class RegressionPolicy(Policy):
-  """Policy for continuous-action regression models."""
+  """The first row of the regression model's `inference_output` is the action."""
 
   def __init__(self, t2r_model, **parent_kwargs):
     super(RegressionPolicy, self).__init__(**parent_kwargs)
     self._t2r_model = t2r_model
 
   def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
-    np_inputs = self._t2r_model.pack_features(state, context, timestep)
-    return self._predictor.predict(np_inputs)['inference_output'][0]
-
-
-class OUExploreRegressionPolicy(Policy):
-  """Adds action noise generated by an Ornstein-Uhlenbeck process."""
-
-  def __init__(self, t2r_model, action_size=2, theta=.2, sigma=.15, use_noise=True, **parent_kwargs):
-    super(OUExploreRegressionPolicy, self).__init__(**parent_kwargs)
-    self._t2r_model = t2r_model
-    self.theta, self.sigma, self.mu = theta, sigma, 0
-    self._action_size = action_size
-    self._x_t = np.zeros(action_size)
-    self._use_noise = use_noise
-
-  def ou_step(self):
-    dx_t = self.theta * (self.mu - self._x_t) + self.sigma * np.random.randn(*self._x_t.shape)
-    self._x_t = self._x_t + dx_t
-    return self._x_t
-
-  def reset(self):
-    self._x_t = np.zeros(self._action_size)
-
-  def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
-    np_inputs = self._t2r_model.pack_features(state, context, timestep)
-    action = self._predictor.predict(np_inputs)['inference_output']
-    noise = self.ou_step() if self._use_noise else 0
-    return action[0] + noise
-
-
-class ScheduledExplorationRegressionPolicy(Policy):
-  """Adds gaussian action noise according to a linear stddev schedule over the global step."""
-
-  def __init__(self, t2r_model, action_size=2, stddev_0=0.2, slope=0, **parent_kwargs):
-    super(ScheduledExplorationRegressionPolicy, self).__init__(**parent_kwargs)
-    self._t2r_model = t2r_model
-    self._action_size = action_size
-    self._stddev_0 = stddev_0
-    self._slope = slope
-
-  def get_noise(self):
-    stddev = max(self._stddev_0 + self.global_step * self._slope, 0)
-    return stddev * np.random.randn(self._action_size)
-
-  def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
-    np_inputs = self._t2r_model.pack_features(state, context, timestep)
-    action = self._predictor.predict(np_inputs)['inference_output']
-    return action[0] + self.get_noise()
-
-
-class PerEpisodeSwitchPolicy(Policy):
-  """Per episode, randomly uses an exploration policy or a greedy policy."""
-
-  def __init__(self, explore_policy_class, greedy_policy_class, explore_prob, **parent_kwargs):
-    super(PerEpisodeSwitchPolicy, self).__init__(**parent_kwargs)
-    self._explore_policy = explore_policy_class()
-    self._greedy_policy = greedy_policy_class()
-    self._explore_prob = explore_prob
-    self._active_policy = None
-
-  def reset(self):
-    self._explore_policy.reset()
-    self._greedy_policy.reset()
-    self._active_policy = self._explore_policy if np.random.random() < self._explore_prob else self._greedy_policy
-
-  def init_randomly(self):
-    self._explore_policy.init_randomly()
-    self._greedy_policy.init_randomly()
-
-  def restore(self):
-    self._explore_policy.restore()
-    self._greedy_policy.restore()
-
-  @property
-  def global_step(self):
-    return self._greedy_policy.global_step
-
-  def SelectAction(self, state, context, timestep):  # pylint: disable=invalid-name
-    return self._active_policy.SelectAction(state, context, timestep)
+    features = self._t2r_model.pack_features(state, context, timestep)
+    return self._predictor.predict(features)['inference_output'][0]

@@ -272,6 +272,92 @@ static void tests_conv() {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// batch-norm operand fusion: fprop / wgrad / dgrad *_bnrelu against the unfused pipeline
+// (t2r_bn_apply -> t2r_conv2d_*) on the device, and the reduction against a CPU loop
+// ------------------------------------------------------------------------------------------
+static void test_bnfuse(const ConvCase& c, bool with_res, bool accumulate) {
+  std::string name = std::string("bnfuse ") + c.name + (with_res ? " +res" : "") + (accumulate ? " +acc" : "");
+  if (g_filter && !strstr(name.c_str(), g_filter)) return;
+  const T2RConvDesc d = mkdesc(c);
+  const size_t nx = size_t(c.N) * c.H * c.W * c.Cin, ny = size_t(c.N) * c.Ho * c.Wo * c.Cout;
+  const int taps = c.KH * c.KW;
+  const size_t nw = size_t(c.Cout) * taps * c.Cin;
+  const float wscale = 1.0f / sqrtf(float(taps * c.Cin));
+  std::vector<float> x = randv(nx, 2.f), w = randv(nw, wscale, false), res = randv(ny), dy = randv(ny), prev = randv(nx),
+                     scale = randv(c.Cin, 1.f, false), shift = randv(c.Cin, 1.f, false);
+  for (auto& v : scale) v = 0.75f + 0.5f * v;
+  Dev<__nv_bfloat16> dx_(nx), dz(nx), dres(ny), ddy(ny), y0(ny), y1(ny), dwf(nw), dwd(nw), g0(nx), g1(nx);
+  Dev<float> dw32(nw), dsc(c.Cin), dsh(c.Cin), dw0(nw), dw1(nw);
+  Dev<double> st0(2 * c.Cout), st1(2 * c.Cout), red(2 * c.Cin);
+  dx_.up(to_bf16(x)); dres.up(to_bf16(res)); ddy.up(to_bf16(dy)); dw32.up(w); dsc.up(scale); dsh.up(shift);
+  T2R(t2r_pack_weights(dw32.p, dwf.p, dwd.p, c.Cout, taps, c.Cin, nullptr));
+  T2R(t2r_bn_apply(dx_.p, dz.p, int64_t(c.N) * c.H * c.W, c.Cin, dsc.p, dsh.p, nullptr, 1, 1, nullptr));
+  const bool one = c.KH == 1 && c.KW == 1;
+  if (one) {
+    T2RConvDesc df = d;
+    df.flags = with_res ? T2R_EPI_RESIDUAL : 0;
+    T2R(t2r_conv2d_fprop_stats(&df, dz.p, dwf.p, nullptr, with_res ? dres.p : nullptr, y0.p, st0.p, nullptr));
+    T2R(t2r_conv2d_fprop_bnrelu(&df, dx_.p, dsc.p, dsh.p, dwf.p, with_res ? dres.p : nullptr, y1.p, st1.p, nullptr));
+    T2R(t2r_conv2d_wgrad(&d, dz.p, ddy.p, dw0.p, nullptr));
+    T2R(t2r_conv2d_wgrad_bnrelu(&d, dx_.p, dsc.p, dsh.p, ddy.p, dw1.p, nullptr));
+  }
+  if (accumulate) { g0.up(to_bf16(prev)); g1.up(to_bf16(prev)); }
+  T2R(t2r_conv2d_dgrad(&d, ddy.p, dwd.p, g0.p, accumulate ? 1 : 0, nullptr));
+  T2R(t2r_conv2d_dgrad_bnrelu(&d, ddy.p, dwd.p, dx_.p, dsc.p, dsh.p, g1.p, accumulate ? 1 : 0, red.p, nullptr));
+  sync_check(name.c_str());
+  if (one) {
+    report(name + " fprop (vs bn_apply+fprop)", from_bf16(y1.down()), from_bf16(y0.down()), 0.f, 0.f);
+    std::vector<double> s0 = st0.down(), s1 = st1.down();
+    std::vector<float> a(s0.begin(), s0.end()), b(s1.begin(), s1.end());
+    report(name + " fprop fused stats", b, a, 1e-5f, 1e-3f);
+    double wmax = 0;
+    std::vector<float> r0 = dw0.down();
+    for (float v : r0) wmax = fmax(wmax, fabs(v));
+    report(name + " wgrad (vs bn_apply+wgrad)", dw1.down(), r0, 1e-4f, float(1e-5 * wmax + 1e-6));
+  }
+  // reference: mask the plain data gradient on the CPU, reduce in double
+  std::vector<float> dzr = from_bf16(g0.down()), gref(nx), redref(2 * c.Cin);
+  std::vector<double> acc(2 * c.Cin, 0.0);
+  for (size_t i = 0; i < nx; ++i) {
+    const int ch = int(i % c.Cin);
+    const bool on = fmaf(x[i], scale[ch], shift[ch]) > 0.f;
+    gref[i] = on ? dzr[i] : 0.f;
+    acc[ch] += gref[i];
+    acc[c.Cin + ch] += double(gref[i]) * x[i];
+  }
+  double rmax = 0;
+  for (int i = 0; i < 2 * c.Cin; ++i) { redref[i] = float(acc[i]); rmax = fmax(rmax, fabs(acc[i])); }
+  std::vector<float> gout = from_bf16(g1.down());
+  // fused launches store the masked gradient; fallback launches (halo / accumulate) store the plain one
+  bool masked = true;
+  for (size_t i = 0; i < nx && masked; ++i) masked = gout[i] == gref[i];
+  report(name + (masked ? " dgrad g (masked)" : " dgrad g (plain, reduce pass)"), gout, masked ? gref : dzr, 0.f, 0.f);
+  std::vector<double> rd = red.down();
+  std::vector<float> rdf(rd.begin(), rd.end());
+  report(name + " dgrad sums", rdf, redref, 2e-4f, float(2e-5 * rmax + 1e-4));
+}
+
+static void tests_bnfuse() {
+  const ConvCase cases[] = {
+      {"1x1 19x17 64->256", 2, 19, 17, 64, 256, 1, 1, 1, 0, 0, 19, 17, 0},       // tma<128> x2 / dgrad tma<64>
+      {"1x1 19x17 256->64", 2, 19, 17, 256, 64, 1, 1, 1, 0, 0, 19, 17, 0},       // tma<64>, 4 K chunks / dgrad tma<128>
+      {"1x1 30x30 512->128", 3, 30, 30, 512, 128, 1, 1, 1, 0, 0, 30, 30, 0},     // dgrad 512 out ch, K = 128
+      {"1x1 9x9 1024->512", 2, 9, 9, 1024, 512, 1, 1, 1, 0, 0, 9, 9, 0},         // igemm<256> register epilogue both ways
+      {"1x1 s2 15x15 256->512", 2, 15, 15, 256, 512, 1, 1, 2, 0, 0, 8, 8, 0},    // strided projection: phase launches
+      {"3x3 s1 20x20 128->128", 2, 20, 20, 128, 128, 3, 3, 1, 1, 1, 20, 20, 0},  // dgrad only (tma<128>)
+      {"3x3 s2 21x21 256->256", 2, 21, 21, 256, 256, 3, 3, 2, 1, 1, 11, 11, 0},  // dgrad only, 4 phases, igemm<256>
+      {"3x3 s1 37x21 64->64 halo", 1, 37, 21, 64, 64, 3, 3, 1, 1, 1, 37, 21, 0}, // halo kernel
+  };
+  for (const auto& c : cases) {
+    test_bnfuse(c, false, false);
+  }
+  test_bnfuse(cases[0], true, false);
+  test_bnfuse(cases[1], false, true);
+  test_bnfuse(cases[3], true, false);
+}
+
 // ------------------------------------------------------------------------------------------
 // batch norm
 // ------------------------------------------------------------------------------------------
@@ -616,12 +702,15 @@ int main(int argc, char** argv) {
   printf("device: %s sm_%d%d, %d SMs, lib version %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
          t2r_version());
   tests_conv();
+  tests_bnfuse();
   test_bn(1000, 64, true, 1, false);
   test_bn(777, 256, false, 1, true);
   test_bn(64, 2048, true, 0, false);
   test_bn(5000, 192, true, 1, true);
   test_maxpool(2, 23, 23, 64, 3, 3, true);
   test_maxpool(2, 22, 21, 64, 3, 2, true);
+  test_maxpool(2, 23, 22, 64, 3, 2, true);
+  test_maxpool(1, 17, 19, 128, 3, 2, false);
   test_maxpool(1, 27, 27, 64, 2, 2, true);
   test_maxpool(1, 12, 12, 128, 2, 2, false);
   test_misc();

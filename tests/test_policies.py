@@ -56,28 +56,19 @@ def test_cem_policy_finds_the_argmax():
   assert predictor.calls[-2:] == ['init', 'restore'] and policy.global_step == 7 and policy.model_path == '/some/path'
 
 
-def test_regression_policies():
-  np.random.seed(1)
+def test_regression_policy_and_device_cem_hook():
   predictor = _QuadraticPredictor([0.1, 0.2])
   state = np.zeros((4, 4, 3))
   np.testing.assert_allclose(policies.RegressionPolicy(_Model(), predictor=predictor).SelectAction(state, None, 0), [0.1, 0.2])
-  ou = policies.OUExploreRegressionPolicy(_Model(), action_size=2, predictor=predictor)
-  a1, a2 = ou.SelectAction(state, None, 0), ou.SelectAction(state, None, 1)
-  assert np.abs(a1 - [0.1, 0.2]).max() > 0 and np.abs(a2 - a1).max() > 0
-  ou.reset()
-  assert np.all(ou._x_t == 0)                                    # pylint: disable=protected-access
-  quiet = policies.OUExploreRegressionPolicy(_Model(), use_noise=False, predictor=predictor)
-  np.testing.assert_allclose(quiet.SelectAction(state, None, 0), [0.1, 0.2])
-  sched = policies.ScheduledExplorationRegressionPolicy(_Model(), stddev_0=0.7, slope=-0.1, predictor=predictor)
-  np.testing.assert_allclose(sched.SelectAction(state, None, 0), [0.1, 0.2])       # stddev = max(0.7 - 7 * 0.1, 0) = 0
-  assert policies.Policy.__abstractmethods__ == frozenset({'SelectAction'})
-  switch = policies.PerEpisodeSwitchPolicy(lambda: policies.RegressionPolicy(_Model(), predictor=_QuadraticPredictor([1., 1.])),
-                                           lambda: policies.RegressionPolicy(_Model(), predictor=predictor), explore_prob=0.5)
-  seen = set()
-  for _ in range(40):
-    switch.reset()
-    seen.add(tuple(switch.SelectAction(state, None, 0)))
-  assert seen == {(1.0, 1.0), (0.1, 0.2)} and switch.global_step == 7
+  with pytest.raises(NotImplementedError):
+    policies.Policy().SelectAction(state, None, 0)
+  assert policies.Policy().global_step == 0 and policies.Policy().model_path == 'No model path defined.'
+  # device mode: the whole search is delegated (engine.device_cem_selector on a GPU); the predictor is not called
+  seen = []
+  device = policies.CEMPolicy(_Model(), action_size=2, predictor=predictor,
+                              device_maximizer=lambda s: (seen.append(s.shape) or np.array([0.5, -0.5]), 0.9))
+  np.testing.assert_allclose(device.SelectAction(state, None, 0), [0.5, -0.5])
+  assert seen == [(4, 4, 3)] and predictor.calls == []
 
 
 def test_predictor_contract_without_gpu():
