@@ -106,6 +106,23 @@ int32_t t2r_conv2d_wgrad_bnrelu(const T2RConvDesc* d, const void* x_raw, const f
 int32_t t2r_conv2d_dgrad_bnrelu(const T2RConvDesc* d, const void* dy, const void* w_dgrad, const void* x_raw,
                                 const float* bn_scale, const float* bn_shift, void* g, int32_t accumulate,
                                 double* red, void* stream);
+/* ---- high-precision PREDICT path (csrc/hp.cu) ----------------------------------------------
+ * fp32 activations; a convolution y = conv(x, w) is evaluated as bf16x3: x3 = [hi | lo | hi] (t2r_hp_split3), w3 =
+ * [w_hi | w_hi | w_lo] (t2r_hp_pack_weights3), then t2r_conv2d_fprop with Cin' = 3*Cin and T2R_EPI_OUT_F32 (fp32
+ * accumulation): products are exact in fp32 and the operands carry 16 mantissa bits, which brings the critics'
+ * q_predicted within 1e-4 of the fp32 restatement of research/qtopt/networks.py:343-615 /
+ * layers/film_resnet_model.py:525-629 (tests/test_high_precision_gpu.py) where bf16 storage gives ~1e-2.
+ * The fp32 pooling / merge / add kernels are the inference-only counterparts of the bf16 ones below. */
+int32_t t2r_hp_split3(const float* x, void* x3_bf16, int64_t rows, int32_t C, void* stream);
+int32_t t2r_hp_pack_weights3(const float* w_ohwi, void* w3_bf16, int32_t Cout, int32_t taps, int32_t Cin, void* stream);
+int32_t t2r_maxpool_f32_fwd(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                            int32_t stride, int32_t pad_top, int32_t pad_left, int32_t Ho, int32_t Wo, void* stream);
+int32_t t2r_global_mean_f32_fwd(const float* x, float* y, int32_t N, int32_t HW, int32_t C, void* stream);
+/* tile_batch(x, A) + ctx[:, None, None, :] in fp32 (research/qtopt/networks.py:513-522). */
+int32_t t2r_add_context_f32_fwd(const float* x, const float* ctx, float* y, int32_t B, int32_t A, int32_t HW, int32_t C,
+                                void* stream);
+int32_t t2r_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+
 /* fp32 master OHWI -> bf16 OHWI (w_fprop) and bf16 [Cin][taps][Cout] (w_dgrad; may be NULL). */
 int32_t t2r_pack_weights(const float* w, void* w_fprop, void* w_dgrad, int32_t Cout,
                          int32_t taps, int32_t Cin, void* stream);

@@ -65,6 +65,12 @@ _PROTOS = {
     't2r_conv2d_wgrad_bnrelu': (_I32, [_CD, _P, _P, _P, _P, _P, _P]),
     't2r_conv2d_dgrad_bnrelu': (_I32, [_CD, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
     't2r_pack_weights': (_I32, [_P, _P, _P, _I32, _I32, _I32, _P]),
+    't2r_hp_split3': (_I32, [_P, _P, _I64, _I32, _P]),
+    't2r_hp_pack_weights3': (_I32, [_P, _P, _I32, _I32, _I32, _P]),
+    't2r_maxpool_f32_fwd': (_I32, [_P, _P] + [_I32] * 10 + [_P]),
+    't2r_global_mean_f32_fwd': (_I32, [_P, _P, _I32, _I32, _I32, _P]),
+    't2r_add_context_f32_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    't2r_add_f32': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_im2col_small_cin': (_I32, [_CD, _P, _P, _I32, _P]),
     't2r_pad_nhwc3_c4': (_I32, [_P, _P] + [_I32] * 7 + [_P]),
     't2r_stem_conv_fprop': (_I32, [_CD, _P, _I32, _I32, _P, _P, _P, _P]),

@@ -277,19 +277,36 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 // operand-fused convolutions.  `piece` is the shared address of the caller's first piece, `n` pieces `step` bytes
 // apart (the caller picks rows that share r & 7, so the chunk position is the same for all of them); sc / sh are the
 // 8 channels of the caller's logical chunk.  Arithmetic and rounding are those of bn_apply_rows_kernel (norm.cu).
-__device__ __forceinline__ void bnrelu_pieces_inplace(uint32_t piece, int n, uint32_t step, const float (&sc)[8],
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));   // rounding is monotonic: relu(rn(z)) == rn(relu(z))
+  return r;
+}
+__device__ __forceinline__ uint4 bnrelu_piece(const uint4 q, const float (&sc)[8], const float (&sh)[8]) {
+  uint4 o;
+  o.x = relu_bf16x2(pack_bf16(fmaf(bf16_lo(q.x), sc[0], sh[0]), fmaf(bf16_hi(q.x), sc[1], sh[1])));
+  o.y = relu_bf16x2(pack_bf16(fmaf(bf16_lo(q.y), sc[2], sh[2]), fmaf(bf16_hi(q.y), sc[3], sh[3])));
+  o.z = relu_bf16x2(pack_bf16(fmaf(bf16_lo(q.z), sc[4], sh[4]), fmaf(bf16_hi(q.z), sc[5], sh[5])));
+  o.w = relu_bf16x2(pack_bf16(fmaf(bf16_lo(q.w), sc[6], sh[6]), fmaf(bf16_hi(q.w), sc[7], sh[7])));
+  return o;
+}
+// `piece` is the shared address of the caller's first piece, kN pieces `step` bytes apart: all loads are issued
+// before the first store so that the eight shared-memory round trips overlap.
+template <int kN>
+__device__ __forceinline__ void bnrelu_pieces_inplace(uint32_t piece, uint32_t step, const float (&sc)[8],
                                                       const float (&sh)[8]) {
-#pragma unroll 4
-  for (int i = 0; i < n; ++i) {
-    uint4 q;
-    const uint32_t a = piece + uint32_t(i) * step;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
-    const float f0 = fmaxf(fmaf(bf16_lo(q.x), sc[0], sh[0]), 0.f), f1 = fmaxf(fmaf(bf16_hi(q.x), sc[1], sh[1]), 0.f);
-    const float f2 = fmaxf(fmaf(bf16_lo(q.y), sc[2], sh[2]), 0.f), f3 = fmaxf(fmaf(bf16_hi(q.y), sc[3], sh[3]), 0.f);
-    const float f4 = fmaxf(fmaf(bf16_lo(q.z), sc[4], sh[4]), 0.f), f5 = fmaxf(fmaf(bf16_hi(q.z), sc[5], sh[5]), 0.f);
-    const float f6 = fmaxf(fmaf(bf16_lo(q.w), sc[6], sh[6]), 0.f), f7 = fmaxf(fmaf(bf16_hi(q.w), sc[7], sh[7]), 0.f);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(f0, f1)), "r"(pack_bf16(f2, f3)),
-                 "r"(pack_bf16(f4, f5)), "r"(pack_bf16(f6, f7))
+  uint4 q[kN];
+#pragma unroll
+  for (int i = 0; i < kN; ++i)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w)
+                 : "r"(piece + uint32_t(i) * step)
+                 : "memory");
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    const uint4 o = bnrelu_piece(q[i], sc, sh);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(piece + uint32_t(i) * step), "r"(o.x), "r"(o.y), "r"(o.z),
+                 "r"(o.w)
                  : "memory");
   }
 }

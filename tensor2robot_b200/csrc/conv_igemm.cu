@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_kernel(const _
           load8(p.bn_scale + c * 64 + j * 8, sc);
           load8(p.bn_shift + c * 64 + j * 8, sh);
           mbar_wait(full_bar(stage), phase);
-          bnrelu_pieces_inplace(smem_base + stage * Cfg::kStageBytes + piece0, 8, 2048u, sc, sh);
+          bnrelu_pieces_inplace<8>(smem_base + stage * Cfg::kStageBytes + piece0, 2048u, sc, sh);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(ready_bar(stage));
@@ -637,9 +637,12 @@ static int32_t dgrad_impl(const T2RConvDesc* d, const void* dy, const void* w_dg
   // Batch-norm backward fusion: the epilogues mask and reduce while they write (kEpiBnBwd) unless the launch
   // accumulates into dx (the mask would have to cover the sum) or runs on the halo kernel; those cases run the
   // plain data gradient followed by the stand-alone reduction pass over (dx, x).
-  static const bool no_bnbwd = std::getenv("T2R_DISABLE_BNBWD_EPI") != nullptr;
+  // Measured on B200 (profiles/r02_bn_fusion.md): the fused epilogue costs ~24 instructions per element where a
+  // memory-bound kernel can afford ~6, e.g. 3.3 ms against 1.1 ms (data gradient) + 1.2 ms (reduction pass) on
+  // 512x118x118x256, so the reduction pass below stays the default and the epilogue is opt-in (T2R_BNBWD_EPI=1).
+  static const bool epi_bnbwd = std::getenv("T2R_BNBWD_EPI") != nullptr && std::getenv("T2R_BNBWD_EPI")[0] == '1';
   const bool want_bn = bn_x != nullptr;
-  bool fuse_bn = want_bn && !no_bnbwd && !accumulate && d->Cin <= kMaxStatChannels;
+  bool fuse_bn = want_bn && epi_bnbwd && !accumulate && d->Cin <= kMaxStatChannels;
   const int s = d->stride;
   const int taps_total = d->KH * d->KW;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

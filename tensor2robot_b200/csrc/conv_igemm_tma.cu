@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(con
           load8(p.bn_scale + c * 64 + j * 8, sc);
           load8(p.bn_shift + c * 64 + j * 8, sh);
           mbar_wait(full_bar(stage), phase);
-          bnrelu_pieces_inplace(smem_base + stage * Cfg::kStageBytes + piece0, 8, 2048u, sc, sh);
+          bnrelu_pieces_inplace<8>(smem_base + stage * Cfg::kStageBytes + piece0, 2048u, sc, sh);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(ready_bar(stage));

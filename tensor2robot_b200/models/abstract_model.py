@@ -14,6 +14,7 @@ Session.run of the reference's train_op.
 """
 import abc
 import collections
+import contextlib
 import logging
 
 import torch
@@ -82,6 +83,7 @@ class AbstractT2RModel(model_interface.ModelInterface):
     self._use_avg_model_params = use_avg_model_params
     self._init_from_checkpoint_fn = init_from_checkpoint_fn
     self._optimizer = None
+    self._reducer = None
     self._device = device
     self._seed = seed
     self._vs = None
@@ -246,19 +248,10 @@ class AbstractT2RModel(model_interface.ModelInterface):
       self.build(features, labels)
     out = self.model_fn(features, labels, TRAIN, config, params)
     task_losses = (out.train_outputs or {}).get(PCGRAD_LOSSES_COLLECTION) if isinstance(out.train_outputs, dict) else None
-    if task_losses and hasattr(self.optimizer, 'compute_gradients'):
-      # research/qtopt/pcgrad.py:99-121 (use_collection_losses): one backward per task loss, projected gradients
-      self.optimizer.compute_gradients(list(task_losses), vs)
-    else:
-      vs.zero_grad()
-      out.loss.backward()
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    grad_scale = 1.0
-    if world > 1:
-      dist.all_reduce(vs.flat_grad, op=dist.ReduceOp.SUM)
-      grad_scale = 1.0 / world
-    self.optimizer.apply_gradients(vs, self.global_step, grad_scale)
-    vs.sync_compute_copies(after_optimizer=True)
+    from tensor2robot_b200 import engine   # the shared step tail (backward, bucketed all-reduce, fused optimizer)
+    if self._reducer is None or self._reducer.vs is not vs:
+      self._reducer = engine.GradientReducer(vs)
+    engine.optimization_step(vs, self.optimizer, self.global_step, out.loss, task_losses, self._reducer)
     self.global_step += 1
     total = out.loss.detach()
     l2 = self.l2_regularization()
@@ -270,16 +263,61 @@ class AbstractT2RModel(model_interface.ModelInterface):
     return self.model_fn(features, None, PREDICT, config, params).predictions
 
   # -- checkpoints (TF variable names / layouts) --------------------------------------
+  # With a MovingAverageOptimizer (use_avg_model_params) the reference installs optimizer.swapping_saver
+  # (models/abstract_model.py:855-863): checkpoints and exports hold the AVERAGED parameters under the variable
+  # names, which is what predictors, the lagged target export and evaluation load; the raw parameters travel beside
+  # them so that training resumes exactly.
+  def _moving_average_shadow(self):
+    return optimizers.moving_average_shadow(self._optimizer)
+
+  @contextlib.contextmanager
+  def averaged_parameters(self):
+    """Runs the body with the averaged parameters swapped in (no-op without a moving average)."""
+    vs, ema = self.variable_store, self._moving_average_shadow()
+    if ema is None or not vs.finalized:
+      yield
+      return
+    raw = vs.flat.clone()
+    vs.flat.copy_(ema)
+    vs.sync_compute_copies()
+    try:
+      yield
+    finally:
+      vs.flat.copy_(raw)
+      vs.sync_compute_copies()
+
+  def export_variables(self):
+    """{reference variable name: array in the TF layout}, averaged parameters when a moving average exists."""
+    vs, ema = self.variable_store, self._moving_average_shadow()
+    if ema is None or not vs.finalized:
+      return vs.export_tf()
+    raw = vs.flat.clone()
+    vs.flat.copy_(ema)
+    try:
+      return vs.export_tf()
+    finally:
+      vs.flat.copy_(raw)
+
   def state_dict(self):
     vs = self.variable_store
-    return {'variables': vs.export_tf(), 'optimizer': self.optimizer.state_dict() if self._optimizer else {},
-            'global_step': self.global_step}
+    state = {'variables': self.export_variables(), 'optimizer': self.optimizer.state_dict() if self._optimizer else {},
+             'global_step': self.global_step}
+    if self._moving_average_shadow() is not None and vs.finalized:
+      state['raw_parameters'] = vs.flat.detach().cpu()    # 'variables' are the averages
+    return state
 
-  def load_state_dict(self, state):
+  def load_state_dict(self, state, restore_training_state=True):
+    """restore_training_state=False (serving): keep whatever 'variables' holds - the averaged parameters when the
+    checkpoint was written with a moving average - and ignore the optimizer slots."""
     vs = self.variable_store
     vs.import_tf(state['variables'])
-    if state.get('optimizer'):
-      self.optimizer.load_state_dict(state['optimizer'], vs)
+    if restore_training_state:
+      if state.get('optimizer'):
+        self.optimizer.load_state_dict(state['optimizer'], vs)
+      raw = state.get('raw_parameters')
+      if raw is not None and raw.numel() == vs.flat.numel():
+        vs.flat.copy_(raw.to(vs.flat.device))
+        vs.sync_compute_copies()
     self.global_step = int(state.get('global_step', 0))
 
   # -- run config / device ----------------------------------------------------------------------

@@ -167,6 +167,18 @@ class MovingAverageOptimizer(Optimizer):
       self.shadow(vs).copy_(state['ema'].to(vs.device))
 
 
+def moving_average_shadow(optimizer):
+  """The EMA shadow buffer (flat fp32, the layout of VariableStore.flat) of a MovingAverageOptimizer, looking
+  through wrappers that hold their optimizer as `_optimizer` / `inner` (PCGrad); None when there is none yet."""
+  seen = 0
+  while optimizer is not None and seen < 4:
+    if isinstance(optimizer, MovingAverageOptimizer):
+      return optimizer._ema   # pylint: disable=protected-access
+    optimizer = getattr(optimizer, '_optimizer', None)
+    seen += 1
+  return None
+
+
 # ---- factories with the reference's names --------------------------------------------------------
 def default_create_optimizer_fn(use_summaries, learning_rate=1e-4):
   del use_summaries

@@ -66,6 +66,15 @@ class Variable(object):
     self.bf16 = None    # bf16 copy in compute layout (conv: OHWI)
     self.dgrad = None   # bf16 [Cin][taps][Cout] for conv layers that need a data gradient
     self.needs_dgrad = False
+    self.store = None   # the VariableStore that owns the variable
+
+  def grad_ready(self):
+    """Called by a backward kernel wrapper once this variable's gradient is complete in the flat buffer: lets the
+    data-parallel reducer start the all-reduce of a finished bucket while the backward pass is still running, and
+    catches a trainable variable used twice in one pass (the kernels OVERWRITE .grad, so the TF `reuse=True`
+    pattern would silently drop a contribution)."""
+    if self.store is not None:
+      self.store.grad_ready(self)
 
   @property
   def numel(self):
@@ -146,6 +155,7 @@ class VariableStore(object):
     v = Variable(full, shape, trainable, regularize, kind, tf_layout)
     value = init(v.shape, self._rng) if callable(init) else np.full(v.shape, init, np.float32)
     v.data = torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32)).to(self.device)
+    v.store = self
     self.vars[full] = v
     return v
 
@@ -206,6 +216,7 @@ class VariableStore(object):
     st = _stream()
     if not self._finalized:
       raise ValueError('finalize() first')
+    self.compute_epoch = getattr(self, 'compute_epoch', 0) + 1   # invalidates weights derived from the masters
     if not after_optimizer:
       _lib.call('t2r_cast_f32_to_bf16', _p(self.flat), _p(self.flat_bf16), self.flat.numel(), st)
     for v in self.vars.values():
@@ -235,6 +246,17 @@ class VariableStore(object):
 
   def zero_grad(self):
     self.flat_grad.zero_()
+    self._grads_written = set()
+
+  def grad_ready(self, var):
+    written = self.__dict__.setdefault('_grads_written', set())
+    if var.name in written:
+      raise _lib.T2RError('variable %s received two gradients in one backward pass: the kernels overwrite .grad, '
+                          'weight sharing (a layer applied twice) is not supported' % var.name)
+    written.add(var.name)
+    listener = getattr(self, 'grad_listener', None)
+    if listener is not None:
+      listener(var)
 
   def scratch(self, key, numel, dtype):
     """Persistent small workspaces (BN statistics etc.), keyed by use site."""
@@ -336,6 +358,94 @@ class _prof(object):
     return False
 
 
+
+# ---------------------------------------------------------------------------------------------
+# high-precision PREDICT mode (csrc/hp.cu): fp32 activations, convolutions as bf16x3
+# ---------------------------------------------------------------------------------------------
+_HIGH_PRECISION = False
+
+
+@contextlib.contextmanager
+def high_precision():
+  """Inference graphs built inside this context keep every activation in fp32 and evaluate convolutions /
+  tensor-core dense layers as bf16x3 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation) on the same
+  tcgen05 kernels: q_predicted within 1e-4 of the fp32 restatement of the reference where bf16 activation
+  storage is ~1e-2 off.  Meant for what consumes Q values - CEM arg-max, Bellman targets, serving; the
+  training step stays bf16.  Images must be fed as fp32."""
+  global _HIGH_PRECISION
+  if torch.is_grad_enabled():
+    raise _lib.T2RError('nn.high_precision() is an inference mode: wrap it in torch.no_grad()')
+  old, _HIGH_PRECISION = _HIGH_PRECISION, True
+  try:
+    yield
+  finally:
+    _HIGH_PRECISION = old
+
+
+def is_high_precision():
+  return _HIGH_PRECISION
+
+
+def _hp_f32(x):
+  return to_f32(x).contiguous() if x.dtype != F32 else x.contiguous()
+
+
+def _hp_cached(v, key, build):
+  """Per-variable cache of derived weights, dropped whenever the store refreshes its compute copies."""
+  vs = current_store()
+  epoch = getattr(vs, 'compute_epoch', 0) if vs.finalized else None
+  cache = v.__dict__.setdefault('_hp_cache', {})
+  hit = cache.get(key)
+  if hit is not None and epoch is not None and hit[0] == epoch:
+    return hit[1]
+  value = build()
+  cache[key] = (epoch, value)
+  return value
+
+
+def _hp_conv(x, wv, bv, kh, kw, stride, ho, wo, pt, pl, residual, relu, small):
+  st = _stream()
+  x = _hp_f32(x)
+  n, h, w, cin = x.shape
+  cout = wv.shape[0]
+  y = torch.empty((n, ho, wo, cout), dtype=F32, device=x.device)
+  bias = bv.data if bv is not None else None
+  if small:   # the 3-channel stem: direct fp32 convolution on the CUDA cores (2 % of the network's flops)
+    w_hwio = _hp_cached(wv, 'hwio', lambda: torch.from_numpy(np.ascontiguousarray(wv.to_tf())).to(x.device))
+    _lib.call('t2r_conv2d_direct_f32_fwd', _p(x), _p(w_hwio), _p(bias), _p(y), n, h, w, cin, cout, kh, kw, stride, pt,
+              pl, ho, wo, st)
+  else:
+    def pack():
+      w3 = torch.empty((cout, kh, kw, 3 * cin), dtype=BF16, device=x.device)
+      _lib.call('t2r_hp_pack_weights3', _p(wv.data), _p(w3), cout, kh * kw, cin, st)
+      return w3
+    w3 = _hp_cached(wv, 'w3', pack)
+    x3 = torch.empty((n, h, w, 3 * cin), dtype=BF16, device=x.device)
+    _lib.call('t2r_hp_split3', _p(x), _p(x3), n * h * w, cin, st)
+    flags = _lib.T2R_EPI_OUT_F32 | (_lib.T2R_EPI_BIAS if bias is not None else 0)
+    d = _conv_desc(n, h, w, 3 * cin, cout, kh, kw, stride, pt, pl, ho, wo, flags)
+    with _prof('fprop', d):
+      _lib.call('t2r_conv2d_fprop', C.byref(d), _p(x3), _p(w3), _p(bias), None, _p(y), st)
+  if residual is not None:
+    _lib.call('t2r_add_f32', _p(y), _p(_hp_f32(residual)), _p(y), y.numel(), st)
+  if relu:
+    _lib.call('t2r_relu_f32_fwd', _p(y), _p(y), y.numel(), st)
+  return y
+
+
+def _hp_batch_norm(x, bn, relu):
+  x = _hp_f32(x)
+  c = x.shape[-1]
+  st = _stream()
+  gamma = bn['gamma'].data if bn['gamma'] is not None else torch.ones(c, dtype=F32, device=x.device)
+  y = torch.empty_like(x)
+  _lib.call('t2r_bn_infer_f32_fwd', _p(x), _p(gamma), _p(bn['beta'].data), _p(bn['moving_mean'].data),
+            _p(bn['moving_variance'].data), _p(y), x.numel() // c, c, bn['eps'], st)
+  if relu:
+    _lib.call('t2r_relu_f32_fwd', _p(y), _p(y), y.numel(), st)
+  return y
+
+
 def _conv_flops(d):
   return 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.KH * d.KW * d.Cin
 
@@ -431,25 +541,30 @@ FOLD_INFERENCE_BN = os.environ.get('T2R_FOLD_INFERENCE_BN', '1') != '0'
 
 
 # Training graphs: batch norm + ReLU and the convolution(s) that consume it run as ONE autograd node
-# (_BnReluConvFn): the data gradient's epilogue masks and reduces for the batch-norm backward
-# (t2r_conv2d_dgrad_bnrelu), and 1x1 consumers that are bound by HBM traffic read the RAW tensor and apply
-# the normalisation to their operand tiles in shared memory (t2r_conv2d_{fprop,wgrad}_bnrelu), so the
-# normalised activation is never written.  T2R_FUSE_BN_NODE=0 restores the separate nodes;
-# T2R_FUSE_BN_OPERAND = 0 | auto | all selects which 1x1 consumers fuse the apply pass.
+# (_BnReluConvFn).  Two kernel fusions hang off that node:
+#   * operand fusion (t2r_conv2d_{fprop,wgrad}_bnrelu): a 1x1 consumer reads the RAW tensor and applies the
+#     normalisation to its operand tiles in shared memory, so the normalised activation is never written.  The
+#     rewrite costs ~5 instructions per element on four extra warps and is repeated for every N tile of the
+#     GEMM, so it pays only where the A operand dominates the traffic and is read once: Cout <= 128 (one N tile),
+#     i.e. the 4C -> C reductions of the bottleneck blocks (measured on B200, profiles/r02_bn_fusion.md: 256->64
+#     at 118x118, batch 512: apply 1.2 ms saved for +0.37 fprop +0.23 wgrad; 256->1024 at 30x30 loses).
+#   * masked / reduced data gradients (t2r_conv2d_dgrad_bnrelu): correct and tested, but the epilogue needs ~24
+#     instructions per element against a budget of ~6 at HBM speed, so the stand-alone reduction pass is faster
+#     (same file); the C entry point therefore fuses only when T2R_BNBWD_EPI=1.
+# T2R_FUSE_BN_NODE=0 restores the separate nodes; T2R_FUSE_BN_OPERAND = 0 | auto | all.
 FUSE_BN_NODE = os.environ.get('T2R_FUSE_BN_NODE', '1') != '0'
 FUSE_BN_OPERAND = os.environ.get('T2R_FUSE_BN_OPERAND', 'auto')
-# flop / byte above which a 1x1 convolution is bound by the tensor pipe rather than by HBM (measured
-# sustained 1.4 PFLOP/s over 6.6 TB/s = 215): there the shared-memory rewrite would cost MMA time
-_BN_OPERAND_MAX_INTENSITY = float(os.environ.get('T2R_BN_OPERAND_MAX_INTENSITY', '180'))
+_BN_OPERAND_MAX_COUT = int(os.environ.get('T2R_BN_OPERAND_MAX_COUT', '128'))
+FUSE_BN_BWD_EPILOGUE = os.environ.get('T2R_BNBWD_EPI', '0') == '1'
 
 
 def _bn_operand_fusable(cin, cout, kh, kw, pt, pl, has_res):
+  del has_res
   if FUSE_BN_OPERAND == '0' or kh != 1 or kw != 1 or pt or pl:
     return False
   if FUSE_BN_OPERAND == 'all':
     return True
-  intensity = 2.0 * cin * cout / (2.0 * (cin + cout * (2 if has_res else 1)))
-  return intensity <= _BN_OPERAND_MAX_INTENSITY
+  return cout <= _BN_OPERAND_MAX_COUT and cin >= 2 * cout
 
 
 def _new_bn_stats(channels, device):
@@ -503,9 +618,11 @@ class _Conv2dFn(torch.autograd.Function):
       rows = dy.numel() // dy.shape[-1]
       ws = torch.empty(2 * dy.shape[-1], dtype=torch.float64, device=dy.device)
       _lib.call('t2r_colsum_bf16', _p(dy), rows, dy.shape[-1], _p(ws), _p(ctx.bias_var.grad), st)
+      ctx.bias_var.grad_ready()
     if var.trainable:
       with _prof('wgrad', d):
         _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(x), _p(dy), _p(var.grad), st)
+      var.grad_ready()
     dx = None
     if ctx.needs_input_grad[0]:
       if var.dgrad is None:
@@ -553,6 +670,7 @@ class _DualConvFn(torch.autograd.Function):
       if var.trainable:
         with _prof('wgrad', d):
           _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(x), _p(dy), _p(var.grad), st)
+        var.grad_ready()
       if dx is not None:
         with _prof('dgrad', d):
           _lib.call('t2r_conv2d_dgrad', C.byref(d), _p(dy), _p(var.dgrad), _p(dx), 1 if wrote else 0, st)
@@ -641,6 +759,7 @@ class _StemConvFn(torch.autograd.Function):
       rows = dy.numel() // dy.shape[-1]
       ws = torch.empty(2 * dy.shape[-1], dtype=torch.float64, device=dy.device)
       _lib.call('t2r_colsum_bf16', _p(dy), rows, dy.shape[-1], _p(ws), _p(ctx.bias_var.grad), st)
+      ctx.bias_var.grad_ready()
     if ctx.var.trainable:
       kh, kw = ctx.geom[0], ctx.geom[1]
       x4p, hp, wp, (key, gen) = ctx.packed
@@ -649,6 +768,7 @@ class _StemConvFn(torch.autograd.Function):
       with _prof('wgrad', ctx.desc):
         _lib.call('t2r_stem_conv_wgrad', C.byref(ctx.desc), _p(x4p), hp, wp, _p(dy), _p(ctx.var.grad), st)
       _lib.call('t2r_stem_mask_grad', _p(ctx.var.grad), ctx.var.shape[0], kh, kw, ctx.geom[2], st)
+      ctx.var.grad_ready()
     if ctx.needs_input_grad[0]:
       raise _lib.T2RError('stem convolution %s has no data gradient (image inputs are leaves)' % ctx.var.name)
     return None, None, None, None, None, None
@@ -755,6 +875,7 @@ class _BnReluConvFn(torch.autograd.Function):
           _lib.call('t2r_conv2d_wgrad_bnrelu', C.byref(d), _p(x), _p(scale), _p(shift), _p(dy), _p(var.grad), st)
         else:
           _lib.call('t2r_conv2d_wgrad', C.byref(d), _p(z), _p(dy), _p(var.grad), st)
+      var.grad_ready()
     dx = None
     if ctx.needs_input_grad[0]:
       # the convolution that covers every input pixel first; a strided projection (conv 0 of a pair) then
@@ -768,7 +889,7 @@ class _BnReluConvFn(torch.autograd.Function):
         if var.dgrad is None:
           raise _lib.T2RError('conv %s needs a data gradient but was built with needs_dgrad=False' % var.name)
         with _prof('dgrad', d):
-          if i == len(live) - 1:
+          if i == len(live) - 1 and FUSE_BN_BWD_EPILOGUE:
             _lib.call('t2r_conv2d_dgrad_bnrelu', C.byref(d), _p(dy), _p(var.dgrad), _p(x), _p(scale), _p(shift), _p(g),
                       1 if i else 0, _p(red), st)
           else:
@@ -777,8 +898,13 @@ class _BnReluConvFn(torch.autograd.Function):
       dgamma = gamma.grad if (gamma is not None and gamma.trainable) else vs.scratch('bn_dgamma', 4096, F32)
       dbeta = bn['beta'].grad if bn['beta'].trainable else vs.scratch('bn_dbeta', 4096, F32)
       dx = torch.empty_like(x)
-      _lib.call('t2r_bn_backward_presummed', _p(g), _p(x), _p(dpass), _p(dx), rows, c, _p(mean), _p(invstd), _p(scale),
-                _p(shift), 1, _p(red), _p(dgamma), _p(dbeta), st)
+      if FUSE_BN_BWD_EPILOGUE:
+        _lib.call('t2r_bn_backward_presummed', _p(g), _p(x), _p(dpass), _p(dx), rows, c, _p(mean), _p(invstd), _p(scale),
+                  _p(shift), 1, _p(red), _p(dgamma), _p(dbeta), st)
+      else:     # reduction pass + apply pass (the default: see FUSE_BN_NODE above)
+        _lib.call('t2r_bn_backward', _p(g), _p(x), _p(dpass), _p(dx), rows, c, _p(gamma.data if gamma is not None else None),
+                  _p(mean), _p(invstd), _p(scale), _p(shift), 1, _p(red), _p(dgamma), _p(dbeta), st)
+      _bn_grads_ready(bn)
     dres = dys[0] if (ctx.has_res and ctx.needs_input_grad[1]) else None
     return dx, dres, None, None, None, None, None, None
 
@@ -870,6 +996,8 @@ def conv2d(x, filters, kernel_size, stride=1, padding='SAME', use_bias=False, sc
     bv = vs.get_variable(names[1], (filters,), 0.0, trainable, False) if use_bias else None
   if not vs.finalized:
     _ensure_bf16(wv)
+  if _HIGH_PRECISION:
+    return _trace('conv', scope, _hp_conv(x, wv, bv, kh, kw, stride, ho, wo, pt, pl, residual, relu, small))
   if deferred_bn is not None:
     if not small and _node_fusable_conv(deferred_bn, wv, bv, relu, out_f32):
       (y,) = deferred_bn.run_convs([(wv, (stride, ho, wo, pt, pl))], residual)
@@ -970,6 +1098,12 @@ def dense(x, units, scope='fc', use_bias=False, initializer=None, regularize=Tru
 # ---------------------------------------------------------------------------------------------
 # batch norm (+ReLU, +FiLM)
 # ---------------------------------------------------------------------------------------------
+def _bn_grads_ready(bn):
+  for key in ('gamma', 'beta'):
+    if bn[key] is not None and bn[key].trainable:
+      bn[key].grad_ready()
+
+
 class _BatchNormFn(torch.autograd.Function):
 
   @staticmethod
@@ -1029,10 +1163,12 @@ class _BatchNormFn(torch.autograd.Function):
       sums = torch.empty((n, 2, c), dtype=F32, device=x.device)
       _lib.call('t2r_bn_film_backward', _p(dy), _p(x), _p(film), _p(dpass), _p(dx), _p(dfilm), rows, c, rows // n,
                 _p(mean), _p(invstd), _p(scale), _p(shift), 1 if ctx.relu else 0, _p(sums), _p(dgamma), _p(dbeta), st)
+      _bn_grads_ready(bn)
       return dx, (dfilm if ctx.needs_input_grad[1] else None), None, None, None, None, None, None
     _lib.call('t2r_bn_backward', _p(dy), _p(x), _p(dpass), _p(dx), rows, c,
               _p(gamma.data if gamma is not None else None), _p(mean), _p(invstd), _p(scale), _p(shift),
               1 if ctx.relu else 0, _p(red), _p(dgamma), _p(dbeta), st)
+    _bn_grads_ready(bn)
     return dx, None, None, None, None, None, None, None
 
 
@@ -1062,6 +1198,10 @@ def batch_norm(x, training, scope='BatchNorm', scale=True, relu=False, momentum=
     for k in ('gamma', 'beta'):
       if bn[k] is not None and bn[k].grad is None:
         bn[k].grad = torch.zeros(bn[k].shape, dtype=F32, device=x.device)
+  if _HIGH_PRECISION:
+    if training or film is not None or passthrough:
+      raise _lib.T2RError('high-precision mode is inference without FiLM')
+    return _trace('bn', scope, _hp_batch_norm(x, bn, relu))
   if deferred is not None:
     # y = relu(conv(u, W) * scale + shift) = relu(conv(u, W * scale) + shift)
     st = _stream()
@@ -1152,6 +1292,13 @@ def max_pool2d(x, kernel_size, stride, padding='SAME'):
   _require_cuda(x, 'max_pool2d')
   _, h, w, _ = x.shape
   geom = conv_geometry(h, w, kernel_size, kernel_size, stride, padding)
+  if _HIGH_PRECISION:
+    x = _hp_f32(x)
+    n, _, _, c = x.shape
+    ho, wo, pt, pl = geom
+    y = torch.empty((n, ho, wo, c), dtype=F32, device=x.device)
+    _lib.call('t2r_maxpool_f32_fwd', _p(x), _p(y), n, h, w, c, kernel_size, stride, pt, pl, ho, wo, _stream())
+    return _trace('pool', None, y)
   return _trace('pool', None, _MaxPoolFn.apply(x.contiguous(), kernel_size, stride, geom))
 
 
@@ -1176,6 +1323,12 @@ class _GlobalMeanFn(torch.autograd.Function):
 def global_mean(x):
   """tf.reduce_mean over the spatial axes (film_resnet_model.py:611-616)."""
   _require_cuda(x, 'global_mean')
+  if _HIGH_PRECISION:
+    x = _hp_f32(x)
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=F32, device=x.device)
+    _lib.call('t2r_global_mean_f32_fwd', _p(x), _p(y), n, h * w, c, _stream())
+    return y
   return _GlobalMeanFn.apply(x.contiguous())
 
 
@@ -1226,6 +1379,12 @@ def add_context(x, context, action_batch_size=1, defer_for_bn=False):
   _require_cuda(x, 'add_context')
   if context.shape[0] != x.shape[0] * action_batch_size:
     raise ValueError('context rows %d != batch %d * action_batch %d' % (context.shape[0], x.shape[0], action_batch_size))
+  if _HIGH_PRECISION:
+    x, context = _hp_f32(x), _hp_f32(context)
+    b, h, w, c = x.shape
+    y = torch.empty((b * action_batch_size, h, w, c), dtype=F32, device=x.device)
+    _lib.call('t2r_add_context_f32_fwd', _p(x), _p(context), _p(y), b, action_batch_size, h * w, c, _stream())
+    return _trace('add_context', None, y)
   if defer_for_bn and FOLD_INFERENCE_BN and not torch.is_grad_enabled():
     return DeferredContext(x.contiguous(), context.contiguous(), action_batch_size)
   return _trace('add_context', None, _AddContextFn.apply(x.contiguous(), context.contiguous(), action_batch_size))
@@ -1336,6 +1495,8 @@ class _CastFn(torch.autograd.Function):
 
 
 def to_bf16(x):
+  if _HIGH_PRECISION:      # activations stay fp32 in the high-precision mode
+    return x if x.dtype == F32 else _CastFn.apply(x.contiguous(), False)
   return x if x.dtype == BF16 else _CastFn.apply(x.contiguous(), True)
 
 
@@ -1378,12 +1539,14 @@ class _Fc32Fn(torch.autograd.Function):
     dy = dy.contiguous()
     if wv.trainable:   # dW[K,N] = x^T dy
       _lib.call('t2r_sgemm', 1, 0, k, n, m, 1.0, _p(x), k, _p(dy), n, 0.0, _p(wv.grad), n, st)
+      wv.grad_ready()
     if bv is not None and bv.trainable:
       db = torch.empty(n, dtype=F32, device=x.device)
       _lib.call('t2r_colsum_f32', _p(dy), _p(db), m, n, st)
       r = bv.shape[0]
       ones = torch.ones(r, dtype=F32, device=x.device)   # every summed bias row receives db
       _lib.call('t2r_sgemm', 0, 0, r, n, 1, 1.0, _p(ones), 1, _p(db), n, 0.0, _p(bv.grad), n, st)
+      bv.grad_ready()
     dx = None
     if ctx.needs_input_grad[0]:   # dx[M,K] = dy W^T
       dx = torch.empty((m, k), dtype=F32, device=x.device)
@@ -1451,8 +1614,10 @@ class _DirectConvFn(torch.autograd.Function):
     st = _stream()
     if wv.trainable:
       _lib.call('t2r_conv2d_direct_f32_wgrad', _p(x), _p(dy), _p(wv.grad), *ctx.dims, st)
+      wv.grad_ready()
     if bv is not None and bv.trainable:
       _lib.call('t2r_colsum_f32', _p(dy), _p(bv.grad), dy.numel() // dy.shape[-1], dy.shape[-1], st)
+      bv.grad_ready()
     dx = None
     if ctx.needs_input_grad[0]:
       dx = torch.empty_like(x)
@@ -1503,6 +1668,9 @@ class _LayerNormFn(torch.autograd.Function):
     want = gv.trainable
     _lib.call('t2r_layer_norm_f32_bwd', _p(x), _p(dy.contiguous()), _p(gv.data), _p(bv.data), _p(mean), _p(rstd), _p(dx),
               _p(gv.grad if want else None), _p(bv.grad if want else None), n, x.numel() // n, c, int(ctx.relu), _stream())
+    if want:
+      gv.grad_ready()
+      bv.grad_ready()
     return dx, None, None, None, None, None
 
 
@@ -1591,6 +1759,7 @@ class _BiasTransformFn(torch.autograd.Function):
     if bv.trainable:
       tail = dy[:, k:].contiguous()
       _lib.call('t2r_colsum_f32', _p(tail), _p(bv.grad), tail.shape[0], tail.shape[1], _stream())
+      bv.grad_ready()
     return dy[:, :k].contiguous(), None, None
 
 
@@ -1652,6 +1821,9 @@ class _BnInferF32Fn(torch.autograd.Function):
     want = gv.trainable
     _lib.call('t2r_bn_infer_f32_bwd', _p(x), _p(dy.contiguous()), _p(gv.data), _p(mv.data), _p(vv.data), _p(dx),
               _p(gv.grad if want else None), _p(bv.grad if want else None), x.numel() // c, c, ctx.eps, _stream())
+    if want:
+      gv.grad_ready()
+      bv.grad_ready()
     return dx, None, None, None, None, None, None
 
 

@@ -56,19 +56,32 @@ def tfdata_image_decoder():
 
 
 class DeviceStager(object):
-  """Pinned host staging + async H2D on a dedicated copy stream, double buffered."""
+  """Pinned host staging + async H2D on a dedicated copy stream, `depth` pinned slots.
 
-  def __init__(self, device, depth=2):
+  Hazards handled here (both would corrupt inputs silently):
+    * a pinned slot is refilled only after the H2D copies that read it have completed (one event per slot,
+      synchronised before the host memcpy into the slot);
+    * the device tensors are allocated on the copy stream but consumed on `consumer_stream`: record_stream tells the
+      caching allocator not to hand their memory to a later copy while the consumer's kernels may still read it.
+  stage() may run on a producer thread (train_eval._batches does): it only touches the copy stream."""
+
+  def __init__(self, device, depth=3):
     self.device = torch.device(device)
     self.stream = torch.cuda.Stream(device=self.device)
     self.depth = depth
     self._pinned = [dict() for _ in range(depth)]
+    self._copied = [None] * depth
     self._slot = 0
 
-  def stage(self, struct):
+  def stage(self, struct, consumer_stream=None):
     """struct: flat {path: numpy | torch CPU tensor}.  Returns (device struct, ready event)."""
-    slot = self._pinned[self._slot]
+    index = self._slot
+    slot = self._pinned[index]
     self._slot = (self._slot + 1) % self.depth
+    if self._copied[index] is not None:
+      self._copied[index].synchronize()
+    if consumer_stream is None:
+      consumer_stream = torch.cuda.current_stream(self.device)
     out = tensorspec_utils.TensorSpecStruct()
     with torch.cuda.stream(self.stream):
       for key, value in struct.items():
@@ -82,9 +95,12 @@ class DeviceStager(object):
         if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
           buf = slot[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
         buf.copy_(t)
-        out[key] = buf.to(self.device, non_blocking=True)
+        dev = buf.to(self.device, non_blocking=True)
+        dev.record_stream(consumer_stream)
+        out[key] = dev
       ready = torch.cuda.Event()
       ready.record(self.stream)
+    self._copied[index] = ready
     return out, ready
 
 
@@ -97,12 +113,25 @@ def latest_checkpoint(model_dir):
   return best
 
 
+def _is_chief():
+  return not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+      torch.distributed.get_rank() == 0
+
+
+def _replace_into_place(tmp, path):
+  """A checkpoint becomes visible under its final name only when complete: readers (other ranks, a restart after a
+  crash, predictors polling model_dir) never see a truncated file."""
+  os.replace(tmp, path)
+
+
 def save_checkpoint(t2r_model, model_dir, keep_checkpoint_max=5):
   path = os.path.join(model_dir, 'model.ckpt-%d.pt' % t2r_model.global_step)
-  if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+  if not _is_chief():
     return path          # replicas hold identical parameters: the chief writes (the Estimator's chief-only saver)
   os.makedirs(model_dir, exist_ok=True)
-  torch.save(t2r_model.state_dict(), path)
+  tmp = path + '.tmp-%d' % os.getpid()
+  torch.save(t2r_model.state_dict(), tmp)
+  _replace_into_place(tmp, path)
   existing = sorted(glob.glob(os.path.join(model_dir, 'model.ckpt-*.pt')),
                     key=lambda p: int(re.search(r'-(\d+)\.pt$', p).group(1)))
   for old in existing[:-keep_checkpoint_max]:
@@ -117,13 +146,22 @@ def save_tf_checkpoint(t2r_model, model_dir):
   from tensor2robot_b200.utils import tf_checkpoint
   name = 'model.ckpt-%d' % t2r_model.global_step
   prefix = os.path.join(model_dir, name)
-  if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+  if not _is_chief():
     return prefix
-  tensors = dict(t2r_model.variable_store.export_tf())
+  os.makedirs(model_dir, exist_ok=True)
+  # with a MovingAverageOptimizer the variable names carry the AVERAGED values (the reference's swapping saver,
+  # models/abstract_model.py:855-863): this is what exports, predictors and the lagged target load
+  export = getattr(t2r_model, 'export_variables', None) or t2r_model.variable_store.export_tf
+  tensors = dict(export())
   tensors['global_step'] = np.asarray(t2r_model.global_step, np.int64)
-  tf_checkpoint.write_checkpoint(prefix, tensors)
-  with open(os.path.join(model_dir, 'checkpoint'), 'w') as f:
+  tmp_prefix = os.path.join(model_dir, '.tmp-%d-%s' % (os.getpid(), name))
+  tf_checkpoint.write_checkpoint(tmp_prefix, tensors)
+  for suffix in ('.data-00000-of-00001', '.index'):      # the index last: it is what readers look for
+    _replace_into_place(tmp_prefix + suffix, prefix + suffix)
+  state = os.path.join(model_dir, 'checkpoint')
+  with open(state + '.tmp', 'w') as f:
     f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (name, name))
+  _replace_into_place(state + '.tmp', state)
   return prefix
 
 
@@ -188,24 +226,31 @@ class Prefetcher(object):
 def _batches(input_generator, t2r_model, mode, device, prefetch=2):
   """Host batches (prefetched on a background thread) -> staged device batches -> preprocessed
   (features, labels)."""
-  stager = DeviceStager(device)
   preprocessor = t2r_model.preprocessor
-  source = input_generator.create_dataset(mode)
-  if prefetch and tfdata_image_decoder() == 'host':
-    # the device JPEG decoder launches kernels on the consumer's CUDA stream: keep it on this thread
-    source = Prefetcher(source, prefetch)
-  for features, labels in source:
-    flat = tensorspec_utils.flatten_spec_structure(features)
-    n_feat = len(flat)
-    merged = tensorspec_utils.TensorSpecStruct([('f/' + k, v) for k, v in flat.items()])
-    if labels is not None:
-      for k, v in tensorspec_utils.flatten_spec_structure(labels).items():
-        merged['l/' + k] = v
-    staged, ready = stager.stage(merged)
-    torch.cuda.current_stream(device).wait_event(ready)
+  consumer_stream = torch.cuda.current_stream(device)
+  on_thread = bool(prefetch) and tfdata_image_decoder() == 'host'
+  # every queued batch holds a pinned slot, plus the one being filled and the one the GPU may still be copying
+  stager = DeviceStager(device, depth=(prefetch + 2) if on_thread else 2)
+
+  def staged_batches():
+    """host batch -> pinned slot -> async H2D.  The 0.5 GB host memcpy of a 512-frame batch stays off the thread
+    that launches kernels when this generator runs inside the Prefetcher."""
+    if on_thread:
+      torch.cuda.set_device(device)
+    for features, labels in input_generator.create_dataset(mode):
+      merged = tensorspec_utils.TensorSpecStruct(
+          [('f/' + k, v) for k, v in tensorspec_utils.flatten_spec_structure(features).items()])
+      if labels is not None:
+        for k, v in tensorspec_utils.flatten_spec_structure(labels).items():
+          merged['l/' + k] = v
+      yield stager.stage(merged, consumer_stream)
+
+  # the device JPEG decoder launches kernels on the consumer's CUDA stream: it stays on this thread
+  source = Prefetcher(staged_batches(), prefetch) if on_thread else staged_batches()
+  for staged, ready in source:
+    consumer_stream.wait_event(ready)
     dev_features = tensorspec_utils.TensorSpecStruct([(k[2:], v) for k, v in staged.items() if k.startswith('f/')])
     dev_labels = tensorspec_utils.TensorSpecStruct([(k[2:], v) for k, v in staged.items() if k.startswith('l/')])
-    del n_feat
     yield preprocessor.preprocess(dev_features, dev_labels if len(dev_labels) else None, mode)
 
 
@@ -221,8 +266,8 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
   if any(x is not None for x in (create_exporters_fn, export_generator, eval_hook_builders)):
     raise NotImplementedError('SavedModel exporters / eval hooks are outside the B200 engine (SURVEY 2)')
   hooks = []
-  is_chief = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
-      torch.distributed.get_rank() == 0
+  is_chief = _is_chief()
+  distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
   for builder in list(train_hook_builders or []) + (list(chief_train_hook_builders or []) if is_chief else []):
     if not hasattr(builder, 'create_hooks'):
       raise NotImplementedError('train hooks must come from a tensor2robot_b200.hooks.HookBuilder; TF SessionRunHooks '
@@ -242,11 +287,17 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
     for features, labels in _batches(input_generator_train, t2r_model, ModeKeys.TRAIN, device):
       if not resumed:
         t2r_model.build(features, labels)
-        ckpt = latest_checkpoint(model_dir)
-        if ckpt:
-          t2r_model.load_state_dict(torch.load(ckpt, weights_only=False))
+        # the chief decides what to resume from and every rank follows (a rank globbing model_dir on its own could
+        # pick a checkpoint the chief is about to rotate away, or disagree about the starting step)
+        ckpt = [latest_checkpoint(model_dir) if is_chief else None]
+        if distributed:
+          torch.distributed.broadcast_object_list(ckpt, src=0)
+        if ckpt[0]:
+          t2r_model.load_state_dict(torch.load(ckpt[0], weights_only=False))
         else:
           save_checkpoint(t2r_model, model_dir, run_config.get('keep_checkpoint_max', 5))   # model.ckpt-0
+        if distributed:
+          torch.distributed.barrier()
         resumed = True
       if t2r_model.global_step >= max_train_steps:
         break
@@ -279,7 +330,8 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
         break
       if not t2r_model.variable_store.finalized:
         t2r_model.build(features, labels)
-      out = t2r_model.model_fn(features, labels, ModeKeys.EVAL)
+      with t2r_model.averaged_parameters():   # the Estimator evaluates checkpoints = the swapped-in averages
+        out = t2r_model.model_fn(features, labels, ModeKeys.EVAL)
       losses.append(out.loss.detach())
     if losses:
       result['eval'] = {'loss': float(torch.stack(losses).mean()), 'steps': len(losses)}
@@ -296,6 +348,6 @@ def predict_from_model(t2r_model=None, input_generator_predict=None, model_dir=N
       t2r_model.build(features, mode=ModeKeys.PREDICT)
       ckpt = latest_checkpoint(model_dir) if model_dir else None
       if ckpt:
-        t2r_model.load_state_dict(torch.load(ckpt, weights_only=False))
+        t2r_model.load_state_dict(torch.load(ckpt, weights_only=False), restore_training_state=False)
       loaded = True
     yield t2r_model.predict(features)

@@ -76,6 +76,72 @@ def test_two_rank_sharding_and_gradient_reduction(tmp_path):
     assert r['ckpt_rank'] == 0                                          # one checkpoint file, written by rank 0
 
 
+class _FakeVar(object):
+
+  def __init__(self, name, offset, numel, regularize):
+    self.name, self.offset, self.numel, self.regularize, self.trainable = name, offset, numel, regularize, True
+
+
+class _FakeStore(object):
+  """What GradientReducer needs of nn.VariableStore: flat layout [regularised | rest], a listener slot."""
+
+  def __init__(self):
+    import collections
+    sizes = [('w%d' % i, 64 * (i + 1), True) for i in range(6)] + [('b%d' % i, 64, False) for i in range(3)]
+    self.vars, off = collections.OrderedDict(), 0
+    for name, n, reg in sizes:
+      self.vars[name] = _FakeVar(name, off, n, reg)
+      off += n
+    self.flat_grad = torch.zeros(off)
+    self.finalized = True
+    self.grad_listener = None
+
+  def grad_ready(self, var):
+    if self.grad_listener is not None:
+      self.grad_listener(var)
+
+
+def _reducer_worker(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from tensor2robot_b200 import engine
+  vs = _FakeStore()
+  reducer = engine.GradientReducer(vs, n_buckets=3)
+  out = {'buckets': [(b[0], b[1], sorted(b[2])) for b in reducer.buckets]}
+  for trial, skip in (('all', ()), ('partial', ('w0', 'b1'))):
+    vs.flat_grad.copy_(torch.arange(vs.flat_grad.numel(), dtype=torch.float32) * (rank + 1))
+    reducer.begin()
+    for name in reversed(list(vs.vars)):          # backward order: last layer first
+      if name not in skip:
+        vs.grad_ready(vs.vars[name])
+    early = reducer.launched_early
+    scale = reducer.finish()
+    out[trial] = {'grad': vs.flat_grad.clone().numpy(), 'scale': scale, 'early': early,
+                  'listener_cleared': vs.grad_listener is None}
+  np.save(os.path.join(out_dir, 'reducer%d.npy' % rank), out, allow_pickle=True)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_bucketed_gradient_reducer_two_ranks(tmp_path):
+  """engine.GradientReducer: buckets cover the flat buffer exactly once, fire as soon as their variables are done
+  (backward order), anything never marked is reduced by finish(); the sum is the same on both ranks."""
+  world, port = 2, _free_port()
+  mp.spawn(_reducer_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+  res = [np.load(os.path.join(str(tmp_path), 'reducer%d.npy' % r), allow_pickle=True).item() for r in range(world)]
+  buckets = res[0]['buckets']
+  assert len(buckets) == 3                                              # weights cut by size + the remainder
+  assert [b[2] for b in buckets[:2]] == [['w0', 'w1', 'w2', 'w3'], ['w4', 'w5']]
+  assert buckets[0][0] == 0 and all(buckets[i][1] == buckets[i + 1][0] for i in range(2))
+  n = 64 * 21 + 3 * 64
+  assert buckets[-1][1] == n and buckets[-1][2] == ['b0', 'b1', 'b2']
+  want = np.arange(n, dtype=np.float32) * 3                             # rank 0 (x1) + rank 1 (x2)
+  for r in res:
+    for trial, early in (('all', 3), ('partial', 1)):
+      np.testing.assert_array_equal(r[trial]['grad'], want)
+      assert r[trial]['scale'] == 0.5 and r[trial]['early'] == early and r[trial]['listener_cleared']
+
+
 def test_single_process_is_identity():
   from tensor2robot_b200 import engine
   g = torch.ones(8)
