@@ -62,6 +62,10 @@ def parse_args():
   p.add_argument('--batch', type=int, default=None, help='units per GPU per step (default: 512 for c2/c3, 256 for c4/c5)')
   p.add_argument('--cpu-batch', type=int, default=8, help='batch of the bounded CPU sample')
   p.add_argument('--cem-chunk', type=int, default=32, help='transitions per post-merge pass of the ResNet-50 CEM')
+  p.add_argument('--data', default='synthetic', choices=['synthetic', 'records'],
+                 help="e2e input: host numpy batches, or TFRecord shards of JPEG-encoded transitions (c2 only): read, CRC, "
+                      "tf.Example parse, split JPEG decode (Huffman on host threads, IDCT/colour on the GPU), step")
+  p.add_argument('--records', type=int, default=2048, help='synthetic transitions written per rank for --data records')
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
   p.add_argument('--no-extras', action='store_true', help='skip the Grasping44 / CEM side measurements of c2')
@@ -457,8 +461,46 @@ def allreduce_probe(rt, vs):
           'in_step': 'bucketed (engine.GradientReducer), launched as each bucket completes during the backward pass'}
 
 
+def write_replay_shards(directory, n_records, shards=8, seed=1234):
+  """SURVEY 8(d) transition records: image_1 = JPEG (quality 90, 4:2:0) of a 512x640 box-filtered noise frame, the
+  QT-Opt action floats and grasp_success, as tf.Examples in uncompressed TFRecord shards.  Returns the file pattern."""
+  import concurrent.futures
+  import io
+  from PIL import Image
+  from tensor2robot_b200.utils import example_proto as ep
+  from tensor2robot_b200.utils import writer
+
+  def make(i):
+    rng = np.random.default_rng(seed=seed + i)
+    noise = rng.integers(0, 256, (512 + 8, 640 + 8, 3)).astype(np.float32)
+    c = np.cumsum(np.cumsum(noise, 0), 1)                       # 8x8 box filter through an integral image
+    box = (c[8:, 8:] - c[:-8, 8:] - c[8:, :-8] + c[:-8, :-8]) / 64.0
+    img = np.clip((box - 127.5) * 2.0 + 127.5, 0, 255).astype(np.uint8)
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, format='JPEG', quality=90, subsampling=2)
+    f = {'image_1': ep.bytes_feature([buf.getvalue()]), 'world_vector': ep.float_feature(rng.uniform(-1, 1, 3)),
+         'vertical_rotation': ep.float_feature(rng.uniform(-1, 1, 2)),
+         'grasp_success': ep.float_feature([float(rng.random() < 0.3)]),
+         'height_to_bottom': ep.float_feature([rng.random()])}
+    for k in ('close_gripper', 'open_gripper', 'terminate_episode', 'gripper_closed'):
+      f[k] = ep.float_feature([float(rng.random() < 0.5)])
+    return ep.Example(f)
+
+  with concurrent.futures.ThreadPoolExecutor(max_workers=usable_host_threads()) as pool:
+    examples = list(pool.map(make, range(n_records)))
+  per = (n_records + shards - 1) // shards
+  total_bytes = 0
+  for s in range(shards):
+    w = writer.TFRecordReplayWriter()
+    w.open(os.path.join(directory, 'replay-%05d' % s))
+    w.write(examples[s * per:(s + 1) * per])
+    w.close()
+    total_bytes += os.path.getsize(os.path.join(directory, 'replay-%05d.tfrecord' % s))
+  return os.path.join(directory, 'replay-*.tfrecord'), total_bytes / max(n_records, 1)
+
+
 # ---- end to end through train_eval_model (the B-1 boundary) ------------------------------------
-def e2e_train_eval(rt, t2r_model, batch, steps, warmup):
+def e2e_train_eval(rt, t2r_model, batch, steps, warmup, records=0):
   """The same metric through the reference's own entry point: host numpy batches -> input generator ->
   train_eval_model (pinned staging + H2D on a copy stream, preprocessor, T2RModel.train_step), the loss read back to
   the host after every step.  Returns (units/s over all ranks, H2D bytes per step, D2H bytes per step, ms/step)."""
@@ -505,11 +547,21 @@ def e2e_train_eval(rt, t2r_model, batch, steps, warmup):
       return [self.hook]
 
   timer = Timer()
-  gen = CyclingGenerator(batch_size=batch)
   with tempfile.TemporaryDirectory() as model_dir:
+    if records:
+      # the reference's record path (utils/tfdata.py:629-689 + default_input_generator.py:77-101): every rank reads its
+      # own shards; the JPEG bytes are what crosses PCIe (as Huffman-decoded coefficients)
+      from tensor2robot_b200.utils import tfdata
+      tfdata.set_image_decoder('device')
+      pattern, record_bytes = write_replay_shards(model_dir, records, seed=1234 + 100000 * rt.rank)
+      gen = gens.DefaultRecordInputGenerator(file_patterns=pattern, batch_size=batch)
+      gen.h2d_bytes = int(batch * (512 * 640 * 1.5 * 2 + 44))      # int16 coefficients of 4:2:0 frames + the floats
+      gen.record_bytes = record_bytes
+    else:
+      gen = CyclingGenerator(batch_size=batch)
     train_eval.train_eval_model(t2r_model=t2r_model, input_generator_train=gen, max_train_steps=warmup + steps,
-                                model_dir=model_dir, train_hook_builders=[Builder(timer)], device=rt.dev,
-                                log_every_n_steps=10**9)
+                                model_dir=os.path.join(model_dir, 'model'), train_hook_builders=[Builder(timer)],
+                                device=rt.dev, log_every_n_steps=10**9)
   seconds = rt.max_over_ranks(timer.t1 - timer.t0)
   return batch * rt.world * steps / seconds, gen.h2d_bytes, 4, seconds / steps * 1e3
 
@@ -584,9 +636,14 @@ def run_critic(args, rt):
       torch.cuda.empty_cache()
       cls = t2r_models.ResNet50QCriticModel if args.model == 'resnet50' else \
           t2r_models.Grasping44E2EOpenCloseTerminateGripperStatusHeightToBottom
-      rate, h2d, d2h, e_ms = e2e_train_eval(rt, cls(device=rt.dev), b, args.steps, max(2, args.warmup))
+      records = args.records if args.data == 'records' else 0
+      rate, h2d, d2h, e_ms = e2e_train_eval(rt, cls(device=rt.dev), b, args.steps, max(2, args.warmup), records)
       e2e = {'value': rate, 'unit': 'transitions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-             'ms_per_step': e_ms, 'api': 'utils.train_eval.train_eval_model + research.qtopt.t2r_models.%s' % cls.__name__}
+             'ms_per_step': e_ms, 'api': 'utils.train_eval.train_eval_model + research.qtopt.t2r_models.%s' % cls.__name__,
+             'input': ('TFRecord shards of JPEG transitions: read + CRC-32C + tf.Example parse + split JPEG decode '
+                       '(Huffman on %d host threads, IDCT / upsampling / colour on the GPU)' % usable_host_threads())
+                      if records else 'host numpy batches (decoded uint8 frames)',
+             'host_threads': usable_host_threads()}
 
   # ---- side measurements of the default run: the reference's own critic and CEM on it ----
   if args.config == 'c2' and args.model == 'resnet50' and not args.no_extras:
@@ -628,14 +685,11 @@ def run_t2r(args, rt):
   from tensor2robot_b200.utils import tensorspec_utils
   model = make_t2r_model(args, rt)
   pre = model.preprocessor
-  rng = np.random.RandomState(1234 + rt.rank)
-
   def device_batch():
     def to_dev(spec):
       host = tensorspec_utils.make_random_numpy(spec, args.batch)
       flat = tensorspec_utils.flatten_spec_structure(host)
       return tensorspec_utils.TensorSpecStruct([(k, torch.from_numpy(np.ascontiguousarray(v)).to(rt.dev)) for k, v in flat.items()])
-    del rng
     return to_dev(pre.get_in_feature_specification('train')), to_dev(pre.get_in_label_specification('train'))
 
   sets = [device_batch() for _ in range(2)]

@@ -217,6 +217,20 @@ int32_t t2r_relu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, 
  * [rows, C]: y = (x - mean) * rsqrt(var + eps) * gamma + beta; bwd overwrites dgamma / dbeta [C] (may both be NULL). */
 int32_t t2r_elu_f32_fwd(const float* x, float* y, int64_t n, void* stream);
 int32_t t2r_elu_f32_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* The batch-norm normaliser and the FiLM conditioning of the spatial-softmax tower (layers/vision_layers.py:72-86,
+ * 100-141): slim.batch_norm(is_training=True, decay, epsilon, scale optional -> gamma may be NULL) on fp32 [rows, C]
+ * with an optional fused ReLU (moving statistics updated in place, batch mean / rstd saved for the backward), and
+ * y = relu((1 + film[n, c]) * x + film[n, C + c]) on fp32 [N, HW, C] with film fp32 [N, 2C]; bwd writes dx and
+ * dfilm (same layout). */
+int32_t t2r_bn_train_f32_fwd(const float* x, const float* gamma, const float* beta, float* y, float* moving_mean,
+                             float* moving_var, float* save_mean, float* save_rstd, int64_t rows, int32_t C, float eps,
+                             float decay, int32_t relu, void* stream);
+int32_t t2r_bn_train_f32_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                             const float* save_rstd, float* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                             int32_t relu, void* stream);
+int32_t t2r_film_relu_f32_fwd(const float* x, const float* film, float* y, int32_t N, int32_t HW, int32_t C, void* stream);
+int32_t t2r_film_relu_f32_bwd(const float* x, const float* film, const float* dy, float* dx, float* dfilm, int32_t N,
+                              int32_t HW, int32_t C, void* stream);
 int32_t t2r_bn_infer_f32_fwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* var,
                              float* y, int64_t rows, int32_t C, float eps, void* stream);
 int32_t t2r_bn_infer_f32_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* var,
@@ -316,6 +330,9 @@ int32_t t2r_add_context_bwd(const void* dy, void* dx, void* dctx, int32_t B, int
                             int32_t HW, int32_t C, void* stream);
 /* y = a + b (bf16), used for gradient fan-in. */
 int32_t t2r_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+/* y = relu(a + b), bf16, n % 8 == 0: the shortcut add + ReLU that closes a ResNet v1 block
+ * (layers/film_resnet_model.py:156-166, 268-276). */
+int32_t t2r_add_relu_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
 int32_t t2r_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, void* stream);
 
 /* ---- image preprocessing (HBM-bound) --------------------------------------------------- */
@@ -393,6 +410,45 @@ int32_t t2r_momentum_step(float* w, const float* g, float* accum, float* ema, vo
 int32_t t2r_adam_step(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16,
                       int64_t n, int64_t n_decay, float lr, float beta1, float beta2, float eps,
                       int64_t step, float l2, float grad_scale, float ema_decay, void* stream);
+
+/* TF RMSPropOptimizer (not centered; research/qtopt/optimizer_builder.py:76-81): ms = decay*ms + (1-decay)*g^2 (the
+ * slot starts at ONE, as TF initialises it), mom = momentum*mom + lr*g/sqrt(ms + eps), w -= mom; l2 / grad_scale /
+ * EMA / bf16 refresh as in the other steps.  All three steps move 16-byte vectors: buffers 16-byte aligned, n and
+ * n_decay multiples of 4 (nn.VariableStore pads every variable to 64 elements). */
+int32_t t2r_rmsprop_step(float* w, const float* g, float* ms, float* mom, float* ema, void* w_bf16, int64_t n,
+                         int64_t n_decay, float lr, float decay, float momentum, float eps, float l2,
+                         float grad_scale, float ema_decay, void* stream);
+
+/* ---- weighted loss tail (BC-Z) ------------------------------------------------------------
+ * research/bcz/model.py:476-585 (training_outputs): tf.losses.huber_loss / mean_squared_error / log_loss per action
+ * component with weights = component weight x (1 - stop_token), the quaternion-norm penalty and the first-waypoint
+ * diagnostics, all with Reduction.SUM_BY_NONZERO_WEIGHTS: loss = sum(l_i w_i) / max(#{w_i != 0}, 1).
+ * One launch evaluates up to T2R_MAX_LOSS_SEGMENTS segments (flat fp32 arrays viewed as [rows, cols]):
+ *   element weight = weight x (row_mask ? (complement ? 1 - row_mask[row] : row_mask[row]) : 1), zero when row_mod > 0
+ *   and row % row_mod != 0 (row_mod = number of waypoints selects the first waypoint of every sample);
+ *   labels == NULL -> every label is label_const; SIGMOID_LOG takes logits and also writes sigmoid(x) to sigmoid_out.
+ * losses[s] receives the segment loss, losses[n_segments] the sum over segments with in_total != 0; dpredictions (if
+ * not NULL) the gradient of losses[s] w.r.t. the predictions / logits. */
+#define T2R_LOSS_HUBER 0
+#define T2R_LOSS_MSE 1
+#define T2R_LOSS_SIGMOID_LOG 2
+#define T2R_MAX_LOSS_SEGMENTS 16
+typedef struct T2RLossSegment {
+  uint32_t struct_size;
+  int32_t kind;                 /* T2R_LOSS_* */
+  const float* predictions;     /* [n] */
+  const float* labels;          /* [n] or NULL */
+  const float* row_mask;        /* [n / cols] or NULL */
+  float* dpredictions;          /* [n] or NULL */
+  float* sigmoid_out;           /* [n] or NULL (SIGMOID_LOG only) */
+  int64_t n;
+  int32_t cols;
+  int32_t row_mod;
+  int32_t row_mask_is_complement;
+  int32_t in_total;
+  float weight, delta, label_const, reserved;
+} T2RLossSegment;
+int32_t t2r_weighted_losses(const T2RLossSegment* segments, int32_t n_segments, float* losses, void* stream);
 
 /* ---- host-side record path (no GPU): TFRecord framing + tf.Example wire format ---------- */
 /* Reference: utils/tfdata.py:174-210,629-689 (reader), :273-424 (tf.parse_example). */

@@ -78,15 +78,32 @@ def _block_v2(b, x, filters, bottleneck, project, strides, film):
   return x
 
 
-def block_layers(b, x, resnet_size, first, last, films=None, num_filters=64, end_points=None):
+def _block_v1(b, x, filters, bottleneck, project, strides, film):
+  """film_resnet_model.py:121-168 / :220-276: post-activation blocks; the projection shortcut has its own batch norm,
+  FiLM modulates the last batch norm's output, the ReLU follows the shortcut add."""
+  shortcut = x
+  if project:
+    shortcut = b.bn(b.conv(x, filters * 4 if bottleneck else filters, 1, strides))
+  if bottleneck:
+    x = b.bn(b.conv(x, filters, 1, 1), relu=True)
+    x = b.bn(b.conv(x, filters, 3, strides), relu=True)
+    x = b.bn(b.conv(x, 4 * filters, 1, 1), film=film)
+  else:
+    x = b.bn(b.conv(x, filters, 3, strides), relu=True)
+    x = b.bn(b.conv(x, filters, 3, 1), film=film)
+  return tf_ops.relu(tf_ops._store(x + shortcut))
+
+
+def block_layers(b, x, resnet_size, first, last, films=None, num_filters=64, end_points=None, version=2):
   sizes = BLOCK_SIZES[resnet_size]
   bottleneck = resnet_size >= 50
   strides = [1, 2, 2, 2]
+  block = _block_v2 if version == 2 else _block_v1
   for i in range(first, last):
     f = num_filters * 2**i
     for j in range(sizes[i]):
       film = films[i][j] if films is not None and films[i] is not None else None
-      x = _block_v2(b, x, f, bottleneck, j == 0, strides[i] if j == 0 else 1, film)
+      x = block(b, x, f, bottleneck, j == 0, strides[i] if j == 0 else 1, film)
     if end_points is not None:
       end_points['block_layer%d' % (i + 1)] = x
   return x
@@ -103,12 +120,19 @@ def stem(b, x, num_filters=64, kernel_size=7, end_points=None):
 
 
 def resnet_model(variables, images, training, num_classes, resnet_size=50, films=None, updates=None,
-                 rng=None, scope='resnet_model/', end_points=None):
-  """layers/resnet.py:147-209 + Model.__call__.  rng != None creates missing variables."""
+                 rng=None, scope='resnet_model/', end_points=None, version=2):
+  """layers/resnet.py:147-209 + Model.__call__.  rng != None creates missing variables.  version 1: BN + ReLU after
+  the stem convolution, post-activation blocks, no final BN (film_resnet_model.py:565-571, 603-610)."""
   b = _Builder(variables, training, scope, updates, rng)
-  x = stem(b, images, end_points=end_points)
-  x = block_layers(b, x, resnet_size, 0, 4, films, end_points=end_points)
-  x = b.bn(x, relu=True)
+  if version == 1:
+    x = b.conv(images, 64, 7, 2)
+    x = b.bn(x, relu=True)
+    x = tf_ops.max_pool(x, 3, 2, 'SAME')
+  else:
+    x = stem(b, images, end_points=end_points)
+  x = block_layers(b, x, resnet_size, 0, 4, films, end_points=end_points, version=version)
+  if version == 2:
+    x = b.bn(x, relu=True)
   x = tf_ops._store(x.mean((1, 2)))
   name = scope + b.namer('dense')
   if rng is not None and name + '/kernel' not in variables:

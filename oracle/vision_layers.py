@@ -33,15 +33,48 @@ def spatial_softmax(net):
   return torch.cat([ex, ey], 1).reshape(b, 2 * c)
 
 
-def images_to_features(images, w, prefix, num_blocks=5):
+def batch_norm(x, w, scope, training, scale, eps=1e-4, decay=0.99, updates=None):
+  """slim.batch_norm as vision_layers.py:72-86 configures it: batch statistics (biased variance) in training, the
+  moving averages otherwise; the moving variance receives the Bessel-corrected batch variance (fused batch norm)."""
+  dims = tuple(range(x.dim() - 1))
+  if training:
+    mean = x.mean(dims)
+    var = ((x - mean) ** 2).mean(dims)
+    if updates is not None:
+      n = x.numel() // x.shape[-1]
+      updates[scope + '/moving_mean'] = w[scope + '/moving_mean'] * decay + mean.detach() * (1 - decay)
+      updates[scope + '/moving_variance'] = w[scope + '/moving_variance'] * decay + var.detach() * n / (n - 1) * (1 - decay)
+  else:
+    mean, var = w[scope + '/moving_mean'], w[scope + '/moving_variance']
+  y = (x - mean) / torch.sqrt(var + eps)
+  if scale:
+    y = y * w[scope + '/gamma']
+  return y + w[scope + '/beta']
+
+
+def images_to_features(images, w, prefix, num_blocks=5, film=None, normalizer='layer_norm', training=True, updates=None):
+  """film: [N, 2 * num_blocks * 32] (all gammas, then all betas), applied as (1 + gamma) * h + beta before the ReLU
+  (vision_layers.py:100-141).  normalizer 'batch_norm': scale only on the final 1x1 convolution (:72-86)."""
   net = images
+
+  def norm(x, s, scale):
+    if normalizer == 'layer_norm':
+      return layer_norm(x, w[s + '/LayerNorm/gamma'], w[s + '/LayerNorm/beta'])
+    return batch_norm(x, w, s + '/BatchNorm', training, scale, updates=updates)
+
   for i in range(num_blocks):
     s = '%s/conv%d' % (prefix, i + 2)
     net = conv_valid(net, w[s + '/weights'], 2 if i < 2 else 1)
-    net = torch.relu(layer_norm(net, w[s + '/LayerNorm/gamma'], w[s + '/LayerNorm/beta']))
+    net = norm(net, s, False)
+    if film is not None:
+      half = num_blocks * 32
+      gamma = 1.0 + film[:, i * 32:(i + 1) * 32][:, None, None, :]
+      beta = film[:, half + i * 32:half + (i + 1) * 32][:, None, None, :]
+      net = gamma * net + beta
+    net = torch.relu(net)
   s = prefix + '/final_conv_1x1'
   net = conv_valid(net, w[s + '/weights'], 1)
-  net = torch.relu(layer_norm(net, w[s + '/LayerNorm/gamma'], w[s + '/LayerNorm/beta']))
+  net = torch.relu(norm(net, s, True))
   return spatial_softmax(net)
 
 

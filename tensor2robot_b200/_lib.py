@@ -41,6 +41,17 @@ class JpegInfo(C.Structure):
               ('coef_count', C.c_int64), ('qt', (C.c_uint16 * 64) * 4)]
 
 
+class LossSegment(C.Structure):
+  """T2RLossSegment (include/t2r_b200.h)."""
+  _fields_ = [('struct_size', C.c_uint32), ('kind', C.c_int32), ('predictions', C.c_void_p), ('labels', C.c_void_p),
+              ('row_mask', C.c_void_p), ('dpredictions', C.c_void_p), ('sigmoid_out', C.c_void_p), ('n', C.c_int64),
+              ('cols', C.c_int32), ('row_mod', C.c_int32), ('row_mask_is_complement', C.c_int32), ('in_total', C.c_int32),
+              ('weight', C.c_float), ('delta', C.c_float), ('label_const', C.c_float), ('reserved', C.c_float)]
+
+
+T2R_LOSS_HUBER, T2R_LOSS_MSE, T2R_LOSS_SIGMOID_LOG, T2R_MAX_LOSS_SEGMENTS = 0, 1, 2, 16
+
+
 class FeaturePlan(C.Structure):
   _fields_ = [('key', C.c_char_p), ('dtype', C.c_int32), ('count', C.c_int32),
               ('required', C.c_int32), ('dst', C.c_void_p), ('dst_len', C.c_void_p),
@@ -106,6 +117,7 @@ _PROTOS = {
     't2r_add_context_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_add_context_bwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     't2r_add_bf16': (_I32, [_P, _P, _P, _I64, _P]),
+    't2r_add_relu_bf16': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_relu_bwd_bf16': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_crop_convert_distort': (_I32, [_P, _P, _P, _P] + [_I32] * 7 + [_U64, _U64, _P]),
     't2r_distort_f32': (_I32, [_P, _P, _P, _P] + [_I32] * 4 + [_U64, _U64, _P]),
@@ -119,6 +131,8 @@ _PROTOS = {
     't2r_bellman_target': (_I32, [_P, _P, _P, _F, _P, _I64, _P]),
     't2r_momentum_step': (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P]),
     't2r_adam_step': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _I64, _F, _F, _F, _P]),
+    't2r_rmsprop_step': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _F, _F, _P]),
+    't2r_weighted_losses': (_I32, [C.POINTER(LossSegment), _I32, _P, _P]),
     't2r_crc32c': (C.c_uint32, [_P, _U64]),
     't2r_masked_crc32c': (C.c_uint32, [_P, _U64]),
     't2r_tfrecord_index': (_I64, [_P, _U64, _P, _P, _I64, _I32]),
@@ -141,6 +155,10 @@ _PROTOS = {
     't2r_elu_f32_bwd': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_bn_infer_f32_fwd': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P]),
     't2r_bn_infer_f32_bwd': (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P]),
+    't2r_bn_train_f32_fwd': (_I32, [_P] * 8 + [_I64, _I32, _F, _F, _I32, _P]),
+    't2r_bn_train_f32_bwd': (_I32, [_P] * 9 + [_I64, _I32, _I32, _P]),
+    't2r_film_relu_f32_fwd': (_I32, [_P, _P, _P, _I32, _I32, _I32, _P]),
+    't2r_film_relu_f32_bwd': (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     't2r_relu_f32_fwd': (_I32, [_P, _P, _I64, _P]),
     't2r_relu_f32_bwd': (_I32, [_P, _P, _P, _I64, _P]),
     't2r_sequence_example_parse_batch': (_I32, [_P, _P, _I32, C.POINTER(FeaturePlan), _I32, _I32, _P]),

@@ -36,7 +36,8 @@ def build_parser():
   p.add_argument('--eval_steps', type=int, default=100)
   p.add_argument('--model_dir', default='/tmp/t2r_b200')
   p.add_argument('--log_every_n_steps', type=int, default=100)
-  p.add_argument('--image_decoder', choices=('host', 'device'), default='host', help='JPEG decoder of the record parser')
+  p.add_argument('--image_decoder', choices=('auto', 'host', 'device'), default='auto',
+                 help="JPEG decoder of the record parser ('auto': the split host/GPU decoder when a GPU is present)")
   return p
 
 

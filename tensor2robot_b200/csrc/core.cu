@@ -188,6 +188,21 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
   }
 }
 
+// y = relu(a + b): the tail of a ResNet v1 block (film_resnet_model.py:156-166)
+__global__ void add_relu_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                     uint4* __restrict__ y, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 p = a[i], q = b[i];
+    uint4 o;
+    o.x = pack_bf16(fmaxf(bf16_lo(p.x) + bf16_lo(q.x), 0.f), fmaxf(bf16_hi(p.x) + bf16_hi(q.x), 0.f));
+    o.y = pack_bf16(fmaxf(bf16_lo(p.y) + bf16_lo(q.y), 0.f), fmaxf(bf16_hi(p.y) + bf16_hi(q.y), 0.f));
+    o.z = pack_bf16(fmaxf(bf16_lo(p.z) + bf16_lo(q.z), 0.f), fmaxf(bf16_hi(p.z) + bf16_hi(q.z), 0.f));
+    o.w = pack_bf16(fmaxf(bf16_lo(p.w) + bf16_lo(q.w), 0.f), fmaxf(bf16_hi(p.w) + bf16_hi(q.w), 0.f));
+    y[i] = o;
+  }
+}
+
 __global__ void add_bf16_tail_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b,
                                      __nv_bfloat16* y, long long start, long long n) {
   const long long i = start + blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -372,6 +387,14 @@ extern "C" int32_t t2r_add_bf16(const void* a, const void* b, void* y, int64_t n
                                            static_cast<__nv_bfloat16*>(y), n8 * 8, n);
     T2R_LAUNCH_OK();
   }
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_add_relu_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) {
+  T2R_CHECK_ARG(a && b && y && n > 0 && n % 8 == 0, "add_relu_bf16: n must be a positive multiple of 8");
+  add_relu_bf16_kernel<<<grid_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(y), n / 8);
+  T2R_LAUNCH_OK();
   return T2R_OK;
 }
 

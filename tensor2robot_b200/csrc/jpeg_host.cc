@@ -100,6 +100,7 @@ int parse_headers(const uint8_t* b, uint64_t len, Parsed* out) {
     if (p + 4 > len) { t2r::set_error("jpeg: truncated before SOS"); return T2R_ERR_PARSE; }
     if (b[p] != 0xFF) { t2r::set_error("jpeg: marker expected at byte %llu", (unsigned long long)p); return T2R_ERR_PARSE; }
     while (p + 1 < len && b[p + 1] == 0xFF) ++p;
+    if (p + 2 > len) { t2r::set_error("jpeg: truncated marker"); return T2R_ERR_PARSE; }   // a run of fill bytes up to the end
     const uint8_t m = b[p + 1];
     p += 2;
     if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;

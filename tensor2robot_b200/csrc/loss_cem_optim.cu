@@ -126,47 +126,91 @@ __global__ void bellman_target_kernel(const float* __restrict__ reward, const fl
     target[i] = reward[i] + gamma * (1.0f - done[i]) * max_q[i];
 }
 
-// TF MomentumOptimizer (use_nesterov=False): accum = momentum*accum + g ; w -= lr*accum.
-__global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ w, const float* __restrict__ g,
-                                                       float* __restrict__ accum, float* __restrict__ ema,
-                                                       __nv_bfloat16* __restrict__ wb, long long n,
-                                                       long long n_decay, float lr, float momentum,
-                                                       float l2, float grad_scale, float ema_decay) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float wi = w[i];
-    float gi = g[i] * grad_scale;
-    if (i < n_decay) gi += l2 * wi;
-    const float a = momentum * accum[i] + gi;
-    accum[i] = a;
-    wi -= lr * a;
-    w[i] = wi;
-    if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * wi;
-    if (wb) wb[i] = __float2bfloat16_rn(wi);
+// Fused optimizer step over the flat parameter buffer: gradient unscale (1 / world size) + slim l2 gradient on the
+// regularised prefix + the optimizer rule + EMA shadow + bf16 compute copy, ONE pass.  HBM-bound (22 - 34 B per
+// parameter), so everything moves as 16-byte vectors: the buffers are 256-byte aligned and every variable is padded
+// to 64 elements (nn.VariableStore.finalize), hence n and n_decay are multiples of 4 and a float4 never straddles
+// the l2 boundary.  `Rule` holds the slot pointers and maps (w, g) -> new w for one element.
+struct MomentumRule {   // TF MomentumOptimizer (use_nesterov=False): accum = momentum*accum + g ; w -= lr*accum
+  float* accum;
+  float lr, momentum;
+  __device__ __forceinline__ void load(long long i4, float4 (&s)[2]) const { s[0] = reinterpret_cast<const float4*>(accum)[i4]; }
+  __device__ __forceinline__ void store(long long i4, const float4 (&s)[2]) const { reinterpret_cast<float4*>(accum)[i4] = s[0]; }
+  __device__ __forceinline__ float apply(float w, float g, float& s0, float&) const {
+    s0 = momentum * s0 + g;
+    return w - lr * s0;
+  }
+};
+struct AdamRule {       // TF AdamOptimizer: m, v moments; w -= lr_t * m / (sqrt(v) + eps), lr_t carries the bias corrections
+  float *m, *v;
+  float lr_t, beta1, beta2, eps;
+  __device__ __forceinline__ void load(long long i4, float4 (&s)[2]) const {
+    s[0] = reinterpret_cast<const float4*>(m)[i4];
+    s[1] = reinterpret_cast<const float4*>(v)[i4];
+  }
+  __device__ __forceinline__ void store(long long i4, const float4 (&s)[2]) const {
+    reinterpret_cast<float4*>(m)[i4] = s[0];
+    reinterpret_cast<float4*>(v)[i4] = s[1];
+  }
+  __device__ __forceinline__ float apply(float w, float g, float& mi, float& vi) const {
+    mi = beta1 * mi + (1.0f - beta1) * g;
+    vi = beta2 * vi + (1.0f - beta2) * g * g;
+    return w - lr_t * mi / (sqrtf(vi) + eps);
+  }
+};
+struct RmsPropRule {    // TF RMSPropOptimizer (not centered): ms = rho*ms + (1-rho)*g^2; mom = momentum*mom + lr*g/sqrt(ms+eps); w -= mom
+  float *ms, *mom;
+  float lr, rho, momentum, eps;
+  __device__ __forceinline__ void load(long long i4, float4 (&s)[2]) const {
+    s[0] = reinterpret_cast<const float4*>(ms)[i4];
+    s[1] = reinterpret_cast<const float4*>(mom)[i4];
+  }
+  __device__ __forceinline__ void store(long long i4, const float4 (&s)[2]) const {
+    reinterpret_cast<float4*>(ms)[i4] = s[0];
+    reinterpret_cast<float4*>(mom)[i4] = s[1];
+  }
+  __device__ __forceinline__ float apply(float w, float g, float& msi, float& momi) const {
+    msi = rho * msi + (1.0f - rho) * g * g;
+    momi = momentum * momi + lr * g / sqrtf(msi + eps);
+    return w - momi;
+  }
+};
+
+template <class Rule>
+__global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                                        float* __restrict__ ema, __nv_bfloat16* __restrict__ wb,
+                                                        long long n4, long long n_decay4, float l2, float grad_scale,
+                                                        float ema_decay, Rule rule) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 w4 = reinterpret_cast<const float4*>(w)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 s[2];
+    rule.load(i, s);
+    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    float s0[4] = {s[0].x, s[0].y, s[0].z, s[0].w}, s1[4] = {s[1].x, s[1].y, s[1].z, s[1].w};
+    const float decay = i < n_decay4 ? l2 : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wv[j] = rule.apply(wv[j], fmaf(decay, wv[j], gv[j] * grad_scale), s0[j], s1[j]);
+    s[0] = make_float4(s0[0], s0[1], s0[2], s0[3]);
+    s[1] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    rule.store(i, s);
+    reinterpret_cast<float4*>(w)[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    if (ema) {
+      float4 e = reinterpret_cast<const float4*>(ema)[i];
+      e.x = ema_decay * e.x + (1.0f - ema_decay) * wv[0];
+      e.y = ema_decay * e.y + (1.0f - ema_decay) * wv[1];
+      e.z = ema_decay * e.z + (1.0f - ema_decay) * wv[2];
+      e.w = ema_decay * e.w + (1.0f - ema_decay) * wv[3];
+      reinterpret_cast<float4*>(ema)[i] = e;
+    }
+    if (wb) reinterpret_cast<uint2*>(wb)[i] = make_uint2(pack_bf16(wv[0], wv[1]), pack_bf16(wv[2], wv[3]));
   }
 }
 
-// TF AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t * m / (sqrt(v) + eps).
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g,
-                                                   float* __restrict__ m, float* __restrict__ v,
-                                                   float* __restrict__ ema, __nv_bfloat16* __restrict__ wb,
-                                                   long long n, long long n_decay, float lr_t, float beta1,
-                                                   float beta2, float eps, float l2, float grad_scale,
-                                                   float ema_decay) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float wi = w[i];
-    float gi = g[i] * grad_scale;
-    if (i < n_decay) gi += l2 * wi;
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    wi -= lr_t * mi / (sqrtf(vi) + eps);
-    w[i] = wi;
-    if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * wi;
-    if (wb) wb[i] = __float2bfloat16_rn(wi);
-  }
+// one full wave of 256-thread blocks, 4 parameters per thread and iteration
+static inline int opt_grid(long long n4) {
+  return int(std::min<long long>(std::max<long long>((n4 + 255) / 256, 1), (long long)num_sms() * 8));
 }
 
 static inline int grid_for(long long n) {
@@ -224,13 +268,19 @@ extern "C" int32_t t2r_bellman_target(const float* reward, const float* done, co
   return T2R_OK;
 }
 
+static bool vector_ok(const void* a, const void* b, const void* c, int64_t n, int64_t n_decay) {
+  return n % 4 == 0 && n_decay % 4 == 0 && (reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                                            reinterpret_cast<uintptr_t>(c)) % 16 == 0;
+}
+
 extern "C" int32_t t2r_momentum_step(float* w, const float* g, float* accum, float* ema, void* w_bf16,
                                      int64_t n, int64_t n_decay, float lr, float momentum, float l2,
                                      float grad_scale, float ema_decay, void* stream) {
   T2R_CHECK_ARG(w && g && accum && n > 0 && n_decay >= 0 && n_decay <= n, "momentum_step: bad args");
-  momentum_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, g, accum, ema, static_cast<__nv_bfloat16*>(w_bf16), n, n_decay, lr, momentum, l2, grad_scale,
-      ema_decay);
+  T2R_CHECK_ARG(vector_ok(w, g, accum, n, n_decay), "momentum_step: buffers must be 16-byte aligned, n and n_decay multiples of 4");
+  const MomentumRule rule{accum, lr, momentum};
+  optimizer_kernel<<<opt_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, g, ema, static_cast<__nv_bfloat16*>(w_bf16), n / 4, n_decay / 4, l2, grad_scale, ema_decay, rule);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
@@ -239,11 +289,26 @@ extern "C" int32_t t2r_adam_step(float* w, const float* g, float* m, float* v, f
                                  int64_t n, int64_t n_decay, float lr, float beta1, float beta2, float eps,
                                  int64_t step, float l2, float grad_scale, float ema_decay, void* stream) {
   T2R_CHECK_ARG(w && g && m && v && n > 0 && step >= 1 && n_decay >= 0 && n_decay <= n, "adam_step: bad args");
+  T2R_CHECK_ARG(vector_ok(w, g, m, n, n_decay) && reinterpret_cast<uintptr_t>(v) % 16 == 0,
+                "adam_step: buffers must be 16-byte aligned, n and n_decay multiples of 4");
   const double lr_t = double(lr) * sqrt(1.0 - pow(double(beta2), double(step))) /
                       (1.0 - pow(double(beta1), double(step)));
-  adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, g, m, v, ema, static_cast<__nv_bfloat16*>(w_bf16), n, n_decay, float(lr_t), beta1, beta2, eps, l2,
-      grad_scale, ema_decay);
+  const AdamRule rule{m, v, float(lr_t), beta1, beta2, eps};
+  optimizer_kernel<<<opt_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, g, ema, static_cast<__nv_bfloat16*>(w_bf16), n / 4, n_decay / 4, l2, grad_scale, ema_decay, rule);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_rmsprop_step(float* w, const float* g, float* ms, float* mom, float* ema, void* w_bf16,
+                                    int64_t n, int64_t n_decay, float lr, float decay, float momentum, float eps,
+                                    float l2, float grad_scale, float ema_decay, void* stream) {
+  T2R_CHECK_ARG(w && g && ms && mom && n > 0 && n_decay >= 0 && n_decay <= n, "rmsprop_step: bad args");
+  T2R_CHECK_ARG(vector_ok(w, g, ms, n, n_decay) && reinterpret_cast<uintptr_t>(mom) % 16 == 0,
+                "rmsprop_step: buffers must be 16-byte aligned, n and n_decay multiples of 4");
+  const RmsPropRule rule{ms, mom, lr, decay, momentum, eps};
+  optimizer_kernel<<<opt_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, g, ema, static_cast<__nv_bfloat16*>(w_bf16), n / 4, n_decay / 4, l2, grad_scale, ema_decay, rule);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

@@ -303,6 +303,118 @@ __global__ void __launch_bounds__(256) elu_f32_bwd_kernel(const float* __restric
     dx[i] = y[i] > 0.f ? dy[i] : dy[i] * (y[i] + 1.f);
 }
 
+
+// FiLM + ReLU on fp32 NHWC (layers/vision_layers.py:139-141): y = relu((1 + g[n,c]) * x + b[n,c]), film = [N][2C]
+// (gammas, then betas).  One block per image, threads over channels (coalesced), loop over pixels.
+__global__ void __launch_bounds__(256) film_relu_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ film,
+                                                                float* __restrict__ y, int HW, int C) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = 1.0f + film[(long long)n * 2 * C + c], b = film[(long long)n * 2 * C + C + c];
+    for (int p = blockIdx.y; p < HW; p += gridDim.y) {
+      const long long i = ((long long)n * HW + p) * C + c;
+      y[i] = fmaxf(fmaf(g, x[i], b), 0.f);
+    }
+  }
+}
+// dx = dy * [y > 0] * (1 + g); dfilm[n, c] = sum_p dy * [y > 0] * x; dfilm[n, C + c] = sum_p dy * [y > 0]
+__global__ void __launch_bounds__(256) film_relu_f32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ film,
+                                                                const float* __restrict__ dy, float* __restrict__ dx,
+                                                                float* __restrict__ dfilm, int HW, int C) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = 1.0f + film[(long long)n * 2 * C + c], b = film[(long long)n * 2 * C + C + c];
+    float sg = 0.f, sb = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      const long long i = ((long long)n * HW + p) * C + c;
+      const float xv = x[i];
+      const float d = fmaf(g, xv, b) > 0.f ? dy[i] : 0.f;
+      dx[i] = d * g;
+      sg = fmaf(d, xv, sg);
+      sb += d;
+    }
+    dfilm[(long long)n * 2 * C + c] = sg;
+    dfilm[(long long)n * 2 * C + C + c] = sb;
+  }
+}
+
+// slim.batch_norm(is_training=True) on fp32 [rows, C] (the batch-norm normaliser of layers/vision_layers.py:72-86,
+// decay .99, eps 1e-4): biased batch variance normalises, the Bessel-corrected one feeds the moving average (fused
+// batch norm); optional ReLU.  One block per channel; double accumulation.
+__global__ void __launch_bounds__(256) bn_train_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ y,
+                                                               float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                                               float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                               long long rows, int C, float eps, float decay, int relu) {
+  __shared__ double sm[2][8];
+  const int c = blockIdx.x;
+  double s = 0.0, q = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const double v = x[r * C + c];
+    s += v;
+    q += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = s; sm[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  s = q = 0.0;
+  for (int i = 0; i < 8; ++i) { s += sm[0][i]; q += sm[1][i]; }
+  const double mean = s / double(rows);
+  double var = q / double(rows) - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = float(1.0 / sqrt(var + double(eps)));
+  const float g = gamma != nullptr ? gamma[c] : 1.0f, b = beta[c], m = float(mean);
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float v = (x[r * C + c] - m) * rstd * g + b;
+    y[r * C + c] = relu ? fmaxf(v, 0.f) : v;
+  }
+  if (threadIdx.x == 0) {
+    save_mean[c] = m;
+    save_rstd[c] = rstd;
+    const double unbiased = rows > 1 ? var * double(rows) / double(rows - 1) : var;
+    moving_mean[c] = moving_mean[c] * decay + m * (1.0f - decay);
+    moving_var[c] = moving_var[c] * decay + float(unbiased) * (1.0f - decay);
+  }
+}
+__global__ void __launch_bounds__(256) bn_train_f32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                               const float* __restrict__ dy, const float* __restrict__ gamma,
+                                                               const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                                               float* __restrict__ dx, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, long long rows, int C, int relu) {
+  __shared__ double sm[2][8];
+  const int c = blockIdx.x;
+  const float m = save_mean[c], rstd = save_rstd[c], g = gamma != nullptr ? gamma[c] : 1.0f;
+  double sb = 0.0, sg = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const long long i = r * C + c;
+    const float d = (relu && !(y[i] > 0.f)) ? 0.f : dy[i];
+    sb += d;
+    sg += double(d) * double((x[i] - m) * rstd);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = sb; sm[1][threadIdx.x >> 5] = sg; }
+  __syncthreads();
+  sb = sg = 0.0;
+  for (int i = 0; i < 8; ++i) { sb += sm[0][i]; sg += sm[1][i]; }
+  const float mb = float(sb / double(rows)), mg = float(sg / double(rows));
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const long long i = r * C + c;
+    const float d = (relu && !(y[i] > 0.f)) ? 0.f : dy[i];
+    const float xh = (x[i] - m) * rstd;
+    dx[i] = g * rstd * (d - mb - xh * mg);
+  }
+  if (threadIdx.x == 0) {
+    if (dgamma != nullptr) dgamma[c] = float(sg);
+    if (dbeta != nullptr) dbeta[c] = float(sb);
+  }
+}
+
 // tf.layers.batch_normalization(training=False) on [rows, C] fp32: y = (x - mean) * rsqrt(var + eps) * gamma + beta.
 __global__ void __launch_bounds__(256) bn_infer_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, const float* __restrict__ mean,
@@ -508,6 +620,43 @@ extern "C" int32_t t2r_bn_infer_f32_bwd(const float* x, const float* dy, const f
                 "bn_infer_f32_bwd: bad args");
   bn_infer_f32_bwd_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, gamma, mean, var, dx, dgamma, dbeta,
                                                                                       rows, C, eps);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_film_relu_f32_fwd(const float* x, const float* film, float* y, int32_t N, int32_t HW, int32_t C,
+                                         void* stream) {
+  T2R_CHECK_ARG(x && film && y && N > 0 && HW > 0 && C > 0, "film_relu_f32_fwd: bad args");
+  film_relu_f32_fwd_kernel<<<dim3(N, std::min(HW, 64)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, film, y, HW, C);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_film_relu_f32_bwd(const float* x, const float* film, const float* dy, float* dx, float* dfilm,
+                                         int32_t N, int32_t HW, int32_t C, void* stream) {
+  T2R_CHECK_ARG(x && film && dy && dx && dfilm && N > 0 && HW > 0 && C > 0, "film_relu_f32_bwd: bad args");
+  film_relu_f32_bwd_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, film, dy, dx, dfilm, HW, C);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_bn_train_f32_fwd(const float* x, const float* gamma, const float* beta, float* y, float* moving_mean,
+                                        float* moving_var, float* save_mean, float* save_rstd, int64_t rows, int32_t C,
+                                        float eps, float decay, int32_t relu, void* stream) {
+  T2R_CHECK_ARG(x && beta && y && moving_mean && moving_var && save_mean && save_rstd && rows > 0 && C > 0,
+                "bn_train_f32_fwd: bad args");
+  bn_train_f32_fwd_kernel<<<C, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, y, moving_mean, moving_var,
+                                                                            save_mean, save_rstd, rows, C, eps, decay, relu);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
+
+extern "C" int32_t t2r_bn_train_f32_bwd(const float* x, const float* y, const float* dy, const float* gamma,
+                                        const float* save_mean, const float* save_rstd, float* dx, float* dgamma,
+                                        float* dbeta, int64_t rows, int32_t C, int32_t relu, void* stream) {
+  T2R_CHECK_ARG(x && y && dy && save_mean && save_rstd && dx && rows > 0 && C > 0, "bn_train_f32_bwd: bad args");
+  bn_train_f32_bwd_kernel<<<C, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, dy, gamma, save_mean, save_rstd, dx, dgamma,
+                                                                            dbeta, rows, C, relu);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }

@@ -116,6 +116,37 @@ def _bottleneck_block_v2(inputs, filters, training, projection_shortcut, strides
   return conv2d_fixed_padding(inputs, 4 * filters, 1, 1, namer, weight_decay, residual=shortcut)
 
 
+def _v1_shortcut(inputs, training, projection_shortcut, namer):
+  """v1: the projection shortcut is followed by its own batch norm (film_resnet_model.py:149-153)."""
+  if projection_shortcut is None:
+    return inputs
+  return batch_norm(projection_shortcut(inputs), training, namer)
+
+
+def _building_block_v1(inputs, filters, training, projection_shortcut, strides, namer, weight_decay,
+                       film_gamma_beta=None):
+  """conv3x3-BN-ReLU-conv3x3-BN-[FiLM] + shortcut, ReLU (film_resnet_model.py:121-168)."""
+  shortcut = _v1_shortcut(inputs, training, projection_shortcut, namer)
+  inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay, defer_for_bn=not training)
+  inputs = batch_norm(inputs, training, namer, relu=True)
+  inputs = conv2d_fixed_padding(inputs, filters, 3, 1, namer, weight_decay, defer_for_bn=not training)
+  inputs = batch_norm(inputs, training, namer, film=_film_tensor(film_gamma_beta))
+  return nn.add_relu(inputs, shortcut)
+
+
+def _bottleneck_block_v1(inputs, filters, training, projection_shortcut, strides, namer, weight_decay,
+                         film_gamma_beta=None):
+  """1x1-BN-ReLU-3x3(stride)-BN-ReLU-1x1(4x)-BN-[FiLM] + shortcut, ReLU (film_resnet_model.py:220-276)."""
+  shortcut = _v1_shortcut(inputs, training, projection_shortcut, namer)
+  inputs = conv2d_fixed_padding(inputs, filters, 1, 1, namer, weight_decay, defer_for_bn=not training)
+  inputs = batch_norm(inputs, training, namer, relu=True)
+  inputs = conv2d_fixed_padding(inputs, filters, 3, strides, namer, weight_decay, defer_for_bn=not training)
+  inputs = batch_norm(inputs, training, namer, relu=True)
+  inputs = conv2d_fixed_padding(inputs, 4 * filters, 1, 1, namer, weight_decay, defer_for_bn=not training)
+  inputs = batch_norm(inputs, training, namer, film=_film_tensor(film_gamma_beta))
+  return nn.add_relu(inputs, shortcut)
+
+
 def block_layer(inputs, filters, bottleneck, block_fn, blocks, strides, training, name, namer,
                 weight_decay, film_gamma_betas):
   """One block layer; only the first block projects and strides (film_resnet_model.py:343-388)."""
@@ -143,15 +174,15 @@ class Model(object):
                resnet_version=DEFAULT_VERSION, data_format=None, dtype=torch.float32):
     if resnet_version not in (1, 2):
       raise ValueError('Resnet version should be 1 or 2. See README for citations.')
-    if resnet_version == 1:
-      raise NotImplementedError('ResNet v1 blocks are not on the hot path (every reference config '
-                                'uses DEFAULT_VERSION=2)')
     if data_format not in (None, 'channels_last'):
       raise ValueError('the B200 engine is NHWC (channels_last) only')
     self.resnet_size = resnet_size
     self.resnet_version = resnet_version
     self.bottleneck = bottleneck
-    self.block_fn = _bottleneck_block_v2 if bottleneck else _building_block_v2
+    if resnet_version == 1:
+      self.block_fn = _bottleneck_block_v1 if bottleneck else _building_block_v1
+    else:
+      self.block_fn = _bottleneck_block_v2 if bottleneck else _building_block_v2
     self.data_format = 'channels_last'
     self.num_classes = num_classes
     self.num_filters = num_filters
@@ -168,10 +199,12 @@ class Model(object):
 
   # The three stages are exposed separately so that a critic can merge the action context
   # between block layers (SURVEY A-15); __call__ chains them exactly like the reference.
-  def stem(self, inputs, namer):
+  def stem(self, inputs, namer, training=False):
     inputs = conv2d_fixed_padding(inputs, self.num_filters, self.kernel_size, self.conv_stride, namer,
                                   self.weight_decay, needs_dgrad=False)
     self.end_points['initial_conv'] = inputs
+    if self.resnet_version == 1:        # v2 leaves BN + ReLU to the first block's pre-activation (:565-571)
+      inputs = batch_norm(inputs, training, namer, relu=True)
     if self.first_pool_size:
       inputs = nn.max_pool2d(inputs, self.first_pool_size, self.first_pool_stride, 'SAME')
       self.end_points['initial_max_pool'] = inputs
@@ -232,6 +265,6 @@ class Model(object):
     self.end_points = {}
     namer = _Namer()
     with nn.variable_scope('resnet_model'):
-      inputs = self.stem(inputs, namer)
+      inputs = self.stem(inputs, namer, training)
       inputs = self.block_layers(inputs, training, namer, film_gamma_betas)
       return self.head(inputs, training, namer)

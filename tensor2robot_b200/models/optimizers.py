@@ -121,6 +121,23 @@ class AdamOptimizer(Optimizer):
               self._epsilon, int(global_step) + 1, self.l2_regularization, grad_scale, ema_decay, _stream())
 
 
+class RMSPropOptimizer(Optimizer):
+  """tf.train.RMSPropOptimizer (centered=False): the `rms` slot starts at one, `momentum` at zero."""
+
+  def __init__(self, learning_rate, decay=0.9, momentum=0.0, epsilon=1e-10):
+    super(RMSPropOptimizer, self).__init__(learning_rate)
+    self._decay, self._momentum, self._epsilon = decay, momentum, epsilon
+
+  def apply_gradients(self, vs, global_step, grad_scale=1.0, ema=None, ema_decay=0.0):
+    fresh = 'rms' not in self._slots or self._slots['rms'].numel() != vs.flat.numel()
+    rms, mom = self._slot(vs, 'rms'), self._slot(vs, 'momentum')
+    if fresh:
+      rms.fill_(1.0)
+    _lib.call('t2r_rmsprop_step', _p(vs.flat), _p(vs.flat_grad), _p(rms), _p(mom), _p(ema), _p(vs.flat_bf16),
+              vs.flat.numel(), vs.n_decay, self.learning_rate(global_step), self._decay, self._momentum, self._epsilon,
+              self.l2_regularization, grad_scale, ema_decay, _stream())
+
+
 class MovingAverageOptimizer(Optimizer):
   """contrib.opt.MovingAverageOptimizer: wraps an optimizer and keeps an EMA shadow of every
   trainable variable (the shadow is what the reference's swapping saver writes to checkpoints)."""

@@ -1408,6 +1408,39 @@ class _ReluFn(torch.autograd.Function):
     return dx
 
 
+class _AddReluFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, a, b):
+    y = torch.empty_like(a)
+    _lib.call('t2r_add_relu_bf16', _p(a), _p(b), _p(y), a.numel(), _stream())
+    ctx.save_for_backward(y)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    (y,) = ctx.saved_tensors
+    dy = dy.contiguous()
+    g = torch.empty_like(dy)
+    _lib.call('t2r_relu_bwd_bf16', _p(dy), _p(y), _p(g), dy.numel(), _stream())
+    return g, g
+
+
+def add_relu(a, b):
+  """relu(a + b) on two bf16 NHWC tensors of the same shape in one pass: the shortcut add that closes a ResNet v1
+  block (layers/film_resnet_model.py:156-166)."""
+  _require_cuda(a, 'add_relu')
+  _require_cuda(b, 'add_relu')
+  if _HIGH_PRECISION:
+    y = torch.empty_like(_hp_f32(a))
+    _lib.call('t2r_add_f32', _p(_hp_f32(a)), _p(_hp_f32(b)), _p(y), y.numel(), _stream())
+    _lib.call('t2r_relu_f32_fwd', _p(y), _p(y), y.numel(), _stream())
+    return y
+  if a.shape != b.shape or a.dtype != BF16 or b.dtype != BF16 or a.numel() % 8:
+    raise ValueError('add_relu expects two bf16 tensors of the same shape (a multiple of 8 elements)')
+  return _AddReluFn.apply(a.contiguous(), b.contiguous())
+
+
 def relu(x):
   """tf.nn.relu on a bf16 or fp32 CUDA tensor (stand-alone; conv / norm epilogues fuse their own)."""
   _require_cuda(x, 'relu')
@@ -1844,6 +1877,100 @@ def batch_normalization_f32(x, scope, eps=1e-3, trainable=True):
   return _BnInferF32Fn.apply(x.contiguous(), vs.anchor, gv, bv, mv, vv, eps)
 
 
+class _FilmReluF32Fn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, film):
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    y = torch.empty_like(x)
+    _lib.call('t2r_film_relu_f32_fwd', _p(x), _p(film), _p(y), n, hw, c, _stream())
+    ctx.save_for_backward(x, film)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, film = ctx.saved_tensors
+    n, c = x.shape[0], x.shape[-1]
+    dx, dfilm = torch.empty_like(x), torch.empty_like(film)
+    _lib.call('t2r_film_relu_f32_bwd', _p(x), _p(film), _p(dy.contiguous()), _p(dx), _p(dfilm), n, x.numel() // (n * c), c,
+              _stream())
+    return dx, dfilm
+
+
+def film_relu_f32(x, film):
+  """relu((1 + gamma[n]) * x + beta[n]) on fp32 [N, ..., C] with film = [N, 2C] = (gammas | betas): the FiLM
+  conditioning of the spatial-softmax tower (layers/vision_layers.py:100-141)."""
+  _require_cuda(x, 'film_relu_f32')
+  if x.dtype != F32 or film.dtype != F32 or film.shape != (x.shape[0], 2 * x.shape[-1]):
+    raise ValueError('film_relu_f32 expects fp32 x [N, ..., C] and film [N, 2C]')
+  return _FilmReluF32Fn.apply(x.contiguous(), film.contiguous())
+
+
+class _BnTrainF32Fn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, anchor, gv, bv, mv, vv, eps, decay, relu):
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty_like(x)
+    mean = torch.empty(c, dtype=F32, device=x.device)
+    rstd = torch.empty(c, dtype=F32, device=x.device)
+    _lib.call('t2r_bn_train_f32_fwd', _p(x), _p(gv.data if gv is not None else None), _p(bv.data), _p(y), _p(mv.data),
+              _p(vv.data), _p(mean), _p(rstd), rows, c, eps, decay, int(relu), _stream())
+    ctx.vars, ctx.relu = (gv, bv), relu
+    ctx.save_for_backward(x, y, mean, rstd)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, y, mean, rstd = ctx.saved_tensors
+    gv, bv = ctx.vars
+    c = x.shape[-1]
+    dx = torch.empty_like(x)
+    dgamma = gv.grad if (gv is not None and gv.trainable) else None
+    dbeta = bv.grad if bv.trainable else None
+    _lib.call('t2r_bn_train_f32_bwd', _p(x), _p(y), _p(dy.contiguous()), _p(gv.data if gv is not None else None), _p(mean),
+              _p(rstd), _p(dx), _p(dgamma), _p(dbeta), x.numel() // c, c, int(ctx.relu), _stream())
+    if dgamma is not None:
+      gv.grad_ready()
+    if dbeta is not None:
+      bv.grad_ready()
+    return dx, None, None, None, None, None, None, None, None
+
+
+def batch_norm_f32(x, is_training, scope='BatchNorm', scale=False, decay=0.99, eps=1e-4, relu=False, trainable=True):
+  """slim.batch_norm on an fp32 [..., C] tensor (the normalizer_fn=slim.batch_norm variant of
+  layers/vision_layers.py:72-86: decay .99, epsilon 1e-4, scale only on the last 1x1 convolution): batch statistics
+  and moving-average update in training, moving statistics otherwise; optional fused ReLU."""
+  _require_cuda(x, 'batch_norm_f32')
+  if x.dtype != F32:
+    raise ValueError('batch_norm_f32 expects fp32 activations')
+  c = x.shape[-1]
+  vs = current_store()
+  with vs.scope(scope):
+    gv = vs.get_variable('gamma', (c,), 1.0, trainable, False, 'other', None) if scale else None
+    bv = vs.get_variable('beta', (c,), 0.0, trainable, False, 'other', None)
+    mv = vs.get_variable('moving_mean', (c,), 0.0, False, False, 'other', None)
+    vv = vs.get_variable('moving_variance', (c,), 1.0, False, False, 'other', None)
+  _ensure_grad(vs, x.device, gv, bv)
+  if is_training and torch.is_grad_enabled():
+    return _BnTrainF32Fn.apply(x.contiguous(), vs.anchor, gv, bv, mv, vv, float(eps), float(decay), relu)
+  ones = gv if gv is not None else None
+  if ones is None:   # scale=False: gamma is the constant one
+    class _One(object):
+      data = torch.ones(c, dtype=F32, device=x.device)
+      grad = None
+      trainable = False
+    ones = _One()
+  y = _BnInferF32Fn.apply(x.contiguous(), vs.anchor, ones, bv, mv, vv, float(eps))
+  return relu_f32(y) if relu else y
+
+
+def relu_f32(x):
+  return _ReluFn.apply(x.contiguous())
+
+
 # ---------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------
@@ -1864,6 +1991,84 @@ class _SigmoidLogLossFn(torch.autograd.Function):
   def backward(ctx, dloss, _dq):
     (dlogit,) = ctx.saved_tensors
     return dlogit * dloss, None
+
+
+class _WeightedLossesFn(torch.autograd.Function):
+  """t2r_weighted_losses: every segment's loss and gradient in one launch (csrc/losses.cu)."""
+
+  @staticmethod
+  def forward(ctx, specs, *preds):
+    dev = preds[0].device
+    n = len(specs)
+    segs = (_lib.LossSegment * n)()
+    losses = torch.empty(n + 1, dtype=F32, device=dev)
+    keep, dpreds, sigmoids = [], [], []
+    for i, (spec, pred) in enumerate(zip(specs, preds)):
+      seg = segs[i]
+      seg.struct_size = C.sizeof(_lib.LossSegment)
+      seg.kind = {'huber': _lib.T2R_LOSS_HUBER, 'mse': _lib.T2R_LOSS_MSE, 'sigmoid_log': _lib.T2R_LOSS_SIGMOID_LOG}[spec['kind']]
+      seg.predictions = pred.data_ptr()
+      labels = spec['labels']
+      if torch.is_tensor(labels):
+        labels = labels.to(device=dev, dtype=F32).contiguous()
+        keep.append(labels)
+        seg.labels = labels.data_ptr()
+      else:
+        seg.labels, seg.label_const = None, float(labels)
+      mask = spec.get('row_mask')
+      if mask is not None:
+        mask = mask.to(device=dev, dtype=F32).contiguous()
+        keep.append(mask)
+        seg.row_mask = mask.data_ptr()
+      seg.row_mask_is_complement = 1 if spec.get('complement') else 0
+      seg.n, seg.cols = pred.numel(), pred.shape[-1]
+      seg.row_mod = int(spec.get('row_mod', 0))
+      seg.in_total = 1 if spec.get('in_total', True) else 0
+      seg.weight, seg.delta = float(spec.get('weight', 1.0)), float(spec.get('delta', 1.0))
+      d = torch.empty_like(pred) if spec.get('differentiable', True) else None
+      dpreds.append(d)
+      seg.dpredictions = d.data_ptr() if d is not None else None
+      q = torch.empty_like(pred) if spec['kind'] == 'sigmoid_log' else None
+      sigmoids.append(q)
+      seg.sigmoid_out = q.data_ptr() if q is not None else None
+    _lib.call('t2r_weighted_losses', segs, n, _p(losses), _stream())
+    ctx.in_total = [bool(sp.get('in_total', True)) for sp in specs]
+    ctx.n = n
+    ctx.save_for_backward(*[d if d is not None else losses.new_zeros(0) for d in dpreds])
+    outs = [q for q in sigmoids if q is not None]
+    ctx.mark_non_differentiable(*outs)
+    return (losses,) + tuple(outs)
+
+  @staticmethod
+  def backward(ctx, dlosses, *_):
+    grads = [None]
+    for i, d in enumerate(ctx.saved_tensors):
+      if d.numel() == 0:
+        grads.append(None)
+        continue
+      g = dlosses[i] + dlosses[ctx.n] if ctx.in_total[i] else dlosses[i]
+      grads.append(d * g)
+    return tuple(grads)
+
+
+def weighted_losses(specs):
+  """Several tf.losses-style weighted losses (Reduction.SUM_BY_NONZERO_WEIGHTS) in one kernel launch.
+
+  specs: list of dicts - kind 'huber' | 'mse' | 'sigmoid_log' (log loss of sigmoid(predictions)), predictions (fp32
+  CUDA tensor [..., cols]; logits for 'sigmoid_log'), labels (tensor of the same shape or a float), weight (float),
+  row_mask ([rows] tensor multiplied into the weights; complement=True uses 1 - row_mask), row_mod (> 0: only rows with
+  row % row_mod == 0 count), delta (huber), in_total, differentiable.  Returns (losses [len(specs) + 1] with the
+  in_total sum last, list of sigmoid(predictions) per 'sigmoid_log' spec in order).
+  Reference: research/bcz/model.py:476-585."""
+  if not specs or len(specs) > _lib.T2R_MAX_LOSS_SEGMENTS:
+    raise ValueError('weighted_losses takes 1..%d segments' % _lib.T2R_MAX_LOSS_SEGMENTS)
+  preds = []
+  for spec in specs:
+    _require_cuda(spec['predictions'], 'weighted_losses')
+    preds.append(to_f32(spec['predictions']).contiguous())
+  meta = [{k: v for k, v in spec.items() if k != 'predictions'} for spec in specs]
+  out = _WeightedLossesFn.apply(meta, *preds)
+  return out[0], list(out[1:])
 
 
 def sigmoid_log_loss(logit, label):

@@ -187,26 +187,60 @@ def training_outputs(labels, network_output_dict, action_components, quaternion_
   else:
     raise ValueError('invalid loss')
   future = labels.future if hasattr(labels, 'future') else labels['future']
-  stop_mask_value = 1.0 - future['stop_token'] if 'stop_token' in future.keys() else 1.0
+  stop_token = future['stop_token'] if 'stop_token' in future.keys() else None
   train_outputs, nonloss_outputs = {}, {}
-  for name, _, is_residual, weight in action_components:
-    key = name + '_residual' if is_residual else name
-    predicted = network_output_dict[key]
-    label = future[key].to(predicted.dtype)
-    if name in ('target_close', 'stop_token'):
-      predicted = torch.sigmoid(predicted)
-      nonloss_outputs[name + '_predicted'] = predicted
-      loss_fn = log_loss
-    else:
-      loss_fn = reg_loss_fn
-    stop_mask = stop_mask_value * torch.ones_like(predicted)
-    train_outputs[name + '_loss'] = loss_fn(labels=label, predictions=predicted, weights=weight * stop_mask)
-    nonloss_outputs['first_' + name + '_error'] = loss_fn(labels=label[..., 0, :], predictions=predicted[..., 0, :],
-                                                          weights=weight)
-  if 'quaternion_norm' in network_output_dict:
-    predicted = network_output_dict['quaternion_norm']
-    train_outputs['quaternion_norm_loss'] = reg_loss_fn(labels=torch.ones_like(predicted), predictions=predicted,
-                                                        weights=quaternion_penalty * stop_mask_value)
+  fused_kind = {'huber': 'huber', 'mse': 'mse'}.get(loss_name)
+  n_segments = 2 * len(action_components) + (1 if 'quaternion_norm' in network_output_dict else 0)
+  if (fused_kind is not None and n_segments <= 16 and
+      all(network_output_dict[n + '_residual' if r else n].is_cuda for n, _, r, _ in action_components)):
+    # every component loss, its first-waypoint diagnostic and the norm penalty: ONE launch (csrc/losses.cu)
+    mask = stop_token.reshape(-1) if stop_token is not None else None
+    specs, names = [], []
+    for name, _, is_residual, weight in action_components:
+      key = name + '_residual' if is_residual else name
+      predicted = network_output_dict[key]
+      kind = 'sigmoid_log' if name in ('target_close', 'stop_token') else fused_kind
+      waypoints = predicted.shape[-2]
+      specs.append(dict(kind=kind, predictions=predicted, labels=future[key], weight=weight, row_mask=mask,
+                        complement=True))
+      names.append(name + '_loss')
+      specs.append(dict(kind=kind, predictions=predicted, labels=future[key], weight=weight, row_mod=waypoints,
+                        in_total=False, differentiable=False))
+      names.append('first_' + name + '_error')
+    if 'quaternion_norm' in network_output_dict:
+      specs.append(dict(kind=fused_kind, predictions=network_output_dict['quaternion_norm'], labels=1.0,
+                        weight=quaternion_penalty, row_mask=mask, complement=True))
+      names.append('quaternion_norm_loss')
+    losses, sigmoids = nn.weighted_losses(specs)
+    fused_total, fused_names = losses[len(specs)], set(n for n, sp in zip(names, specs) if sp.get('in_total', True))
+    sigmoids = iter(sigmoids)
+    for i, (spec, out_name) in enumerate(zip(specs, names)):
+      (train_outputs if spec.get('in_total', True) else nonloss_outputs)[out_name] = losses[i]
+      if spec['kind'] == 'sigmoid_log':
+        q = next(sigmoids)
+        if spec.get('in_total', True):
+          nonloss_outputs[out_name[:-len('_loss')] + '_predicted'] = q
+  else:
+    fused_total, fused_names = None, set()
+    stop_mask_value = 1.0 - stop_token if stop_token is not None else 1.0
+    for name, _, is_residual, weight in action_components:
+      key = name + '_residual' if is_residual else name
+      predicted = network_output_dict[key]
+      label = future[key].to(predicted.dtype)
+      if name in ('target_close', 'stop_token'):
+        predicted = torch.sigmoid(predicted)
+        nonloss_outputs[name + '_predicted'] = predicted
+        loss_fn = log_loss
+      else:
+        loss_fn = reg_loss_fn
+      stop_mask = stop_mask_value * torch.ones_like(predicted)
+      train_outputs[name + '_loss'] = loss_fn(labels=label, predictions=predicted, weights=weight * stop_mask)
+      nonloss_outputs['first_' + name + '_error'] = loss_fn(labels=label[..., 0, :], predictions=predicted[..., 0, :],
+                                                            weights=weight)
+    if 'quaternion_norm' in network_output_dict:
+      predicted = network_output_dict['quaternion_norm']
+      train_outputs['quaternion_norm_loss'] = reg_loss_fn(labels=torch.ones_like(predicted), predictions=predicted,
+                                                          weights=quaternion_penalty * stop_mask_value)
   if 'stop_state' in network_output_dict:          # stop state prediction loss (model.py:566-573)
     if stop_state_class_weights is None:
       raise ValueError('compute_stop_state_loss.class_weights is required (gin.REQUIRED in the reference)')
@@ -215,7 +249,9 @@ def training_outputs(labels, network_output_dict, action_components, quaternion_
                                                                stop_state_class_weights)
   if regularization_loss is not None:
     train_outputs['total_regularization_loss'] = regularization_loss
-  loss = sum(train_outputs.values())
+  loss = sum(v for k, v in train_outputs.items() if k not in fused_names)   # the kernel already summed its terms
+  if fused_total is not None:
+    loss = fused_total + loss
   train_outputs.update(nonloss_outputs)
   for name, tensor in train_outputs.items():          # each of the losses joins the golden collection (:581-583)
     golden_values_hook_builder.add_golden_tensor(tensor, name)

@@ -17,8 +17,8 @@ class HParams(dict):
 
 def BuildOpt(hparams):  # pylint: disable=invalid-name
   """Staircase exponential LR decay every int(examples_per_epoch / batch_size * num_epochs_per_decay)
-  steps; momentum (default) / adam(beta1=momentum); optionally wrapped in MovingAverageOptimizer.
-  RMSProp is not used by any shipped QT-Opt configuration and is not implemented."""
+  steps; momentum (default) / rmsprop(decay, momentum, epsilon) / adam(beta1=momentum); optionally wrapped in
+  MovingAverageOptimizer."""
   decay_steps = int(hparams.examples_per_epoch / hparams.batch_size * hparams.num_epochs_per_decay)
   learning_rate = optimizers.create_exp_decaying_learning_rate(
       hparams.learning_rate, decay_steps, hparams.learning_rate_decay_factor, staircase=True)
@@ -26,7 +26,8 @@ def BuildOpt(hparams):  # pylint: disable=invalid-name
   if optimizer == 'momentum':
     opt = optimizers.MomentumOptimizer(learning_rate, hparams.momentum)
   elif optimizer == 'rmsprop':
-    raise NotImplementedError('rmsprop: no fused kernel yet (no reference config selects it)')
+    opt = optimizers.RMSPropOptimizer(learning_rate, decay=hparams.rmsprop_decay, momentum=hparams.momentum,
+                                      epsilon=hparams.rmsprop_epsilon)
   else:
     opt = optimizers.AdamOptimizer(learning_rate, beta1=hparams.momentum, beta2=hparams.get('adam_beta2', 0.999),
                                    epsilon=hparams.get('adam_epsilon', 1e-8))

@@ -40,7 +40,7 @@ class ResNet50QCritic(networks.Grasping44E2EOpenCloseTerminateGripperStatusHeigh
     namer = namer or resnet_lib._Namer()
     films = self._resnet.film_params(None, None)
     with nn.variable_scope('resnet_model'):
-      net = self._resnet.stem(grasp_image, namer)
+      net = self._resnet.stem(grasp_image, namer, is_training)
       net = self._resnet.block_layers(net, is_training, namer, films, 0, self._merge_after)
     if end_points is not None:
       end_points['pool2'] = net  # the staged feature map (name kept from Grasping44)

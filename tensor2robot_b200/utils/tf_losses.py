@@ -8,7 +8,8 @@ def compute_weighted_loss(loss, weights=1.0):
   w = torch.as_tensor(weights, dtype=loss.dtype, device=loss.device)
   w = torch.broadcast_to(w, loss.shape)
   nonzero = (w != 0).sum().to(loss.dtype)
-  return (loss * w).sum() / torch.clamp(nonzero, min=1.0) if nonzero > 0 else (loss * w).sum()
+  # no non-zero weight => the numerator is zero too: the safe division needs no host-side branch (and no sync)
+  return (loss * w).sum() / torch.clamp(nonzero, min=1.0)
 
 
 def huber_loss(labels, predictions, weights=1.0, delta=1.0):

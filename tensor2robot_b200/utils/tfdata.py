@@ -156,14 +156,23 @@ _POOL = None
 # Where encoded images are decoded: 'host' (libjpeg-turbo / libpng through PIL on host threads, numpy out) or
 # 'device' (baseline JPEGs: Huffman on host threads, IDCT / upsampling / colour on the GPU, uint8 CUDA tensor
 # out, bit-identical; anything the split decoder rejects falls back to 'host').  utils/jpeg.py.
-IMAGE_DECODER = os.environ.get('T2R_IMAGE_DECODER', 'host')
+# 'auto' (the default) = 'device' on a machine with a GPU - the record path of a training run - else 'host'.
+IMAGE_DECODER = os.environ.get('T2R_IMAGE_DECODER', 'auto')
 
 
 def set_image_decoder(kind):
   global IMAGE_DECODER
-  if kind not in ('host', 'device'):
-    raise ValueError("image decoder must be 'host' or 'device'")
+  if kind not in ('host', 'device', 'auto'):
+    raise ValueError("image decoder must be 'host', 'device' or 'auto'")
   IMAGE_DECODER = kind
+
+
+def image_decoder():
+  """The decoder in effect: 'host' or 'device'."""
+  if IMAGE_DECODER != 'auto':
+    return IMAGE_DECODER
+  import torch
+  return 'device' if torch.cuda.is_available() else 'host'
 
 
 def _pool():
@@ -187,7 +196,7 @@ def _decode_images(tensor_spec, byte_rows):
   np_dtype = tensor_spec.dtype.as_numpy_dtype
   flat = [b for row in byte_rows for b in row]
   per_row = len(byte_rows[0]) if byte_rows else 0
-  if IMAGE_DECODER == 'device' and np_dtype == np.uint8 and flat and all(b[:2] == b'\xff\xd8' for b in flat):
+  if image_decoder() == 'device' and np_dtype == np.uint8 and flat and all(b[:2] == b'\xff\xd8' for b in flat):
     from tensor2robot_b200.utils import jpeg
     try:
       out = jpeg.decode_batch(flat, channels=dims[2])

@@ -52,7 +52,7 @@ def provide_input_generator_with_model_information(input_generator_or_generators
 
 def tfdata_image_decoder():
   from tensor2robot_b200.utils import tfdata
-  return tfdata.IMAGE_DECODER
+  return tfdata.image_decoder()
 
 
 class DeviceStager(object):
@@ -86,7 +86,9 @@ class DeviceStager(object):
     with torch.cuda.stream(self.stream):
       for key, value in struct.items():
         if isinstance(value, torch.Tensor) and value.is_cuda:
-          out[key] = value          # already on the device (e.g. frames from the split JPEG decoder)
+          # already on the device: frames the split JPEG decoder produced on this (copy) stream
+          value.record_stream(consumer_stream)
+          out[key] = value
           continue
         t = value if isinstance(value, torch.Tensor) else torch.from_numpy(value)
         if t.dtype == torch.float64:
@@ -228,16 +230,29 @@ def _batches(input_generator, t2r_model, mode, device, prefetch=2):
   (features, labels)."""
   preprocessor = t2r_model.preprocessor
   consumer_stream = torch.cuda.current_stream(device)
-  on_thread = bool(prefetch) and tfdata_image_decoder() == 'host'
+  on_thread = bool(prefetch)
   # every queued batch holds a pinned slot, plus the one being filled and the one the GPU may still be copying
   stager = DeviceStager(device, depth=(prefetch + 2) if on_thread else 2)
+
+  def host_batches():
+    """The input generator's batches.  With the split JPEG decoder the generator itself launches kernels (IDCT / colour
+    on the GPU): they go to the stager's copy stream, like the H2D copies, so that the whole record path - read, parse,
+    Huffman threads, device half of the decode - runs ahead of the training step on the producer thread."""
+    it = iter(input_generator.create_dataset(mode))
+    while True:
+      with torch.cuda.stream(stager.stream):
+        try:
+          item = next(it)
+        except StopIteration:
+          return
+      yield item
 
   def staged_batches():
     """host batch -> pinned slot -> async H2D.  The 0.5 GB host memcpy of a 512-frame batch stays off the thread
     that launches kernels when this generator runs inside the Prefetcher."""
     if on_thread:
       torch.cuda.set_device(device)
-    for features, labels in input_generator.create_dataset(mode):
+    for features, labels in host_batches():
       merged = tensorspec_utils.TensorSpecStruct(
           [('f/' + k, v) for k, v in tensorspec_utils.flatten_spec_structure(features).items()])
       if labels is not None:
@@ -245,7 +260,6 @@ def _batches(input_generator, t2r_model, mode, device, prefetch=2):
           merged['l/' + k] = v
       yield stager.stage(merged, consumer_stream)
 
-  # the device JPEG decoder launches kernels on the consumer's CUDA stream: it stays on this thread
   source = Prefetcher(staged_batches(), prefetch) if on_thread else staged_batches()
   for staged, ready in source:
     consumer_stream.wait_event(ready)

@@ -535,7 +535,7 @@ static void test_misc() {
     report("logloss dlogit", dl.down(), dr, 1e-4f, 1e-8f);
   }
   {  // optimizers
-    const int n = 1003, nd = 600;
+    const int n = 1004, nd = 600;   // 16-byte vectors: n and nd are multiples of 4
     std::vector<float> w = randv(n, 1.f, false), g = randv(n, 1.f, false), a = randv(n, 0.1f, false), e = w, v(n);
     for (int i = 0; i < n; ++i) v[i] = fabsf(a[i]);
     Dev<float> dw(n), dg(n), da(n), de(n), dm(n), dv(n), dw2(n), de2(n);
@@ -543,8 +543,20 @@ static void test_misc() {
     dw.up(w); dg.up(g); da.up(a); de.up(e); dw2.up(w); de2.up(e); dm.up(a); dv.up(v);
     T2R(t2r_momentum_step(dw.p, dg.p, da.p, de.p, wb.p, n, nd, 0.01f, 0.9f, 7e-5f, 0.5f, 0.999f, nullptr));
     T2R(t2r_adam_step(dw2.p, dg.p, dm.p, dv.p, de2.p, nullptr, n, nd, 1e-3f, 0.9f, 0.999f, 1e-8f, 3, 7e-5f, 0.5f, 0.999f, nullptr));
+    std::vector<float> ms0(n), mom0 = randv(n, 0.05f, false);
+    for (int i = 0; i < n; ++i) ms0[i] = 0.5f + fabsf(a[i]);
+    Dev<float> dw3(n), dms(n), dmom(n);
+    dw3.up(w); dms.up(ms0); dmom.up(mom0);
+    T2R(t2r_rmsprop_step(dw3.p, dg.p, dms.p, dmom.p, nullptr, nullptr, n, nd, 0.01f, 0.9f, 0.8f, 1.0f, 7e-5f, 0.5f, 0.f, nullptr));
+    T2R(t2r_momentum_step(dw.p + 1, dg.p, da.p, nullptr, nullptr, 4, 0, 0.01f, 0.9f, 0.f, 1.f, 0.f, nullptr) == T2R_ERR_INVALID_ARG ? 0 : 1);
     sync_check("optim");
-    std::vector<float> wr(n), er(n), wr2(n);
+    std::vector<float> wr(n), er(n), wr2(n), wr3(n);
+    for (int i = 0; i < n; ++i) {
+      const float gi = g[i] * 0.5f + (i < nd ? 7e-5f * w[i] : 0.f);
+      const float msi = 0.9f * ms0[i] + 0.1f * gi * gi;
+      const float momi = 0.8f * mom0[i] + 0.01f * gi / sqrtf(msi + 1.0f);
+      wr3[i] = w[i] - momi;
+    }
     const double lrt = 1e-3 * sqrt(1 - pow(0.999, 3)) / (1 - pow(0.9, 3));
     for (int i = 0; i < n; ++i) {
       float gi = g[i] * 0.5f + (i < nd ? 7e-5f * w[i] : 0.f);
@@ -558,6 +570,7 @@ static void test_misc() {
     report("momentum ema", de.down(), er, 1e-6f, 1e-7f);
     report("momentum w_bf16", from_bf16(wb.down()), wr, 8e-3f, 1e-6f);
     report("adam w", dw2.down(), wr2, 1e-5f, 1e-6f);
+    report("rmsprop w", dw3.down(), wr3, 1e-5f, 1e-6f);
   }
   {  // CEM refit + bellman
     const int B = 4, A = 64, D = 10, E = 10;

@@ -54,3 +54,43 @@ def test_bcz_predict(tmp_path):
   assert torch.allclose(q.norm(dim=-1), torch.ones(2, 3, device=q.device), atol=1e-4)   # unit quaternions
   g = preds['action/target_close'].float()
   assert float(g.min()) >= 0.2 - 1e-6 and float(g.max()) <= 1 + 1e-6                     # rescaled gripper range
+
+
+@pytest.mark.parametrize('loss_name', ['huber', 'mse'])
+@pytest.mark.parametrize('with_stop', [False, True])
+def test_training_outputs_fused_kernel_matches_eager(loss_name, with_stop):
+  """research/bcz/model.py:476-585: every loss term, diagnostic and gradient of the one-launch kernel
+  (t2r_weighted_losses) against the op-by-op restatement of the same formulas on CPU tensors."""
+  from tensor2robot_b200.research.bcz import model as bcz
+  from tensor2robot_b200.research.bcz import pose_components_lib
+  from tensor2robot_b200.utils import tensorspec_utils
+  rng = np.random.RandomState(11)
+  b, w = 6, 5
+  components = list(pose_components_lib.DEFAULT_ACTION_COMPONENTS)
+  net_cpu, future = {}, tensorspec_utils.TensorSpecStruct()
+  for name, size, residual, _ in components:
+    key = name + '_residual' if residual else name
+    net_cpu[key] = torch.from_numpy(rng.standard_normal((b, w, size)).astype(np.float32) * 1.5).requires_grad_(True)
+    future[key] = torch.from_numpy(rng.uniform(0, 1, (b, w, size)).astype(np.float32))
+  net_cpu['quaternion_norm'] = torch.from_numpy(rng.uniform(0.5, 2.5, (b, w, 1)).astype(np.float32)).requires_grad_(True)
+  if with_stop:
+    future['stop_token'] = torch.from_numpy((rng.uniform(size=(b, w, 1)) < 0.4).astype(np.float32))
+  labels_cpu = tensorspec_utils.TensorSpecStruct(future=future)
+  loss_cpu, out_cpu = bcz.training_outputs(labels_cpu, net_cpu, components, loss_name=loss_name)
+  loss_cpu.backward()
+
+  net_gpu = {k: v.detach().cuda().requires_grad_(True) for k, v in net_cpu.items()}
+  labels_gpu = tensorspec_utils.TensorSpecStruct(
+      future=tensorspec_utils.TensorSpecStruct([(k, v.cuda()) for k, v in future.items()]))
+  from tensor2robot_b200 import _lib
+  launches0 = _lib.launch_count()
+  loss_gpu, out_gpu = bcz.training_outputs(labels_gpu, net_gpu, components, loss_name=loss_name)
+  assert _lib.launch_count() - launches0 == 1                    # the whole loss tail is one kernel
+  loss_gpu.backward()
+  assert sorted(out_gpu) == sorted(out_cpu)
+  np.testing.assert_allclose(float(loss_gpu), float(loss_cpu), rtol=2e-6)
+  for k in out_cpu:
+    np.testing.assert_allclose(out_gpu[k].detach().cpu().numpy(), out_cpu[k].detach().numpy(), rtol=1e-5, atol=1e-7,
+                               err_msg=k)
+  for k in net_cpu:
+    np.testing.assert_allclose(net_gpu[k].grad.cpu().numpy(), net_cpu[k].grad.numpy(), rtol=1e-5, atol=1e-8, err_msg=k)

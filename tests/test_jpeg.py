@@ -155,7 +155,7 @@ def test_parser_with_device_decoder_matches_host_decoder():
   try:
     dev = parse(records).state.image
   finally:
-    tfdata.set_image_decoder('host')
+    tfdata.set_image_decoder('auto')
   assert hasattr(dev, 'is_cuda') and dev.is_cuda and tuple(dev.shape) == host.shape
   np.testing.assert_array_equal(dev.cpu().numpy(), host)
 

@@ -228,7 +228,8 @@ def test_optimizers_match_tf_formulas():
   from tensor2robot_b200.models import optimizers
   rng = np.random.RandomState(5)
   for make, ref_fn in ((lambda: optimizers.MomentumOptimizer(0.1, 0.9), 'momentum'),
-                       (lambda: optimizers.AdamOptimizer(0.01), 'adam')):
+                       (lambda: optimizers.AdamOptimizer(0.01), 'adam'),
+                       (lambda: optimizers.RMSPropOptimizer(0.05, decay=0.9, momentum=0.9, epsilon=1.0), 'rmsprop')):
     vs = nn.VariableStore('cuda')
     w0 = rng.standard_normal((7, 13)).astype(np.float32)
     with nn.variable_store(vs):
@@ -239,6 +240,7 @@ def test_optimizers_match_tf_formulas():
     w = w0.astype(np.float64).copy()
     ema = w.copy()
     m = np.zeros_like(w); vv = np.zeros_like(w)
+    rms = np.ones_like(w)              # tf.train.RMSPropOptimizer initialises its rms slot to one
     for step in range(4):
       g = rng.standard_normal((7, 13)).astype(np.float32)
       v.grad.copy_(torch.from_numpy(g))
@@ -247,6 +249,10 @@ def test_optimizers_match_tf_formulas():
       if ref_fn == 'momentum':
         m = 0.9 * m + gg
         w = w - 0.1 * m
+      elif ref_fn == 'rmsprop':           # research/qtopt/optimizer_builder.py:76-81 (decay .9, momentum, epsilon 1.0)
+        rms = 0.9 * rms + 0.1 * gg * gg
+        m = 0.9 * m + 0.05 * gg / np.sqrt(rms + 1.0)
+        w = w - m
       else:
         t = step + 1
         m = 0.9 * m + 0.1 * gg
@@ -412,3 +418,43 @@ def test_parallel_cheap_and_depth_distortions():
   assert any(changed) and not all(changed)                                   # the coin is drawn per list entry
   for o in outs:
     assert float(o.min()) >= 0.25 and float(o.max()) <= 2.5
+
+
+@pytest.mark.gpu
+def test_crop_convert_distort_vector_path_matches_scalar_path(tmp_path):
+  """The 16-byte-vector kernel (crop width % 8 == 0) against the oracle for every source byte alignment
+  (crop_x * 3 mod 16), and bit for bit against the scalar kernel - including the Philox noise, which is
+  indexed by pixel - run in a second process with T2R_DISABLE_VEC_CROP=1."""
+  import os
+  import subprocess
+  import sys
+  from oracle import image_ops as oracle
+  from tensor2robot_b200.preprocessors import image_ops
+  rng = np.random.RandomState(8)
+  frames = rng.randint(0, 256, (3, 70, 150, 3)).astype(np.uint8)
+  d = torch.from_numpy(frames).cuda()
+  for crop_x in range(0, 17):                                    # all alignments of the first source byte
+    p = image_ops.identity_params(3, 3, crop_x)
+    ref = oracle.convert_image_dtype_f32(oracle.crop(frames, 3, crop_x, 63, 104))   # 63 rows: a partial last block
+    out = image_ops.crop_convert_distort(d, (63, 104), p, torch.float32)
+    assert np.array_equal(out.cpu().numpy(), ref), crop_x
+    out_b = image_ops.crop_convert_distort(d, (63, 104), p, torch.bfloat16)
+    assert torch.equal(out_b.cpu(), torch.from_numpy(ref).to(torch.bfloat16)), crop_x
+  script = '''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from tensor2robot_b200.preprocessors import image_ops
+frames = np.load(%r)
+p = image_ops.identity_params(3, 2, 7)
+p['noise_stddev'] = 0.05; p['brightness_delta'] = 0.03; p['saturation_scale'] = 1.2; p['hue_delta'] = -0.1; p['contrast_scale'] = 0.8
+out = image_ops.crop_convert_distort(torch.from_numpy(frames).cuda(), (64, 136), p, torch.float32, seed=5, offset=3)
+np.save(sys.argv[1], out.cpu().numpy())
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / 'frames.npy'))
+  np.save(str(tmp_path / 'frames.npy'), frames)
+  outs = {}
+  for name, env in (('vector', {}), ('scalar', {'T2R_DISABLE_VEC_CROP': '1'})):
+    path = str(tmp_path / (name + '.npy'))
+    subprocess.run([sys.executable, '-c', script, path], check=True, env=dict(os.environ, **env), timeout=300)
+    outs[name] = np.load(path)
+  assert np.array_equal(outs['vector'], outs['scalar'])
+  assert outs['vector'].std() > 0.1

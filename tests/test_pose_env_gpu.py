@@ -201,3 +201,83 @@ def test_train_on_reference_fixture(tmp_path, which):
   init = torch.load(str(tmp_path / 'model.ckpt-0.pt'), weights_only=False)
   moved = [k for k in init['variables'] if np.abs(state['variables'][k] - init['variables'][k]).max() > 0]
   assert len(moved) == len(init['variables']), sorted(set(init['variables']) - set(moved))
+
+
+@pytest.mark.parametrize('normalizer,with_film', [('layer_norm', True), ('batch_norm', False), ('batch_norm', True)])
+def test_vision_tower_film_and_batch_norm_variants_match_oracle(normalizer, with_film):
+  """layers/vision_layers.py:72-86 (slim.batch_norm normaliser: decay .99, eps 1e-4, scale only on the final 1x1
+  convolution) and :100-141, 162-181 (FiLM: (1 + gamma) * h + beta before the ReLU, parameters from a linear layer on
+  the embedding): feature points, every gradient and the moving statistics against the float64 oracle."""
+  from oracle import vision_layers as oracle
+  from tensor2robot_b200 import nn
+  from tensor2robot_b200.layers import vision_layers
+  rng = np.random.RandomState(17)
+  b = 6
+  img = rng.uniform(0, 1, (b, 64, 64, 3)).astype(np.float32)
+  emb = rng.standard_normal((b, 12)).astype(np.float32)
+  wts = rng.standard_normal((b, 64)).astype(np.float32)
+  vs = nn.VariableStore('cuda:0', seed=4)
+  img_t, emb_t, wts_t = (torch.from_numpy(a).cuda() for a in (img, emb, wts))
+
+  def run(training):
+    with nn.variable_scope('tower'):
+      film = vision_layers.BuildFILMParams(emb_t) if with_film else None
+      points, extra = vision_layers.BuildImagesToFeaturesModel(img_t, is_training=training, normalizer_fn=normalizer,
+                                                               film_output_params=film)
+    return points, extra
+
+  with torch.no_grad(), nn.variable_store(vs):
+    run(False)
+  vs.finalize()
+  names = sorted(vs.export_tf())
+  tag = 'LayerNorm' if normalizer == 'layer_norm' else 'BatchNorm'
+  assert ('tower/conv2/%s/beta' % tag) in names and ('tower/final_conv_1x1/%s/gamma' % tag) in names
+  if normalizer == 'batch_norm':
+    assert 'tower/conv2/BatchNorm/gamma' not in names and 'tower/conv2/BatchNorm/moving_variance' in names   # scale=False
+  if with_film:
+    assert vs.export_tf()['tower/film/weights'].shape == (12, 2 * 5 * 32)
+  ov = _randomise(vs, 9)
+  for k in ov:
+    if k.endswith('moving_variance'):
+      ov[k] = ov[k].abs() + 0.5
+  vs.import_tf({k: v.numpy().astype(np.float32) for k, v in ov.items()})
+  for v in ov.values():
+    v.requires_grad_(True)
+  with nn.variable_store(vs):
+    points, extra = run(True)
+    loss = (points * wts_t).sum()
+    vs.zero_grad()
+    loss.backward()
+  torch.cuda.synchronize()
+  assert tuple(points.shape) == (b, 64) and tuple(extra['softmax'].shape)[0] == b
+  updates = {}
+  film_o = None
+  if with_film:
+    film_o = torch.from_numpy(emb.astype(np.float64)) @ ov['tower/film/weights'] + ov['tower/film/biases'].reshape(1, -1)
+  points_o = oracle.images_to_features(torch.from_numpy(img.astype(np.float64)), ov, 'tower', film=film_o,
+                                       normalizer=normalizer, training=True, updates=updates)
+  (points_o * torch.from_numpy(wts.astype(np.float64))).sum().backward()
+  err = _rel(points.detach().cpu().numpy(), points_o.detach().numpy())
+  grads = vs.export_tf_grads()
+  worst = 0.0
+  for k, g in grads.items():
+    go = ov[k].grad
+    if go is None:
+      continue
+    worst = max(worst, _rel(g, go.numpy()))
+  new = vs.export_tf()
+  for k, u in updates.items():
+    assert _rel(new[k], u.detach().numpy()) < 1e-5, k
+  print('%s film=%s: points rel %.2e, worst gradient rel %.2e, %d moving statistics' % (normalizer, with_film, err, worst,
+                                                                                       len(updates)))
+  assert err < 2e-5 and worst < 5e-4
+  # inference mode reads the moving statistics
+  with torch.no_grad(), nn.variable_store(vs):
+    p_eval, _ = run(False)
+  ov2 = {k: torch.from_numpy(np.asarray(v, np.float64)) for k, v in new.items()}
+  film_e = None
+  if with_film:
+    film_e = torch.from_numpy(emb.astype(np.float64)) @ ov2['tower/film/weights'] + ov2['tower/film/biases'].reshape(1, -1)
+  p_eval_o = oracle.images_to_features(torch.from_numpy(img.astype(np.float64)), ov2, 'tower', film=film_e,
+                                       normalizer=normalizer, training=False)
+  assert _rel(p_eval.cpu().numpy(), p_eval_o.numpy()) < 2e-5

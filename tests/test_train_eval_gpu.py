@@ -107,7 +107,7 @@ def test_record_train_with_device_jpeg_decoder(tmp_path):
                                                                                     seed=0),
           max_train_steps=1, model_dir=str(tmp_path / ('run_' + kind)))
     finally:
-      tfdata.set_image_decoder('host')
+      tfdata.set_image_decoder('auto')
     assert out['global_step'] == 1 and np.isfinite(out['loss'])
     losses[kind] = out['loss']
   assert abs(losses['host'] - losses['device']) < 0.05 * abs(losses['host']), losses

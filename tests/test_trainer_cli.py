@@ -18,7 +18,7 @@ def test_flags_and_model_resolution():
     cli.resolve('tensor2robot_b200.research.pose_env.pose_env_models')
   args = cli.build_parser().parse_args(['--model', MODEL, '--model_kwargs', json.dumps({'action_size': 2}),
                                         '--train_file_patterns', FIXTURE, '--batch_size', '4', '--max_train_steps', '7'])
-  assert args.max_train_steps == 7 and args.eval_steps == 100 and args.image_decoder == 'host'
+  assert args.max_train_steps == 7 and args.eval_steps == 100 and args.image_decoder == 'auto'
   train, evaluation = cli.make_generators(args, (0, 1))
   assert isinstance(train, gens.DefaultRecordInputGenerator) and evaluation is None
   args = cli.build_parser().parse_args(['--model', MODEL])
@@ -32,7 +32,7 @@ def test_cli_trains_on_the_fixture(tmp_path, capsys):
                      '--batch_size', '4', '--max_train_steps', '2', '--eval_steps', '1', '--model_dir', str(tmp_path),
                      '--image_decoder', 'device'])
   from tensor2robot_b200.utils import tfdata
-  tfdata.set_image_decoder('host')
+  tfdata.set_image_decoder('auto')
   assert result['global_step'] == 2 and result['eval']['steps'] == 1
   assert json.loads(capsys.readouterr().out.strip().splitlines()[-1])['global_step'] == 2
   assert os.path.exists(str(tmp_path / 'model.ckpt-2.pt'))
