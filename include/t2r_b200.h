@@ -419,6 +419,9 @@ int32_t t2r_rmsprop_step(float* w, const float* g, float* ms, float* mom, float*
                          int64_t n_decay, float lr, float decay, float momentum, float eps, float l2,
                          float grad_scale, float ema_decay, void* stream);
 
+/* Mixup (research/bcz/model.py:164-172): y[b] = lambda*x[b] + (1-lambda)*x[B-1-b] on fp32 [B, inner]; x != y. */
+int32_t t2r_mixup_reverse_f32(const float* x, float* y, int32_t B, int64_t inner, float lambda, void* stream);
+
 /* ---- weighted loss tail (BC-Z) ------------------------------------------------------------
  * research/bcz/model.py:476-585 (training_outputs): tf.losses.huber_loss / mean_squared_error / log_loss per action
  * component with weights = component weight x (1 - stop_token), the quaternion-norm penalty and the first-waypoint

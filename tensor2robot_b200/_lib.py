@@ -132,6 +132,7 @@ _PROTOS = {
     't2r_momentum_step': (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P]),
     't2r_adam_step': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _I64, _F, _F, _F, _P]),
     't2r_rmsprop_step': (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _F, _F, _P]),
+    't2r_mixup_reverse_f32': (_I32, [_P, _P, _I32, _I64, _F, _P]),
     't2r_weighted_losses': (_I32, [C.POINTER(LossSegment), _I32, _P, _P]),
     't2r_crc32c': (C.c_uint32, [_P, _U64]),
     't2r_masked_crc32c': (C.c_uint32, [_P, _U64]),

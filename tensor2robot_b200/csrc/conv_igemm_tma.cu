@@ -16,6 +16,7 @@
 // BLOCK_N = 128 (warpgroup h owns 64-channel sub-tile h) or 64 (the two warpgroups split one
 // sub-tile).  Main loop, warp roles and barriers are those of conv_igemm.cu.
 #include <algorithm>
+#include <cstdlib>
 
 #include "conv_common.cuh"
 
@@ -47,8 +48,14 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 }
 
 // kPro: see conv_igemm.cu (warps 12..15 rewrite each landed A tile as relu(bn_scale * x + bn_shift)).
-template <int BLOCK_N, bool kPro>
-__global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(const __grid_constant__ IgemmTmaParams pp) {
+// kEpiWarps: 8, or 16 for BLOCK_N = 128 without kPro.  The layers this kernel serves are bound by their output /
+// residual traffic, and two consecutive tiles' epilogues run on the same warps: with 8 warps each converts two
+// 32-column chunks per tile (~2 x 900 cycles of dependent TMEM load -> shared load -> convert -> shared store ->
+// column sums) and the tile rate is latency bound at ~0.6 of the HBM roofline; 16 warps take one chunk each.
+template <int BLOCK_N, bool kPro, int kEpiWarps>
+__global__ void __launch_bounds__(128 + 32 * kEpiWarps + (kPro ? 128 : 0), 1)
+conv_igemm_tma_kernel(const __grid_constant__ IgemmTmaParams pp) {
+  static_assert(kEpiWarps == 8 || (kEpiWarps == 16 && BLOCK_N == 128 && !kPro), "16 epilogue warps: BLOCK_N 128 only");
   using Cfg = IgemmTmaCfg<BLOCK_N>;
   const IgemmParams& p = pp.g;
   extern __shared__ uint8_t smem_raw[];
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);
+      mbar_init(tempty_bar(s), kEpiWarps);
       mbar_init(cfull_bar(s), 1);
       mbar_init(cempty_bar(s), Cfg::kSubTiles);  // one arrival per store-issuing thread
     }
@@ -225,19 +232,26 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(con
           }
         }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps =====================
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+    // ===================== epilogue: 8 or 16 warps =====================
+    // Warp w reads TMEM lanes 32 * (w % 4) .. +31 (one output pixel per thread); `part` picks the columns:
+    //   BLOCK_N 128,  8 warps: part = sub-tile (64 channels, two 32-column chunks per warp)
+    //   BLOCK_N 128, 16 warps: part = 32-column chunk 0..3 (sub-tile part / 2)
+    //   BLOCK_N  64,  8 warps: part = 32-column half of the single sub-tile
     const int ew = warp - 4;
     const int quad = ew & 3;
-    const int half = ew >> 2;
-    constexpr int kChunks = BLOCK_N == 128 ? 2 : 1;
-    const int sub = BLOCK_N == 128 ? half : 0;          // 64-channel sub-tile this warpgroup writes
-    const int col0 = BLOCK_N == 128 ? 0 : half * 32;    // first column inside the sub-tile
+    const int part = ew >> 2;
+    constexpr bool kWide = kEpiWarps == 16;
+    constexpr int kChunks = (BLOCK_N == 128 && !kWide) ? 2 : 1;
+    const int sub = BLOCK_N == 128 ? (kWide ? part >> 1 : part) : 0;            // 64-channel sub-tile this warp writes
+    const int col0 = BLOCK_N == 128 ? (kWide ? (part & 1) * 32 : 0) : part * 32;   // first column inside the sub-tile
+    const int half = sub;
     const int row = quad * 32 + lane;
     const int th = row / p.TW;
     const int tw = row - th * p.TW;
     const uint32_t rsw = uint32_t(row) & 7u;
-    const bool elected = (quad == 0 && lane == 0) && (BLOCK_N == 128 || half == 0);
+    // one thread per sub-tile issues its TMA store
+    const bool elected = (quad == 0 && lane == 0) && (BLOCK_N == 128 ? (!kWide || (part & 1) == 0) : part == 0);
     int as = 0, cb = 0, pending_cb = -1;
     uint32_t aphase = 0, cphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -361,8 +375,8 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(con
       if (lane == 0) mbar_arrive(tempty_bar(as));
       // hand the finished sub-tile to TMA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (BLOCK_N == 128) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      if (BLOCK_N == 128) {   // the warps that wrote sub-tile `sub`
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(kWide ? 256 : 128) : "memory");
       } else {
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -382,8 +396,8 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(con
     }
     if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.stats != nullptr) {
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += 256) {
+      asm volatile("bar.sync 3, %0;" ::"r"(32 * kEpiWarps) : "memory");
+      for (int i = threadIdx.x - 128; i < 2 * p.Cout; i += 32 * kEpiWarps) {
         const float x = stat_acc[i];
         if (x != 0.f) atomicAdd(p.stats + i, double(x));
       }
@@ -398,23 +412,34 @@ __global__ void __launch_bounds__(kPro ? 512 : 384, 1) conv_igemm_tma_kernel(con
   }
 }
 
-template <int BLOCK_N, bool kPro>
+template <int BLOCK_N, bool kPro, int kEpiWarps>
 static int launch_v(const IgemmTmaParams& pp, cudaStream_t stream) {
   using Cfg = IgemmTmaCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_tma_kernel<BLOCK_N, kPro>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
+    T2R_CUDA_OK(cudaFuncSetAttribute(conv_igemm_tma_kernel<BLOCK_N, kPro, kEpiWarps>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = std::min(pp.g.total_tiles, num_sms());
-  conv_igemm_tma_kernel<BLOCK_N, kPro><<<grid, kPro ? 512 : 384, Cfg::kSmemBytes, stream>>>(pp);
+  conv_igemm_tma_kernel<BLOCK_N, kPro, kEpiWarps><<<grid, 128 + 32 * kEpiWarps + (kPro ? 128 : 0), Cfg::kSmemBytes, stream>>>(pp);
   T2R_LAUNCH_OK();
   return T2R_OK;
 }
 template <int BLOCK_N>
 static int launch(const IgemmTmaParams& pp, cudaStream_t stream) {
-  return (pp.g.flags & kProBnRelu) ? launch_v<BLOCK_N, true>(pp, stream) : launch_v<BLOCK_N, false>(pp, stream);
+  if (pp.g.flags & kProBnRelu) return launch_v<BLOCK_N, true, 8>(pp, stream);
+  return launch_v<BLOCK_N, false, 8>(pp, stream);
+}
+// BLOCK_N 128: 16 epilogue warps where the tile is bound by its epilogue (few k-iterations per tile): T2R_TMA_EPI_WARPS
+// = 8 | 16 | auto (default: 16 when the GEMM K <= 512).
+template <>
+int launch<128>(const IgemmTmaParams& pp, cudaStream_t stream) {
+  if (pp.g.flags & kProBnRelu) return launch_v<128, true, 8>(pp, stream);
+  static const char* mode = std::getenv("T2R_TMA_EPI_WARPS");
+  const int k_iters = pp.g.n_taps * pp.g.chunks_per_tap;
+  const bool wide = mode == nullptr || mode[0] == 'a' ? k_iters <= 8 : (mode[0] == '1');
+  return wide ? launch_v<128, false, 16>(pp, stream) : launch_v<128, false, 8>(pp, stream);
 }
 
 int conv_igemm_tma_launch(const IgemmParams& p, int block_n, cudaStream_t stream) {

@@ -324,9 +324,29 @@ __global__ void __launch_bounds__(256) depth_distort_kernel(const float* __restr
   }
 }
 
+// Mixup regularisation (research/bcz/model.py:164-172): y[b] = lambda * x[b] + (1 - lambda) * x[B - 1 - b]
+// (tf.reverse along the batch axis), fp32 [B, inner].
+__global__ void __launch_bounds__(256) mixup_reverse_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                                long long inner, float lambda) {
+  const long long total = (long long)B * inner;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long b = i / inner, j = i - b * inner;
+    y[i] = lambda * x[i] + (1.0f - lambda) * x[(B - 1 - b) * inner + j];
+  }
+}
+
 }  // namespace t2r
 
 using namespace t2r;
+
+extern "C" int32_t t2r_mixup_reverse_f32(const float* x, float* y, int32_t B, int64_t inner, float lambda, void* stream) {
+  T2R_CHECK_ARG(x && y && x != y && B > 0 && inner > 0, "mixup_reverse_f32: bad args (out of place only)");
+  const long long total = (long long)B * inner;
+  const int grid = int(std::min<long long>((total + 255) / 256, 148LL * 16));
+  mixup_reverse_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, B, inner, lambda);
+  T2R_LAUNCH_OK();
+  return T2R_OK;
+}
 
 extern "C" int32_t t2r_crop_convert_distort(const uint8_t* src, void* dst, const T2RDistortParams* params,
                                             float* chan_mean, int32_t N, int32_t H, int32_t W, int32_t h,

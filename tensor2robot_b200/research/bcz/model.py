@@ -1,6 +1,6 @@
 """BC-Z (research/bcz/model.py): FiLM-conditioned ResNet image-to-action network with one MLP head per pose
 component (:245-285), pose assembly (:321-460), weighted huber / log losses (:476-585), the BCZPreprocessor
-(:69-196) and the BCZModel T2R class (:641-950).  Not built: mixup, eval metrics."""
+(:69-196, mixup included) and the BCZModel T2R class (:641-950).  Not built: cutout (the reference raises too), eval metrics."""
 from tensor2robot_b200 import nn
 from tensor2robot_b200.layers import bcz_networks
 from tensor2robot_b200.layers import resnet
@@ -295,14 +295,26 @@ class ConditionMode(enum.Enum):
   LANGUAGE_EMBEDDING = 2
 
 
+def mixup_reverse(x, lmbda):
+  """lmbda * x + (1 - lmbda) * tf.reverse(x, axis=[0]) on a [B, ...] tensor (fp32 on the device kernel)."""
+  import ctypes as C
+  from tensor2robot_b200 import _lib
+  if not x.is_cuda:
+    return lmbda * x + (1.0 - lmbda) * torch.flip(x, dims=[0])
+  xf = x.float().contiguous()
+  y = torch.empty_like(xf)
+  _lib.call('t2r_mixup_reverse_f32', C.c_void_p(xf.data_ptr()), C.c_void_p(y.data_ptr()), xf.shape[0],
+            xf.numel() // xf.shape[0], float(lmbda), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+  return y.to(x.dtype) if x.dtype.is_floating_point else y
+
+
 class BCZPreprocessor(spec_transformation_preprocessor.SpecTransformationPreprocessor):
   """Image conversion / crop / resize for single frames (model.py:69-196)."""
 
   def __init__(self, image_size=(100, 100), crop_size=(512, 640), input_size=(512, 640), is_sequence=False,
                mixup_alpha=0.0, cutout_size=0, mock_subtask=False, binarize_gripper=True, rescale_gripper=False,
                image_distortion_fn=None, **kwargs):
-    if mixup_alpha > 0.0:
-      raise NotImplementedError('mixup regularisation is not built')
+    self._mixup_alpha = float(mixup_alpha)
     self._image_size = tuple(image_size)
     self._crop_size = tuple(crop_size)
     self._input_size = tuple(input_size)
@@ -336,6 +348,13 @@ class BCZPreprocessor(spec_transformation_preprocessor.SpecTransformationPreproc
     image = distortion.preprocess_image(features.image, mode, self._is_sequence, input_size=self._input_size,
                                         target_size=self._image_size, crop_size=self._crop_size,
                                         image_distortion_fn=self._image_distortion_fn)
+    if self._mixup_alpha > 0.0 and labels is not None and mode == TRAIN:
+      # Mixup (model.py:164-172): ONE lambda ~ Beta(alpha, alpha) per batch blends every sample with the batch
+      # reversed, image and future labels alike
+      lmbda = float(_RNG.beta(self._mixup_alpha, self._mixup_alpha))
+      image = mixup_reverse(image, lmbda)
+      for key in list(labels.future.keys()):
+        labels.future[key] = mixup_reverse(labels.future[key], lmbda)
     features.image = nn.to_bf16(image)          # the tower computes in bf16
     if self._cutout_size > 0 and mode == TRAIN:
       raise NotImplementedError('Open-source BC-Z Model does not support cutout augmentation.')

@@ -77,10 +77,14 @@ class Grasp2VecPreprocessor(spec_transformation_preprocessor.SpecTransformationP
 class Grasp2VecModel(abstract_model.AbstractT2RModel):
   """Basic Grasp2Vec model."""
 
-  def __init__(self, scene_size, goal_size, embedding_loss_fn=losses.NPairsLoss, **kwargs):
+  def __init__(self, scene_size, goal_size, embedding_loss_fn=losses.NPairsLoss, global_negatives=False, **kwargs):
+    """global_negatives=True (data-parallel runs, SURVEY 8e opt-in): the n-pairs loss draws its negatives from every
+    replica's batch through an all-gather of the [B, 1024] embeddings; the default keeps the reference's per-replica
+    loss."""
     self._scene_size = tuple(scene_size)
     self._goal_size = tuple(goal_size)
     self._embedding_loss_fn = embedding_loss_fn
+    self._global_negatives = global_negatives
     super(Grasp2VecModel, self).__init__(**kwargs)
 
   def get_feature_specification(self, mode):
@@ -110,6 +114,7 @@ class Grasp2VecModel(abstract_model.AbstractT2RModel):
             'goal_vector': goal_v, 'goal_spatial': goal_s}
 
   def model_train_fn(self, features, labels, inference_outputs, mode, config=None, params=None):
+    kwargs = {'global_negatives': True} if self._global_negatives else {}
     embed_loss = self._embedding_loss_fn(inference_outputs['pre_vector'], inference_outputs['goal_vector'],
-                                         inference_outputs['post_vector'])
+                                         inference_outputs['post_vector'], **kwargs)
     return embed_loss, {'embed_loss': embed_loss}

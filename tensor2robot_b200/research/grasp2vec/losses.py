@@ -4,17 +4,52 @@ import torch
 from tensor2robot_b200 import nn
 
 
+class _AllGatherRows(torch.autograd.Function):
+  """[B_local, D] -> [world * B_local, D] over the default process group; the backward hands every rank the rows of
+  the gradient that belong to its own embeddings (each rank evaluates the same global loss)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ctx.rank, ctx.rows = rank, x.shape[0]
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous())
+    return out
+
+  @staticmethod
+  def backward(ctx, grad):
+    return grad[ctx.rank * ctx.rows:(ctx.rank + 1) * ctx.rows].contiguous()
+
+
+def gather_global_batch(*embeddings):
+  """SURVEY 8(e), opt-in: all-gathers [B_local, D] embeddings (2 MB per GPU at B = 256, D = 1024) so that a contrastive
+  loss sees the GLOBAL batch as negatives.  Returns (gathered tensors, loss scale): every rank then evaluates the same
+  global loss and back-propagates it through its own rows only, so the summed parameter gradient is the gradient of
+  ONE global loss; the data-parallel step divides gradients by the world size, hence the loss is scaled by it.
+  Without an initialised process group (or world size 1) this is the identity.  The reference never does this
+  (single-replica loss, research/grasp2vec/grasp2vec_model.py:205-240)."""
+  import torch.distributed as dist
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    return embeddings, 1.0
+  return tuple(_AllGatherRows.apply(e) for e in embeddings), float(dist.get_world_size())
+
+
 def NPairsLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding,  # pylint: disable=invalid-name
-               non_negativity_constraint=False):
-  """npairs_loss in both directions between (pre - post) and the goal embedding (losses.py:152-181)."""
+               non_negativity_constraint=False, global_negatives=False):
+  """npairs_loss in both directions between (pre - post) and the goal embedding (losses.py:152-181).
+  global_negatives=True: the negatives come from every replica's batch (gather_global_batch)."""
   pre, post, goal = (nn.to_f32(t) for t in (pregrasp_embedding, postgrasp_embedding, goal_embedding))
   pair_a = pre - post                 # [B, 1024] fp32: a host-scale elementwise op, left to torch autograd
   if non_negativity_constraint:
     pair_a = torch.relu(pair_a)
   pair_b = goal
+  scale = 1.0
+  if global_negatives:
+    (pair_a, pair_b), scale = gather_global_batch(pair_a, pair_b)
   loss_1 = nn.npairs_loss(pair_a, pair_b)
   loss_2 = nn.npairs_loss(pair_b, pair_a)
-  return loss_1 + loss_2
+  return (loss_1 + loss_2) * scale if scale != 1.0 else loss_1 + loss_2
 
 
 def TripletLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding):  # pylint: disable=invalid-name

@@ -94,3 +94,45 @@ def test_training_outputs_fused_kernel_matches_eager(loss_name, with_stop):
                                err_msg=k)
   for k in net_cpu:
     np.testing.assert_allclose(net_gpu[k].grad.cpu().numpy(), net_cpu[k].grad.numpy(), rtol=1e-5, atol=1e-8, err_msg=k)
+
+
+def test_mixup_preprocessing_blends_images_and_labels():
+  """BCZPreprocessor(mixup_alpha > 0) in TRAIN mode (research/bcz/model.py:164-172): image and every future label are
+  blended with the reversed batch by ONE Beta(alpha, alpha) draw; EVAL mode is untouched."""
+  from tensor2robot_b200.research.bcz import model as bcz
+  from tensor2robot_b200.utils import tensorspec_utils
+  rng = np.random.RandomState(2)
+  x = torch.from_numpy(rng.standard_normal((6, 5, 7)).astype(np.float32)).cuda()
+  for lmbda in (0.0, 0.3, 1.0):
+    got = bcz.mixup_reverse(x, lmbda).cpu().numpy()
+    np.testing.assert_allclose(got, lmbda * x.cpu().numpy() + (1 - lmbda) * x.cpu().numpy()[::-1], rtol=1e-6, atol=1e-7)
+  pre = lambda alpha, **kw: bcz.BCZPreprocessor(image_size=(96, 96), crop_size=(104, 128), input_size=(112, 144),
+                                                binarize_gripper=False, mixup_alpha=alpha, **kw)
+  outs = {}
+  for alpha in (0.0, 0.4):
+    model = bcz.BCZModel(image_size=(96, 96), input_size=(112, 144), resnet_size=18, num_waypoints=2,
+                         preprocessor_cls=lambda a=alpha, **kw: pre(a, **kw))
+    p = model.preprocessor
+    rs = np.random.RandomState(5)
+    feats = tensorspec_utils.make_random_numpy(p.get_in_feature_specification('train'), 4)
+    labels = tensorspec_utils.make_random_numpy(p.get_in_label_specification('train'), 4)
+    del rs
+    to_dev = lambda st: tensorspec_utils.TensorSpecStruct(
+        [(k, torch.from_numpy(np.ascontiguousarray(v)).cuda()) for k, v in tensorspec_utils.flatten_spec_structure(st).items()])
+    np.random.seed(0)
+    bcz._RNG = np.random.RandomState(9)
+    from tensor2robot_b200.preprocessors import image_transformations
+    image_transformations.seed(0)
+    f, l = p.preprocess(to_dev(feats), to_dev(labels), 'train')
+    outs[alpha] = (feats, labels, f, l)
+  # identical inputs are not guaranteed across the two random draws, so check the blend relation within the mixup run
+  feats, labels, f, l = outs[0.4]
+  lab_in = np.asarray(labels['future/xyz_residual'])
+  lab_out = l.future['xyz_residual'].cpu().numpy()
+  # solve lambda from one element, then every element must satisfy the same blend
+  num = lab_out - lab_in[::-1]
+  den = lab_in - lab_in[::-1]
+  lam = float(np.median(num[np.abs(den) > 1e-3] / den[np.abs(den) > 1e-3]))
+  assert 0.0 <= lam <= 1.0
+  np.testing.assert_allclose(lab_out, lam * lab_in + (1 - lam) * lab_in[::-1], rtol=1e-4, atol=1e-5)
+  assert f.image.dtype == torch.bfloat16 and tuple(f.image.shape) == (4, 96, 96, 3)

@@ -134,3 +134,13 @@ def test_stop_state_loss_and_spec():
   spec = m.get_label_specification('train')['future/stop_state']
   assert spec.shape == () and spec.name == 'present/stop_state'
   assert 'future/stop_state' not in bcz.BCZModel().get_label_specification('train').keys()
+
+
+def test_mixup_reverse_formula():
+  """research/bcz/model.py:164-172: lmbda * x + (1 - lmbda) * tf.reverse(x, axis=[0])."""
+  import torch
+  from tensor2robot_b200.research.bcz import model as bcz
+  x = torch.arange(24, dtype=torch.float32).reshape(4, 3, 2)
+  y = bcz.mixup_reverse(x, 0.25)
+  np.testing.assert_allclose(y.numpy(), 0.25 * x.numpy() + 0.75 * x.numpy()[::-1])
+  assert bcz.BCZPreprocessor.__init__.__defaults__[4] == 0.0          # mixup_alpha is off by default

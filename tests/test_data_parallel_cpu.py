@@ -147,3 +147,42 @@ def test_single_process_is_identity():
   g = torch.ones(8)
   assert engine.reduce_gradients(g) == 1.0 and engine.shard_for_rank() == (0, 1)
   assert torch.equal(g, torch.ones(8))
+
+
+def _gather_worker(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from oracle import grasp2vec as oracle
+  from tensor2robot_b200.research.grasp2vec import losses
+  rng = np.random.RandomState(0)
+  a_all = rng.standard_normal((world * 3, 8)) * 0.5
+  p_all = rng.standard_normal((world * 3, 8)) * 0.5
+  a = torch.from_numpy(a_all[rank * 3:(rank + 1) * 3]).requires_grad_(True)
+  p = torch.from_numpy(p_all[rank * 3:(rank + 1) * 3]).requires_grad_(True)
+  (ga, gp), scale = losses.gather_global_batch(a, p)
+  loss = (oracle.npairs_loss(ga, gp) + oracle.npairs_loss(gp, ga)) * scale
+  loss.backward()
+  np.save(os.path.join(out_dir, 'gather%d.npy' % rank), {'loss': float(loss.detach()), 'scale': scale, 'shape': tuple(ga.shape),
+                                                         'da': a.grad.numpy(), 'dp': p.grad.numpy()}, allow_pickle=True)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_global_negatives_gather_two_ranks(tmp_path):
+  """SURVEY 8(e) opt-in for Grasp2Vec: the n-pairs loss over the all-gathered embeddings.  Every rank computes the same
+  global loss; after the step's 1 / world gradient scaling the per-sample gradients equal those of ONE process holding
+  the whole batch."""
+  from oracle import grasp2vec as oracle
+  world, port = 2, _free_port()
+  mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+  res = [np.load(os.path.join(str(tmp_path), 'gather%d.npy' % r), allow_pickle=True).item() for r in range(world)]
+  rng = np.random.RandomState(0)
+  a = torch.from_numpy(rng.standard_normal((world * 3, 8)) * 0.5).requires_grad_(True)
+  p = torch.from_numpy(rng.standard_normal((world * 3, 8)) * 0.5).requires_grad_(True)
+  single = oracle.npairs_loss(a, p) + oracle.npairs_loss(p, a)
+  single.backward()
+  for r, out in enumerate(res):
+    assert out['shape'] == (world * 3, 8) and out['scale'] == float(world)
+    np.testing.assert_allclose(out['loss'] / world, float(single.detach()), rtol=1e-10)
+    np.testing.assert_allclose(out['da'] / world, a.grad.numpy()[r * 3:(r + 1) * 3], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out['dp'] / world, p.grad.numpy()[r * 3:(r + 1) * 3], rtol=1e-9, atol=1e-12)

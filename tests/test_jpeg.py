@@ -150,6 +150,7 @@ def test_parser_with_device_decoder_matches_host_decoder():
                                                                   data_format='jpeg')))
   records = oracle_tfrecord.read_tfrecords(FIXTURE)[:6]
   parse = tfdata.create_parse_tf_example_fn(spec)
+  tfdata.set_image_decoder('host')
   host = parse(records).state.image
   tfdata.set_image_decoder('device')
   try:
