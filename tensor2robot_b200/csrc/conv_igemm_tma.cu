@@ -431,14 +431,15 @@ static int launch(const IgemmTmaParams& pp, cudaStream_t stream) {
   if (pp.g.flags & kProBnRelu) return launch_v<BLOCK_N, true, 8>(pp, stream);
   return launch_v<BLOCK_N, false, 8>(pp, stream);
 }
-// BLOCK_N 128: 16 epilogue warps where the tile is bound by its epilogue (few k-iterations per tile): T2R_TMA_EPI_WARPS
-// = 8 | 16 | auto (default: 16 when the GEMM K <= 512).
+// BLOCK_N 128: T2R_TMA_EPI_WARPS=16 runs the epilogue on 16 warps (one 32-column chunk each).  Measured on the
+// ResNet-50 step (gpurun_out/r02i_detail_epi{8,auto}.txt): no gain (64->256 1x1 at 118x118: 2.03 -> 1.99 ms; step
+// 142.6 -> 143.5 ms), so 8 stays the default - the low-K layers are not bound by the epilogue's latency.
 template <>
 int launch<128>(const IgemmTmaParams& pp, cudaStream_t stream) {
   if (pp.g.flags & kProBnRelu) return launch_v<128, true, 8>(pp, stream);
   static const char* mode = std::getenv("T2R_TMA_EPI_WARPS");
   const int k_iters = pp.g.n_taps * pp.g.chunks_per_tap;
-  const bool wide = mode == nullptr || mode[0] == 'a' ? k_iters <= 8 : (mode[0] == '1');
+  const bool wide = mode != nullptr && (mode[0] == 'a' ? k_iters <= 8 : (mode[0] == '1' && mode[1] == '6'));
   return wide ? launch_v<128, false, 16>(pp, stream) : launch_v<128, false, 8>(pp, stream);
 }
 
