@@ -259,8 +259,13 @@ class AbstractT2RModel(model_interface.ModelInterface):
       total = total + nn.l2_regularization_loss(l2, vs)
     return total
 
-  def predict(self, features, config=None, params=None):
-    return self.model_fn(features, None, PREDICT, config, params).predictions
+  def predict(self, features, config=None, params=None, high_precision=False):
+    """PREDICT outputs.  high_precision=True evaluates the graph in nn.high_precision() (fp32 activations, bf16x3
+    convolutions): what serving / CEM callers that need Q values within 1e-3 relative of an fp32 evaluation ask for."""
+    if not high_precision:
+      return self.model_fn(features, None, PREDICT, config, params).predictions
+    with torch.no_grad(), nn.high_precision():
+      return self.model_fn(features, None, PREDICT, config, params).predictions
 
   # -- checkpoints (TF variable names / layouts; SURVEY 5) --------------------------------------
   # With a MovingAverageOptimizer (use_avg_model_params) the reference installs optimizer.swapping_saver

@@ -10,6 +10,7 @@ import time
 import numpy as np
 import torch
 
+from tensor2robot_b200 import nn
 from tensor2robot_b200.predictors import abstract_predictor
 from tensor2robot_b200.utils import tensorspec_utils
 from tensor2robot_b200.utils import train_eval
@@ -20,12 +21,13 @@ _BUSY_WAITING_SLEEP_TIME_IN_SECS = 1
 
 class CheckpointPredictor(abstract_predictor.AbstractPredictor):
 
-  def __init__(self, t2r_model, checkpoint_dir=None, use_gpu=True, timeout=600, device=None):
+  def __init__(self, t2r_model, checkpoint_dir=None, use_gpu=True, timeout=600, device=None, high_precision=False):
     if not use_gpu:
       raise ValueError('the B200 engine has no CPU inference path (use_gpu=False)')
     self._checkpoint_dir = checkpoint_dir
     self._timeout = timeout
     self._t2r_model = t2r_model
+    self._high_precision = high_precision   # nn.high_precision(): fp32 activations, bf16x3 convolutions
     self._preprocessor = t2r_model.preprocessor
     feature_tspec = self._preprocessor.get_in_feature_specification(PREDICT)
     # inference: only the required tensors
@@ -62,7 +64,11 @@ class CheckpointPredictor(abstract_predictor.AbstractPredictor):
   def predict(self, features):
     self.assert_is_loaded()
     with torch.no_grad():
-      predictions = self._t2r_model.predict(self._preprocess(features))
+      if self._high_precision:
+        with nn.high_precision():          # the preprocessor sees the mode too and keeps images in fp32
+          predictions = self._t2r_model.predict(self._preprocess(features), high_precision=True)
+      else:
+        predictions = self._t2r_model.predict(self._preprocess(features))
     return {k: v.detach().float().cpu().numpy() if torch.is_tensor(v) else v for k, v in predictions.items()}
 
   def get_feature_specification(self):

@@ -33,8 +33,9 @@ def valid_export_versions(export_dir):
 
 class ExportedModelPredictor(checkpoint_predictor.CheckpointPredictor):
 
-  def __init__(self, export_dir, t2r_model, timeout=600, device=None):
-    super(ExportedModelPredictor, self).__init__(t2r_model=t2r_model, checkpoint_dir=None, timeout=timeout, device=device)
+  def __init__(self, export_dir, t2r_model, timeout=600, device=None, high_precision=False):
+    super(ExportedModelPredictor, self).__init__(t2r_model=t2r_model, checkpoint_dir=None, timeout=timeout, device=device,
+                                                 high_precision=high_precision)
     self._export_dir = export_dir
     self._latest_export_dir = None
     self._exported_feature_spec = None

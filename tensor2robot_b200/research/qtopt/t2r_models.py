@@ -9,6 +9,8 @@ plus `ResNet50QCriticModel`, the BASELINE C2/C3 critic (our composition, see res
 """
 import abc
 
+import torch
+
 from tensor2robot_b200 import nn
 from tensor2robot_b200.models import critic_model
 from tensor2robot_b200.models import model_interface
@@ -116,7 +118,8 @@ class DefaultGrasping44ImagePreprocessor(spec_transformation_preprocessor.SpecTr
     image = crop([features.state.image], INPUT_SHAPE, TARGET_SHAPE)[0]
     params = image_transformations.draw_photometric_params() if mode == TRAIN else None
     # convert_image_dtype(float32) + ApplyPhotometricImageDistortions + clip: one kernel, bf16 storage
-    features.state.image = image_transformations.convert_and_distort(image, params)
+    out_dtype = torch.float32 if (mode != TRAIN and nn.is_high_precision()) else torch.bfloat16
+    features.state.image = image_transformations.convert_and_distort(image, params, out_dtype)
     return features, labels
 
 

@@ -214,3 +214,53 @@ def test_lagged_target_network_tracks_online_critic_with_a_lag():
   cem.calls = 0
   _, q2, _ = cem.maximize(x)
   assert not torch.equal(q0, q2)
+
+
+@pytest.mark.gpu
+def test_bellman_critic_train_step_is_cem_target_plus_supervised_step():
+  """engine.BellmanCriticTrainStep (BASELINE config C3): the step trains on y = r + gamma (1 - done) max_a Q'(s', a).
+  (1) terminal transitions (done = 1): y == r, and the step is bit-identical to the supervised step on r;
+  (2) non-terminal: y equals the stand-alone CEMTargetComputer on the same target store / counter, chunked CEM
+  (cem_chunk = 1) gives the same targets, and r <= y <= r + gamma."""
+  from tensor2robot_b200 import engine
+  from tensor2robot_b200.models import optimizers
+  from tensor2robot_b200.research.qtopt import networks
+  rng = np.random.RandomState(3)
+  b = 3
+  images = torch.from_numpy(rng.randint(0, 256, (b, 512, 640, 3)).astype(np.uint8)).cuda()
+  nxt = torch.from_numpy(rng.randint(0, 256, (b, 512, 640, 3)).astype(np.uint8)).cuda()
+  actions = torch.from_numpy(rng.uniform(-1, 1, (b, 10)).astype(np.float32)).cuda()
+  reward = torch.tensor([[0.0], [1.0], [0.0]], device='cuda')
+
+  def make(cls, **kw):
+    torch.manual_seed(0)
+    np.random.seed(0)
+    critic = networks.Grasping44E2EOpenCloseTerminateGripperStatusHeightToBottom()
+    return cls(critic, optimizers.MomentumOptimizer(learning_rate=0.01, momentum=0.9), seed=0, **kw)
+
+  plain = make(engine.CriticTrainStep)
+  bell = make(engine.BellmanCriticTrainStep, gamma=0.9, cem_samples=16, cem_iters=2, num_elites=4)
+  plain.build(images, actions)
+  bell.build(images, actions)
+  assert torch.equal(plain.vs.flat, bell.vs.flat)
+  loss_plain = plain.step(images, actions, reward)
+  loss_bell = bell.step(images, actions, reward, nxt, torch.ones((b, 1), device='cuda'))
+  np.testing.assert_array_equal(bell.last_target.cpu().numpy(), reward.reshape(-1).cpu().numpy())
+  assert float(loss_plain) == float(loss_bell) and torch.equal(plain.vs.flat, bell.vs.flat)
+
+  chunked = make(engine.BellmanCriticTrainStep, gamma=0.9, cem_samples=16, cem_iters=2, num_elites=4, cem_chunk=1)
+  chunked.build(images, actions)
+  whole = make(engine.BellmanCriticTrainStep, gamma=0.9, cem_samples=16, cem_iters=2, num_elites=4)
+  whole.build(images, actions)
+  done = torch.zeros((b, 1), device='cuda')
+  chunked.step(images, actions, reward, nxt, done)
+  whole.step(images, actions, reward, nxt, done)
+  y = whole.last_target.cpu().numpy()
+  np.testing.assert_allclose(chunked.last_target.cpu().numpy(), y, atol=2e-3)   # batch-size dependent kernel paths
+  r = reward.reshape(-1).cpu().numpy()
+  assert (y >= r - 1e-6).all() and (y <= r + 0.9 + 1e-6).all() and (y > r).any()
+  # the same target from the stand-alone computer on a fresh copy of the (still initial) target network
+  ref = make(engine.BellmanCriticTrainStep, gamma=0.9, cem_samples=16, cem_iters=2, num_elites=4)
+  ref.build(images, actions)
+  _, max_q, _ = ref.cem.maximize(ref.preprocess(nxt, training=False))
+  np.testing.assert_allclose(y, r + 0.9 * max_q.cpu().numpy(), rtol=1e-6)

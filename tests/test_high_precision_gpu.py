@@ -127,3 +127,31 @@ def test_high_precision_is_inference_only():
   with pytest.raises(_lib.T2RError):
     with nn.high_precision():
       pass
+
+
+def test_checkpoint_predictor_high_precision_option():
+  """Serving entry point: CheckpointPredictor(high_precision=True) keeps the preprocessed image in fp32 and evaluates
+  the PREDICT graph in nn.high_precision(); same weights, Q close to the bf16 path (the accuracy itself is measured by the tests above)."""
+  from tensor2robot_b200.predictors import checkpoint_predictor
+  from tensor2robot_b200.research.qtopt import t2r_models
+  from tensor2robot_b200.utils import tensorspec_utils
+  model = t2r_models.Grasping44E2EOpenCloseTerminateGripperStatusHeightToBottom(action_batch_size=64)
+  fast = checkpoint_predictor.CheckpointPredictor(t2r_model=model)
+  fast.init_randomly()
+  exact = checkpoint_predictor.CheckpointPredictor(t2r_model=model, high_precision=True)
+  exact.init_randomly()                  # same variable store: already built, nothing re-initialised
+  features = tensorspec_utils.make_random_numpy(fast.get_feature_specification(), batch_size=2)
+  seen = []
+  convert = model.preprocessor._preprocess_fn   # pylint: disable=protected-access
+
+  def spy(f, l, mode):
+    f, l = convert(f, l, mode)
+    seen.append(f.state.image.dtype)
+    return f, l
+
+  model.preprocessor._preprocess_fn = spy       # pylint: disable=protected-access
+  q_fast = fast.predict(features)['q_predicted']
+  q_exact = exact.predict(features)['q_predicted']
+  assert seen == [torch.bfloat16, torch.float32]
+  assert q_fast.shape == q_exact.shape == (2, 64) and np.isfinite(q_exact).all()
+  np.testing.assert_allclose(q_exact, q_fast, atol=5e-3)
