@@ -374,8 +374,15 @@ def timed_steps(rt, fn, steps, warmup, profile=True, sample_clocks=False):
 
 def conv_roofline(prof, elapsed_ms_total, steps, rank):
   by_kind, by_shape = {}, {}
-  for tag, flops, e0, e1 in prof:
+  peaks = measured_peaks()
+  bound_ms = {'tensor': 0.0, 'hbm': 0.0}     # per-launch roofline time, split by which roof binds that launch
+  spent_ms = {'tensor': 0.0, 'hbm': 0.0}
+  for tag, flops, e0, e1, nbytes in prof:
     ms = e0.elapsed_time(e1)
+    t_tensor, t_hbm = flops / (peaks['tflops'] * 1e9), nbytes / (peaks['hbm_gbs'] * 1e6)
+    roof = 'hbm' if t_hbm > t_tensor else 'tensor'
+    bound_ms[roof] += max(t_tensor, t_hbm)
+    spent_ms[roof] += ms
     for table, key in ((by_kind, tag.split('|')[0]), (by_shape, tag)):
       d = table.setdefault(key, [0.0, 0.0, 0])
       d[0] += flops
@@ -385,7 +392,6 @@ def conv_roofline(prof, elapsed_ms_total, steps, rank):
     for key, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
       sys.stderr.write('%-48s n=%3d  %8.3f ms/step  %7.1f TFLOP/s\n' % (
           key, v[2] // steps, v[1] / steps, v[0] / max(v[1], 1e-9) / 1e9))
-  peaks = measured_peaks()
   conv_ms = sum(v[1] for v in by_kind.values())
   conv_flops = sum(v[0] for v in by_kind.values())
   dominant = max(by_kind.items(), key=lambda kv: kv[1][1])[0] if by_kind else None
@@ -400,6 +406,14 @@ def conv_roofline(prof, elapsed_ms_total, steps, rank):
       'traffic': traffic['dram_bytes_per_launch'] if traffic else None,
       'traffic_kernel': (traffic or {}).get('kernel'), 'traffic_algorithmic_bytes': (traffic or {}).get('algorithmic_bytes'),
       'dominant': dominant, 'by_kind': kinds,
+      # every launch against ITS OWN roof (max of flops / sustained tensor peak and in + out bytes / copy peak): the
+      # layer-1 / layer-2 1x1 convolutions are HBM-bound, so 'frac' above (all flops / tensor peak) understates them
+      'per_launch_roofline': {
+          'frac': (bound_ms['tensor'] + bound_ms['hbm']) / max(conv_ms, 1e-9),
+          'tensor_bound': {'ms_per_step': spent_ms['tensor'] / max(steps, 1),
+                           'frac': bound_ms['tensor'] / max(spent_ms['tensor'], 1e-9)},
+          'hbm_bound': {'ms_per_step': spent_ms['hbm'] / max(steps, 1), 'frac': bound_ms['hbm'] / max(spent_ms['hbm'], 1e-9),
+                        'bytes': 'input + output once (bf16); residual / weight reads not counted', 'peak_gbs': peaks['hbm_gbs']}},
       'share_of_step': conv_ms / max(elapsed_ms_total, 1e-9),
       'algorithmic_tflop_per_step': conv_flops / max(steps, 1) / 1e12,
   }

@@ -329,7 +329,7 @@ TRACE = None
 
 
 # When a list is installed here, every tensor-core kernel launch is bracketed by CUDA events on the
-# launching stream and (kind, algorithmic_flops, start_event, end_event) is appended: bench.py's
+# launching stream and (kind, algorithmic_flops, start_event, end_event, algorithmic_bytes) is appended: bench.py's
 # live roofline measurement.  None in production.
 PROFILE = None
 
@@ -338,11 +338,13 @@ class _prof(object):
   """with _prof('fprop', flops): <one kernel launch>"""
 
   def __init__(self, kind, flops):
-    if not isinstance(flops, float):     # a ConvDesc: algorithmic flops + a shape tag
+    nbytes = 0.0
+    if not isinstance(flops, float):     # a ConvDesc: algorithmic flops + bytes (input + output once, bf16) + a shape tag
       d = flops
       flops = _conv_flops(d)
+      nbytes = 2.0 * d.N * (d.H * d.W * d.Cin + d.Ho * d.Wo * d.Cout)
       kind = '%s|%dx%dx%dx%d->%d k%d s%d' % (kind, d.N, d.H, d.W, d.Cin, d.Cout, d.KH, d.stride)
-    self.kind, self.flops = kind, flops
+    self.kind, self.flops, self.nbytes = kind, flops, nbytes
 
   def __enter__(self):
     if PROFILE is not None:
@@ -354,7 +356,7 @@ class _prof(object):
   def __exit__(self, *exc):
     if PROFILE is not None:
       self.end.record()
-      PROFILE.append((self.kind, self.flops, self.start, self.end))
+      PROFILE.append((self.kind, self.flops, self.start, self.end, self.nbytes))
     return False
 
 

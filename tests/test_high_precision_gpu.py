@@ -142,14 +142,21 @@ def test_checkpoint_predictor_high_precision_option():
   exact.init_randomly()                  # same variable store: already built, nothing re-initialised
   features = tensorspec_utils.make_random_numpy(fast.get_feature_specification(), batch_size=2)
   seen = []
-  convert = model.preprocessor._preprocess_fn   # pylint: disable=protected-access
 
-  def spy(f, l, mode):
-    f, l = convert(f, l, mode)
-    seen.append(f.state.image.dtype)
-    return f, l
+  def spy_on(predictor):
+    pre = predictor._preprocessor                 # pylint: disable=protected-access
+    convert = pre._preprocess_fn                  # pylint: disable=protected-access
 
-  model.preprocessor._preprocess_fn = spy       # pylint: disable=protected-access
+    def spy(features, labels, mode):
+      features, labels = convert(features, labels, mode)
+      seen.append(features.state.image.dtype)
+      return features, labels
+
+    pre._preprocess_fn = spy                      # pylint: disable=protected-access
+
+  spy_on(fast)
+  if exact._preprocessor is not fast._preprocessor:   # pylint: disable=protected-access
+    spy_on(exact)
   q_fast = fast.predict(features)['q_predicted']
   q_exact = exact.predict(features)['q_predicted']
   assert seen == [torch.bfloat16, torch.float32]
