@@ -31,6 +31,8 @@ const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18,
                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+constexpr int kFastAcBits = 10;
+
 struct Huff {
   // 9-bit lookahead: entry = (length << 8) | symbol for codes of length <= 9, 0 otherwise
   uint16_t fast[512];
@@ -38,9 +40,9 @@ struct Huff {
   int32_t valptr[17];
   int32_t mincode[17];
   uint8_t symbols[256];
-  // AC tables only: for a 9-bit lookahead that holds a whole (code, magnitude bits) pair with a small
+  // AC tables only: for a kFastAcBits lookahead that holds a whole (code, magnitude bits) pair with a small
   // value, (value << 8) | (run << 4) | total_bits; 0 otherwise (stb_image's "fast AC" idea)
-  int16_t fast_ac[512];
+  int16_t fast_ac[1 << kFastAcBits];
   bool present = false;
 };
 
@@ -74,14 +76,14 @@ bool build_huff(const uint8_t* counts, const uint8_t* symbols, int total, Huff* 
     code <<= 1;
   }
   h->maxcode[17] = 0x7fffffff;
-  for (int i = 0; i < 512; ++i) {
+  for (int i = 0; i < (1 << kFastAcBits); ++i) {
     h->fast_ac[i] = 0;
-    const uint16_t f = h->fast[i];
+    const uint16_t f = h->fast[i >> (kFastAcBits - 9)];
     if (!f) continue;
     const int len = f >> 8, rs = f & 0xFF, run = rs >> 4, mag = rs & 15;
-    if (mag == 0 || len + mag > 9) continue;
-    int k = ((i << len) & 511) >> (9 - mag);          // the magnitude bits that follow the code
-    if (k < (1 << (mag - 1))) k += 1 - (1 << mag);    // EXTEND
+    if (mag == 0 || len + mag > kFastAcBits) continue;
+    int k = (i >> (kFastAcBits - len - mag)) & ((1 << mag) - 1);   // the magnitude bits that follow the code
+    if (k < (1 << (mag - 1))) k += 1 - (1 << mag);                  // EXTEND
     if (k >= -128 && k <= 127) h->fast_ac[i] = int16_t(k * 256 + run * 16 + len + mag);
   }
   h->present = true;
@@ -246,28 +248,6 @@ struct BitReader {
   }
   inline uint32_t peek(int k) { return uint32_t(acc >> (64 - k)); }
   inline void skip(int k) { acc <<= k; n -= k; }
-  inline int32_t receive_extend(int s) {
-    if (!s) return 0;
-    fill();
-    const int32_t v = int32_t(peek(s));
-    skip(s);
-    return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
-  }
-  inline int decode(const Huff& h) {
-    fill();
-    const uint16_t f = h.fast[peek(9)];
-    if (f) { skip(f >> 8); return f & 0xFF; }
-    int32_t code = int32_t(peek(9));
-    int len = 9;
-    skip(9);
-    while (len < 17 && (h.maxcode[len] < 0 || code > h.maxcode[len])) {
-      code = (code << 1) | int32_t(peek(1));
-      skip(1);
-      ++len;
-    }
-    if (len > 16) return -1;
-    return h.symbols[h.valptr[len] + code - h.mincode[len]];
-  }
   void restart() {
     n = 0; acc = 0; hit_marker = false;
     while (p + 1 < end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) ++p;
@@ -275,15 +255,89 @@ struct BitReader {
   }
 };
 
-int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t* coef) {
-  const T2RJpegInfo& in = ps.info;
-  memset(coef, 0, size_t(in.coef_count) * sizeof(int16_t));
-  for (int c = 0; c < in.ncomp; ++c)
-    if (!ps.dc[ps.td[c]].present || !ps.ac[ps.ta[c]].present) {
-      t2r::set_error("jpeg: scan refers to a Huffman table that was never defined");
-      return T2R_ERR_PARSE;
+// Reader over an UN-STUFFED copy of the entropy-coded segment (FF00 -> FF, cut at the first marker, zero padded): the
+// refill is one unconditional 4-byte big-endian load.  Used for scans without restart markers (what PIL / libjpeg
+// write by default and what the replay records hold); scans with a restart interval keep the byte-wise BitReader.
+struct FastBits {
+  const uint8_t* p;
+  const uint8_t* lim;          // end of the real (un-stuffed) bytes; >= 4 zero bytes follow
+  uint64_t acc = 0;
+  int n = 0;
+  bool past_end = false;       // a refill wanted bytes beyond `lim`
+  inline void fill() {         // afterwards n >= 33: one fill covers a 16-bit code plus its magnitude bits
+    if (n <= 32) {
+      uint32_t v = 0;
+      if (p < lim) {
+        memcpy(&v, p, 4);
+        v = __builtin_bswap32(v);
+        p += 4;
+      } else {
+        past_end = true;
+      }
+      acc |= uint64_t(v) << (32 - n);
+      n += 32;
     }
-  BitReader br{data + ps.scan_offset, data + len};
+  }
+  inline uint32_t peek(int k) { return uint32_t(acc >> (64 - k)); }
+  inline void skip(int k) { acc <<= k; n -= k; }
+  void restart() {}
+};
+
+// Copies the scan that starts at data[0] into `out` with byte stuffing removed; stops at the first marker.  Returns
+// true when a marker ended the segment, false when the input simply ran out.
+bool unstuff_scan(const uint8_t* data, uint64_t len, std::vector<uint8_t>* out) {
+  out->resize(size_t(len) + 8);
+  uint8_t* dst = out->data();
+  const uint8_t* p = data;
+  const uint8_t* end = data + len;
+  bool marker = false;
+  while (p < end) {
+    const uint8_t* ff = static_cast<const uint8_t*>(memchr(p, 0xFF, size_t(end - p)));
+    if (!ff) {
+      memcpy(dst, p, size_t(end - p));
+      dst += end - p;
+      break;
+    }
+    memcpy(dst, p, size_t(ff - p));
+    dst += ff - p;
+    if (ff + 1 < end && ff[1] != 0) { marker = true; break; }     // FF xx: a marker, not data
+    *dst++ = 0xFF;                                                  // FF 00 (or a lone trailing FF): the data byte FF
+    p = ff + 2;
+  }
+  const size_t n = size_t(dst - out->data());
+  memset(dst, 0, 8);
+  out->resize(n + 8);
+  return marker;
+}
+
+// The bits after a fill(): Huffman code (<= 16 bits) then `s` magnitude bits, no further refill needed.
+template <class BR>
+inline int decode_symbol(BR& br, const Huff& h) {
+  const uint16_t f = h.fast[br.peek(9)];
+  if (f) { br.skip(f >> 8); return f & 0xFF; }
+  int32_t code = int32_t(br.peek(9));
+  int len = 9;
+  br.skip(9);
+  while (len < 17 && (h.maxcode[len] < 0 || code > h.maxcode[len])) {
+    code = (code << 1) | int32_t(br.peek(1));
+    br.skip(1);
+    ++len;
+  }
+  if (len > 16) return -1;
+  return h.symbols[h.valptr[len] + code - h.mincode[len]];
+}
+
+template <class BR>
+inline int32_t receive_extend(BR& br, int s) {
+  if (!s) return 0;
+  const int32_t v = int32_t(br.peek(s));
+  br.skip(s);
+  return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+template <class BR>
+int entropy_decode_with(BR& br, const Parsed& ps, int16_t* coef) {
+  const T2RJpegInfo& in = ps.info;
   int pred[3] = {0, 0, 0};
   int64_t count = 0;
   for (int my = 0; my < in.mcuy; ++my)
@@ -295,17 +349,19 @@ int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t*
       ++count;
       for (int c = 0; c < in.ncomp; ++c) {
         const int bw = in.mcux * in.h[c];
+        const Huff& hdc = ps.dc[ps.td[c]];
+        const Huff& hac = ps.ac[ps.ta[c]];
         for (int by = 0; by < in.v[c]; ++by)
           for (int bx = 0; bx < in.h[c]; ++bx) {
             int16_t* blk = coef + in.coef_offset[c] + (int64_t(my * in.v[c] + by) * bw + (mx * in.h[c] + bx)) * 64;
-            const int t = br.decode(ps.dc[ps.td[c]]);
+            br.fill();
+            const int t = decode_symbol(br, hdc);
             if (t < 0 || t > 11) { t2r::set_error("jpeg: bad DC Huffman code"); return T2R_ERR_PARSE; }
-            pred[c] += br.receive_extend(t);
+            pred[c] += receive_extend(br, t);
             blk[0] = int16_t(pred[c]);
-            const Huff& hac = ps.ac[ps.ta[c]];
             for (int k = 1; k < 64;) {
               br.fill();
-              const int fa = hac.fast_ac[br.peek(9)];
+              const int fa = hac.fast_ac[br.peek(kFastAcBits)];
               if (fa) {                                   // code + magnitude bits in one lookup
                 k += (fa >> 4) & 15;
                 if (k > 63) { t2r::set_error("jpeg: AC coefficient index out of range"); return T2R_ERR_PARSE; }
@@ -313,7 +369,7 @@ int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t*
                 blk[kZigzag[k++]] = int16_t(fa >> 8);
                 continue;
               }
-              const int rs = br.decode(hac);
+              const int rs = decode_symbol(br, hac);
               if (rs < 0) { t2r::set_error("jpeg: bad AC Huffman code"); return T2R_ERR_PARSE; }
               const int r = rs >> 4, s = rs & 15;
               if (s == 0) {
@@ -323,13 +379,38 @@ int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t*
               }
               k += r;
               if (k > 63) { t2r::set_error("jpeg: AC coefficient index out of range"); return T2R_ERR_PARSE; }
-              blk[kZigzag[k]] = int16_t(br.receive_extend(s));
+              blk[kZigzag[k]] = int16_t(receive_extend(br, s));
               ++k;
             }
           }
       }
     }
-  if (br.exhausted) {      // what tf.image.decode_image reports for a truncated file (try_recover_truncated = False)
+  return T2R_OK;
+}
+
+int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t* coef) {
+  const T2RJpegInfo& in = ps.info;
+  memset(coef, 0, size_t(in.coef_count) * sizeof(int16_t));
+  for (int c = 0; c < in.ncomp; ++c)
+    if (!ps.dc[ps.td[c]].present || !ps.ac[ps.ta[c]].present) {
+      t2r::set_error("jpeg: scan refers to a Huffman table that was never defined");
+      return T2R_ERR_PARSE;
+    }
+  bool exhausted;
+  if (in.restart_interval == 0) {
+    static thread_local std::vector<uint8_t> scan;
+    const bool marker = unstuff_scan(data + ps.scan_offset, len - ps.scan_offset, &scan);
+    FastBits br{scan.data(), scan.data() + scan.size() - 8};
+    const int rc = entropy_decode_with(br, ps, coef);
+    if (rc != T2R_OK) return rc;
+    exhausted = br.past_end && !marker;
+  } else {
+    BitReader br{data + ps.scan_offset, data + len};
+    const int rc = entropy_decode_with(br, ps, coef);
+    if (rc != T2R_OK) return rc;
+    exhausted = br.exhausted;
+  }
+  if (exhausted) {      // what tf.image.decode_image reports for a truncated file (try_recover_truncated = False)
     t2r::set_error("jpeg: premature end of data inside the entropy-coded segment");
     return T2R_ERR_PARSE;
   }

@@ -6,10 +6,11 @@ readers, :273-543 create_parse_tf_example_fn, :629-689 default_input_fn_tmpl) wi
   * TFRecord framing + CRC-32C and the tf.Example wire format walked by the host C++ side of
     libt2r_b200.so (csrc/host_io.cc, no protobuf/TensorFlow), values copied bit-exactly into numpy
     buffers described by a parse plan compiled from the specs;
-  * JPEG/PNG decode through libjpeg-turbo / libpng (PIL) on a host thread pool - the same decoder
-    family TensorFlow links, bit-identical on the reference fixture.  A GPU JPEG
-    decoder is the listed next step (DESIGN.md);
-  * shuffle / repeat / batch(drop_remainder) with the reference's structure and buffer sizes.
+  * baseline JPEG decode by the split decoder (Huffman on the host worker pool, IDCT / upsampling / colour on the GPU)
+    or completely on the host pool (csrc/jpeg_host.cc, csrc/jpeg.cu), both bit-identical with libjpeg-turbo, the
+    decoder TensorFlow links (SURVEY 8c-10); PNG and the JPEG flavours those refuse go through PIL;
+  * shuffle / repeat / batch(drop_remainder) with the reference's structure and buffer sizes; up to
+    PARSE_PIPELINE_DEPTH batches are parsed / decoded concurrently (the reference's num_parallel_calls).
 
 Semantics kept (SURVEY A-3..A-6): features are looked up by `dataset_key + name` and returned keyed
 by spec *path*; specs without a name are not parsed; bfloat16 specs are parsed as float32 and cast;
@@ -29,6 +30,7 @@ import struct
 
 import numpy as np
 from PIL import Image
+import torch
 
 from tensor2robot_b200 import _lib
 from tensor2robot_b200.models import model_interface
@@ -39,6 +41,7 @@ ModeKeys = model_interface.ModeKeys
 DATA_FORMAT = {'tfrecord': 'tfrecord'}    # recordio / sstable are Google-internal containers
 SUPPORTED_PIXEL_ENCODINGS = (dtypes.uint8, dtypes.uint16)
 SHUFFLE_BUFFER_SIZE = 500                 # utils/tfdata.py:665
+PARSE_PIPELINE_DEPTH = 2                   # batches parsed / decoded concurrently (bounded: each holds its pinned buffers)
 
 
 def get_batch_size(params, batch_size):
@@ -455,10 +458,11 @@ def create_parse_tf_example_fn(feature_tspec, label_tspec=None, decode_images=Tr
 # ---------------------------------------------------------------------------------------------
 # the input pipeline
 # ---------------------------------------------------------------------------------------------
-def record_stream(filenames, mode, seed=None, shard=(0, 1), verify_crc=True):
+def record_stream(filenames, mode, seed=None, shard=(0, 1), verify_crc=True, keepalive=None):
   """Yields (address, length) record pointers: files shuffled and repeated forever in TRAIN, a single
   ordered pass otherwise; `shard=(rank, world)` keeps every world-th file (or record when there are
-  fewer files than ranks)."""
+  fewer files than ranks).  The pointers are into the files' mappings: a consumer that uses them after this generator
+  has finished passes a `keepalive` list, which receives every opened file."""
   rank, world = shard
   rng = np.random.RandomState(seed)
   files = list(filenames)
@@ -474,6 +478,8 @@ def record_stream(filenames, mode, seed=None, shard=(0, 1), verify_crc=True):
       f = opened.get(fi)
       if f is None:
         f = opened[fi] = TFRecordFile(files[fi], verify_crc)
+        if keepalive is not None:
+          keepalive.append(f)
       idx = range(rank, len(f), world) if by_record else range(len(f))
       for i in idx:
         yield f.pointer(i)
@@ -503,27 +509,73 @@ def default_input_fn_tmpl(file_patterns, batch_size, feature_spec, label_spec, n
                           **unused):
   """Generator of (features, labels) batches: list files -> shuffle -> repeat -> batch(drop_remainder)
   -> parse -> preprocess (utils/tfdata.py:629-689)."""
-  del num_parallel_calls, shuffle_filenames, unused
+  del shuffle_filenames, unused
+  mapped = []        # the opened record files: batches in flight hold pointers into their mappings
   if isinstance(file_patterns, dict):
     streams = {}
     for key, patterns in file_patterns.items():
       _, filenames = get_data_format_and_filenames(patterns)
-      streams[key] = record_stream(filenames, mode, seed, shard)
+      streams[key] = record_stream(filenames, mode, seed, shard, keepalive=mapped)
   else:
     _, filenames = get_data_format_and_filenames(file_patterns)
-    streams = {'': record_stream(filenames, mode, seed, shard)}
+    streams = {'': record_stream(filenames, mode, seed, shard, keepalive=mapped)}
   if is_training or mode == ModeKeys.TRAIN:
     streams = {k: shuffled(s, shuffle_buffer_size, seed) for k, s in streams.items()}
   parse_fn = create_parse_tf_example_fn(feature_spec, label_spec)
-  while True:
+
+  def draw():
     batch = {k: list(itertools.islice(s, batch_size)) for k, s in streams.items()}
     if any(len(v) < batch_size for v in batch.values()):
-      return                                   # drop_remainder=True
-    parsed = parse_fn(batch if len(batch) > 1 or '' not in batch else batch[''])
+      return None                                # drop_remainder=True
+    return batch if len(batch) > 1 or '' not in batch else batch['']
+
+  def finish(parsed):
     features, labels = parsed if label_spec is not None else (parsed, None)
     if preprocess_fn is not None:
       features, labels = preprocess_fn(features, labels)
-    yield features, labels
+    return features, labels
+
+  in_flight = max(1, min(int(num_parallel_calls or 1), PARSE_PIPELINE_DEPTH))
+  if in_flight == 1:
+    while True:
+      batch = draw()
+      if batch is None:
+        return
+      yield finish(parse_fn(batch))
+  # The reference's `num_parallel_calls` (parallel map over parse): up to PARSE_PIPELINE_DEPTH batches are parsed
+  # concurrently and yielded in order.  The serial parts of one batch (CRC, wire parse, copies of the image strings) then
+  # overlap the threaded Huffman stage of its neighbour; records are still drawn in order on this thread.
+  cuda = torch.cuda.is_available() and torch.cuda.is_initialized()
+  device = torch.cuda.current_device() if cuda else None
+
+  def work(batch, stream):
+    if stream is None:
+      return parse_fn(batch)
+    torch.cuda.set_device(device)                # device and stream are per-thread state
+    with torch.cuda.stream(stream):
+      return parse_fn(batch)
+
+  pool = concurrent.futures.ThreadPoolExecutor(max_workers=in_flight, thread_name_prefix='t2r-parse')
+  pending = collections.deque()
+  try:
+    exhausted = False
+    while True:
+      while not exhausted and len(pending) < in_flight:
+        batch = draw()
+        if batch is None:
+          exhausted = True
+          break
+        # the device half of the split JPEG decoder launches on the stream that is current HERE at submit time
+        stream = torch.cuda.current_stream() if cuda else None
+        pending.append(pool.submit(work, batch, stream))
+      if not pending:
+        return
+      yield finish(pending.popleft().result())
+  finally:
+    for f in pending:
+      f.cancel()
+    pool.shutdown(wait=True)       # a parse that is still running reads the mappings in `mapped`
+    del mapped
 
 
 def get_input_fn(feature_spec, label_spec, file_patterns, mode, batch_size, preprocess_fn=None, **kwargs):
