@@ -236,6 +236,32 @@ def _decode_images(tensor_spec, byte_rows):
   return out
 
 
+def _decode_jpeg_pointers(tensor_spec, addresses, lengths, b, count, owner):
+  """The common case of `_decode_images` without materialising the JPEG strings: every image of the batch is present
+  and a baseline JPEG that the C++ / split decoder accepts; the decoders read the bytes where the record parser found
+  them (inside the mapped record file).  None = take the general path."""
+  dims = tuple(tensor_spec.shape[-3:])
+  if (len(tensor_spec.shape) < 3 or dims[2] not in (1, 3) or tensor_spec.dtype != dtypes.uint8 or b * count == 0 or
+      not addresses.all() or int(lengths.min()) < 4):
+    return None
+  from tensor2robot_b200.utils import jpeg
+  images = jpeg.RecordBytes(addresses, lengths, owner)
+  if any(images.head(i, 2) != b'\xff\xd8' for i in range(len(images))):
+    return None
+  try:
+    if image_decoder() == 'device':
+      out = jpeg.decode_batch(images, channels=dims[2])
+    else:
+      out = jpeg.decode_batch_host(images, dims[0], dims[1], dims[2])
+  except jpeg.UnsupportedJpeg:
+    return None
+  if tuple(out.shape[1:]) != dims:
+    return None                                   # the general path reports the InvalidArgument
+  if len(tensor_spec.shape) > 3 or tensor_spec.varlen_default_value is not None:
+    out = out.reshape((b, count) + dims)
+  return out
+
+
 def _records_as_pointers(serialized):
   """list of bytes -> (keep-alive list, pointer array, length array)."""
   n = len(serialized)
@@ -391,6 +417,11 @@ def _parse_examples(serialized, tensor_spec_dict, decode_images):
   for key, spec in tensor_spec_dict.items():
     kind, dst, dst_len, count = buffers[key]
     if kind in ('bytes', 'strings'):
+      if kind == 'bytes':
+        fast = _decode_jpeg_pointers(spec, dst, dst_len, b, count, keep)
+        if fast is not None:
+          parsed[key] = fast
+          continue
       rows = [[C.string_at(int(dst[r * count + j]), int(dst_len[r * count + j])) if dst[r * count + j] else b''
                for j in range(count)] for r in range(b)]
       if kind == 'bytes':
