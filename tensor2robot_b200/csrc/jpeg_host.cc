@@ -248,6 +248,7 @@ struct BitReader {
   }
   inline uint32_t peek(int k) { return uint32_t(acc >> (64 - k)); }
   inline void skip(int k) { acc <<= k; n -= k; }
+  inline void clamp() {}
   void restart() {
     n = 0; acc = 0; hit_marker = false;
     while (p + 1 < end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) ++p;
@@ -259,34 +260,37 @@ struct BitReader {
 // refill is one unconditional 4-byte big-endian load.  Used for scans without restart markers (what PIL / libjpeg
 // write by default and what the replay records hold); scans with a restart interval keep the byte-wise BitReader.
 struct FastBits {
-  const uint8_t* p;
-  const uint8_t* lim;          // end of the real (un-stuffed) bytes; >= 4 zero bytes follow
-  uint64_t acc = 0;
-  int n = 0;
-  bool past_end = false;       // a refill wanted bytes beyond `lim`
-  inline void fill() {         // afterwards n >= 33: one fill covers a 16-bit code plus its magnitude bits
-    if (n <= 32) {
-      uint32_t v = 0;
-      if (p < lim) {
-        memcpy(&v, p, 4);
-        v = __builtin_bswap32(v);
-        p += 4;
-      } else {
-        past_end = true;
-      }
-      acc |= uint64_t(v) << (32 - n);
-      n += 32;
-    }
+  const uint8_t* p;            // first byte that is not yet completely in `acc`
+  const uint8_t* lim;          // end of the real (un-stuffed) bytes; kScanPad zero bytes follow
+  uint64_t acc = 0;            // bit buffer, next bit at the top
+  int n = 0;                   // valid bits in `acc`
+  bool past_end = false;       // the decoder consumed bits beyond `lim`
+  bool drained() const { return past_end || p >= lim; }   // every real byte has been loaded
+  // Branch-free refill: OR the next eight stream bytes in below the valid bits and advance by the whole bytes that fit.
+  // Afterwards 56 <= n <= 63: one fill covers a 16-bit code plus its magnitude bits several times over.
+  inline void fill() {
+    uint64_t next;
+    memcpy(&next, p, 8);
+    next = __builtin_bswap64(next);
+    acc |= next >> n;
+    p += (63 - n) >> 3;
+    n |= 56;
+  }
+  // Called once per block: a block consumes at most 64 * 31 bits = 248 bytes, the padding is larger.
+  inline void clamp() {
+    if (p > lim && (p - lim) * 8 > n) { p = lim; past_end = true; acc = 0; n = 0; }   // bits beyond the data were consumed
   }
   inline uint32_t peek(int k) { return uint32_t(acc >> (64 - k)); }
   inline void skip(int k) { acc <<= k; n -= k; }
   void restart() {}
 };
 
+constexpr size_t kScanPad = 512;
+
 // Copies the scan that starts at data[0] into `out` with byte stuffing removed; stops at the first marker.  Returns
 // true when a marker ended the segment, false when the input simply ran out.
 bool unstuff_scan(const uint8_t* data, uint64_t len, std::vector<uint8_t>* out) {
-  out->resize(size_t(len) + 8);
+  out->resize(size_t(len) + kScanPad);
   uint8_t* dst = out->data();
   const uint8_t* p = data;
   const uint8_t* end = data + len;
@@ -305,8 +309,8 @@ bool unstuff_scan(const uint8_t* data, uint64_t len, std::vector<uint8_t>* out) 
     p = ff + 2;
   }
   const size_t n = size_t(dst - out->data());
-  memset(dst, 0, 8);
-  out->resize(n + 8);
+  memset(dst, 0, kScanPad);
+  out->resize(n + kScanPad);
   return marker;
 }
 
@@ -354,6 +358,7 @@ int entropy_decode_with(BR& br, const Parsed& ps, int16_t* coef) {
         for (int by = 0; by < in.v[c]; ++by)
           for (int bx = 0; bx < in.h[c]; ++bx) {
             int16_t* blk = coef + in.coef_offset[c] + (int64_t(my * in.v[c] + by) * bw + (mx * in.h[c] + bx)) * 64;
+            br.clamp();
             br.fill();
             const int t = decode_symbol(br, hdc);
             if (t < 0 || t > 11) { t2r::set_error("jpeg: bad DC Huffman code"); return T2R_ERR_PARSE; }
@@ -400,10 +405,11 @@ int entropy_decode(const uint8_t* data, uint64_t len, const Parsed& ps, int16_t*
   if (in.restart_interval == 0) {
     static thread_local std::vector<uint8_t> scan;
     const bool marker = unstuff_scan(data + ps.scan_offset, len - ps.scan_offset, &scan);
-    FastBits br{scan.data(), scan.data() + scan.size() - 8};
+    FastBits br{scan.data(), scan.data() + scan.size() - kScanPad};
     const int rc = entropy_decode_with(br, ps, coef);
     if (rc != T2R_OK) return rc;
-    exhausted = br.past_end && !marker;
+    br.clamp();
+    exhausted = !marker && br.drained();     // no marker ends the segment and the reader ran into its end
   } else {
     BitReader br{data + ps.scan_offset, data + len};
     const int rc = entropy_decode_with(br, ps, coef);
