@@ -369,6 +369,25 @@ class BCZPreprocessor(spec_transformation_preprocessor.SpecTransformationPreproc
     return features, labels
 
 
+def get_gripper_accuracy_metrics(inference_outputs, features, labels):
+  """Closing / opening prediction of the first waypoint against the sensed gripper state
+  (research/bcz/model.py:588-617): accuracy, AUC, precision, recall and the positive frequency of both events."""
+  from tensor2robot_b200.utils import metrics
+  key = 'target_close'
+  current = features.present[key].float()
+  predicted = inference_outputs[key][:, 0].float() - current
+  label = labels.future[key][:, 0].float() - current
+  out = {}
+  for name, lab, pred in (('closing', label > 0, predicted > 0), ('opening', label < 0, predicted < 0)):
+    lab, pred = lab.float(), pred.float()
+    out[name + '_accuracy'] = metrics.accuracy(lab, pred)
+    out[name + '_auc'] = metrics.auc(lab, pred)
+    out[name + '_precision'] = metrics.precision(lab, pred)
+    out[name + '_recall'] = metrics.recall(lab, pred)
+    out[name + '_pos_freq'] = metrics.accuracy(torch.ones_like(lab), lab)
+  return out
+
+
 class BCZModel(abstract_model.AbstractT2RModel):
   """Single-image configurable regression model for BC-Z (model.py:641-950)."""
 
@@ -513,3 +532,20 @@ class BCZModel(abstract_model.AbstractT2RModel):
     del features, mode, config, params
     return training_outputs(labels, inference_outputs, self._action_components,
                             stop_state_class_weights=self._stop_state_class_weights)
+
+  def model_eval_fn(self, features, labels, inference_outputs, train_loss, train_outputs, mode, config=None,
+                    params=None):
+    """Streaming means of every train output, the stop-state accuracy and the gripper open / close classification
+    metrics (research/bcz/model.py:894-929)."""
+    del train_loss, mode, config, params
+    from tensor2robot_b200.utils import metrics
+    out = {}
+    if train_outputs is not None:
+      for key, value in train_outputs.items():
+        out['mean_' + key] = metrics.mean(value)
+    if self._predict_stop:
+      predictions = torch.argmax(inference_outputs['stop_state'], dim=-1)
+      out['accuracy_stop_state'] = metrics.accuracy(labels.future.stop_state.long(), predictions)
+    if train_outputs and labels is not None and 'target_close' in self.action_component_names:
+      out.update(get_gripper_accuracy_metrics(inference_outputs, features, labels))
+    return out

@@ -136,3 +136,23 @@ def test_mixup_preprocessing_blends_images_and_labels():
   assert 0.0 <= lam <= 1.0
   np.testing.assert_allclose(lab_out, lam * lab_in + (1 - lam) * lab_in[::-1], rtol=1e-4, atol=1e-5)
   assert f.image.dtype == torch.bfloat16 and tuple(f.image.shape) == (4, 96, 96, 3)
+
+
+def test_bcz_eval_metrics(tmp_path):
+  """model_eval_fn (research/bcz/model.py:894-929) through train_eval_model's evaluation pass: streaming means of the
+  train outputs, stop-state accuracy, gripper closing / opening classification metrics."""
+  from tensor2robot_b200.input_generators import default_input_generator as gens
+  from tensor2robot_b200.utils import train_eval
+  model = _model(predict_stop=True, stop_state_class_weights=[1.0, 2.0, 2.0])
+  out = train_eval.train_eval_model(t2r_model=model, input_generator_train=gens.DefaultRandomInputGenerator(batch_size=4),
+                                    input_generator_eval=gens.DefaultRandomInputGenerator(batch_size=4),
+                                    max_train_steps=1, eval_steps=3, model_dir=str(tmp_path))
+  ev = out['eval']
+  assert ev['steps'] == 3 and np.isfinite(ev['loss'])
+  for name in ('closing', 'opening'):
+    for kind in ('accuracy', 'auc', 'precision', 'recall', 'pos_freq'):
+      assert 0.0 <= ev['%s_%s' % (name, kind)] <= 1.0 + 1e-9, (name, kind, ev)
+  assert 0.0 <= ev['accuracy_stop_state'] <= 1.0
+  means = [k for k in ev if k.startswith('mean_')]
+  assert 'mean_first_xyz_error' in means and len(means) >= 4
+  assert all(np.isfinite(ev[k]) for k in means)
