@@ -371,7 +371,7 @@ def train_eval_model(t2r_model=None, input_generator_train=None, input_generator
       with t2r_model.averaged_parameters():   # the Estimator evaluates checkpoints = the swapped-in averages
         out = t2r_model.model_fn(features, labels, ModeKeys.EVAL)
       losses.append(out.loss.detach())
-      streaming.update(out.metrics)            # model_eval_fn's streaming metrics: statistics summed over the batches
+      streaming.update(out.eval_metrics)            # model_eval_fn's streaming metrics: statistics summed over the batches
     if losses:
       result['eval'] = dict(streaming.results(), loss=float(torch.stack(losses).mean()), steps=len(losses))
   return result

@@ -42,7 +42,9 @@ def pytest_runtest_logreport(report):
   try:
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, 'a') as f:
-      f.write(json.dumps({'test': report.nodeid, 'outcome': report.outcome, 'seconds': round(report.duration, 3),
-                          'measured': lines}) + '\n')
+      record = {'test': report.nodeid, 'outcome': report.outcome, 'seconds': round(report.duration, 3), 'measured': lines}
+      if report.outcome == 'failed':
+        record['error'] = str(report.longrepr)[-1500:]
+      f.write(json.dumps(record) + '\n')
   except OSError:
     pass
