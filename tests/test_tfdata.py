@@ -421,3 +421,26 @@ def test_compress_decompress_on_the_fixture():
   restored, _ = tfdata.create_decompress_fn(feature_spec, label_spec)(packed, dict(flat_l.items()))
   assert restored['state'].shape == (5, 64, 64, 3)
   np.testing.assert_almost_equal(original.astype(np.float32) / 255, restored['state'].astype(np.float32) / 255, decimal=1)
+
+
+def test_pipelined_input_fn_yields_the_same_batches_in_order(monkeypatch):
+  """default_input_fn_tmpl parses up to PARSE_PIPELINE_DEPTH batches concurrently (the reference's num_parallel_calls,
+  utils/tfdata.py:629-689); the stream of batches - order, contents, drop_remainder, end of data while parses are still
+  in flight (the record mappings must outlive the generator of pointers) - equals the one-at-a-time pipeline."""
+  feature_spec, label_spec = _pose_env_specs()
+
+  def run(depth, mode):
+    monkeypatch.setattr(tfdata, 'PARSE_PIPELINE_DEPTH', depth)
+    out = []
+    for features, labels in tfdata.default_input_fn_tmpl(FIXTURE, 16, feature_spec, label_spec, mode=mode, seed=3):
+      out.append((features.state.image.copy(), features.action.pose.copy(), labels.reward.copy()))
+      if len(out) == 9:                      # TRAIN repeats forever
+        break
+    return out
+
+  for mode in (tfdata.ModeKeys.EVAL, tfdata.ModeKeys.TRAIN):
+    serial, piped = run(1, mode), run(2, mode)
+    assert len(serial) == len(piped) == (6 if mode == tfdata.ModeKeys.EVAL else 9)   # 100 records: 6 full batches of 16
+    for a, b in zip(serial, piped):
+      for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
