@@ -162,3 +162,41 @@ def test_checkpoint_predictor_high_precision_option():
   assert seen == [torch.bfloat16, torch.float32]
   assert q_fast.shape == q_exact.shape == (2, 64) and np.isfinite(q_exact).all()
   np.testing.assert_allclose(q_exact, q_fast, atol=5e-3)
+
+
+@pytest.mark.parametrize('scale', [1.0, 3.0])
+def test_grasping44_train_mode_error_is_the_bf16_storage_error(scale):
+  """The TRAINING path (bf16 storage, batch statistics) at the reference's initialisation (truncated normal 0.01,
+  research/qtopt/networks.py:425-600) and at 3x that scale, batch 8 at 472 x 472.  Batch normalisation rescales every
+  layer to unit variance, so the rounding of bf16 activation storage is amplified whatever the weight scale: the
+  north star's 1e-3 relative tolerance is NOT met by the training path (measured ~1e-2 here, recorded in
+  profiles/r02_parity.json); it is met by the PREDICT high-precision mode above.  What is asserted: the engine is as
+  close to the bf16-storage restatement of the reference as that restatement is to the fp32 one (the same criterion as
+  tests/test_qtopt_networks_gpu.py), i.e. the whole error is the storage format, not the kernels."""
+  from oracle import qtopt_networks as oracle
+  from tensor2robot_b200 import nn
+  from test_qtopt_networks_gpu import COND_FACTOR, _build_engine, _inputs, _oracle_step, _variables
+  b = 8
+  img, grasp, reward = _inputs(b, seed=31)
+  variables = oracle.init_variables(seed=7) if scale == 1.0 else _variables(7, scale=scale)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  grasp_t, reward_t = torch.from_numpy(grasp).cuda(), torch.from_numpy(reward).cuda()
+  vs, net = _build_engine(img_t, grasp_t, variables)
+  with nn.variable_store(vs):
+    logits, _ = net.model((None, img_t), grasp_t, is_training=True)
+    loss, q = nn.sigmoid_log_loss(logits, reward_t)
+  q_e, loss_e = q.float().cpu().numpy().reshape(-1), float(loss.detach())
+  img_o = img_t.float().cpu()
+  _, _, q_b, loss_b = _oracle_step(variables, img_o, grasp, reward, torch.bfloat16)
+  _, _, q_f, loss_f = _oracle_step(variables, img_o, grasp, reward, None)
+  rel = lambda x, y: float((np.abs(x - y) / np.abs(y)).max())
+  e_f, e_b, cond = rel(q_e, q_f), rel(q_e, q_b), rel(q_b, q_f)
+  print('grasping44 train mode x%.0f: q in [%.4f, %.4f]; max rel err engine vs fp32 oracle %.3e, engine vs bf16-storage '
+        'oracle %.3e, bf16-storage vs fp32 oracle %.3e; loss %.6f / %.6f / %.6f' % (
+            scale, q_f.min(), q_f.max(), e_f, e_b, cond, loss_e, loss_b, loss_f))
+  _record('grasping44_train_mode_472', weight_scale=scale, batch=b, q_min=float(q_f.min()), q_max=float(q_f.max()),
+          rel_err_engine_vs_fp32_oracle=e_f, rel_err_engine_vs_bf16_storage_oracle=e_b,
+          rel_err_bf16_storage_vs_fp32_oracle=cond, loss_engine=loss_e, loss_bf16_storage_oracle=loss_b,
+          loss_fp32_oracle=loss_f, north_star_tolerance=REL_TOL, north_star_met=bool(e_f < REL_TOL))
+  assert e_b <= COND_FACTOR * cond + 1e-3
+  assert e_f <= (1 + COND_FACTOR) * cond + 1e-3
