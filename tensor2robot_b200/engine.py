@@ -165,7 +165,7 @@ class CriticTrainStep(object):
     self.reducer = None
 
   # -- preprocessing (DefaultGrasping44ImagePreprocessor._preprocess_fn, t2r_models.py:277-308) ----
-  def preprocess(self, images_u8, training=True):
+  def preprocess(self, images_u8, training=True, out_dtype=torch.bfloat16):
     n = images_u8.shape[0]
     (ih, iw), (th, tw) = images_u8.shape[1:3], self.target_hw
     if training:   # RandomCropImages: ONE offset pair per batch (image_transformations.py:25-59)
@@ -189,7 +189,7 @@ class CriticTrainStep(object):
       if level and not self._rng.uniform() > d.get('random_noise_apply_probability', 0.5):
         params['noise_stddev'] = level
         seed, offset = int(self._rng.randint(0, 2**31 - 1)), self.global_step
-    return image_ops.crop_convert_distort(images_u8, (th, tw), params, torch.bfloat16, seed, offset)
+    return image_ops.crop_convert_distort(images_u8, (th, tw), params, out_dtype, seed, offset)
 
   # -- build -------------------------------------------------------------------------------------
   def build(self, images_u8, actions):
@@ -225,11 +225,17 @@ class CriticTrainStep(object):
     return total
 
   @torch.no_grad()
-  def predict(self, images_u8, actions):
-    """PREDICT mode: centre crop, moving-average BN, q_predicted [B] or [B, A]."""
+  def predict(self, images_u8, actions, high_precision=False):
+    """PREDICT mode: centre crop, moving-average BN, q_predicted [B] or [B, A].  high_precision: fp32 activations and
+    bf16x3 convolutions (nn.high_precision), Q within 1e-3 relative of an fp32 evaluation."""
     with nn.variable_store(self.vs):
-      x = self.preprocess(images_u8, training=False)
-      _, end_points = self.critic.model((None, x), actions, is_training=False)
+      if high_precision:
+        with nn.high_precision():
+          x = self.preprocess(images_u8, training=False, out_dtype=torch.float32)
+          _, end_points = self.critic.model((None, x), actions, is_training=False)
+      else:
+        x = self.preprocess(images_u8, training=False)
+        _, end_points = self.critic.model((None, x), actions, is_training=False)
     return end_points['predictions']
 
 
@@ -291,16 +297,22 @@ class CEMTargetComputer(object):
   """
 
   def __init__(self, critic, vs, action_size=10, cem_samples=64, cem_iters=2, num_elites=10, seed=0,
-               chunk=None):
+               chunk=None, high_precision=False):
+    """high_precision: evaluate the tower and every Q batch in nn.high_precision() (feed fp32 frames): the arg-max and
+    the target then see Q within 1e-3 relative of an fp32 evaluation, at 3x the tensor work of the bf16 path."""
     self.critic, self.vs, self.chunk = critic, vs, chunk
+    self.high_precision = high_precision
     self.action_size, self.cem_samples, self.cem_iters, self.num_elites = action_size, cem_samples, cem_iters, num_elites
     self.seed = seed
     self.calls = 0
 
   @torch.no_grad()
   def maximize(self, images_bf16):
-    """images_bf16 [B,h,w,3] preprocessed next-state frames.  Returns (best_action [B,D], max_q [B],
-    debug dict with the final mean/stddev)."""
+    """images_bf16 [B,h,w,3] preprocessed next-state frames (fp32 with high_precision).  Returns (best_action [B,D],
+    max_q [B], debug dict with the final mean/stddev)."""
+    if self.high_precision and not nn.is_high_precision():
+      with nn.high_precision():
+        return self.maximize(images_bf16)
     import ctypes as C
     from tensor2robot_b200 import _lib
     dev = images_bf16.device
@@ -357,12 +369,13 @@ class BellmanCriticTrainStep(CriticTrainStep):
   research/qtopt/README.md:9-12): parity of the target is unpinned by construction, its invariants are tested."""
 
   def __init__(self, critic, optimizer, gamma=0.9, cem_samples=64, cem_iters=2, num_elites=10, target_update_every=100,
-               target_source='online', cem_chunk=None, **kwargs):
+               target_source='online', cem_chunk=None, high_precision_target=False, **kwargs):
     super(BellmanCriticTrainStep, self).__init__(critic, optimizer, **kwargs)
     self.gamma = gamma
     self.target = LaggedTarget(self, update_every=target_update_every, source=target_source)
     self.cem = CEMTargetComputer(critic, self.target.vs, action_size=10, cem_samples=cem_samples, cem_iters=cem_iters,
-                                 num_elites=num_elites, seed=kwargs.get('rank', 0), chunk=cem_chunk)
+                                 num_elites=num_elites, seed=kwargs.get('rank', 0), chunk=cem_chunk,
+                                 high_precision=high_precision_target)
     self.last_target = None
 
   def build(self, images_u8, actions):
@@ -377,7 +390,8 @@ class BellmanCriticTrainStep(CriticTrainStep):
     if not self._built:
       self.build(images_u8, actions)
     self.target.update()
-    x_next = self.preprocess(next_images_u8, training=False)
+    x_next = self.preprocess(next_images_u8, training=False,
+                             out_dtype=torch.float32 if self.cem.high_precision else torch.bfloat16)
     _, max_q, _ = self.cem.maximize(x_next)
     y = self.cem.bellman_target(reward.reshape(-1).float(), done.reshape(-1).float(), max_q, self.gamma)
     self.last_target = y
