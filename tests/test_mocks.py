@@ -29,6 +29,29 @@ def test_tensorflow_trained_weights_separate_the_mock_dataset():
   assert (np.abs(logits) > 0.9).mean() > 0.95
 
 
+def test_oracle_matches_the_inference_graph_tensorflow_exported():
+  """The strongest pin the reference's fixtures allow without TensorFlow: its exported SavedModel
+  (test_data/mock_exported_savedmodel/saved_model.pb, written by TF from utils/mocks.py:150-176) is evaluated op by op
+  with numpy (tests/graphdef_interp.py) on the checkpoint beside it, and the restatement in oracle/mocks.py must
+  reproduce it: same op order (dense -> bias -> elu -> moving-statistics batch norm with epsilon 1e-3, three times,
+  then the linear head), same numbers."""
+  import graphdef_interp
+  graph = graphdef_interp.Graph(open(os.path.join(HERE, 'golden', 'mock_saved_model.pb'), 'rb').read())
+  out = 'MockT2RModel.dense.4/BiasAdd'
+  block = ['MatMul', 'BiasAdd', 'Elu', 'AddV2', 'Rsqrt', 'Mul', 'Mul', 'Mul', 'Sub', 'AddV2']
+  assert graph.ops_on_path(out) == block * 3 + ['MatMul', 'BiasAdd']
+  weights = _tf_weights()
+  rng = np.random.RandomState(0)
+  x = np.concatenate([mocks.MockInputGenerator(batch_size=32).create_numpy_data()[0],
+                      rng.uniform(-2, 2, (64, 3))]).astype(np.float32)
+  want = graph.run(out, {'measured_position': x}, {k: np.asarray(v, np.float32) for k, v in weights.items()})
+  eps = graph.run('MockT2RModel.batch_norm.0/batchnorm/add/y', {}, {})
+  assert abs(float(eps) - 1e-3) < 1e-9
+  got = oracle.forward(weights, x)
+  assert want.shape == got.shape == (x.shape[0], 1)
+  np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)       # fp32 graph evaluation against the float64 restatement
+
+
 def test_input_generator_batches():
   from tensor2robot_b200.utils import train_eval
   model = mocks.MockT2RModel()
