@@ -66,8 +66,7 @@ def TripletLoss(pregrasp_embedding, goal_embedding, postgrasp_embedding):  # pyl
 
 # ---------------------------------------------------------------------------------------------
 # Alternative / auxiliary embedding losses (losses.py:29-53, 80-157, 222-238).  [B, D] embedding-sized tails:
-# plain torch on whatever device the embeddings live on.  Not built: NPairsLossMultilabel (sparse-label slim loss)
-# and TYloss (feature-map sized; no shipped config selects them).
+# plain torch on whatever device the embeddings live on.
 # ---------------------------------------------------------------------------------------------
 def _masked_mean(values, mask):
   """tf.dynamic_partition(values, mask, 2)[1] averaged; zeros(1) when the mask is empty (the tf.cond else-branch)."""
@@ -115,3 +114,47 @@ def MatchNormsLoss(anchor_tensors, paired_tensors):  # pylint: disable=invalid-n
   anchor_norms = torch.linalg.norm(nn.to_f32(anchor_tensors), dim=1).detach()
   paired_norms = torch.linalg.norm(nn.to_f32(paired_tensors), dim=1)
   return ((anchor_norms - paired_norms) ** 2).sum() / 2
+
+
+def NPairsLossMultilabel(pregrasp_embedding, goal_embedding, postgrasp_embedding, grasp_success, params=None):  # pylint: disable=invalid-name
+  """npairs_loss_multilabel in both directions (losses.py:188-219).  Example i carries the single class i * success_i of
+  B + 1 classes, so every failed grasp shares class 0 (with example 0 as well); slim's loss then is the softmax
+  cross-entropy of the similarity matrix against the row-normalised label adjacency (shared classes between examples
+  i and j) plus the embedding regulariser 0.25 * 0.002 * (mean |a|^2 + mean |p|^2).  With every grasp successful the
+  adjacency is the identity and this equals NPairsLoss (the reference's own test)."""
+  del params
+  pre, post, goal = (nn.to_f32(t) for t in (pregrasp_embedding, postgrasp_embedding, goal_embedding))
+  pair_a, pair_b = pre - post, goal
+  b = pre.shape[0]
+  success = torch.as_tensor(grasp_success, device=pre.device).reshape(-1).long()
+  classes = torch.arange(b, device=pre.device) * success
+  labels = torch.nn.functional.one_hot(classes, b + 1).float()
+  adjacency = labels @ labels.t()
+  target = adjacency / adjacency.sum(1, keepdim=True)
+
+  def one_direction(anchor, positive):
+    reg = 0.25 * 0.002 * ((anchor ** 2).sum(1).mean() + (positive ** 2).sum(1).mean())
+    similarity = anchor @ positive.t()
+    return reg - (target * torch.log_softmax(similarity, dim=1)).sum(1).mean()
+
+  return one_direction(pair_a, pair_b) + one_direction(pair_b, pair_a)
+
+
+def _GetSoftMaxResponse(goal_embedding, scene_spatial):  # pylint: disable=invalid-name
+  """Heat map <scene_spatial[b, y, x, :], goal_embedding[b]>: its maximum and the maximum of its spatial softmax
+  (losses.py:241-266)."""
+  goal, scene = nn.to_f32(goal_embedding), nn.to_f32(scene_spatial)
+  b = goal.shape[0]
+  heat = (scene * goal.reshape(b, 1, 1, -1)).sum(3).reshape(b, -1)
+  return heat.max(1).values, torch.softmax(heat, dim=1).max(1).values
+
+
+def TYloss(pregrasp_spatial, postgrasp_spatial, goal_embedding):  # pylint: disable=invalid-name
+  """mean over the batch of (max cosine response of the goal in the postgrasp map) - (the same in the pregrasp map):
+  the object should be found before the grasp and not after it (losses.py:269-303)."""
+  l2n = lambda t: torch.nn.functional.normalize(nn.to_f32(t), dim=-1, eps=1e-6)
+  pre, post, goal = l2n(pregrasp_spatial), l2n(postgrasp_spatial), l2n(goal_embedding)
+  goal = goal[:, None, None, :]
+  pre_max = (pre * goal).sum(-1).flatten(1).max(1).values
+  post_max = (post * goal).sum(-1).flatten(1).max(1).values
+  return (post_max - pre_max).mean()

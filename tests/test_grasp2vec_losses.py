@@ -82,3 +82,61 @@ def test_reference_arithmetic_loss_cases(mask_kind):
 def test_reference_keypoint_accuracy_cases(keypoints, labels, expected_accuracy):
   acc, _ = losses.KeypointAccuracy(torch.tensor(keypoints, dtype=torch.float32), torch.tensor(labels))
   assert float(acc) == expected_accuracy
+
+
+def _np_npairs(anchor, positive, target):
+  reg = 0.25 * 0.002 * ((anchor ** 2).sum(1).mean() + (positive ** 2).sum(1).mean())
+  sim = anchor @ positive.T
+  logp = sim - sim.max(1, keepdims=True)
+  logp = logp - np.log(np.exp(logp).sum(1, keepdims=True))
+  return reg - (target * logp).sum(1).mean()
+
+
+def test_reference_npairs_multilabel_case():
+  """research/grasp2vec/losses_test.py:150-177: with every grasp successful the multilabel loss equals the n-pairs loss
+  (to 5 places); with failures it is larger than both.  Values against the numpy restatement of slim's
+  npairs_loss_multilabel (softmax cross-entropy against the row-normalised label adjacency + embedding regulariser)."""
+  rng = np.random.RandomState(0)
+  a, c, small = rng.rand(16), rng.rand(16), rng.rand(16) / 10
+  pre = np.array([a + small, a, c]).astype(np.float32)
+  post = np.zeros_like(pre)
+  goal = pre.copy()
+  t = torch.from_numpy
+
+  def both(target):
+    pa = (pre - post).astype(np.float64)
+    return _np_npairs(pa, goal.astype(np.float64), target) + _np_npairs(goal.astype(np.float64), pa, target)
+
+  all_ok = float(losses.NPairsLossMultilabel(t(pre), t(goal), t(post), np.ones(3, np.int32), {}))
+  single = both(np.eye(3))
+  assert abs(all_ok - single) < 1e-5                                   # == NPairsLoss (identity adjacency)
+  success = np.array([0, 0, 1])
+  failed = float(losses.NPairsLossMultilabel(t(pre), t(goal), t(post), success, {}))
+  labels = np.eye(4)[np.arange(3) * success]
+  adjacency = labels @ labels.T
+  assert abs(failed - both(adjacency / adjacency.sum(1, keepdims=True))) < 1e-5
+  assert failed > single and failed > all_ok
+
+
+def test_soft_max_response_and_ty_loss():
+  """losses.py:241-303 against direct numpy restatements; TYloss is negative when the goal is present before the grasp
+  and absent after it."""
+  rng = np.random.RandomState(1)
+  b, h, w, d = 3, 4, 5, 6
+  goal = rng.standard_normal((b, d)).astype(np.float32)
+  pre = rng.standard_normal((b, h, w, d)).astype(np.float32)
+  post = rng.standard_normal((b, h, w, d)).astype(np.float32)
+  t = torch.from_numpy
+  max_heat, max_soft = losses._GetSoftMaxResponse(t(goal), t(pre))    # pylint: disable=protected-access
+  heat = (pre * goal[:, None, None, :]).sum(3).reshape(b, -1)
+  soft = np.exp(heat - heat.max(1, keepdims=True))
+  soft /= soft.sum(1, keepdims=True)
+  np.testing.assert_allclose(max_heat.numpy(), heat.max(1), rtol=1e-5)
+  np.testing.assert_allclose(max_soft.numpy(), soft.max(1), rtol=1e-5)
+  n = lambda x: x / np.sqrt(np.maximum((x ** 2).sum(-1, keepdims=True), 1e-12))
+  want = ((n(post) * n(goal)[:, None, None, :]).sum(-1).reshape(b, -1).max(1) -
+          (n(pre) * n(goal)[:, None, None, :]).sum(-1).reshape(b, -1).max(1)).mean()
+  np.testing.assert_allclose(float(losses.TYloss(t(pre), t(post), t(goal))), want, rtol=1e-5, atol=1e-6)
+  pre[:, 1, 2, :] = goal * 3.0                                         # the object is in the pregrasp scene ...
+  post = -np.abs(post) * np.sign(goal)[:, None, None, :]               # ... and every postgrasp location points away
+  assert float(losses.TYloss(t(pre), t(post), t(goal))) < -1.0
