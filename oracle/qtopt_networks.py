@@ -85,8 +85,10 @@ def regularized_names(variables):
   return [k for k in variables if k.endswith('/weights')]
 
 
-def model(variables, image, grasp_params, is_training, scope=TOP_SCOPE, updates=None, end_points=None):
-  """image: [B,H,W,3] float32 in [0,1]; grasp_params: [B,10] or [B,A,10].  Returns logits [M,1]."""
+def model(variables, image, grasp_params, is_training, scope=TOP_SCOPE, updates=None, end_points=None,
+          goal_spatial=None, goal_vector=None):
+  """image: [B,H,W,3] float32 in [0,1]; grasp_params: [B,10] or [B,A,10].  Returns logits [M,1].
+  goal_spatial [G,h,w,C] / goal_vector [G,D]: what goal_spatial_fn() / goal_vector_fn() return (networks.py:548-561)."""
   v, p = variables, scope + '/'
   ep = end_points if end_points is not None else {}
   tile = grasp_params.dim() == 3
@@ -127,7 +129,12 @@ def model(variables, image, grasp_params, is_training, scope=TOP_SCOPE, updates=
   for l in range(14, 17):                                                                     # :536-539
     net = conv_bn_relu(net, 'conv%d' % l, 'VALID')
   ep['final_conv'] = net
-  net = net.reshape(net.shape[0], -1)                                                         # :553 flatten
+  batch = net.shape[0]
+  if goal_spatial is not None:                                                                # :548-553 tf.tile + concat
+    net = torch.cat([net, tf_ops._store(goal_spatial).repeat(batch // goal_spatial.shape[0], 1, 1, 1)], dim=3)
+  net = net.reshape(net.shape[0], -1)                                                         # :554 flatten
+  if goal_vector is not None:                                                                 # :558-561
+    net = torch.cat([net, tf_ops._store(goal_vector).repeat(batch // goal_vector.shape[0], 1)], dim=1)
   for l in range(2):                                                                          # :562-563
     net = tf_ops.relu(bn(tf_ops.dense(net, v[p + 'fc%d/weights' % l]), 'fc%d/BatchNorm' % l))
   logits = tf_ops.dense(net, v[p + 'logit/weights'], v[p + 'logit/biases'], fp32_path=True)   # :568-574

@@ -107,8 +107,8 @@ class Grasping44FlexibleGraspParams(GraspingModel):
       end_points['fcgrasp'] = fc
     return fc
 
-  def q_head(self, net, is_training, num_classes, end_points):
-    """conv8.. -> pool3 -> conv14..16 (VALID) -> fc0, fc1 -> logit (networks.py:524-573)."""
+  def q_head(self, net, is_training, num_classes, end_points, goal_spatial_fn=None, goal_vector_fn=None):
+    """conv8.. -> pool3 -> conv14..16 (VALID) -> [goal merge] -> fc0, fc1 -> logit (networks.py:524-573)."""
     first = 2 + sum(self.num_convs[:1])
     for l in range(first, 2 + sum(self.num_convs[:2])):
       net = self._conv_bn_relu(net, 3, 'conv%d' % l, is_training)
@@ -116,9 +116,25 @@ class Grasping44FlexibleGraspParams(GraspingModel):
     for l in range(2 + sum(self.num_convs[:2]), 2 + sum(self.num_convs[:3])):
       net = self._conv_bn_relu(net, 3, 'conv%d' % l, is_training, padding='VALID')
     end_points['final_conv'] = net
-    net = net.reshape(net.shape[0], -1)  # slim.flatten: NHWC order
+    batch = net.shape[0]
+    if goal_spatial_fn is not None:
+      # a goal feature map concatenated on the channel axis, tf.tile'd up to the (CEM-tiled) batch (networks.py:548-553)
+      goal = nn.to_bf16(goal_spatial_fn())
+      net = torch.cat([net, goal.repeat(batch // goal.shape[0], 1, 1, 1)], dim=3)
+    net = net.reshape(batch, -1)  # slim.flatten: NHWC order
+    if goal_vector_fn is not None:
+      goal = nn.to_bf16(goal_vector_fn())                                             # networks.py:558-561
+      net = torch.cat([net, goal.repeat(batch // goal.shape[0], 1)], dim=1)
     for l in range(self.hid_layers):
-      net = self._fc_bn_relu(net, 64, 'fc%d' % l, is_training)
+      if net.shape[1] % 64:
+        # a goal merge can leave an inner dimension that the tensor-core path does not take: the fp32 FC kernel keeps
+        # the reference's [K, 64] weight shape
+        net = nn.to_bf16(nn.dense_f32(nn.to_f32(net), 64, scope='fc%d' % l, bias_rows=0,
+                                      initializer=nn.truncated_normal(0.01)))
+        net = nn.batch_norm(net, is_training, scope='fc%d/BatchNorm' % l, scale=True, relu=True,
+                            momentum=self._batch_norm_decay, eps=self._batch_norm_epsilon)
+      else:
+        net = self._fc_bn_relu(net, 64, 'fc%d' % l, is_training)
     name = 'logit' if num_classes == 1 else 'logit_%d' % num_classes
     logits = nn.dense_f32(nn.to_f32(net), num_classes, scope=name, initializer=nn.truncated_normal(0.01))
     return logits
@@ -133,8 +149,6 @@ class Grasping44FlexibleGraspParams(GraspingModel):
     del kwargs, reuse
     if not restore:
       raise ValueError("This model doesn't yet support restore=False")
-    if goal_spatial_fn is not None or goal_vector_fn is not None:
-      raise NotImplementedError('goal conditioning is outside the QT-Opt hot path')
     if softmax:
       raise NotImplementedError('softmax head is not used by the QT-Opt critic')
     end_points = {}
@@ -159,7 +173,7 @@ class Grasping44FlexibleGraspParams(GraspingModel):
                                     is_training, end_points)
       net = nn.add_context(net, context, a)   # tile_batch + tf.add, never materialised
       end_points['vsum'] = net
-      logits = self.q_head(net, is_training, num_classes, end_points)
+      logits = self.q_head(net, is_training, num_classes, end_points, goal_spatial_fn, goal_vector_fn)
     end_points['logits'] = logits
     predictions = nn.sigmoid(logits.detach())
     if tile_batch:

@@ -187,3 +187,68 @@ def test_grasping44_predict_action_batch_matches_oracle():
         (np.abs(q_e - res['bf16']).max(), np.abs(q_e - res['fp32']).max()))
   assert np.abs(q_e - res['bf16']).max() < Q_TOL_PREDICT
   assert np.abs(q_e - res['fp32']).max() < Q_TOL_FP32_ORACLE
+
+
+@pytest.mark.parametrize('kind', ['vector', 'spatial', 'both'])
+def test_grasping44_goal_conditioning_matches_oracle(kind):
+  """goal_spatial_fn / goal_vector_fn (research/qtopt/networks.py:548-561; the Grasp2Vec-conditioned critic): the goal
+  map is concatenated to the final convolution map on the channel axis, the goal vector to the flattened features, both
+  tiled up to the CEM-tiled batch with tf.tile's block order; fc0 grows accordingly.  PREDICT with an action batch
+  against the oracle, and the gradient reaches the goal tensors in TRAIN mode."""
+  from oracle import qtopt_networks as oracle
+  from oracle import tf_ops
+  from tensor2robot_b200 import nn
+  from tensor2robot_b200.research.qtopt import networks
+  b, a = 2, 8
+  img, grasp, _ = _inputs(b, a, seed=9)
+  img_t = torch.from_numpy(img).cuda().to(torch.bfloat16)
+  grasp_t = torch.from_numpy(grasp).cuda()
+  rng = np.random.RandomState(12)
+  # the size of the final convolution map
+  vs0, net0 = _build_engine(img_t, grasp_t[:, 0], oracle.init_variables(seed=4))
+  with torch.no_grad(), nn.variable_store(vs0):
+    _, ep0 = net0.model((None, img_t), grasp_t[:, 0], is_training=False)
+  _, fh, fw, fc = ep0['final_conv'].shape
+  goal_spatial = rng.uniform(0, 1, (b, fh, fw, 8)).astype(np.float32) if kind in ('spatial', 'both') else None
+  goal_vector = rng.uniform(-1, 1, (b, 40)).astype(np.float32) if kind in ('vector', 'both') else None
+  k = fh * fw * (fc + (8 if goal_spatial is not None else 0)) + (40 if goal_vector is not None else 0)
+  variables = _variables(4, scale=5.0)
+  prefix = oracle.TOP_SCOPE + '/'
+  variables[prefix + 'fc0/weights'] = (rng.standard_normal((k, 64)) * 0.05).astype(np.float32)
+  gs = torch.from_numpy(goal_spatial).cuda().requires_grad_(True) if goal_spatial is not None else None
+  gv = torch.from_numpy(goal_vector).cuda().requires_grad_(True) if goal_vector is not None else None
+  fns = dict(goal_spatial_fn=(lambda: gs) if gs is not None else None, goal_vector_fn=(lambda: gv) if gv is not None else None)
+  vs = nn.VariableStore('cuda', seed=1)
+  net = networks.Grasping44E2EOpenCloseTerminateGripperStatusHeightToBottom()
+  with torch.no_grad(), nn.variable_store(vs):
+    net.model((None, img_t), grasp_t[:, 0], is_training=False, **fns)
+  vs.finalize()
+  assert vs.vars[prefix + 'fc0/weights'].numel == k * 64
+  vs.import_tf(variables)
+  with torch.no_grad(), nn.variable_store(vs):
+    _, ep = net.model((None, img_t), grasp_t, is_training=False, **fns)
+  q_e = ep['predictions'].float().cpu().numpy()
+  tf_ops.STORAGE_DTYPE = torch.bfloat16
+  try:
+    ep_o = {}
+    with torch.no_grad():
+      oracle.model(oracle.to_torch(variables, False), img_t.float().cpu(), torch.from_numpy(grasp), False, end_points=ep_o,
+                   goal_spatial=None if goal_spatial is None else torch.from_numpy(goal_spatial),
+                   goal_vector=None if goal_vector is None else torch.from_numpy(goal_vector))
+    q_o = ep_o['predictions'].numpy()
+  finally:
+    tf_ops.STORAGE_DTYPE = None
+  print('goal conditioning (%s): fc0 takes %d features; max|dq| vs bf16-storage oracle %.3e, q in [%.3f, %.3f]' % (
+      kind, k, np.abs(q_e - q_o).max(), q_o.min(), q_o.max()))
+  assert q_e.shape == q_o.shape == (b, a)
+  assert np.abs(q_e - q_o).max() < 2 * Q_TOL_PREDICT
+  assert q_o.max() - q_o.min() > 2e-3                      # the comparison is not vacuous
+  # TRAIN mode: gradients flow back into the goal tensors
+  with nn.variable_store(vs):
+    logits, _ = net.model((None, img_t), grasp_t[:, 0], is_training=True, **fns)
+    loss, _ = nn.sigmoid_log_loss(logits, torch.ones((b, 1), device='cuda'))
+    vs.zero_grad()
+    loss.backward()
+  for g in (gs, gv):
+    if g is not None:
+      assert g.grad is not None and float(g.grad.abs().max()) > 0
