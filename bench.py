@@ -526,8 +526,18 @@ def e2e_train_eval(rt, t2r_model, batch, steps, warmup, records=0):
     """Two fixed host batches in turn (drawing 0.5 GB of fresh random numbers per step would time numpy)."""
 
     def _generator_fn(self, batch_size):
-      sets = [(tensorspec_utils.make_random_numpy(self._feature_spec, batch_size, self._sequence_length),
-               tensorspec_utils.make_random_numpy(self._label_spec, batch_size, self._sequence_length)) for _ in range(2)]
+      def pinned(struct):
+        """The batches live in page-locked host memory, as the contract's e2e leg asks (and as a reader that parses into
+        pinned buffers provides): every step still pays the H2D copy of its 0.25-0.75 GB of frames."""
+        flat = tensorspec_utils.flatten_spec_structure(struct)
+        for k in list(flat.keys()):
+          a = np.ascontiguousarray(flat[k])
+          flat[k] = torch.from_numpy(a).pin_memory().numpy() if torch.cuda.is_available() and a.nbytes >= (1 << 20) else a
+        return flat
+
+      sets = [(pinned(tensorspec_utils.make_random_numpy(self._feature_spec, batch_size, self._sequence_length)),
+               pinned(tensorspec_utils.make_random_numpy(self._label_spec, batch_size, self._sequence_length)))
+              for _ in range(2)]
       self.h2d_bytes = sum(int(np.asarray(v).nbytes) for part in sets[0]
                            for v in tensorspec_utils.flatten_spec_structure(part).values())
       i = 0
@@ -656,7 +666,7 @@ def run_critic(args, rt):
              'ms_per_step': e_ms, 'api': 'utils.train_eval.train_eval_model + research.qtopt.t2r_models.%s' % cls.__name__,
              'input': ('TFRecord shards of JPEG transitions: read + CRC-32C + tf.Example parse + split JPEG decode '
                        '(Huffman on %d host threads, IDCT / upsampling / colour on the GPU)' % usable_host_threads())
-                      if records else 'host numpy batches (decoded uint8 frames)',
+                      if records else 'host numpy batches in pinned memory (decoded uint8 frames)',
              'host_threads': usable_host_threads()}
 
   # ---- side measurements of the default run: the reference's own critic and CEM on it ----

@@ -116,8 +116,16 @@ class DeviceStager(object):
         t = value if isinstance(value, torch.Tensor) else torch.from_numpy(value)
         if t.dtype == torch.float64:
           t = t.float()
+        if t.numel() * t.element_size() >= self._PARALLEL_COPY_BYTES and t.is_contiguous() and t.is_pinned():
+          # the producer already parsed / decoded into page-locked memory (a record reader's output buffers, a
+          # generator that owns pinned arrays): DMA straight from it; the slot keeps it alive until the copy is done
+          slot[key] = t
+          dev = t.to(self.device, non_blocking=True)
+          dev.record_stream(consumer_stream)
+          out[key] = dev
+          continue
         buf = slot.get(key)
-        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype or buf is t:
           buf = slot[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
         self._fill(buf, t)
         dev = buf.to(self.device, non_blocking=True)
