@@ -64,7 +64,9 @@ class DeviceStager(object):
       synchronised before the host memcpy into the slot);
     * the device tensors are allocated on the copy stream but consumed on `consumer_stream`: record_stream tells the
       caching allocator not to hand their memory to a later copy while the consumer's kernels may still read it.
-  stage() may run on a producer thread (train_eval._batches does): it only touches the copy stream."""
+  stage() may run on a producer thread (train_eval._batches does): it only touches the copy stream.  Large sources that
+  are already page-locked are not copied on the host at all; their owner must not rewrite them before `depth` further
+  batches have been staged."""
 
   def __init__(self, device, depth=3):
     self.device = torch.device(device)
