@@ -317,7 +317,7 @@ class CEMTargetComputer(object):
     from tensor2robot_b200 import _lib
     dev = images_bf16.device
     b, a, d = images_bf16.shape[0], self.cem_samples, self.action_size
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    st = _lib.current_stream_ptr()
     p = lambda t: C.c_void_p(t.data_ptr())
     mean = torch.zeros((b, d), dtype=torch.float32, device=dev)
     std = torch.ones((b, d), dtype=torch.float32, device=dev)
@@ -353,7 +353,7 @@ class CEMTargetComputer(object):
     target = torch.empty_like(max_q)
     _lib.call('t2r_bellman_target', C.c_void_p(reward.contiguous().data_ptr()),
               C.c_void_p(done.contiguous().data_ptr()), C.c_void_p(max_q.data_ptr()), float(gamma),
-              C.c_void_p(target.data_ptr()), max_q.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+              C.c_void_p(target.data_ptr()), max_q.numel(), _lib.current_stream_ptr())
     return target
 
 

@@ -22,7 +22,7 @@ def _p(t):
 
 
 def _stream():
-  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+  return _lib.current_stream_ptr()
 
 
 # ---- learning-rate functions (called with the global step) --------------------------------------

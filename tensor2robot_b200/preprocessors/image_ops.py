@@ -24,7 +24,7 @@ def _p(t):
 
 
 def _stream():
-  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+  return _lib.current_stream_ptr()
 
 
 def identity_params(n, crop_y=0, crop_x=0):

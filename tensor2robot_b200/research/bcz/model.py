@@ -283,6 +283,16 @@ from tensor2robot_b200.utils import tensorspec_utils  # pylint: disable=wrong-im
 EVAL, PREDICT = 'eval', 'infer'
 TensorSpec = tensorspec_utils.ExtendedTensorSpec
 _RNG = np.random.RandomState(0)
+_NOISE_GENERATORS = {}     # device -> torch.Generator of the task-embedding noise, seeded from _RNG on first use
+
+
+def _noise_generator(device):
+  key = (str(device), id(_RNG))
+  gen = _NOISE_GENERATORS.get(key)
+  if gen is None:
+    gen = _NOISE_GENERATORS[key] = torch.Generator(device=device)
+    gen.manual_seed(int(_RNG.randint(0, 2**31 - 1)))
+  return gen
 
 
 def _one_hot(ids, depth):
@@ -304,7 +314,7 @@ def mixup_reverse(x, lmbda):
   xf = x.float().contiguous()
   y = torch.empty_like(xf)
   _lib.call('t2r_mixup_reverse_f32', C.c_void_p(xf.data_ptr()), C.c_void_p(y.data_ptr()), xf.shape[0],
-            xf.numel() // xf.shape[0], float(lmbda), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            xf.numel() // xf.shape[0], float(lmbda), _lib.current_stream_ptr())
   return y.to(x.dtype) if x.dtype.is_floating_point else y
 
 
@@ -487,8 +497,14 @@ class BCZModel(abstract_model.AbstractT2RModel):
 
   def augment_condition_input(self, condition_input, features, is_training):
     if self._task_embedding_noise_std is not None and is_training:
-      noise = _RNG.standard_normal(tuple(condition_input.shape)).astype(np.float32) * self._task_embedding_noise_std
-      condition_input = condition_input + torch.from_numpy(noise).to(condition_input.device)
+      # tf.random.normal on the embedding (model.py:815-817), drawn on the device: a host draw of [B, 512] normals plus its
+      # pageable H2D copy cost ~2 ms of a 13.5 ms step and synchronised the launching thread
+      if condition_input.is_cuda:
+        noise = torch.randn(condition_input.shape, dtype=torch.float32, device=condition_input.device,
+                            generator=_noise_generator(condition_input.device))
+      else:
+        noise = torch.from_numpy(_RNG.standard_normal(tuple(condition_input.shape)).astype(np.float32))
+      condition_input = condition_input + noise * self._task_embedding_noise_std
     if self._ignore_task_embedding:
       condition_input = None
     extra = []

@@ -61,7 +61,7 @@ class PCGrad(optimizers.Optimizer):
     off, length, use, count = self._segment_tables(vs)
     gram = vs.scratch('pcgrad_gram', count * MAX_TASKS * MAX_TASKS, torch.float32)
     coef = vs.scratch('pcgrad_coef', count * MAX_TASKS, torch.float32)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stream = _lib.current_stream_ptr()
     _lib.call('t2r_pcgrad_project', _p(task_grads), t, n, _p(off), _p(length), _p(use), count, 1e-5, _p(gram), _p(coef),
               _p(vs.flat_grad), stream)
     return vs.flat_grad
