@@ -275,6 +275,132 @@ __global__ void __launch_bounds__(256) crop_convert_distort_vec_kernel(
   for (int t = threadIdx.x; t < out_vecs; t += blockDim.x) gdst[t] = reinterpret_cast<const uint4*>(out_sm)[t];
 }
 
+// Persistent, double-buffered variant: a block walks over (image, 8-row group) items; the aligned 16-byte source vectors
+// of the NEXT item are in flight (cp.async into the other shared buffer) while the current one is converted and stored,
+// so the load latency that bounded the one-shot kernels (load phase, barrier, convert / store phase) is hidden.
+constexpr int kPipeRows = 8;
+
+template <bool OUT_F32>
+__device__ __forceinline__ void crop_convert_group(const uint8_t* in_row, int off, const T2RDistortParams& pr, const float* m,
+                                                   int use_contrast, uint64_t seed, uint64_t offset, uint64_t pixel_index0,
+                                                   uint8_t* o) {
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(in_row) + (off >> 2);
+  const uint32_t sh = uint32_t(off & 3) * 8u;
+  uint32_t wv[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) wv[k] = words[k];
+  uint32_t px[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) px[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(px);
+  float outv[24];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float r_ = float(bytes[3 * j]) * (1.0f / 255.0f), g_ = float(bytes[3 * j + 1]) * (1.0f / 255.0f),
+          b_ = float(bytes[3 * j + 2]) * (1.0f / 255.0f);
+    pre_contrast(pr, r_, g_, b_);
+    if (use_contrast && pr.contrast_scale != 1.f) {
+      r_ = (r_ - m[0]) * pr.contrast_scale + m[0];
+      g_ = (g_ - m[1]) * pr.contrast_scale + m[1];
+      b_ = (b_ - m[2]) * pr.contrast_scale + m[2];
+    }
+    if (pr.noise_stddev != 0.f) {
+      const Philox4 rnd = philox4x32_10(seed, pixel_index0 + j, offset);
+      float z0, z1, z2, z3;
+      box_muller(rnd.v[0], rnd.v[1], &z0, &z1);
+      box_muller(rnd.v[2], rnd.v[3], &z2, &z3);
+      r_ += pr.noise_stddev * z0; g_ += pr.noise_stddev * z1; b_ += pr.noise_stddev * z2;
+    }
+    outv[3 * j] = fminf(fmaxf(r_, 0.f), 1.f);
+    outv[3 * j + 1] = fminf(fmaxf(g_, 0.f), 1.f);
+    outv[3 * j + 2] = fminf(fmaxf(b_, 0.f), 1.f);
+  }
+  if (OUT_F32) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      reinterpret_cast<float4*>(o)[k] = make_float4(outv[4 * k], outv[4 * k + 1], outv[4 * k + 2], outv[4 * k + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      reinterpret_cast<uint4*>(o)[k] = make_uint4(pack_bf16(outv[8 * k], outv[8 * k + 1]), pack_bf16(outv[8 * k + 2], outv[8 * k + 3]),
+                                                  pack_bf16(outv[8 * k + 4], outv[8 * k + 5]), pack_bf16(outv[8 * k + 6], outv[8 * k + 7]));
+  }
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) crop_convert_distort_pipe_kernel(
+    const uint8_t* __restrict__ src, void* __restrict__ dst, const T2RDistortParams* __restrict__ params,
+    const float* __restrict__ chan_mean, int N, int H, int W, int h, int w, int use_contrast, uint64_t seed, uint64_t offset,
+    int row_pitch) {
+  extern __shared__ uint4 smem_v[];
+  uint8_t* bufs[2] = {reinterpret_cast<uint8_t*>(smem_v), reinterpret_cast<uint8_t*>(smem_v) + kPipeRows * row_pitch};
+  constexpr int kOutBytes = OUT_F32 ? 12 : 6;
+  const int groups_y = (h + kPipeRows - 1) / kPipeRows;
+  const int items = N * groups_y;
+  const uint8_t* src_end = src + (size_t)N * H * W * 3;
+  const int vecs_per_row = row_pitch / 16;
+  const int total = h * w;
+
+  auto issue = [&](int item, uint8_t* buf) {      // the source vectors of one item -> shared memory, asynchronously
+    const int n = item / groups_y, y0 = (item - n * groups_y) * kPipeRows;
+    const int rows = min(kPipeRows, h - y0);
+    const int cy = params[n].crop_y, cx = params[n].crop_x;
+    const uint8_t* img = src + (size_t)n * H * W * 3;
+    for (int t = threadIdx.x; t < rows * vecs_per_row; t += blockDim.x) {
+      const int r = t / vecs_per_row, v = t - r * vecs_per_row;
+      const uint8_t* start = img + ((size_t)(y0 + r + cy) * W + cx) * 3;
+      const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(start) & ~uintptr_t(15));
+      const uint8_t* p = a0 + (size_t)v * 16;
+      uint4* d = reinterpret_cast<uint4*>(buf + r * row_pitch) + v;
+      if (p >= start + 3 * w) {
+        *d = make_uint4(0, 0, 0, 0);
+      } else if (p + 16 <= src_end && p >= src) {
+        const uint32_t daddr = static_cast<uint32_t>(__cvta_generic_to_shared(d));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(daddr), "l"(p) : "memory");
+      } else {   // the vector straddles the end (or the start) of the buffer: byte loads of what exists
+        uint8_t b[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) b[k] = (p + k >= src && p + k < src_end) ? p[k] : uint8_t(0);
+        uint4 q;
+        memcpy(&q, b, 16);
+        *d = q;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item = blockIdx.x;
+  if (item >= items) return;
+  issue(item, bufs[0]);
+  for (int it = 0; item < items; item += gridDim.x, ++it) {
+    uint8_t* cur = bufs[it & 1];
+    const int next = item + gridDim.x;
+    if (next < items) {
+      issue(next, bufs[(it + 1) & 1]);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                               // every thread's vectors of `cur` have landed
+    const int n = item / groups_y, y0 = (item - n * groups_y) * kPipeRows;
+    const int rows = min(kPipeRows, h - y0);
+    const T2RDistortParams pr = params[n];
+    float m[3] = {0.f, 0.f, 0.f};
+    if (use_contrast) { m[0] = chan_mean[n * 3]; m[1] = chan_mean[n * 3 + 1]; m[2] = chan_mean[n * 3 + 2]; }
+    const uint8_t* img = src + (size_t)n * H * W * 3;
+    const int groups_per_row = w / 8;
+    for (int t = threadIdx.x; t < rows * groups_per_row; t += blockDim.x) {
+      const int r = t / groups_per_row, gi = t - r * groups_per_row;
+      const uint8_t* start = img + ((size_t)(y0 + r + pr.crop_y) * W + pr.crop_x) * 3;
+      const int off = int(reinterpret_cast<uintptr_t>(start) & 15) + gi * 24;
+      const size_t pix = (size_t)(y0 + r) * w + gi * 8;
+      uint8_t* o = static_cast<uint8_t*>(dst) + ((size_t)n * total + pix) * kOutBytes;
+      crop_convert_group<OUT_F32>(cur + r * row_pitch, off, pr, m, use_contrast, seed, offset, (uint64_t)n * total + pix, o);
+    }
+    __syncthreads();                               // `cur` is free for the loads of the item after next
+  }
+}
+
 // TF1 tf.image.resize_images(BILINEAR), align_corners=False, legacy sampling: src = dst * scale.
 __global__ void __launch_bounds__(256) resize_bilinear_legacy_kernel(const float* __restrict__ src,
                                                                      float* __restrict__ dst, int N, int H,
@@ -375,6 +501,20 @@ extern "C" int32_t t2r_crop_convert_distort(const uint8_t* src, void* dst, const
   if (!no_vec && w % 8 == 0 && vec_smem <= 48 * 1024 && reinterpret_cast<uintptr_t>(dst) % 16 == 0 &&
       (size_t(h) * w * out_bytes) % 16 == 0) {
     // measured on B200 (472 x 472 crops, batch 512, CUDA events): direct stores 0.390 ms, staged stores 0.515 ms
+    static const bool pipe = getenv("T2R_CROP_PIPE") != nullptr && getenv("T2R_CROP_PIPE")[0] == '1';
+    if (pipe) {
+      const int items = N * ((h + kPipeRows - 1) / kPipeRows);
+      const int grid = std::min(items, 148 * 6);
+      const size_t smem = size_t(2) * kPipeRows * row_pitch;
+      if (out_f32)
+        crop_convert_distort_pipe_kernel<true><<<grid, 256, smem, st>>>(src, dst, params, chan_mean, N, H, W, h, w,
+                                                                        use_contrast, seed, offset, row_pitch);
+      else
+        crop_convert_distort_pipe_kernel<false><<<grid, 256, smem, st>>>(src, dst, params, chan_mean, N, H, W, h, w,
+                                                                         use_contrast, seed, offset, row_pitch);
+      T2R_LAUNCH_OK();
+      return T2R_OK;
+    }
     static const bool direct = !(getenv("T2R_CROP_DIRECT") != nullptr && getenv("T2R_CROP_DIRECT")[0] == '0');
     if (direct) {
       const dim3 grid((h + kVecRowsDirect - 1) / kVecRowsDirect, N);
